@@ -1,0 +1,170 @@
+/*
+ * spp_b200.h -- C ABI of libspp_b200.so: the B200-native (sm_100a, FP64) implementation of the
+ * nonlinear-least-squares hot path of SLAM++ (linearise -> landmark Schur complement -> FP64
+ * Cholesky of the reduced camera / pose system -> landmark back-substitution).
+ *
+ * This is the drop-in boundary. Plain pointers and sizes only; every host pointer is BORROWED for
+ * the duration of the call and never retained; the context owns all device memory. One caller
+ * thread per context (the reference's solvers are single-caller, parallelism is internal); one
+ * context drives one GPU (one process per GPU; the multi-GPU reduction is plugged in through
+ * spp_set_allreduce()). There is NO CPU fallback: every entry point fails with SPP_ERR_CUDA when
+ * no sm_100 device is usable.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the SLAM++ tree).
+ * Return codes: 0 ok, SPP_NOT_POSDEF (1) = the factorisation met a non-positive pivot (the
+ * reference's solvers return false in that case), < 0 = error, text via spp_last_error().
+ */
+#ifndef SPP_B200_H
+#define SPP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPP_OK 0
+#define SPP_NOT_POSDEF 1
+#define SPP_ERR_INVALID (-1)   /* bad argument / call order / unsupported structure */
+#define SPP_ERR_CUDA (-2)      /* CUDA runtime error or no usable device */
+#define SPP_ERR_NOMEM (-3)     /* host or device allocation failed (adapters throw std::bad_alloc) */
+#define SPP_ERR_COMM (-4)      /* the all-reduce hook failed */
+
+typedef struct spp_ctx *spp_ctx_t; /* opaque; models optimizer_t of include/ba_interface_example/BAOptimizer.h:120 */
+
+/* Jacobian evaluation of the BA / SE(3) edges */
+#define SPP_JAC_FD_REFERENCE 0 /* forward differences, delta = 1e-9, same operation order as the reference
+                                  (include/slam/BASolverBase.h:579-619, include/slam/3DSolverBase.h:1336-1370) */
+#define SPP_JAC_ANALYTIC 1     /* closed-form derivatives (agrees with the FD variant at the FD noise floor) */
+
+/* report of one spp_*_optimize() call; mirrors what CNonlinearSolver_Lambda_LM::Optimize() prints / keeps
+ * (include/slam/NonlinearSolver_Lambda_LM.h:796-1116) */
+#define SPP_MAX_TRACE 64
+typedef struct {
+	int32_t n_iterations;       /* linear solves performed (incl. rejected LM steps) */
+	int32_t n_accepted;         /* accepted steps */
+	int32_t n_rejected;         /* rejected steps ("warning: chi2 rising") */
+	int32_t status;             /* 0 ok, SPP_NOT_POSDEF if a factorisation failed (the loop stops, as the reference) */
+	double chi2_initial;        /* f_Chi_Squared_Error_Denorm() before the first step */
+	double chi2_final;          /* after the last accepted step */
+	double alpha_initial;       /* LM: tau * max per-edge Hessian diagonal (LM.h:151-199); 0 for Gauss-Newton */
+	double alpha_final;
+	double last_dx_norm;        /* "residual norm" of the last increment */
+	/* per-solve trace, first min(n_iterations, SPP_MAX_TRACE) entries */
+	double trace_alpha[SPP_MAX_TRACE];    /* damping used by the solve */
+	double trace_chi2[SPP_MAX_TRACE];     /* chi2 after applying the step (before accept/reject) */
+	double trace_dx_norm[SPP_MAX_TRACE];
+	uint8_t trace_accepted[SPP_MAX_TRACE];
+	/* device time of the phases, milliseconds, summed over the call (CUDA events); phase names follow the
+	 * reference's Dump() (LM.h:547-..): lambda, rhs/schur, linsolve, update, chi2 */
+	double ms_linearise, ms_schur, ms_factor, ms_backsubst, ms_update, ms_chi2, ms_total;
+} spp_report_t;
+
+/* ---- context ---------------------------------------------------------------------------------------- */
+
+/* replaces New_Optimizer() / Free_Optimizer() (include/ba_interface_example/BAOptimizer.h:122-123) */
+int spp_create(int device, spp_ctx_t *p_ctx);
+void spp_destroy(spp_ctx_t ctx);
+/* last error text of this context (valid until the next call); ctx may be NULL for creation errors */
+const char *spp_last_error(spp_ctx_t ctx);
+/* library / device identification: writes a short text such as "spp_b200 0.1 sm_100 NVIDIA B200" */
+int spp_describe(spp_ctx_t ctx, char *p_buffer, size_t n_buffer_size);
+/* number of kernel launches issued by this context since creation (bench.py reports it) */
+uint64_t spp_kernel_launches(spp_ctx_t ctx);
+/* the CUDA stream (cudaStream_t) all kernels of this context are launched on; for event timing by the caller */
+void *spp_stream(spp_ctx_t ctx);
+int spp_synchronize(spp_ctx_t ctx);
+
+/* Multi-GPU hook. When set, the partial reduced camera system [S_upper | b] (and the scalar partial sums of
+ * chi2, |dx|^2, ...) of this rank are summed over ranks by calling fn(user, device_pointer, n_doubles) -- the
+ * caller implements it with torch.distributed / ncclAllReduce(sum, double) on the stream returned by
+ * spp_stream() or any stream ordered after a spp_synchronize(). fn returns 0 on success.
+ * rank / world select this rank's landmark slice (contiguous, balanced by sum k_p^2).
+ * The reference has no counterpart (single process, OpenMP). */
+typedef int (*spp_allreduce_fn)(void *p_user, void *p_device_doubles, size_t n_doubles);
+int spp_set_allreduce(spp_ctx_t ctx, spp_allreduce_fn fn, void *p_user, int rank, int world);
+
+/* ---- slot 3: bundle adjustment system resident on the device --------------------------------------- */
+
+/* Replaces Add_CamVertex / Add_XYZVertex / Add_P2C3DEdge called in a loop (BAOptimizer.h:130-133;
+ * src/ba_interface_example/BAOptimizer.cpp:214-230 -> CFlatSystem::r_Get_Vertex / r_Add_Edge) plus the one-time
+ * structure build of lambda_utils::CLambdaOps2::Extend_Lambda (include/slam/NonlinearSolver_Lambda_Base.h:1634,
+ * 1853-1931) and CLinearSolver_Schur::SymbolicDecomposition_Blocky (include/slam/LinearSolver_Schur.h:1566-1606).
+ *   p_vertex_type[n_vertices]  0 = camera (6 DoF), 1 = point (3 DoF); vertex ids are shared, as in CFlatSystem
+ *   p_cam_params[11 * C]       per camera in id order: t(3), axis-angle(3), fx, fy, cx, cy, d   (CVertexCam, BA_Types.h:54-75)
+ *   p_points[3 * P]            per point in id order                                          (CVertexXYZ, BA_Types.h:355)
+ *   p_obs_point / p_obs_camera vertex ids of each observation, in edge insertion order       (CEdgeP2C3D, BA_Types.h:403)
+ *   p_z[2 * O], p_info[4 * O]  measurement and 2x2 information matrix per observation
+ * The first vertex (id 0) receives the reference's automatic unary factor (identity information,
+ * FlatSystem.h:337,432-473; Lambda_Base.h:1903-1923). */
+int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_type,
+	const double *p_cam_params, const double *p_points, size_t n_observations,
+	const uint64_t *p_obs_point, const uint64_t *p_obs_camera, const double *p_z, const double *p_info);
+
+/* Overwrite / read the vertex states (CBAOptimizer::r_Vertex_State, BAOptimizer.cpp:196-204).
+ * p_cam_states[6 * C] (t, axis-angle), p_points[3 * P]; either pointer may be NULL. */
+int spp_ba_set_states(spp_ctx_t ctx, const double *p_cam_states, const double *p_points);
+int spp_ba_get_states(spp_ctx_t ctx, double *p_cam_states, double *p_points);
+
+int spp_ba_set_jacobian_mode(spp_ctx_t ctx, int mode); /* SPP_JAC_* ; default SPP_JAC_FD_REFERENCE */
+
+/* Replaces CLambdaOps2::Refresh_Lambda + Collect_RightHandSide_Vector (Lambda_Base.h:1659-1706):
+ * per-edge Jacobians (CEdgeP2C3D::Calculate_Jacobians_Expectation_Error, BA_Types.h:494-505), Hessian blocks
+ * (CBaseEdgeImpl::Calculate_Hessians_v2, BaseTypes_Binary.h:759-848) and their reduction into lambda / eta. */
+int spp_ba_linearise(spp_ctx_t ctx);
+
+/* Export of the linearised system in the reference's own layout (upper block-triangular, vertex id order,
+ * column-major blocks; CUberBlockMatrix accessors BlockMatrix.h:343-430,470-485), WITHOUT damping.
+ * Call first with p_values == NULL to obtain the sizes. Used by the parity tests. */
+int spp_ba_get_lambda(spp_ctx_t ctx, uint64_t *p_n_block_cols, uint64_t *p_n_blocks, uint64_t *p_n_values,
+	uint64_t *p_col_dims, uint64_t *p_col_ptr, uint64_t *p_row_idx, double *p_values, double *p_eta);
+
+/* Replaces CNonlinearSolver_Lambda_LM::f_Chi_Squared_Error_Denorm (NonlinearSolver_Base.h:278-297 ->
+ * CEdgeP2C3D::f_Chi_Squared_Error, BA_Types.h:511-531). */
+int spp_ba_chi2(spp_ctx_t ctx, double *p_chi2);
+
+/* One damped Newton step on the current linearisation: solves (lambda + alpha I) dx = eta through the landmark
+ * Schur complement and returns dx in vertex id order (6 per camera, 3 per point). Does not move the vertices.
+ * = Apply_Damping + LinearSolve of LM.h:942-967,1512-1568. */
+int spp_ba_solve_step(spp_ctx_t ctx, double alpha, double *p_dx);
+
+/* Replaces CNonlinearSolver_Lambda_LM::Optimize(max_iter, min_dx_norm) (LM.h:796-1116), control flow included
+ * (initial damping, rho test, rollback, <= 10 extra iterations on rejected steps). */
+int spp_ba_optimize(spp_ctx_t ctx, size_t n_max_iterations, double f_min_dx_norm, spp_report_t *p_report);
+
+/* ---- slot 1: linear solver on a lambda given by the caller ------------------------------------------ */
+
+/* Replaces CLinearSolver_Schur::SymbolicDecomposition_Blocky(lambda) (LinearSolver_Schur.h:1566-1606): takes the
+ * block structure of an upper block-triangular lambda (block columns with dims in {3, 6}; guided ordering =
+ * 6-wide vertices first, then 3-wide, original order kept within each group, Schur.cpp:771-838).
+ *   p_col_dims[n]      width of each block column
+ *   p_col_ptr[n + 1]   block column pointers
+ *   p_row_idx[nnzb]    block row of every block (ascending within a column; the diagonal block is the last)
+ * Optional outputs: p_order[n] receives the ordering (new position -> original block column), *p_cut = #6-wide. */
+int spp_schur_symbolic(spp_ctx_t ctx, size_t n_block_cols, const uint64_t *p_col_dims, const uint64_t *p_col_ptr,
+	const uint64_t *p_row_idx, uint64_t *p_order, uint64_t *p_cut);
+
+/* Replaces CLinearSolver_Schur::Solve_PosDef_Blocky(lambda, eta) (LinearSolver_Schur.h:1623-1935): p_values are
+ * the blocks of lambda in the order of the structure given to spp_schur_symbolic (column-major blocks);
+ * p_eta_dx[n_scalars] is the right-hand side on input and the solution on output.
+ * Returns SPP_NOT_POSDEF where the reference returns false. */
+int spp_schur_solve(spp_ctx_t ctx, const double *p_values, double *p_eta_dx);
+
+/* Stage outputs of the last Schur solve, for the parity tests: the reduced camera system as a
+ * dense column-major (6C x 6C) matrix (upper triangle valid), its right-hand side, and the pattern of non-zero
+ * 6x6 blocks of the upper triangle (row-major bitmap, C*C bytes). Any pointer may be NULL. */
+int spp_schur_get_reduced_system(spp_ctx_t ctx, uint64_t *p_n, double *p_S, double *p_rhs, uint8_t *p_block_pattern);
+
+/* ---- dense FP64 Cholesky (the reduced camera system solver) ----------------------------------------- */
+
+/* Replaces CLinearSolver_DenseEigen::Solve_PosDef (src/slam/LinearSolver_Schur.cpp:2314-2333): Eigen::LLT<MatrixXd,
+ * Upper> of a dense column-major n x n matrix of which only the upper triangle is read, then two triangular
+ * solves; p_rhs_x is the right-hand side on input, the solution on output. Host pointers. */
+int spp_dense_posdef_solve(spp_ctx_t ctx, size_t n, const double *p_A, double *p_rhs_x);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SPP_B200_H */

@@ -1,0 +1,279 @@
+"""ctypes binding of libspp_b200.so (include/spp_b200.h). Plumbing only: every numeric step runs in the library.
+
+The library is built in-tree by ``__graft_entry__.build()`` (``make -C slam_plus_plus_b200/csrc``). There is no
+CPU fallback: loading fails loudly when the shared object is missing, and ``Context()`` raises when no sm_100
+device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspp_b200.so")
+
+SPP_OK, SPP_NOT_POSDEF = 0, 1
+SPP_ERR_INVALID, SPP_ERR_CUDA, SPP_ERR_NOMEM, SPP_ERR_COMM = -1, -2, -3, -4
+JAC_FD_REFERENCE, JAC_ANALYTIC = 0, 1
+MAX_TRACE = 64
+
+# every symbol include/spp_b200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "spp_create", "spp_destroy", "spp_last_error", "spp_describe", "spp_kernel_launches", "spp_stream",
+    "spp_synchronize", "spp_set_allreduce", "spp_ba_set_graph", "spp_ba_set_states", "spp_ba_get_states",
+    "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_chi2", "spp_ba_solve_step",
+    "spp_ba_optimize", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_get_reduced_system",
+    "spp_dense_posdef_solve",
+]
+
+
+class Report(C.Structure):
+    _fields_ = [
+        ("n_iterations", C.c_int32), ("n_accepted", C.c_int32), ("n_rejected", C.c_int32), ("status", C.c_int32),
+        ("chi2_initial", C.c_double), ("chi2_final", C.c_double), ("alpha_initial", C.c_double),
+        ("alpha_final", C.c_double), ("last_dx_norm", C.c_double),
+        ("trace_alpha", C.c_double * MAX_TRACE), ("trace_chi2", C.c_double * MAX_TRACE),
+        ("trace_dx_norm", C.c_double * MAX_TRACE), ("trace_accepted", C.c_uint8 * MAX_TRACE),
+        ("ms_linearise", C.c_double), ("ms_schur", C.c_double), ("ms_factor", C.c_double),
+        ("ms_backsubst", C.c_double), ("ms_update", C.c_double), ("ms_chi2", C.c_double), ("ms_total", C.c_double),
+    ]
+
+    def as_dict(self) -> dict:
+        n = min(self.n_iterations, MAX_TRACE)
+        return dict(
+            n_iterations=self.n_iterations, n_accepted=self.n_accepted, n_rejected=self.n_rejected,
+            status=self.status, chi2_initial=self.chi2_initial, chi2_final=self.chi2_final,
+            alpha_initial=self.alpha_initial, alpha_final=self.alpha_final, last_dx_norm=self.last_dx_norm,
+            trace_alpha=list(self.trace_alpha[:n]), trace_chi2=list(self.trace_chi2[:n]),
+            trace_dx_norm=list(self.trace_dx_norm[:n]), trace_accepted=[int(x) for x in self.trace_accepted[:n]],
+            ms=dict(linearise=self.ms_linearise, schur=self.ms_schur, factor=self.ms_factor,
+                    backsubst=self.ms_backsubst, update=self.ms_update, chi2=self.ms_chi2, total=self.ms_total))
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads libspp_b200.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (make -C slam_plus_plus_b200/csrc). "
+                           "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, dp, u64p, u8p = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)
+    lib.spp_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.spp_destroy.argtypes = [vp]
+    lib.spp_destroy.restype = None
+    lib.spp_last_error.argtypes = [vp]
+    lib.spp_last_error.restype = C.c_char_p
+    lib.spp_describe.argtypes = [vp, C.c_char_p, C.c_size_t]
+    lib.spp_kernel_launches.argtypes = [vp]
+    lib.spp_kernel_launches.restype = C.c_uint64
+    lib.spp_stream.argtypes = [vp]
+    lib.spp_stream.restype = vp
+    lib.spp_synchronize.argtypes = [vp]
+    lib.spp_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp, C.c_int, C.c_int]
+    lib.spp_ba_set_graph.argtypes = [vp, C.c_size_t, u8p, dp, dp, C.c_size_t, u64p, u64p, dp, dp]
+    lib.spp_ba_set_states.argtypes = [vp, dp, dp]
+    lib.spp_ba_get_states.argtypes = [vp, dp, dp]
+    lib.spp_ba_set_jacobian_mode.argtypes = [vp, C.c_int]
+    lib.spp_ba_linearise.argtypes = [vp]
+    lib.spp_ba_get_lambda.argtypes = [vp, u64p, u64p, u64p, u64p, u64p, u64p, dp, dp]
+    lib.spp_ba_chi2.argtypes = [vp, dp]
+    lib.spp_ba_solve_step.argtypes = [vp, C.c_double, dp]
+    lib.spp_ba_optimize.argtypes = [vp, C.c_size_t, C.c_double, C.POINTER(Report)]
+    lib.spp_schur_symbolic.argtypes = [vp, C.c_size_t, u64p, u64p, u64p, u64p, u64p]
+    lib.spp_schur_solve.argtypes = [vp, dp, dp]
+    lib.spp_schur_get_reduced_system.argtypes = [vp, u64p, dp, dp, u8p]
+    lib.spp_dense_posdef_solve.argtypes = [vp, C.c_size_t, dp, dp]
+    _lib = lib
+    return lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _u64p(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def _u8p(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+class SppError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libspp_b200 error {code}: {msg}")
+        self.code = code
+
+
+class NotPositiveDefinite(ArithmeticError):
+    """The factorisation met a non-positive pivot (the reference's solvers return false)."""
+
+
+class Context:
+    """One solver context on one GPU (``optimizer_t`` of the reference's C API)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.spp_create(device, C.byref(h))
+        if rc != SPP_OK:
+            raise SppError(rc, self.lib.spp_last_error(None).decode())
+        self.h = h
+        self._cb = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.spp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> int:
+        if rc == SPP_NOT_POSDEF:
+            raise NotPositiveDefinite("matrix is not positive definite")
+        if rc != SPP_OK:
+            raise SppError(rc, self.lib.spp_last_error(self.h).decode())
+        return rc
+
+    def describe(self) -> str:
+        buf = C.create_string_buffer(256)
+        self._check(self.lib.spp_describe(self.h, buf, 256))
+        return buf.value.decode()
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.spp_kernel_launches(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.spp_stream(self.h) or 0)
+
+    def synchronize(self):
+        self._check(self.lib.spp_synchronize(self.h))
+
+    def set_allreduce(self, fn, rank: int, world: int):
+        """fn(device_ptr:int, n_doubles:int) -> None sums the buffer over ranks (torch.distributed / NCCL)."""
+        if fn is None:
+            self._cb = ALLREDUCE_FN(0)
+        else:
+            def tramp(_user, ptr, n):
+                try:
+                    fn(int(ptr), int(n))
+                    return 0
+                except Exception:  # pragma: no cover - reported through the C status
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            self._cb = ALLREDUCE_FN(tramp)
+        self._check(self.lib.spp_set_allreduce(self.h, self._cb, None, rank, world))
+
+    # ---- bundle adjustment ----------------------------------------------------------------------
+    def ba_set_graph(self, g):
+        vtype = np.ascontiguousarray(g.vtype, np.uint8)
+        cams = np.ascontiguousarray(g.cams, np.float64)
+        pts = np.ascontiguousarray(g.pts, np.float64)
+        op = np.ascontiguousarray(g.obs_pt, np.uint64)
+        oc = np.ascontiguousarray(g.obs_cam, np.uint64)
+        z = np.ascontiguousarray(g.z, np.float64)
+        info = np.ascontiguousarray(g.info, np.float64)
+        self._ba_dims = (int(cams.shape[0]), int(pts.shape[0]), int(op.shape[0]), int(vtype.shape[0]))
+        self._check(self.lib.spp_ba_set_graph(self.h, vtype.shape[0], _u8p(vtype), _dp(cams), _dp(pts), op.shape[0],
+                                              _u64p(op), _u64p(oc), _dp(z), _dp(info)))
+
+    def ba_set_states(self, cam_states=None, pts=None):
+        cs = None if cam_states is None else np.ascontiguousarray(cam_states, np.float64)
+        ps = None if pts is None else np.ascontiguousarray(pts, np.float64)
+        self._check(self.lib.spp_ba_set_states(self.h, _dp(cs), _dp(ps)))
+
+    def ba_get_states(self):
+        c, p, _, _ = self._ba_dims
+        cs = np.empty((c, 6))
+        ps = np.empty((p, 3))
+        self._check(self.lib.spp_ba_get_states(self.h, _dp(cs), _dp(ps)))
+        return cs, ps
+
+    def ba_set_jacobian_mode(self, mode: int):
+        self._check(self.lib.spp_ba_set_jacobian_mode(self.h, mode))
+
+    def ba_linearise(self):
+        self._check(self.lib.spp_ba_linearise(self.h))
+
+    def ba_get_lambda(self):
+        """Returns (col_dims, col_ptr, row_idx, values, eta) in the reference's block layout."""
+        nbc, nb, nv = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.spp_ba_get_lambda(self.h, C.byref(nbc), C.byref(nb), C.byref(nv), None, None, None, None, None))
+        col_dims = np.empty(nbc.value, np.uint64)
+        col_ptr = np.empty(nbc.value + 1, np.uint64)
+        row_idx = np.empty(nb.value, np.uint64)
+        vals = np.empty(nv.value)
+        eta = np.empty(int(self._ba_dims[0] * 6 + self._ba_dims[1] * 3))
+        self._check(self.lib.spp_ba_get_lambda(self.h, None, None, None, _u64p(col_dims), _u64p(col_ptr), _u64p(row_idx),
+                                               _dp(vals), _dp(eta)))
+        return col_dims, col_ptr, row_idx, vals, eta
+
+    def ba_chi2(self) -> float:
+        v = C.c_double()
+        self._check(self.lib.spp_ba_chi2(self.h, C.byref(v)))
+        return v.value
+
+    def ba_solve_step(self, alpha: float) -> np.ndarray:
+        dx = np.empty(int(self._ba_dims[0] * 6 + self._ba_dims[1] * 3))
+        self._check(self.lib.spp_ba_solve_step(self.h, alpha, _dp(dx)))
+        return dx
+
+    def ba_optimize(self, max_iterations: int = 5, min_dx_norm: float = 0.01) -> dict:
+        rep = Report()
+        self._check(self.lib.spp_ba_optimize(self.h, max_iterations, min_dx_norm, C.byref(rep)))
+        return rep.as_dict()
+
+    # ---- slot 1: Schur linear solver on a caller-supplied lambda ---------------------------------
+    def schur_symbolic(self, col_dims, col_ptr, row_idx):
+        cd = np.ascontiguousarray(col_dims, np.uint64)
+        cp = np.ascontiguousarray(col_ptr, np.uint64)
+        ri = np.ascontiguousarray(row_idx, np.uint64)
+        order = np.empty(cd.shape[0], np.uint64)
+        cut = C.c_uint64()
+        self._check(self.lib.spp_schur_symbolic(self.h, cd.shape[0], _u64p(cd), _u64p(cp), _u64p(ri), _u64p(order),
+                                                C.byref(cut)))
+        self._schur_n = int(cd.astype(np.int64).sum())
+        return order.astype(np.int64), int(cut.value)
+
+    def schur_solve(self, values, eta) -> np.ndarray:
+        v = np.ascontiguousarray(values, np.float64)
+        x = np.array(eta, np.float64, copy=True)
+        self._check(self.lib.spp_schur_solve(self.h, _dp(v), _dp(x)))
+        return x
+
+    def schur_get_reduced_system(self, want_values: bool = True):
+        n = C.c_uint64()
+        self._check(self.lib.spp_schur_get_reduced_system(self.h, C.byref(n), None, None, None))
+        n = int(n.value)
+        c = n // 6
+        pat = np.zeros((c, c), np.uint8)
+        if want_values:
+            S = np.empty((n, n))
+            rhs = np.empty(n)
+            self._check(self.lib.spp_schur_get_reduced_system(self.h, None, _dp(S), _dp(rhs), _u8p(pat)))
+            return S.T.copy(), rhs, pat  # library writes column-major
+        self._check(self.lib.spp_schur_get_reduced_system(self.h, None, None, None, _u8p(pat)))
+        return None, None, pat
+
+    # ---- dense Cholesky --------------------------------------------------------------------------
+    def dense_posdef_solve(self, A, b) -> np.ndarray:
+        A = np.asfortranarray(A, np.float64)
+        x = np.array(b, np.float64, copy=True)
+        self._check(self.lib.spp_dense_posdef_solve(self.h, A.shape[0], A.ctypes.data_as(C.POINTER(C.c_double)), _dp(x)))
+        return x

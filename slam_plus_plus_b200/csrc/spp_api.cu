@@ -1,0 +1,646 @@
+// spp_api.cu -- the C ABI of libspp_b200.so (include/spp_b200.h) and the host control flow of the
+// nonlinear solvers (LM loop), mirroring CNonlinearSolver_Lambda_LM::Optimize
+// (include/slam/NonlinearSolver_Lambda_LM.h:796-1116) with the system resident on the device.
+
+#include "spp_ctx.h"
+#include <string.h>
+#include <math.h>
+#include <algorithm>
+
+namespace spp {
+
+// kernels / stages implemented in the other translation units
+void build_schur_structure(spp_ctx *ctx, size_t C, size_t P, const std::vector<uint32_t> &h_cam,
+	const std::vector<uint32_t> &h_pt, std::vector<uint32_t> &obs_orig, std::vector<uint32_t> &t_cam,
+	std::vector<uint32_t> &t_pt);
+void ba_linearise(spp_ctx *ctx, bool b_want_maxdiag);
+void ba_chi2_device(spp_ctx *ctx, double *d_out);
+void ba_step_dots_device(spp_ctx *ctx, double alpha, double *d_out);
+void ba_apply_update(spp_ctx *ctx);
+void schur_form_reduced_system(spp_ctx *ctx, double alpha);
+void schur_backsubstitute(spp_ctx *ctx);
+size_t dense_chol_ld(size_t n);
+size_t dense_chol_storage(size_t n);
+int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x);
+void slot_symbolic(spp_ctx *ctx, size_t n, const uint64_t *col_dims, const uint64_t *col_ptr, const uint64_t *row_idx,
+	uint64_t *p_order, uint64_t *p_cut);
+int slot_solve(spp_ctx *ctx, const double *p_values, double *p_eta_dx);
+
+static thread_local std::string g_create_error;
+
+struct EventTimer {
+	spp_ctx *ctx;
+	cudaEvent_t a, b;
+	EventTimer(spp_ctx *c) : ctx(c), a(c->ev[0]), b(c->ev[1]) {}
+	void start() { cudaEventRecord(a, ctx->stream); }
+	double stop_ms()
+	{
+		cudaEventRecord(b, ctx->stream);
+		cudaEventSynchronize(b);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, a, b);
+		return ms;
+	}
+};
+
+// Solves the damped Schur system on the current (U, V, W, gc, gp): dxc, dxp. Returns SPP_OK / SPP_NOT_POSDEF.
+int schur_solve_current(spp_ctx *ctx, double alpha, spp_report_t *rep)
+{
+	SchurSystem &s = ctx->sys;
+	const size_t n = s.C * 6;
+	EventTimer tm(ctx);
+	tm.start();
+	schur_form_reduced_system(ctx, alpha); // S lives in the padded storage of the dense solver
+	if(ctx->allreduce && ctx->world > 1) {
+		// TODO(multi-GPU): pack [S_upper | b], all-reduce
+	}
+	if(s.keep_reduced) {
+		s.S_copy.resize(s.S.size());
+		s.b_copy.resize(n);
+		SPP_CUDA(cudaMemcpyAsync(s.S_copy.p(), s.S.p(), s.S.size() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+		SPP_CUDA(cudaMemcpyAsync(s.b_copy.p(), s.b.p(), n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+	}
+	if(rep) rep->ms_schur += tm.stop_ms();
+	tm.start();
+	int rc = dense_chol_solve_device(ctx, s.S.p(), n, s.b.p());
+	if(rep) rep->ms_factor += tm.stop_ms();
+	if(rc != SPP_OK)
+		return rc;
+	tm.start();
+	s.dxc.resize(n);
+	SPP_CUDA(cudaMemcpyAsync(s.dxc.p(), s.b.p(), n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+	schur_backsubstitute(ctx);
+	if(rep) rep->ms_backsubst += tm.stop_ms();
+	return SPP_OK;
+}
+
+static double read_scalar(spp_ctx *ctx, const double *d_ptr, int n, double *out)
+{
+	ctx->h_scalars.resize(16);
+	SPP_CUDA(cudaMemcpyAsync(ctx->h_scalars.p(), d_ptr, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	for(int i = 0; i < n; ++ i)
+		out[i] = ctx->h_scalars[i];
+	return out[0];
+}
+
+static double ba_chi2_host(spp_ctx *ctx)
+{
+	BAProblem &ba = ctx->ba;
+	ba.partial.resize(4 * 1024);
+	double *d_out = ba.partial.p() + 2048;
+	ba_chi2_device(ctx, d_out);
+	double v;
+	read_scalar(ctx, d_out, 1, &v);
+	return v;
+}
+
+static void ba_save_state(spp_ctx *ctx)
+{
+	BAProblem &ba = ctx->ba;
+	ba.cam_state_saved.resize(ba.cam_state.size());
+	ba.pts_saved.resize(ba.pts.size());
+	SPP_CUDA(cudaMemcpyAsync(ba.cam_state_saved.p(), ba.cam_state.p(), ba.cam_state.size() * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	SPP_CUDA(cudaMemcpyAsync(ba.pts_saved.p(), ba.pts.p(), ba.pts.size() * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+}
+
+static void ba_load_state(spp_ctx *ctx)
+{
+	BAProblem &ba = ctx->ba;
+	SPP_CUDA(cudaMemcpyAsync(ba.cam_state.p(), ba.cam_state_saved.p(), ba.cam_state.size() * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	SPP_CUDA(cudaMemcpyAsync(ba.pts.p(), ba.pts_saved.p(), ba.pts.size() * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+}
+
+// CNonlinearSolver_Lambda_LM::Optimize, LM.h:796-1116 (batch use: the system is "dirty" on entry)
+static int ba_optimize(spp_ctx *ctx, size_t n_max_iteration_num, double f_min_dx_norm, spp_report_t *rep)
+{
+	BAProblem &ba = ctx->ba;
+	SchurSystem &s = ctx->sys;
+	memset(rep, 0, sizeof(*rep));
+	if(!s.O)
+		return SPP_OK; // "the system contains no edges at all: nothing to optimize"
+	EventTimer total(ctx);
+	cudaEvent_t t0 = ctx->ev[2], t1 = ctx->ev[3];
+	SPP_CUDA(cudaEventRecord(t0, ctx->stream));
+	EventTimer tm(ctx);
+
+	tm.start();
+	ba_linearise(ctx, true); // Refresh_Lambda, LM.h:828-831
+	rep->ms_linearise += tm.stop_ms();
+	// f_InitialDamping: tau * max over edges of the per-edge vertex Hessian diagonals, LM.h:151-199
+	unsigned long long bits = 0;
+	SPP_CUDA(cudaMemcpyAsync(&bits, ba.maxdiag.p(), 8, cudaMemcpyDeviceToHost, ctx->stream));
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	double f_max_diag;
+	memcpy(&f_max_diag, &bits, 8);
+	double f_alpha = f_max_diag * 1e-3;
+	double f_nu = 2.0;
+	rep->alpha_initial = f_alpha;
+
+	tm.start();
+	double f_last_error = ba_chi2_host(ctx); // LM.h:899
+	rep->ms_chi2 += tm.stop_ms();
+	rep->chi2_initial = f_last_error;
+	rep->chi2_final = f_last_error;
+
+	bool b_system_dirty = false; // lambda matches the current linearisation point
+	int fail = 10;
+	for(size_t n_iteration = 0; n_iteration < n_max_iteration_num; ++ n_iteration) {
+		if(n_iteration && b_system_dirty) {
+			tm.start();
+			ba_linearise(ctx, false); // LM.h:942-949; a rejected step only re-damps (alpha is applied on the fly)
+			rep->ms_linearise += tm.stop_ms();
+		}
+		b_system_dirty = false;
+
+		int rc = schur_solve_current(ctx, f_alpha, rep); // LinearSolve, LM.h:1512-1568
+		const int it = rep->n_iterations;
+		++ rep->n_iterations;
+		if(it < SPP_MAX_TRACE)
+			rep->trace_alpha[it] = f_alpha;
+		if(rc != SPP_OK) {
+			rep->status = rc;
+			break; // "in case cholesky failed, quit", LM.h:972-974
+		}
+
+		double dots[2];
+		ba.partial.resize(4 * 1024);
+		ba_step_dots_device(ctx, f_alpha, ba.partial.p() + 2048);
+		read_scalar(ctx, ba.partial.p() + 2048, 2, dots);
+		const double f_residual_norm = sqrt(dots[0]);
+		rep->last_dx_norm = f_residual_norm;
+		if(it < SPP_MAX_TRACE)
+			rep->trace_dx_norm[it] = f_residual_norm;
+		if(f_residual_norm <= f_min_dx_norm)
+			break; // LM.h:1054
+
+		tm.start();
+		ba_save_state(ctx);       // LM.h:1062
+		ba_apply_update(ctx);     // PushValuesInGraphSystem, LM.h:1066
+		rep->ms_update += tm.stop_ms();
+
+		tm.start();
+		const double f_error = ba_chi2_host(ctx); // LM.h:1078
+		rep->ms_chi2 += tm.stop_ms();
+		if(it < SPP_MAX_TRACE)
+			rep->trace_chi2[it] = f_error;
+
+		// CLevenbergMarquardt_Baseline::Aftermath, LM.h:204-223
+		const double rho = (f_last_error - f_error) / dots[1];
+		if(rho > 0) {
+			f_alpha *= std::max(1 / 3.0, 1.0 - pow((2 * rho - 1), 3));
+			f_nu = 2;
+			f_last_error = f_error;
+			rep->chi2_final = f_error;
+			++ rep->n_accepted;
+			if(it < SPP_MAX_TRACE)
+				rep->trace_accepted[it] = 1;
+			b_system_dirty = true;
+		} else {
+			f_alpha *= f_nu;
+			f_nu *= 2;
+			++ rep->n_rejected;
+			ba_load_state(ctx); // "warning: chi2 rising", LM.h:1096-1106
+			if(fail > 0) {
+				-- fail;
+				++ n_max_iteration_num;
+			}
+		}
+	}
+	rep->alpha_final = f_alpha;
+	ba.linearised = !b_system_dirty;
+	SPP_CUDA(cudaEventRecord(t1, ctx->stream));
+	SPP_CUDA(cudaEventSynchronize(t1));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, t0, t1);
+	rep->ms_total = ms;
+	return SPP_OK;
+}
+
+} // namespace spp
+
+using namespace spp;
+
+// ---------------------------------------------------------------------------------------------------
+
+#define API_BEGIN(ctx) if(!(ctx)) return SPP_ERR_INVALID; try { SPP_CUDA(cudaSetDevice((ctx)->device));
+#define API_END(ctx) } catch(const std::bad_alloc&) { (ctx)->last_error = "out of memory"; return SPP_ERR_NOMEM; } \
+	catch(const spp::invalid_error &e) { (ctx)->last_error = e.what(); return SPP_ERR_INVALID; } \
+	catch(const std::exception &e) { (ctx)->last_error = e.what(); return SPP_ERR_CUDA; } return SPP_OK;
+
+extern "C" {
+
+int spp_create(int device, spp_ctx_t *p_ctx)
+{
+	if(!p_ctx)
+		return SPP_ERR_INVALID;
+	*p_ctx = 0;
+	int n_dev = 0;
+	cudaError_t e = cudaGetDeviceCount(&n_dev);
+	if(e != cudaSuccess || n_dev == 0) {
+		g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libspp_b200 has no CPU fallback)";
+		return SPP_ERR_CUDA;
+	}
+	if(device < 0 || device >= n_dev) {
+		g_create_error = "device index out of range";
+		return SPP_ERR_INVALID;
+	}
+	cudaDeviceProp prop;
+	if(cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+		g_create_error = "libspp_b200 is built for sm_100a (B200) only";
+		return SPP_ERR_CUDA;
+	}
+	spp_ctx *ctx = new(std::nothrow) spp_ctx();
+	if(!ctx)
+		return SPP_ERR_NOMEM;
+	ctx->device = device;
+	ctx->n_launches = 0;
+	ctx->allreduce = 0;
+	ctx->allreduce_user = 0;
+	ctx->rank = 0;
+	ctx->world = 1;
+	ctx->stream = 0;
+	for(int i = 0; i < 16; ++ i) ctx->ev[i] = 0;
+	try {
+		SPP_CUDA(cudaSetDevice(device));
+		SPP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+		for(int i = 0; i < 16; ++ i)
+			SPP_CUDA(cudaEventCreate(&ctx->ev[i]));
+		ctx->h_scalars.resize(16);
+	} catch(const std::exception &ex) {
+		g_create_error = ex.what();
+		delete ctx;
+		return SPP_ERR_CUDA;
+	}
+	char buf[256];
+	snprintf(buf, sizeof(buf), "spp_b200 0.1 sm_%d%d %s (%d SMs)", prop.major, prop.minor, prop.name, prop.multiProcessorCount);
+	ctx->description = buf;
+	*p_ctx = ctx;
+	return SPP_OK;
+}
+
+void spp_destroy(spp_ctx_t ctx)
+{
+	if(!ctx)
+		return;
+	cudaSetDevice(ctx->device);
+	if(ctx->stream) {
+		cudaStreamSynchronize(ctx->stream);
+		cudaStreamDestroy(ctx->stream);
+	}
+	for(int i = 0; i < 16; ++ i)
+		if(ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+	delete ctx;
+}
+
+const char *spp_last_error(spp_ctx_t ctx)
+{
+	return ctx? ctx->last_error.c_str() : g_create_error.c_str();
+}
+
+int spp_describe(spp_ctx_t ctx, char *p_buffer, size_t n_buffer_size)
+{
+	if(!ctx || !p_buffer || !n_buffer_size)
+		return SPP_ERR_INVALID;
+	snprintf(p_buffer, n_buffer_size, "%s", ctx->description.c_str());
+	return SPP_OK;
+}
+
+uint64_t spp_kernel_launches(spp_ctx_t ctx)
+{
+	return ctx? ctx->n_launches : 0;
+}
+
+void *spp_stream(spp_ctx_t ctx)
+{
+	return ctx? (void*)ctx->stream : 0;
+}
+
+int spp_synchronize(spp_ctx_t ctx)
+{
+	API_BEGIN(ctx)
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	API_END(ctx)
+}
+
+int spp_set_allreduce(spp_ctx_t ctx, spp_allreduce_fn fn, void *p_user, int rank, int world)
+{
+	if(!ctx || world < 1 || rank < 0 || rank >= world)
+		return SPP_ERR_INVALID;
+	ctx->allreduce = fn;
+	ctx->allreduce_user = p_user;
+	ctx->rank = rank;
+	ctx->world = world;
+	return SPP_OK;
+}
+
+int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_type,
+	const double *p_cam_params, const double *p_points, size_t n_observations,
+	const uint64_t *p_obs_point, const uint64_t *p_obs_camera, const double *p_z, const double *p_info)
+{
+	API_BEGIN(ctx)
+	BAProblem &ba = ctx->ba;
+	ba.valid = false;
+	ctx->slot.valid = false;
+	if(!p_vertex_type || (n_observations && (!p_obs_point || !p_obs_camera || !p_z || !p_info)))
+		throw invalid_error("null argument");
+	ba.n_vertices = n_vertices;
+	ba.vtype.assign(p_vertex_type, p_vertex_type + n_vertices);
+	ba.vertex_local.resize(n_vertices);
+	ba.cam_vertex.clear();
+	ba.pt_vertex.clear();
+	for(size_t v = 0; v < n_vertices; ++ v) {
+		if(p_vertex_type[v] == 0) {
+			ba.vertex_local[v] = (uint32_t)ba.cam_vertex.size();
+			ba.cam_vertex.push_back((uint32_t)v);
+		} else if(p_vertex_type[v] == 1) {
+			ba.vertex_local[v] = (uint32_t)ba.pt_vertex.size();
+			ba.pt_vertex.push_back((uint32_t)v);
+		} else
+			throw invalid_error("vertex type must be 0 (camera) or 1 (point)");
+	}
+	const size_t C = ba.cam_vertex.size(), P = ba.pt_vertex.size(), O = n_observations;
+	if((C && !p_cam_params) || (P && !p_points))
+		throw invalid_error("null vertex data");
+	ba.uf_is_cam = n_vertices? (p_vertex_type[0] == 0) : 1;
+	ba.uf_index = n_vertices? 0 : -1; // vertex id 0 is local index 0 of its type
+
+	std::vector<uint32_t> h_cam(O), h_pt(O);
+	for(size_t e = 0; e < O; ++ e) {
+		uint64_t vp = p_obs_point[e], vc = p_obs_camera[e];
+		if(vp >= n_vertices || vc >= n_vertices || p_vertex_type[vp] != 1 || p_vertex_type[vc] != 0)
+			throw invalid_error("observation references a vertex of the wrong type or out of range");
+		h_cam[e] = ba.vertex_local[vc];
+		h_pt[e] = ba.vertex_local[vp];
+	}
+	build_schur_structure(ctx, C, P, h_cam, h_pt, ba.obs_orig, ba.h_obs_cam, ba.h_obs_pt);
+
+	cudaStream_t st = ctx->stream;
+	std::vector<double> cs(C * 6), ci(C * 5);
+	for(size_t c = 0; c < C; ++ c) {
+		for(int k = 0; k < 6; ++ k) cs[c * 6 + k] = p_cam_params[c * 11 + k];
+		for(int k = 0; k < 5; ++ k) ci[c * 5 + k] = p_cam_params[c * 11 + 6 + k];
+	}
+	ba.cam_state.upload(cs, st);
+	ba.cam_intr.upload(ci, st);
+	ba.pts.upload(p_points, P * 3, st);
+	std::vector<double> tz(O * 2), ti(O * 4);
+	for(size_t k = 0; k < O; ++ k) {
+		size_t e = ba.obs_orig[k];
+		tz[k * 2] = p_z[e * 2]; tz[k * 2 + 1] = p_z[e * 2 + 1];
+		for(int q = 0; q < 4; ++ q) ti[k * 4 + q] = p_info[e * 4 + q];
+	}
+	ba.z.upload(tz, st);
+	ba.info.upload(ti, st);
+	ba.camRt.resize(C * 84);
+	ba.camK.resize(C * 5);
+	ba.partial.resize(4 * 1024);
+	ba.maxdiag.resize(1);
+	SPP_CUDA(cudaStreamSynchronize(st));
+	ba.linearised = false;
+	ba.valid = true;
+	API_END(ctx)
+}
+
+int spp_ba_set_states(spp_ctx_t ctx, const double *p_cam_states, const double *p_points)
+{
+	API_BEGIN(ctx)
+	if(!ctx->ba.valid) throw invalid_error("no BA graph");
+	if(p_cam_states)
+		SPP_CUDA(cudaMemcpyAsync(ctx->ba.cam_state.p(), p_cam_states, ctx->sys.C * 6 * 8, cudaMemcpyHostToDevice, ctx->stream));
+	if(p_points)
+		SPP_CUDA(cudaMemcpyAsync(ctx->ba.pts.p(), p_points, ctx->sys.P * 3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->ba.linearised = false;
+	API_END(ctx)
+}
+
+int spp_ba_get_states(spp_ctx_t ctx, double *p_cam_states, double *p_points)
+{
+	API_BEGIN(ctx)
+	if(!ctx->ba.valid) throw invalid_error("no BA graph");
+	if(p_cam_states)
+		ctx->ba.cam_state.download(p_cam_states, ctx->sys.C * 6, ctx->stream);
+	if(p_points)
+		ctx->ba.pts.download(p_points, ctx->sys.P * 3, ctx->stream);
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	API_END(ctx)
+}
+
+int spp_ba_set_jacobian_mode(spp_ctx_t ctx, int mode)
+{
+	if(!ctx || (mode != SPP_JAC_FD_REFERENCE && mode != SPP_JAC_ANALYTIC))
+		return SPP_ERR_INVALID;
+	ctx->ba.jac_mode = mode;
+	ctx->ba.linearised = false;
+	return SPP_OK;
+}
+
+int spp_ba_linearise(spp_ctx_t ctx)
+{
+	API_BEGIN(ctx)
+	if(!ctx->ba.valid) throw invalid_error("no BA graph");
+	ba_linearise(ctx, true);
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	API_END(ctx)
+}
+
+int spp_ba_get_lambda(spp_ctx_t ctx, uint64_t *p_n_block_cols, uint64_t *p_n_blocks, uint64_t *p_n_values,
+	uint64_t *p_col_dims, uint64_t *p_col_ptr, uint64_t *p_row_idx, double *p_values, double *p_eta)
+{
+	API_BEGIN(ctx)
+	BAProblem &ba = ctx->ba;
+	SchurSystem &s = ctx->sys;
+	if(!ba.valid) throw invalid_error("no BA graph");
+	const size_t NV = ba.n_vertices, O = s.O;
+	// structure in vertex id order: column v holds the off-diagonal blocks (row u < v) and the diagonal block last
+	std::vector<std::vector<std::pair<uint32_t, uint32_t> > > cols(NV); // (row vertex, track position)
+	for(size_t k = 0; k < O; ++ k) {
+		uint32_t vc = ba.cam_vertex[ba.h_obs_cam[k]], vp = ba.pt_vertex[ba.h_obs_pt[k]];
+		uint32_t r = std::min(vc, vp), c = std::max(vc, vp);
+		cols[c].push_back(std::make_pair(r, (uint32_t)k));
+	}
+	size_t n_blocks_total = 0, n_values = 0;
+	for(size_t v = 0; v < NV; ++ v) {
+		std::sort(cols[v].begin(), cols[v].end());
+		n_blocks_total += cols[v].size() + 1;
+		size_t d = ba.vtype[v] == 0? 6 : 3;
+		n_values += cols[v].size() * 18 + d * d;
+	}
+	if(p_n_block_cols) *p_n_block_cols = NV;
+	if(p_n_blocks) *p_n_blocks = n_blocks_total;
+	if(p_n_values) *p_n_values = n_values;
+	if(p_col_dims)
+		for(size_t v = 0; v < NV; ++ v) p_col_dims[v] = ba.vtype[v] == 0? 6 : 3;
+	if(p_col_ptr || p_row_idx || p_values) {
+		if(p_values && !ba.linearised) throw invalid_error("spp_ba_linearise() has not been called");
+		std::vector<double> hU, hV, hW;
+		if(p_values) {
+			hU.resize(s.C * 36); hV.resize(s.P * 9); hW.resize(O * 18);
+			s.U.download(hU.data(), hU.size(), ctx->stream);
+			s.V.download(hV.data(), hV.size(), ctx->stream);
+			s.W.download(hW.data(), hW.size(), ctx->stream);
+			SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+		}
+		size_t nb = 0, nv = 0;
+		for(size_t v = 0; v < NV; ++ v) {
+			if(p_col_ptr) p_col_ptr[v] = nb;
+			const bool v_is_cam = ba.vtype[v] == 0;
+			for(size_t q = 0; q < cols[v].size(); ++ q, ++ nb) {
+				if(p_row_idx) p_row_idx[nb] = cols[v][q].first;
+				if(p_values) {
+					const double *w = &hW[(size_t)cols[v][q].second * 18]; // 6x3 column-major
+					if(!v_is_cam) { // row = camera, column = point: block is W (6x3)
+						for(int i = 0; i < 18; ++ i) p_values[nv + i] = w[i];
+					} else { // row = point, column = camera: block is W^T (3x6)
+						for(int c = 0; c < 6; ++ c)
+							for(int r = 0; r < 3; ++ r)
+								p_values[nv + c * 3 + r] = w[r * 6 + c];
+					}
+				}
+				nv += 18;
+			}
+			if(p_row_idx) p_row_idx[nb] = v;
+			++ nb;
+			const size_t d = v_is_cam? 6 : 3;
+			if(p_values) {
+				const double *src = v_is_cam? &hU[(size_t)ba.vertex_local[v] * 36] : &hV[(size_t)ba.vertex_local[v] * 9];
+				for(size_t i = 0; i < d * d; ++ i) p_values[nv + i] = src[i];
+			}
+			nv += d * d;
+		}
+		if(p_col_ptr) p_col_ptr[NV] = nb;
+	}
+	if(p_eta) {
+		if(!ba.linearised) throw invalid_error("spp_ba_linearise() has not been called");
+		std::vector<double> hgc(s.C * 6), hgp(s.P * 3);
+		s.gc.download(hgc.data(), hgc.size(), ctx->stream);
+		s.gp.download(hgp.data(), hgp.size(), ctx->stream);
+		SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+		size_t off = 0;
+		for(size_t v = 0; v < NV; ++ v) {
+			if(ba.vtype[v] == 0) {
+				for(int i = 0; i < 6; ++ i) p_eta[off + i] = hgc[(size_t)ba.vertex_local[v] * 6 + i];
+				off += 6;
+			} else {
+				for(int i = 0; i < 3; ++ i) p_eta[off + i] = hgp[(size_t)ba.vertex_local[v] * 3 + i];
+				off += 3;
+			}
+		}
+	}
+	API_END(ctx)
+}
+
+int spp_ba_chi2(spp_ctx_t ctx, double *p_chi2)
+{
+	API_BEGIN(ctx)
+	if(!ctx->ba.valid || !p_chi2) throw invalid_error("no BA graph");
+	*p_chi2 = ba_chi2_host(ctx);
+	API_END(ctx)
+}
+
+static void ba_download_dx(spp_ctx *ctx, double *p_dx)
+{
+	BAProblem &ba = ctx->ba;
+	SchurSystem &s = ctx->sys;
+	std::vector<double> hc(s.C * 6), hp(s.P * 3);
+	s.dxc.download(hc.data(), hc.size(), ctx->stream);
+	s.dxp.download(hp.data(), hp.size(), ctx->stream);
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	size_t off = 0;
+	for(size_t v = 0; v < ba.n_vertices; ++ v) {
+		if(ba.vtype[v] == 0) {
+			for(int i = 0; i < 6; ++ i) p_dx[off + i] = hc[(size_t)ba.vertex_local[v] * 6 + i];
+			off += 6;
+		} else {
+			for(int i = 0; i < 3; ++ i) p_dx[off + i] = hp[(size_t)ba.vertex_local[v] * 3 + i];
+			off += 3;
+		}
+	}
+}
+
+int spp_ba_solve_step(spp_ctx_t ctx, double alpha, double *p_dx)
+{
+	int rc = SPP_OK;
+	API_BEGIN(ctx)
+	if(!ctx->ba.valid) throw invalid_error("no BA graph");
+	if(!ctx->ba.linearised) ba_linearise(ctx, true);
+	rc = schur_solve_current(ctx, alpha, 0);
+	if(rc == SPP_OK && p_dx)
+		ba_download_dx(ctx, p_dx);
+	if(rc != SPP_OK) return rc;
+	API_END(ctx)
+}
+
+int spp_ba_optimize(spp_ctx_t ctx, size_t n_max_iterations, double f_min_dx_norm, spp_report_t *p_report)
+{
+	API_BEGIN(ctx)
+	if(!ctx->ba.valid) throw invalid_error("no BA graph");
+	spp_report_t local;
+	ba_optimize(ctx, n_max_iterations, f_min_dx_norm, p_report? p_report : &local);
+	API_END(ctx)
+}
+
+int spp_schur_symbolic(spp_ctx_t ctx, size_t n_block_cols, const uint64_t *p_col_dims, const uint64_t *p_col_ptr,
+	const uint64_t *p_row_idx, uint64_t *p_order, uint64_t *p_cut)
+{
+	API_BEGIN(ctx)
+	if(!n_block_cols || !p_col_dims || !p_col_ptr || !p_row_idx) throw invalid_error("null argument");
+	slot_symbolic(ctx, n_block_cols, p_col_dims, p_col_ptr, p_row_idx, p_order, p_cut);
+	API_END(ctx)
+}
+
+int spp_schur_solve(spp_ctx_t ctx, const double *p_values, double *p_eta_dx)
+{
+	int rc = SPP_OK;
+	API_BEGIN(ctx)
+	if(!p_values || !p_eta_dx) throw invalid_error("null argument");
+	rc = slot_solve(ctx, p_values, p_eta_dx);
+	if(rc != SPP_OK) return rc;
+	API_END(ctx)
+}
+
+int spp_schur_get_reduced_system(spp_ctx_t ctx, uint64_t *p_n, double *p_S, double *p_rhs, uint8_t *p_block_pattern)
+{
+	API_BEGIN(ctx)
+	SchurSystem &s = ctx->sys;
+	const size_t n = s.C * 6;
+	if(p_n) *p_n = n;
+	if(p_S || p_rhs) {
+		if(!s.keep_reduced || s.S_copy.size() == 0)
+			throw invalid_error("no reduced system kept: solve first (the context keeps a copy after the first query)");
+		const size_t ld = dense_chol_ld(n);
+		if(p_S)
+			SPP_CUDA(cudaMemcpy2DAsync(p_S, n * 8, s.S_copy.p(), ld * 8, n * 8, n, cudaMemcpyDeviceToHost, ctx->stream));
+		if(p_rhs)
+			s.b_copy.download(p_rhs, n, ctx->stream);
+		SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	if(p_block_pattern) {
+		memset(p_block_pattern, 0, s.C * s.C);
+		for(size_t i = 0; i < s.h_blk_row.size(); ++ i)
+			p_block_pattern[(size_t)s.h_blk_row[i] * s.C + s.h_blk_col[i]] = 1;
+	}
+	s.keep_reduced = true;
+	API_END(ctx)
+}
+
+int spp_dense_posdef_solve(spp_ctx_t ctx, size_t n, const double *p_A, double *p_rhs_x)
+{
+	int rc = SPP_OK;
+	API_BEGIN(ctx)
+	if(!n || !p_A || !p_rhs_x) throw invalid_error("null argument");
+	const size_t ld = dense_chol_ld(n);
+	DBuf<double> A, b;
+	A.resize(dense_chol_storage(n));
+	A.zero(ctx->stream);
+	b.upload(p_rhs_x, n, ctx->stream);
+	SPP_CUDA(cudaMemcpy2DAsync(A.p(), ld * 8, p_A, n * 8, n * 8, n, cudaMemcpyHostToDevice, ctx->stream));
+	rc = dense_chol_solve_device(ctx, A.p(), n, b.p());
+	b.download(p_rhs_x, n, ctx->stream);
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	if(rc != SPP_OK) return rc;
+	API_END(ctx)
+}
+
+} // extern "C"

@@ -1,0 +1,98 @@
+// spp_ctx.h -- the solver context: device-resident system, symbolic structures, work buffers.
+#pragma once
+
+#include "spp_common.cuh"
+
+namespace spp {
+
+// landmark Schur system: the layout every BA stage kernel works on. Cameras and points are in the
+// reference's guided Schur ordering (6-wide vertices first, then 3-wide, id order kept inside each group;
+// src/slam/LinearSolver_Schur.cpp:771-838); observations are sorted by point so that a landmark's
+// W / Y blocks are contiguous (a "track").
+struct SchurSystem {
+	size_t C, P, O; // cameras, points, observations
+	// structure (device)
+	DBuf<uint32_t> obs_cam, obs_pt;  // [O] local camera / point index of each observation (track order)
+	DBuf<uint32_t> pt_ptr;           // [P+1] track of point p = observations pt_ptr[p] .. pt_ptr[p+1]
+	DBuf<uint32_t> cam_ptr, cam_obs; // [C+1], [O] per camera: observation indices (edge insertion order)
+	// reduced camera system structure: upper-triangular 6x6 block list and, per block, the pairs of
+	// observations (a, b) of one landmark that contribute Y_a W_b^T (ascending landmark order)
+	size_t n_blocks, n_pairs;
+	DBuf<uint32_t> blk_row, blk_col; // [n_blocks] camera indices i <= j
+	DBuf<uint64_t> blk_ptr;          // [n_blocks+1]
+	DBuf<uint32_t> pair_a, pair_b;   // [n_pairs]
+	std::vector<uint32_t> h_blk_row, h_blk_col; // host copy of the block pattern
+	// values (device)
+	DBuf<double> U;    // [C*36] camera diagonal blocks (column-major 6x6, undamped, incl. unary factor)
+	DBuf<double> V;    // [P*9]  point diagonal blocks
+	DBuf<double> W;    // [O*18] camera x point blocks J_c^T Sigma^-1 J_p (column-major 6x3), track order
+	DBuf<double> gc, gp; // [6C], [3P] gradient eta
+	DBuf<double> Cinv; // [P*9]  (V + alpha I)^-1
+	DBuf<double> Y;    // [O*18] W C^-1
+	DBuf<double> S;    // [n*n] dense column-major reduced camera system, n = 6C (upper triangle valid)
+	DBuf<double> S_copy; // optional copy kept for spp_schur_get_reduced_system
+	DBuf<double> b, b_copy; // [n] reduced right-hand side / camera increment
+	DBuf<double> dxc, dxp; // [6C], [3P] increments
+	bool keep_reduced;
+	SchurSystem() : C(0), P(0), O(0), n_blocks(0), n_pairs(0), keep_reduced(false) {}
+};
+
+struct BAProblem {
+	bool valid;
+	size_t n_vertices;
+	std::vector<uint8_t> vtype;          // per vertex id
+	std::vector<uint32_t> vertex_local;  // vertex id -> camera / point index
+	std::vector<uint32_t> cam_vertex, pt_vertex; // local index -> vertex id
+	std::vector<uint32_t> obs_orig;      // track position -> original edge index
+	std::vector<uint32_t> h_obs_cam, h_obs_pt; // host copies (track order)
+	int uf_is_cam; long uf_index;        // vertex id 0 carries the unary factor
+	int jac_mode;
+	// device state
+	DBuf<double> cam_state, cam_intr, pts;        // [6C], [5C], [3P]
+	DBuf<double> cam_state_saved, pts_saved;
+	DBuf<double> z, info;                         // [2O], [4O] track order
+	DBuf<double> camRt;                           // [C*7*12] base + 6 perturbed [R|t]
+	DBuf<double> camK;                            // [C*5] fx fy cx cy k
+	DBuf<double> partial;                         // reduction scratch
+	DBuf<unsigned long long> maxdiag;             // [1] bits of the max per-edge Hessian diagonal
+	bool linearised;
+	BAProblem() : valid(false), n_vertices(0), uf_is_cam(1), uf_index(0), jac_mode(0), linearised(false) {}
+};
+
+// slot-1 state: map from the caller's lambda values to the SchurSystem arrays
+struct SchurSlot {
+	bool valid;
+	size_t n_bcols, n_scalars, n_values;
+	std::vector<uint64_t> col_base;       // scalar offset of each block column
+	std::vector<uint64_t> order;          // new position -> original block column
+	size_t cut;
+	DBuf<double> vals, eta;               // staging of the caller's arrays
+	DBuf<uint64_t> u_src, v_src, w_src;   // value offsets of the U / V / W blocks
+	DBuf<uint8_t> w_transposed;           // W block stored 3x6 in lambda (point id < camera id)
+	DBuf<uint64_t> cam_eta_off, pt_eta_off; // scalar offsets in eta
+	SchurSlot() : valid(false), n_bcols(0), n_scalars(0), n_values(0), cut(0) {}
+};
+
+struct DenseChol {
+	DBuf<double> work;
+	DBuf<int> info;
+};
+
+} // namespace spp
+
+struct spp_ctx {
+	int device;
+	cudaStream_t stream;
+	std::string last_error;
+	std::string description;
+	uint64_t n_launches;
+	spp_allreduce_fn allreduce;
+	void *allreduce_user;
+	int rank, world;
+	spp::SchurSystem sys;
+	spp::BAProblem ba;
+	spp::SchurSlot slot;
+	spp::DenseChol chol;
+	spp::HPinned<double> h_scalars;
+	cudaEvent_t ev[16];
+};

@@ -1,0 +1,201 @@
+// symbolic.cpp -- host-side symbolic analysis of the landmark Schur system (integer work, one-time).
+//
+// Replaces the structural part of lambda_utils::CLambdaOps2::AddEntriesInSparseSystem
+// (include/slam/NonlinearSolver_Lambda_Base.h:1853-1931), the guided Schur ordering
+// (src/slam/LinearSolver_Schur.cpp:771-838; cameras first, points after, id order kept) and the symbolic
+// phase of the two block products (include/slam/BlockMatrixFBS.inl:684-834): the list of upper-triangular
+// 6x6 blocks of the reduced camera system and, per block, the observation pairs that feed it, in
+// ascending landmark order -- the order in which the reference accumulates them.
+
+#include "spp_ctx.h"
+#include <algorithm>
+#include <numeric>
+
+namespace spp {
+
+// h_cam / h_pt: local camera / point index per observation in ORIGINAL edge order.
+// Fills the track-ordered structure of s (device) and the permutation track position -> original edge.
+void build_schur_structure(spp_ctx *ctx, size_t C, size_t P, const std::vector<uint32_t> &h_cam,
+	const std::vector<uint32_t> &h_pt, std::vector<uint32_t> &obs_orig, std::vector<uint32_t> &t_cam,
+	std::vector<uint32_t> &t_pt)
+{
+	SchurSystem &s = ctx->sys;
+	const size_t O = h_cam.size();
+	if(O >= 0xffffffffu || C >= 0xffffffffu || P >= 0xffffffffu)
+		throw invalid_error("graph too large for 32-bit indices");
+	s.C = C; s.P = P; s.O = O;
+
+	// stable counting sort of the observations by point -> tracks
+	std::vector<uint32_t> pt_ptr(P + 1, 0);
+	for(size_t e = 0; e < O; ++ e)
+		++ pt_ptr[h_pt[e] + 1];
+	for(size_t p = 0; p < P; ++ p)
+		pt_ptr[p + 1] += pt_ptr[p];
+	obs_orig.resize(O);
+	std::vector<uint32_t> pos_of_edge(O);
+	{
+		std::vector<uint32_t> fill(pt_ptr.begin(), pt_ptr.end() - 1);
+		for(size_t e = 0; e < O; ++ e) {
+			uint32_t pos = fill[h_pt[e]] ++;
+			obs_orig[pos] = (uint32_t)e;
+			pos_of_edge[e] = pos;
+		}
+	}
+	t_cam.resize(O);
+	t_pt.resize(O);
+	for(size_t k = 0; k < O; ++ k) {
+		t_cam[k] = h_cam[obs_orig[k]];
+		t_pt[k] = h_pt[obs_orig[k]];
+	}
+
+	// per camera: its observations (track positions), in edge insertion order
+	std::vector<uint32_t> cam_ptr(C + 1, 0), cam_obs(O);
+	for(size_t e = 0; e < O; ++ e)
+		++ cam_ptr[h_cam[e] + 1];
+	for(size_t c = 0; c < C; ++ c)
+		cam_ptr[c + 1] += cam_ptr[c];
+	{
+		std::vector<uint32_t> fill(cam_ptr.begin(), cam_ptr.end() - 1);
+		for(size_t e = 0; e < O; ++ e)
+			cam_obs[fill[h_cam[e]] ++] = pos_of_edge[e];
+	}
+
+	// reduced camera system: count the pairs of every upper block (i <= j)
+	// pass 1: histogram over block keys; dense table when C^2 is affordable, sorted keys otherwise
+	std::vector<uint32_t> blk_row, blk_col;
+	std::vector<uint64_t> blk_ptr;
+	std::vector<uint32_t> pair_a, pair_b;
+	size_t n_pairs = 0;
+	for(size_t p = 0; p < P; ++ p) {
+		size_t k = pt_ptr[p + 1] - pt_ptr[p];
+		n_pairs += k * (k + 1) / 2;
+	}
+	const bool b_dense_table = C * C <= (size_t(1) << 28);
+	std::vector<uint64_t> keys; // sorted unique keys (sparse mode)
+	std::vector<uint32_t> table; // key -> block index + 1 (dense mode)
+	auto key_of = [C](uint32_t i, uint32_t j) { return (uint64_t)i * C + j; };
+	if(b_dense_table) {
+		std::vector<uint32_t> count(C * C, 0);
+		for(size_t p = 0; p < P; ++ p) {
+			for(uint32_t a = pt_ptr[p]; a < pt_ptr[p + 1]; ++ a) {
+				for(uint32_t b = pt_ptr[p]; b < pt_ptr[p + 1]; ++ b) {
+					uint32_t ca = t_cam[a], cb = t_cam[b];
+					if(ca < cb || a == b)
+						++ count[key_of(ca, cb)];
+					else if(ca == cb && a != b)
+						throw invalid_error("a landmark is observed twice by the same camera (duplicate edge)");
+				}
+			}
+		}
+		// cameras without observations still own their diagonal block
+		table.assign(C * C, 0);
+		blk_ptr.push_back(0);
+		for(size_t i = 0; i < C; ++ i) {
+			for(size_t j = i; j < C; ++ j) {
+				uint32_t n = count[i * C + j];
+				if(n || i == j) {
+					blk_row.push_back((uint32_t)i);
+					blk_col.push_back((uint32_t)j);
+					table[i * C + j] = (uint32_t)blk_row.size();
+					blk_ptr.push_back(blk_ptr.back() + n);
+				}
+			}
+		}
+	} else {
+		keys.reserve(n_pairs + C);
+		for(size_t i = 0; i < C; ++ i)
+			keys.push_back(key_of((uint32_t)i, (uint32_t)i));
+		for(size_t p = 0; p < P; ++ p) {
+			for(uint32_t a = pt_ptr[p]; a < pt_ptr[p + 1]; ++ a) {
+				for(uint32_t b = pt_ptr[p]; b < pt_ptr[p + 1]; ++ b) {
+					uint32_t ca = t_cam[a], cb = t_cam[b];
+					if(ca < cb)
+						keys.push_back(key_of(ca, cb));
+					else if(ca == cb && a != b)
+						throw invalid_error("a landmark is observed twice by the same camera (duplicate edge)");
+				}
+			}
+		}
+		std::sort(keys.begin(), keys.end());
+		std::vector<uint64_t> uniq;
+		std::vector<uint64_t> cnt;
+		for(size_t i = 0; i < keys.size();) {
+			size_t j = i;
+			while(j < keys.size() && keys[j] == keys[i]) ++ j;
+			uniq.push_back(keys[i]);
+			uint64_t n = j - i;
+			if(keys[i] / C == keys[i] % C)
+				-- n; // the seed entry of the diagonal
+			cnt.push_back(n);
+			i = j;
+		}
+		keys.swap(uniq);
+		blk_ptr.push_back(0);
+		for(size_t i = 0; i < keys.size(); ++ i) {
+			blk_row.push_back((uint32_t)(keys[i] / C));
+			blk_col.push_back((uint32_t)(keys[i] % C));
+			blk_ptr.push_back(blk_ptr.back() + cnt[i]);
+		}
+		// diagonal pairs (a, a) were not emitted above: add their counts
+		std::vector<uint64_t> diag_extra(C, 0);
+		for(size_t k = 0; k < O; ++ k)
+			++ diag_extra[t_cam[k]];
+		std::vector<uint64_t> new_ptr(blk_ptr.size());
+		uint64_t shift = 0;
+		for(size_t i = 0; i < keys.size(); ++ i) {
+			new_ptr[i] = blk_ptr[i] + shift;
+			if(blk_row[i] == blk_col[i])
+				shift += diag_extra[blk_row[i]];
+		}
+		new_ptr[keys.size()] = blk_ptr[keys.size()] + shift;
+		blk_ptr.swap(new_ptr);
+	}
+	const size_t n_blk = blk_row.size();
+	if(blk_ptr.back() != n_pairs)
+		throw invalid_error("internal error: pair count mismatch in the Schur symbolic phase");
+	// pass 2: scatter the pairs; iterating landmarks in ascending order keeps every list landmark-sorted
+	pair_a.resize(n_pairs);
+	pair_b.resize(n_pairs);
+	{
+		std::vector<uint64_t> fill(blk_ptr.begin(), blk_ptr.end() - 1);
+		for(size_t p = 0; p < P; ++ p) {
+			for(uint32_t a = pt_ptr[p]; a < pt_ptr[p + 1]; ++ a) {
+				for(uint32_t b = pt_ptr[p]; b < pt_ptr[p + 1]; ++ b) {
+					uint32_t ca = t_cam[a], cb = t_cam[b];
+					if(!(ca < cb || a == b))
+						continue;
+					size_t blk;
+					if(b_dense_table)
+						blk = table[key_of(ca, cb)] - 1;
+					else
+						blk = std::lower_bound(keys.begin(), keys.end(), key_of(ca, cb)) - keys.begin();
+					uint64_t dst = fill[blk] ++;
+					pair_a[dst] = a;
+					pair_b[dst] = b;
+				}
+			}
+		}
+	}
+
+	cudaStream_t st = ctx->stream;
+	s.obs_cam.upload(t_cam, st);
+	s.obs_pt.upload(t_pt, st);
+	s.pt_ptr.upload(pt_ptr, st);
+	s.cam_ptr.upload(cam_ptr, st);
+	s.cam_obs.upload(cam_obs, st);
+	s.n_blocks = n_blk;
+	s.n_pairs = n_pairs;
+	s.blk_row.upload(blk_row, st);
+	s.blk_col.upload(blk_col, st);
+	s.blk_ptr.upload(blk_ptr, st);
+	s.pair_a.upload(pair_a, st);
+	s.pair_b.upload(pair_b, st);
+	s.h_blk_row.swap(blk_row);
+	s.h_blk_col.swap(blk_col);
+	s.U.resize(C * 36); s.V.resize(P * 9); s.W.resize(O * 18);
+	s.gc.resize(C * 6); s.gp.resize(P * 3);
+	s.dxc.resize(C * 6); s.dxp.resize(P * 3);
+	SPP_CUDA(cudaStreamSynchronize(st)); // the host vectors go out of scope
+}
+
+} // namespace spp

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures under tests/golden/ by running the UNMODIFIED reference (oracle/_ref, built by
+oracle/build_ref.sh from /root/reference) on small seeded graphs. Needs /root/reference, hence runs only in the
+build container; the resulting .npz files are committed and are what the CPU and GPU test suites read.
+
+usage: python tests/golden/make_golden.py
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from slam_plus_plus_b200 import graphs, sppio  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_BA = os.path.join(ROOT, "oracle", "_ref", "ref_driver_ba")
+
+BA_CASES = {
+    # name: (generator kwargs, max_iter, which solves to keep in full)
+    "ba_tiny": (dict(shape="tiny"), 5, "all"),
+    "ba_tiny_interleaved": (dict(shape="tiny", interleave_ids=True, shuffle_edges=True, distortion=-0.05), 5, "all"),
+    "ba_small": (dict(shape="small", cam_noise=5e-2, pt_noise=5e-2, rot_noise=5e-3), 5, "first"),
+    "ba_small_hard": (dict(shape="small", cam_noise=0.3, pt_noise=0.3, rot_noise=5e-2, distortion=0.1,
+                           interleave_ids=True, shuffle_edges=True), 6, "first"),
+}
+
+
+def run_ba(name, spec):
+    kw, max_iter, keep = spec
+    kw = dict(kw)
+    g = graphs.ba_shape(kw.pop("shape"), **kw)
+    with tempfile.TemporaryDirectory() as td:
+        gp = os.path.join(td, "g.bin")
+        dp = os.path.join(td, "d.dump")
+        sppio.write_graph(gp, g)
+        subprocess.run([REF_BA, "dump", gp, dp, str(max_iter), "0"], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1"))
+        d = sppio.read_dump(dp)
+    out = dict(g_vtype=g.vtype, g_cams=g.cams, g_pts=g.pts, g_obs_pt=g.obs_pt, g_obs_cam=g.obs_cam, g_z=g.z,
+               g_info=g.info, max_iter=np.array([max_iter]))
+    n_solves = int(d["n_solves"][0])
+    for k, v in d.items():
+        if k[0] == "L" and k[1].isdigit():
+            idx = int(k[1:].split(".")[0])
+            if keep == "first" and idx != 0 and not k.endswith(".dx") and not k.endswith(".ok"):
+                continue
+        out[k] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: C={g.n_cams} P={g.n_pts} O={g.n_obs} solves={n_solves} chi2 {d['chi2_0'][0]:.6g} -> {d['chi2'][0]:.6g} "
+          f"accepted={d['lm_trace'].reshape(-1, 6)[:, 4].astype(int).tolist()}")
+
+
+if __name__ == "__main__":
+    if not os.path.exists(REF_BA):
+        sys.exit("oracle/_ref/ref_driver_ba missing: run oracle/build_ref.sh (needs /root/reference)")
+    for name, spec in BA_CASES.items():
+        run_ba(name, spec)
