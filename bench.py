@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 NLS hot path (BASELINE.json: BA LM iterations/s, Venice-871 shape).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the reference's own CPU solver (oracle/_ref)
+
+One "step" = one CNonlinearSolver_Lambda_LM::Optimize(max_iter = 5, min_dx = 0) on the synthetic Venice-871-shape
+graph (871 cameras, 530 304 points, 2 837 687 observations; slam_plus_plus_b200/graphs.py, seed 871):
+linearise -> landmark Schur complement -> dense FP64 Cholesky of the 5226 x 5226 reduced camera system ->
+back-substitution -> update -> chi2, five times, with the reference's LM control flow. `value` counts linear
+solves (LM iterations) per second with the graph resident in HBM (vertex states are restored from a device
+snapshot at the start of every step); `e2e` times the full public call sequence with HOST buffers:
+spp_ba_set_graph (H2D + symbolic analysis) + spp_ba_optimize + spp_ba_get_states (D2H).
+
+Rank 0 prints ONE JSON line. Timing: CUDA events on the context's stream, barrier + synchronize on both sides,
+max over ranks. The working set (W, Y: 2 x 409 MB; S: 220 MB) is far larger than the 126 MB L2, so consecutive
+steps do not find their inputs in cache ("inputs larger than L2").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "ba_lm_iterations_per_s"
+UNIT = "LM iterations/s"
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_driver_ba")
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no nvidia-smi samples"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[3 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def measure_fp64_peak(torch, dev):
+    """FP64 matrix-pipe peak of this GPU: cuBLAS DGEMM 4096^3 through torch.matmul, best of 5 (TFLOP/s).
+    MEASURED_PEAKS.json carries no FP64 entry (SURVEY 7 'hard parts'), so the denominator is measured in-run."""
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    torch.cuda.synchronize(dev)
+    best = 0.0
+    for _ in range(5):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    del a, b
+    return best
+
+
+def write_graph_file(g):
+    from slam_plus_plus_b200 import sppio
+    path = os.path.join(tempfile.gettempdir(), f"spp_bench_{os.getpid()}.bin")
+    sppio.write_graph(path, g)
+    return path
+
+
+def run_reference_steps(graph_path, warmup, steps, threads=None):
+    """Runs the reference's own LM solver (oracle/_ref, compiled from the unmodified reference sources) and returns
+    the per-step seconds of Optimize(1, 0) calls on the resident system."""
+    from slam_plus_plus_b200 import sppio
+    if not os.path.exists(REF_BIN):
+        raise RuntimeError("oracle/_ref/ref_driver_ba is missing (built by __graft_entry__.build() where /root/reference exists)")
+    out = os.path.join(tempfile.gettempdir(), f"spp_bench_ref_{os.getpid()}.dump")
+    env = dict(os.environ)
+    if threads:
+        env["OMP_NUM_THREADS"] = str(threads)
+    subprocess.run([REF_BIN, "steps", graph_path, out, str(warmup), str(steps)], check=True, env=env,
+                   stdout=subprocess.DEVNULL)
+    d = sppio.read_dump(out)
+    os.unlink(out)
+    return d["step_seconds"], int(d["omp_threads"][0]), d
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from slam_plus_plus_b200 import graphs
+    g = graphs.ba_shape(args.shape)
+    path = write_graph_file(g)
+    try:
+        secs, threads, d = run_reference_steps(path, args.warmup, args.steps)
+    finally:
+        os.unlink(path)
+    timed = secs[args.warmup:]
+    total = float(np.sum(timed))
+    value = len(timed) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(len(timed), 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.shape}-shape BA, reference CNonlinearSolver_Lambda_LM + CLinearSolver_Schur (dense LLT), "
+                               "one LM iteration (Optimize(1, 0)) per step on the resident system",
+                   "cameras": g.n_cams, "points": g.n_pts, "observations": g.n_obs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                         "sample": "each step = Optimize(max_iter=1) of the unmodified reference on the full graph "
+                                   "(structure build excluded: it happens in the first warm-up step)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from slam_plus_plus_b200 import capi, graphs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    g = graphs.ba_shape(args.shape)
+    ctx = capi.Context(local)
+    if world > 1:
+        from slam_plus_plus_b200.parallel import attach_torch_allreduce
+        attach_torch_allreduce(ctx, rank, world)
+    t0 = time.time()
+    ctx.ba_set_graph(g)
+    setup_s = time.time() - t0
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def one_step():
+        ctx.ba_restore_initial()
+        return ctx.ba_optimize(args.lm_iters, 0.0)
+
+    for _ in range(max(args.warmup, 3)):
+        rep = one_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    launches0 = ctx.kernel_launches
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    n_iters = 0
+    phase = {}
+    for _ in range(args.steps):
+        rep = one_step()
+        n_iters += rep["n_iterations"]
+        for k, v in rep["ms"].items():
+            phase[k] = phase.get(k, 0.0) + v
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n_iters / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers (pinned), every step: H2D graph, optimise, D2H states
+    vtype = np.ascontiguousarray(g.vtype, np.uint8)
+    host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in
+            (g.cams, g.pts, g.obs_pt.astype(np.uint64).view(np.int64), g.obs_cam.astype(np.uint64).view(np.int64), g.z, g.info)]
+    h2d = int(vtype.nbytes + sum(t.numel() * t.element_size() for t in host))
+    d2h = int(g.n_cams * 6 * 8 + g.n_pts * 3 * 8)
+    from slam_plus_plus_b200.sppio import BAGraph
+    gh = BAGraph(vtype, host[0].numpy(), host[1].numpy(), host[2].numpy().view(np.uint64), host[3].numpy().view(np.uint64),
+                 host[4].numpy(), host[5].numpy())
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_iters = 0
+    for _ in range(e2e_steps):
+        ctx.ba_set_graph(gh)
+        r = ctx.ba_optimize(args.lm_iters, 0.0)
+        ctx.ba_get_states()
+        e2e_iters += r["n_iterations"]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = e2e_iters / e2e_s
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel group: the dense Cholesky of the reduced camera system
+    n = 6 * g.n_cams
+    chol_flops = n ** 3 / 3.0
+    chol_ms = phase["factor"] / max(n_iters, 1)
+    fp64_peak = measure_fp64_peak(torch, dev)
+    achieved = chol_flops / (chol_ms * 1e-3) / 1e12
+    hbm_peak, hbm_src = load_peaks()
+    O, P, Cn = g.n_obs, g.n_pts, g.n_cams
+    bytes_lin = 200 * O + 120 * P + 424 * Cn
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.shape}-shape BA, LM Optimize({args.lm_iters}, 0) per step, Schur + dense FP64 Cholesky",
+                   "cameras": Cn, "points": P, "observations": O, "lm_iterations_per_step": n_iters / args.steps,
+                   "jacobians": "forward differences, delta=1e-9 (reference parity mode)",
+                   "l2_policy": "inputs larger than L2 (W+Y 817 MB, S 220 MB vs 126 MB L2)",
+                   "parallelism": f"landmark-sharded x{world}" if world > 1 else "single GPU",
+                   "symbolic_setup_s": setup_s},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "note": "spp_ba_set_graph(host, incl. symbolic analysis) + spp_ba_optimize + spp_ba_get_states"},
+        "gpu_launches": int(launches),
+        "phase_ms_per_lm_iteration": {k: v / max(n_iters, 1) for k, v in phase.items()},
+        "roofline": {"bound": "tensor", "kernel": "dense Cholesky 5226^2 (k_potrf_diag + k_trsm_panel + k_syrk_update DMMA)",
+                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                     "traffic": None, "flops_per_launch": chol_flops,
+                     "peak_source": "FP64: cuBLAS DGEMM 4096^3 via torch.matmul measured in this run (no FP64 entry in MEASURED_PEAKS.json)",
+                     "hbm_stage": {"kernel": "linearise (k_linearise_cams + k_linearise_points)",
+                                   "achieved_gbs": bytes_lin / (phase["linearise"] / max(n_iters, 1) * 1e-3) / 1e9,
+                                   "peak_gbs": hbm_peak, "peak_source": hbm_src}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            path = write_graph_file(g)
+            secs, threads, _ = run_reference_steps(path, 1, 1)
+            os.unlink(path)
+            line["cpu_baseline"] = {"value": 1.0 / float(secs[1]), "unit": UNIT, "cores": threads, "kind": "reference",
+                                    "sample": "unmodified reference (oracle/_ref), full graph, second Optimize(max_iter=1) call "
+                                              "(the first call, which also builds the structure, took %.1f s)" % float(secs[0])}
+        except Exception as ex:  # the bench line must still be printed
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shape", default="venice871")
+    ap.add_argument("--lm-iters", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

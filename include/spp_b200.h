@@ -107,6 +107,10 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 int spp_ba_set_states(spp_ctx_t ctx, const double *p_cam_states, const double *p_points);
 int spp_ba_get_states(spp_ctx_t ctx, double *p_cam_states, double *p_points);
 
+/* Restores the vertex states uploaded by the last spp_ba_set_graph() from a device-side snapshot (no host
+ * traffic); lets a benchmark repeat Optimize() on the same resident problem. No reference counterpart. */
+int spp_ba_restore_initial(spp_ctx_t ctx);
+
 int spp_ba_set_jacobian_mode(spp_ctx_t ctx, int mode); /* SPP_JAC_* ; default SPP_JAC_FD_REFERENCE */
 
 /* Replaces CLambdaOps2::Refresh_Lambda + Collect_RightHandSide_Vector (Lambda_Base.h:1659-1706):

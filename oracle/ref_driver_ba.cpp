@@ -237,7 +237,27 @@ int main(int n_arg_num, const char **p_arg_list)
 
 	double f_opt_time, f_chi2;
 	uint64_t n_threads = omp_get_max_threads();
-	if(!b_dump) {
+	if(!strcmp(p_arg_list[1], "steps")) {
+		// bench.py --impl reference: <warmup> <steps> calls of Optimize(1, 0) on the resident system
+		const size_t n_warmup = (n_arg_num > 4)? atol(p_arg_list[4]) : 0;
+		const size_t n_steps = (n_arg_num > 5)? atol(p_arg_list[5]) : 1;
+		typedef CNonlinearSolver_Lambda_LM<CSystemType, CRefLinearSolver> CSolver;
+		CSolver solver(system, TIncrementalSolveSetting(), TMarginalsComputationPolicy(),
+			getenv("SPP_REF_VERBOSE") != 0, CRefLinearSolver(), true);
+		FILE *p_keep = g_dump;
+		g_dump = 0;
+		std::vector<double> step_seconds;
+		double f_begin = timer.f_Time();
+		for(size_t i = 0; i < n_warmup + n_steps; ++ i) {
+			double f_start = timer.f_Time();
+			solver.Optimize(1, 0);
+			step_seconds.push_back(timer.f_Time() - f_start);
+		}
+		f_opt_time = timer.f_Time() - f_begin;
+		g_dump = p_keep;
+		f_chi2 = solver.f_Chi_Squared_Error_Denorm();
+		spp_dump_f64(g_dump, "step_seconds", step_seconds.size(), &step_seconds[0]);
+	} else if(!b_dump) {
 		typedef CNonlinearSolver_Lambda_LM<CSystemType, CRefLinearSolver> CSolver;
 		CSolver solver(system, TIncrementalSolveSetting(), TMarginalsComputationPolicy(),
 			getenv("SPP_REF_VERBOSE") != 0, CRefLinearSolver(), true);

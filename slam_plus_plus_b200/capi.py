@@ -23,7 +23,7 @@ MAX_TRACE = 64
 EXPORTED_SYMBOLS = [
     "spp_create", "spp_destroy", "spp_last_error", "spp_describe", "spp_kernel_launches", "spp_stream",
     "spp_synchronize", "spp_set_allreduce", "spp_ba_set_graph", "spp_ba_set_states", "spp_ba_get_states",
-    "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_chi2", "spp_ba_solve_step",
+    "spp_ba_restore_initial", "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_chi2", "spp_ba_solve_step",
     "spp_ba_optimize", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_get_reduced_system",
     "spp_dense_posdef_solve",
 ]
@@ -82,6 +82,7 @@ def load_library() -> C.CDLL:
     lib.spp_ba_set_graph.argtypes = [vp, C.c_size_t, u8p, dp, dp, C.c_size_t, u64p, u64p, dp, dp]
     lib.spp_ba_set_states.argtypes = [vp, dp, dp]
     lib.spp_ba_get_states.argtypes = [vp, dp, dp]
+    lib.spp_ba_restore_initial.argtypes = [vp]
     lib.spp_ba_set_jacobian_mode.argtypes = [vp, C.c_int]
     lib.spp_ba_linearise.argtypes = [vp]
     lib.spp_ba_get_lambda.argtypes = [vp, u64p, u64p, u64p, u64p, u64p, u64p, dp, dp]
@@ -204,6 +205,9 @@ class Context:
         ps = np.empty((p, 3))
         self._check(self.lib.spp_ba_get_states(self.h, _dp(cs), _dp(ps)))
         return cs, ps
+
+    def ba_restore_initial(self):
+        self._check(self.lib.spp_ba_restore_initial(self.h))
 
     def ba_set_jacobian_mode(self, mode: int):
         self._check(self.lib.spp_ba_set_jacobian_mode(self.h, mode))

@@ -384,6 +384,8 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 	ba.cam_state.upload(cs, st);
 	ba.cam_intr.upload(ci, st);
 	ba.pts.upload(p_points, P * 3, st);
+	ba.cam_state0.upload(cs, st);
+	ba.pts0.upload(p_points, P * 3, st);
 	std::vector<double> tz(O * 2), ti(O * 4);
 	for(size_t k = 0; k < O; ++ k) {
 		size_t e = ba.obs_orig[k];
@@ -424,6 +426,17 @@ int spp_ba_get_states(spp_ctx_t ctx, double *p_cam_states, double *p_points)
 	if(p_points)
 		ctx->ba.pts.download(p_points, ctx->sys.P * 3, ctx->stream);
 	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	API_END(ctx)
+}
+
+int spp_ba_restore_initial(spp_ctx_t ctx)
+{
+	API_BEGIN(ctx)
+	BAProblem &ba = ctx->ba;
+	if(!ba.valid) throw invalid_error("no BA graph");
+	SPP_CUDA(cudaMemcpyAsync(ba.cam_state.p(), ba.cam_state0.p(), ba.cam_state.size() * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	SPP_CUDA(cudaMemcpyAsync(ba.pts.p(), ba.pts0.p(), ba.pts.size() * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	ba.linearised = false;
 	API_END(ctx)
 }
 

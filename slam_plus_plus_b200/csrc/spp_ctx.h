@@ -50,6 +50,7 @@ struct BAProblem {
 	// device state
 	DBuf<double> cam_state, cam_intr, pts;        // [6C], [5C], [3P]
 	DBuf<double> cam_state_saved, pts_saved;
+	DBuf<double> cam_state0, pts0;                // snapshot taken by spp_ba_set_graph
 	DBuf<double> z, info;                         // [2O], [4O] track order
 	DBuf<double> camRt;                           // [C*7*12] base + 6 perturbed [R|t]
 	DBuf<double> camK;                            // [C*5] fx fy cx cy k
