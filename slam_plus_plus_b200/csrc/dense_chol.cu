@@ -5,105 +5,219 @@
 // (src/slam/LinearSolver_Schur.cpp:2314-2333) = Convert_to_Dense + Eigen::LLT<MatrixXd, Eigen::Upper>::compute
 // (reads the upper triangle only, fails on a non-positive pivot) + LLT::solve (two triangular solves).
 //
-// Layout: column-major, leading dimension ld = n rounded up to a multiple of the panel width; the padding
-// carries an identity diagonal so that no kernel needs bounds checks. The right-hand side rides along as an
-// extra column block right of the matrix: the panel solve and the trailing update turn it into
+// Layout: column-major, leading dimension ld = n rounded up to a multiple of the panel width (128); the
+// padding carries an identity diagonal so that no kernel needs bounds checks. The right-hand side rides along
+// as an extra column block right of the matrix: the panel solve and the trailing update turn it into
 // y = R^-T b for free (augmented-matrix trick), which leaves one backward solve R x = y.
 //
-// Blocked right-looking factorisation, panel width CH_NB:
-//   k_potrf_diag   one CTA, diagonal block in shared memory
-//   k_trsm_panel   R_kk^-T applied to the block row right of the diagonal (thread per column)
-//   k_syrk_update  trailing update C -= P^T P on FP64 tensor cores (mma.sync m8n8k4 DMMA), 64x64 CTA tiles
-// Backward solve: k_invert_diag (all diagonal blocks at once, off the critical path) + k_backsolve, one
-// persistent CTA per block row that consumes x_j as soon as block row j publishes it.
+// Blocked right-looking factorisation, panel width 128, one-step look-ahead on two streams:
+//   k_potrf128      one CTA: 128x128 diagonal block in shared memory, 32-wide sub-blocks (register Cholesky in
+//                   one warp, sub-row solve, rank-32 update), then the inverse of the triangular factor
+//   k_gemm_tn<TRSM> block row right of the diagonal: P <- Rinv_kk^T P        (FP64 tensor cores)
+//   k_gemm_tn<SYRK> trailing update C -= P^T P, upper tiles only             (FP64 tensor cores)
+//                   critical stream: the tile row that the next panel needs (64x64 tiles, look-ahead)
+//                   bulk stream    : everything below it (128x128 tiles)
+// The GEMM kernel stages K-contiguous operand tiles with a 3-deep cp.async pipeline and issues
+// mma.sync.m8n8k4.f64 (DMMA); tcgen05 has no FP64 kind, so this is the tensor path for FP64 on sm_100a.
+// Backward solve: one persistent CTA per block row consumes x_j as soon as block row j publishes it and
+// finishes with the inverse diagonal block computed by k_potrf128.
 
 #include "spp_ctx.h"
+#include <cuda_pipeline_primitives.h>
 
 namespace spp {
 
 #define LAUNCH_CHECK(ctx) do { ++ (ctx)->n_launches; SPP_CUDA(cudaGetLastError()); } while(0)
 
-#define CH_NB 64          // panel width
-#define CH_TILE 64        // CTA tile of the trailing update
-#define CH_BK 16          // k-chunk staged in shared memory
+#define CH_NB 128          // panel width = K of every GEMM
+#define CH_BK 16           // k-chunk staged in shared memory
 #define CH_LDS (CH_BK + 4) // padded row length: conflict-free DMMA fragment loads
+#define CH_STAGES 3
+#define CH_TP (CH_NB + 1)  // padded row of the potrf tile
 
-// ---- diagonal block ------------------------------------------------------------------------------
+// ---- diagonal block: factor + invert -----------------------------------------------------------------
 
-__global__ void __launch_bounds__(256) k_potrf_diag(double *__restrict__ A, size_t ld, size_t k0, int *__restrict__ info)
+// packed index of the 32x32 block (a, b), a <= b, of the 4x4 upper block grid
+__device__ __forceinline__ int xblk(int a, int b) { return a * 4 - a * (a - 1) / 2 + (b - a); }
+
+#define XB_LD 33
+#define XB_SIZE (32 * XB_LD)
+
+#define PT 256              // threads of k_potrf128
+#define PW (PT / 32)
+
+__global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size_t ld, size_t k0,
+	double *__restrict__ Rinv_out, int *__restrict__ info)
 {
-	__shared__ double T[CH_NB][CH_NB + 1];
+	extern __shared__ double smem[];
+	double (*T)[CH_TP] = reinterpret_cast<double (*)[CH_TP]>(smem); // T[r][c], upper
+	double *Xs = smem + CH_NB * CH_TP;       // 10 packed 32x33 blocks of the inverse
+	double *rdinv = Xs + 10 * XB_SIZE;       // 128 reciprocal pivots
+	// scratch block g of the inversion lives in the (unused) strictly lower part of T: rows 96.., columns g*32..
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	double *Akk = A + k0 * ld + k0;
-	for(int idx = threadIdx.x; idx < CH_NB * CH_NB; idx += 256) {
-		int c = idx / CH_NB, r = idx % CH_NB;
+	for(int idx = tid; idx < CH_NB * CH_NB; idx += PT) {
+		const int c = idx >> 7, r = idx & 127;
 		T[r][c] = (r <= c)? Akk[(size_t)c * ld + r] : 0.0;
 	}
 	__syncthreads();
-	for(int j = 0; j < CH_NB; ++ j) {
-		if(threadIdx.x == 0) {
-			double d = T[j][j];
-			if(!(d > 0)) { // Eigen's LLT stops at a non-positive pivot (and so does a NaN)
-				if(*info == 0)
-					*info = int(k0) + j + 1;
-				d = 1;
+
+	for(int kb = 0; kb < 4; ++ kb) {
+		const int o = kb * 32;
+		if(warp == 0) {
+			// lane r owns row r of L = R^T (column r of the block); left-looking register Cholesky
+			double a[32], L[32];
+			#pragma unroll
+			for(int c = 0; c < 32; ++ c)
+				a[c] = T[o + c][o + lane]; // zero for c > lane
+			bool bad = false;
+			#pragma unroll
+			for(int j = 0; j < 32; ++ j) {
+				double s = a[j];
+				#pragma unroll
+				for(int k = 0; k < j; ++ k)
+					s -= L[k] * __shfl_sync(0xffffffffu, L[k], j);
+				double piv = __shfl_sync(0xffffffffu, s, j);
+				if(!(piv > 0)) { // Eigen's LLT stops at a non-positive pivot (NaN fails the test as well)
+					bad = true;
+					piv = 1;
+				}
+				const double d = sqrt(piv), rd = 1.0 / d;
+				L[j] = (lane == j)? d : ((lane > j)? s * rd : 0.0);
+				if(lane == j)
+					rdinv[o + j] = rd;
 			}
-			T[j][j] = sqrt(d);
+			#pragma unroll
+			for(int c = 0; c < 32; ++ c)
+				if(c <= lane) T[o + c][o + lane] = L[c];
+			if(bad && lane == 0 && *info == 0)
+				*info = int(k0) + o + 1;
 		}
 		__syncthreads();
-		const double djj = T[j][j];
-		for(int c = j + 1 + threadIdx.x; c < CH_NB; c += 256)
-			T[j][c] /= djj;
+		// sub-row: solve R_bb^T X = T[o..o+31][o+32..127], thread per column
+		const int nrem = CH_NB - o - 32;
+		if(tid < nrem) {
+			const int c = o + 32 + tid;
+			double x[32];
+			#pragma unroll
+			for(int j = 0; j < 32; ++ j)
+				x[j] = T[o + j][c];
+			#pragma unroll
+			for(int j = 0; j < 32; ++ j) {
+				double s = x[j];
+				#pragma unroll
+				for(int i = 0; i < j; ++ i)
+					s -= T[o + i][o + j] * x[i];
+				x[j] = s * rdinv[o + j];
+			}
+			#pragma unroll
+			for(int j = 0; j < 32; ++ j)
+				T[o + j][c] = x[j];
+		}
 		__syncthreads();
-		const int m = CH_NB - 1 - j;
-		for(int idx = threadIdx.x; idx < m * m; idx += 256) {
-			int r = j + 1 + idx / m, c = j + 1 + idx % m;
-			if(r <= c)
-				T[r][c] -= T[j][r] * T[j][c];
+		// rank-32 update of the remaining upper sub-blocks; thread (ty, tx): rows ty + PW q, column tx
+		const int ty = tid >> 5, tx = lane;
+		for(int bi = kb + 1; bi < 4; ++ bi) {
+			for(int bj = bi; bj < 4; ++ bj) {
+				const int i0 = bi * 32 + ty, j = bj * 32 + tx;
+				double s[32 / PW];
+				#pragma unroll
+				for(int q = 0; q < 32 / PW; ++ q) s[q] = 0;
+				#pragma unroll 8
+				for(int k = 0; k < 32; ++ k) {
+					const double tj = T[o + k][j];
+					#pragma unroll
+					for(int q = 0; q < 32 / PW; ++ q)
+						s[q] += T[o + k][i0 + PW * q] * tj;
+				}
+				#pragma unroll
+				for(int q = 0; q < 32 / PW; ++ q)
+					T[i0 + PW * q][j] -= s[q];
+			}
 		}
 		__syncthreads();
 	}
-	for(int idx = threadIdx.x; idx < CH_NB * CH_NB; idx += 256) {
-		int c = idx / CH_NB, r = idx % CH_NB;
+	// R back to global (upper triangle)
+	for(int idx = tid; idx < CH_NB * CH_NB; idx += PT) {
+		const int c = idx >> 7, r = idx & 127;
 		if(r <= c)
 			Akk[(size_t)c * ld + r] = T[r][c];
 	}
-}
 
-// ---- block row: solve R_kk^T X = A(k-block, columns right of it) -------------------------------------
-
-__global__ void __launch_bounds__(64) k_trsm_panel(double *__restrict__ A, size_t ld, size_t k0, size_t c0, size_t n_cols)
-{
-	__shared__ double R[CH_NB][CH_NB + 1]; // R[j][i], upper
-	const double *Akk = A + k0 * ld + k0;
-	for(int idx = threadIdx.x; idx < CH_NB * CH_NB; idx += 64) {
-		int c = idx / CH_NB, r = idx % CH_NB;
-		R[r][c] = (r <= c)? Akk[(size_t)c * ld + r] : 0.0;
+	// ---- inverse of the upper-triangular factor, 32x32 blocks ----
+	// phase A: diagonal blocks, warp a, lane c solves R_aa x = e_c (uniform formula, zeros above c stay zero)
+	if(warp < 4) {
+		const int o = warp * 32;
+		double x[32];
+		#pragma unroll
+		for(int r = 31; r >= 0; -- r) {
+			double s = (r == lane)? 1.0 : 0.0;
+			#pragma unroll
+			for(int k = r + 1; k < 32; ++ k)
+				s -= T[o + r][o + k] * x[k];
+			x[r] = s * rdinv[o + r];
+		}
+		double *X = Xs + xblk(warp, warp) * XB_SIZE;
+		#pragma unroll
+		for(int r = 0; r < 32; ++ r)
+			X[r * XB_LD + lane] = x[r];
 	}
 	__syncthreads();
-	size_t col = c0 + blockIdx.x * (size_t)64 + threadIdx.x;
-	if(col >= n_cols)
-		return;
-	double *p = A + col * ld + k0;
-	double x[CH_NB];
-	#pragma unroll
-	for(int i = 0; i < CH_NB; i += 2) {
-		double2 t = *reinterpret_cast<const double2*>(p + i);
-		x[i] = t.x; x[i + 1] = t.y;
+	// phase B: X_ab = -X_aa (sum_{m=a+1..b} R_am X_mb), by distance d = b - a; PW / 4 warps per block
+	for(int d = 1; d < 4; ++ d) {
+		constexpr int WG = PW / 4, RPW = 32 / WG; // warps per block, rows per warp
+		const int nblk_d = 4 - d, g = warp / WG, w4 = warp % WG; // block group / warp inside the group
+		if(g < nblk_d) {
+			const int a = g, b = g + d;
+			double acc[RPW];
+			#pragma unroll
+			for(int q = 0; q < RPW; ++ q) acc[q] = 0;
+			for(int m = a + 1; m <= b; ++ m) {
+				const double *Xm = Xs + xblk(m, b) * XB_SIZE;
+				#pragma unroll 4
+				for(int k = 0; k < 32; ++ k) {
+					const double xv = Xm[k * XB_LD + lane];
+					#pragma unroll
+					for(int q = 0; q < RPW; ++ q)
+						acc[q] += T[a * 32 + w4 * RPW + q][m * 32 + k] * xv;
+				}
+			}
+			#pragma unroll
+			for(int q = 0; q < RPW; ++ q)
+				T[96 + w4 * RPW + q][g * 32 + lane] = acc[q];
+		}
+		__syncthreads();
+		if(g < nblk_d) {
+			const int a = g, b = g + d;
+			const double *Xa = Xs + xblk(a, a) * XB_SIZE;
+			double acc[RPW];
+			#pragma unroll
+			for(int q = 0; q < RPW; ++ q) acc[q] = 0;
+			#pragma unroll 4
+			for(int k = 0; k < 32; ++ k) {
+				const double tv = T[96 + k][g * 32 + lane];
+				#pragma unroll
+				for(int q = 0; q < RPW; ++ q)
+					acc[q] += Xa[(w4 * RPW + q) * XB_LD + k] * tv;
+			}
+			double *X = Xs + xblk(a, b) * XB_SIZE;
+			#pragma unroll
+			for(int q = 0; q < RPW; ++ q)
+				X[(w4 * RPW + q) * XB_LD + lane] = -acc[q];
+		}
+		__syncthreads();
 	}
-	#pragma unroll
-	for(int j = 0; j < CH_NB; ++ j) {
-		const double yj = x[j] / R[j][j];
-		x[j] = yj;
-		#pragma unroll
-		for(int i = j + 1; i < CH_NB; ++ i)
-			x[i] -= R[j][i] * yj;
+	// column-major 128x128 inverse (zeros below the diagonal blocks)
+	for(int idx = tid; idx < CH_NB * CH_NB; idx += PT) {
+		const int c = idx >> 7, r = idx & 127;
+		const int a = r >> 5, b = c >> 5;
+		Rinv_out[idx] = (a <= b)? Xs[xblk(a, b) * XB_SIZE + (r & 31) * XB_LD + (c & 31)] : 0.0;
 	}
-	#pragma unroll
-	for(int i = 0; i < CH_NB; i += 2)
-		*reinterpret_cast<double2*>(p + i) = make_double2(x[i], x[i + 1]);
 }
 
-// ---- trailing update on the FP64 tensor cores ------------------------------------------------------
+static const size_t POTRF_SMEM = (size_t)(CH_NB * CH_TP + 10 * XB_SIZE + CH_NB) * sizeof(double);
+
+// ---- FP64 tensor-core GEMM: C (op)= A^T B with K = 128, operands K-contiguous ---------------------------
 
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
 {
@@ -111,133 +225,169 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 		: "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// C(i0.., j0..) -= P(:, i0..)^T P(:, j0..) for the upper tiles; P = rows k0 .. k0+CH_NB of A.
-// grid: x = column tile (covers the matrix columns right of the panel and the rhs block), y = row tile.
-__global__ void __launch_bounds__(128) k_syrk_update(double *__restrict__ A, size_t ld, size_t k0, size_t c0,
-	size_t n_rows_end)
+enum { GEMM_SYRK = 0, GEMM_TRSM = 1 };
+
+// SYRK: C(i0.., j0..) -= P(:, i0..)^T P(:, j0..), P = rows k0..k0+127 of A; tiles with i0 > j0 are skipped.
+//       grid.x = column tile (from column cbase), grid.y = row tile (from row rbase).
+// TRSM: P(:, j0..) <- Rinv^T P(:, j0..) in place; BM must be 128 (a CTA owns whole columns of the panel).
+template <int MODE, int BM, int BN>
+__global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_gemm_tn(double *__restrict__ A, size_t ld, size_t k0,
+	size_t rbase, size_t cbase, const double *__restrict__ Rinv)
 {
-	const size_t i0 = c0 + blockIdx.y * (size_t)CH_TILE, j0 = c0 + blockIdx.x * (size_t)CH_TILE;
-	if(i0 > j0 || i0 >= n_rows_end)
-		return;
-	__shared__ double As[CH_TILE][CH_LDS];
-	__shared__ double Bs[CH_TILE][CH_LDS];
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int wi = (warp >> 1) * 32, wj = (warp & 1) * 32; // warp tile origin inside the CTA tile
+	constexpr int WARPS_N = BN / 32, NT = (BM / 32) * (BN / 32) * 32;
+	size_t i0, j0;
+	if(MODE == GEMM_SYRK) {
+		i0 = rbase + blockIdx.y * (size_t)BM;
+		j0 = cbase + blockIdx.x * (size_t)BN;
+		if(i0 > j0 + (BN - 1))
+			return; // strictly below the diagonal
+	} else {
+		i0 = 0;
+		j0 = cbase + blockIdx.x * (size_t)BN;
+	}
+	extern __shared__ double smem[];
+	double (*As)[BM][CH_LDS] = reinterpret_cast<double (*)[BM][CH_LDS]>(smem);
+	double (*Bs)[BN][CH_LDS] = reinterpret_cast<double (*)[BN][CH_LDS]>(smem + CH_STAGES * BM * CH_LDS);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int wi = (warp / WARPS_N) * 32, wj = (warp % WARPS_N) * 32;
 	const int g = lane >> 2, t = lane & 3;
+
+	// operand pointers: element (k, m) at base[m * stride + k]
+	const double *pa; size_t sa;
+	if(MODE == GEMM_SYRK) { pa = A + i0 * ld + k0; sa = ld; }
+	else { pa = Rinv; sa = CH_NB; }
+	const double *pb = A + j0 * ld + k0;
+
+	auto stage_load = [&](int st, int kc) {
+		// BM (BN) rows x 8 chunks of 16 bytes
+		for(int idx = tid; idx < BM * 8; idx += NT) {
+			const int m = idx >> 3, q = idx & 7;
+			__pipeline_memcpy_async(&As[st][m][q * 2], pa + (size_t)m * sa + kc * CH_BK + q * 2, 16);
+		}
+		for(int idx = tid; idx < BN * 8; idx += NT) {
+			const int m = idx >> 3, q = idx & 7;
+			__pipeline_memcpy_async(&Bs[st][m][q * 2], pb + (size_t)m * ld + kc * CH_BK + q * 2, 16);
+		}
+	};
+
 	double acc[4][4][2];
 	#pragma unroll
 	for(int a = 0; a < 4; ++ a)
 		#pragma unroll
 		for(int b = 0; b < 4; ++ b)
 			acc[a][b][0] = acc[a][b][1] = 0;
-	// staging: thread -> (column, half of the 16-deep chunk)
-	const int lc = threadIdx.x >> 1, lh = (threadIdx.x & 1) * 8;
-	const double *pa = A + (i0 + lc) * ld + k0 + lh;
-	const double *pb = A + (j0 + lc) * ld + k0 + lh;
-	for(int kk = 0; kk < CH_NB; kk += CH_BK) {
-		#pragma unroll
-		for(int q = 0; q < 8; q += 2) {
-			double2 va = *reinterpret_cast<const double2*>(pa + kk + q);
-			double2 vb = *reinterpret_cast<const double2*>(pb + kk + q);
-			*reinterpret_cast<double2*>(&As[lc][lh + q]) = va;
-			*reinterpret_cast<double2*>(&Bs[lc][lh + q]) = vb;
-		}
+
+	constexpr int KT = CH_NB / CH_BK;
+	#pragma unroll
+	for(int s = 0; s < CH_STAGES - 1; ++ s) {
+		stage_load(s, s);
+		__pipeline_commit();
+	}
+	for(int kt = 0; kt < KT; ++ kt) {
+		__pipeline_wait_prior(CH_STAGES - 2);
 		__syncthreads();
+		if(kt + CH_STAGES - 1 < KT)
+			stage_load((kt + CH_STAGES - 1) % CH_STAGES, kt + CH_STAGES - 1);
+		__pipeline_commit();
+		const int st = kt % CH_STAGES;
 		#pragma unroll
 		for(int k4 = 0; k4 < CH_BK; k4 += 4) {
 			double fa[4], fb[4];
 			#pragma unroll
 			for(int a = 0; a < 4; ++ a)
-				fa[a] = As[wi + a * 8 + g][k4 + t];
+				fa[a] = As[st][wi + a * 8 + g][k4 + t];
 			#pragma unroll
 			for(int b = 0; b < 4; ++ b)
-				fb[b] = Bs[wj + b * 8 + g][k4 + t];
+				fb[b] = Bs[st][wj + b * 8 + g][k4 + t];
 			#pragma unroll
 			for(int a = 0; a < 4; ++ a)
 				#pragma unroll
 				for(int b = 0; b < 4; ++ b)
 					dmma_m8n8k4(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
 		}
-		__syncthreads();
 	}
+	__pipeline_wait_prior(0);
+	if(MODE == GEMM_TRSM)
+		__syncthreads(); // every warp is done reading the panel (through smem) before anyone overwrites it
 	#pragma unroll
 	for(int a = 0; a < 4; ++ a) {
 		#pragma unroll
 		for(int b = 0; b < 4; ++ b) {
-			const size_t r = i0 + wi + a * 8 + g, c = j0 + wj + b * 8 + 2 * t;
-			A[c * ld + r] -= acc[a][b][0];
-			A[(c + 1) * ld + r] -= acc[a][b][1];
+			const size_t c = j0 + wj + b * 8 + 2 * t;
+			if(MODE == GEMM_SYRK) {
+				const size_t r = i0 + wi + a * 8 + g;
+				A[c * ld + r] -= acc[a][b][0];
+				A[(c + 1) * ld + r] -= acc[a][b][1];
+			} else {
+				const size_t r = k0 + wi + a * 8 + g;
+				A[c * ld + r] = acc[a][b][0];
+				A[(c + 1) * ld + r] = acc[a][b][1];
+			}
 		}
 	}
 }
 
-// ---- backward solve ---------------------------------------------------------------------------------
+template <int BM, int BN>
+constexpr size_t gemm_smem() { return (size_t)CH_STAGES * (BM + BN) * CH_LDS * sizeof(double); }
 
-// Rinv[blk] = inverse of the upper-triangular diagonal block blk (column-major CH_NB x CH_NB)
-__global__ void __launch_bounds__(CH_NB) k_invert_diag(const double *__restrict__ A, size_t ld, double *__restrict__ Rinv)
-{
-	__shared__ double X[CH_NB][CH_NB + 1]; // X[i][c]; thread c owns column c
-	const size_t k0 = blockIdx.x * (size_t)CH_NB;
-	const double *Akk = A + k0 * ld + k0; // R(i, j) = Akk[j * ld + i]; all threads read the same element (broadcast)
-	const int c = threadIdx.x;
-	for(int i = CH_NB - 1; i >= 0; -- i) {
-		double v = 0;
-		const double rii = Akk[(size_t)i * ld + i];
-		if(i == c)
-			v = 1.0 / rii;
-		else if(i < c) {
-			double s = 0;
-			for(int j = i + 1; j <= c; ++ j)
-				s += Akk[(size_t)j * ld + i] * X[j][c];
-			v = -s / rii;
-		}
-		X[i][c] = v;
-	}
-	__syncthreads();
-	double *out = Rinv + blockIdx.x * (size_t)(CH_NB * CH_NB);
-	for(int idx = threadIdx.x; idx < CH_NB * CH_NB; idx += CH_NB) {
-		int cc = idx / CH_NB, r = idx % CH_NB;
-		out[idx] = X[r][cc];
-	}
-}
+// ---- backward solve R x = y ---------------------------------------------------------------------------
 
-// R x = y. One CTA per block row (blockIdx 0 = last block row), CH_NB threads, thread r owns row r.
-__global__ void __launch_bounds__(CH_NB) k_backsolve(const double *__restrict__ A, size_t ld, size_t n_blk,
+// One CTA per block row (blockIdx 0 = last block row), 256 threads: thread (r, h) owns row r, column half h.
+__global__ void __launch_bounds__(256) k_backsolve(const double *__restrict__ A, size_t ld, size_t n_blk,
 	const double *__restrict__ Rinv, double *__restrict__ y /* in: y, out: x */, volatile int *flags)
 {
 	__shared__ double xs[CH_NB];
+	__shared__ double part[2][CH_NB];
 	const size_t bi = n_blk - 1 - blockIdx.x;
-	const int r = threadIdx.x;
-	double acc = y[bi * CH_NB + r];
+	const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
+	double acc = (h == 0)? y[bi * CH_NB + r] : 0.0;
 	for(size_t bj = n_blk - 1; bj > bi; -- bj) {
+		// the 64 matrix entries of this thread do not depend on x_j: fetch them before waiting
+		const double *row = A + (bj * CH_NB + h * 64) * ld + bi * CH_NB + r;
+		double m[64];
+		#pragma unroll
+		for(int c = 0; c < 64; ++ c)
+			m[c] = __ldg(row + (size_t)c * ld);
 		if(threadIdx.x == 0) {
 			while(flags[bj] == 0)
 				;
 			__threadfence();
 		}
 		__syncthreads();
-		xs[r] = ((volatile double*)y)[bj * CH_NB + r];
+		if(threadIdx.x < CH_NB)
+			xs[threadIdx.x] = ((volatile double*)y)[bj * CH_NB + threadIdx.x];
 		__syncthreads();
-		const double *row = A + (bj * CH_NB) * ld + bi * CH_NB + r;
 		double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-		#pragma unroll 4
-		for(int c = 0; c < CH_NB; c += 4) {
-			s0 += row[(size_t)c * ld] * xs[c];
-			s1 += row[(size_t)(c + 1) * ld] * xs[c + 1];
-			s2 += row[(size_t)(c + 2) * ld] * xs[c + 2];
-			s3 += row[(size_t)(c + 3) * ld] * xs[c + 3];
+		#pragma unroll
+		for(int c = 0; c < 64; c += 4) {
+			s0 += m[c] * xs[h * 64 + c];
+			s1 += m[c + 1] * xs[h * 64 + c + 1];
+			s2 += m[c + 2] * xs[h * 64 + c + 2];
+			s3 += m[c + 3] * xs[h * 64 + c + 3];
 		}
 		acc -= (s0 + s1) + (s2 + s3);
 		__syncthreads();
 	}
-	xs[r] = acc;
+	part[h][r] = acc;
 	__syncthreads();
+	if(threadIdx.x < CH_NB)
+		xs[threadIdx.x] = part[0][threadIdx.x] + part[1][threadIdx.x];
+	__syncthreads();
+	// x_i = Rinv_ii (upper triangular) * acc
 	const double *Ri = Rinv + bi * (size_t)(CH_NB * CH_NB);
-	double x = 0;
-	for(int c = r; c < CH_NB; ++ c) // upper triangular inverse
-		x += Ri[(size_t)c * CH_NB + r] * xs[c];
-	y[bi * CH_NB + r] = x;
-	__threadfence();
+	double s0 = 0, s1 = 0;
+	#pragma unroll 8
+	for(int c = h * 64; c < h * 64 + 64; c += 2) {
+		s0 += Ri[(size_t)c * CH_NB + r] * xs[c];
+		s1 += Ri[(size_t)(c + 1) * CH_NB + r] * xs[c + 1];
+	}
+	__syncthreads();
+	part[h][r] = s0 + s1;
+	__syncthreads();
+	if(threadIdx.x < CH_NB) {
+		y[bi * CH_NB + threadIdx.x] = part[0][threadIdx.x] + part[1][threadIdx.x];
+		__threadfence();
+	}
 	__syncthreads();
 	if(threadIdx.x == 0)
 		flags[bi] = 1;
@@ -264,11 +414,22 @@ size_t dense_chol_ld(size_t n)
 	return (n + CH_NB - 1) / CH_NB * CH_NB;
 }
 
-// number of doubles of the augmented storage: ld x (ld + CH_TILE)
+// number of doubles of the augmented storage: ld x (ld + 128)
 size_t dense_chol_storage(size_t n)
 {
 	size_t ld = dense_chol_ld(n);
-	return ld * (ld + CH_TILE);
+	return ld * (ld + CH_NB);
+}
+
+static void chol_init_attributes()
+{
+	static bool done = false;
+	if(done) return;
+	SPP_CUDA(cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 128>()));
+	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64, 64>()));
+	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_TRSM, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
+	done = true;
 }
 
 // A: device, augmented storage (upper triangle of the n x n matrix filled, everything else zero, rhs NOT yet
@@ -276,9 +437,14 @@ size_t dense_chol_storage(size_t n)
 int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 {
 	DenseChol &ch = ctx->chol;
+	chol_init_attributes();
 	const size_t ld = dense_chol_ld(n), n_blk = ld / CH_NB;
-	const size_t n_cols = ld + CH_TILE; // matrix + rhs block
 	cudaStream_t st = ctx->stream;
+	if(!ch.bulk_stream) {
+		SPP_CUDA(cudaStreamCreateWithFlags(&ch.bulk_stream, cudaStreamNonBlocking));
+		SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_panel, cudaEventDisableTiming));
+		SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_bulk, cudaEventDisableTiming));
+	}
 	ch.info.resize(1 + n_blk);
 	SPP_CUDA(cudaMemsetAsync(ch.info.p(), 0, (1 + n_blk) * sizeof(int), st));
 	ch.work.resize(n_blk * CH_NB * CH_NB);
@@ -289,23 +455,47 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 	double *rhs_col = A + ld * ld; // first column of the rhs block
 	k_copy_rhs<<<n_blocks(n, 256), 256, 0, st>>>(rhs_col, d_rhs_x, n);
 	LAUNCH_CHECK(ctx);
-	for(size_t b = 0; b < n_blk; ++ b) {
-		const size_t k0 = b * CH_NB, c0 = k0 + CH_NB;
-		k_potrf_diag<<<1, 256, 0, st>>>(A, ld, k0, ch.info.p());
-		LAUNCH_CHECK(ctx);
-		// block row right of the diagonal, including the rhs column (only its first column matters)
-		const size_t n_trsm_cols = ld + 1;
-		k_trsm_panel<<<n_blocks(n_trsm_cols - c0, 64), 64, 0, st>>>(A, ld, k0, c0, n_trsm_cols);
-		LAUNCH_CHECK(ctx);
-		if(c0 < ld) {
-			dim3 grid((unsigned)((n_cols - c0) / CH_TILE), (unsigned)((ld - c0) / CH_TILE));
-			k_syrk_update<<<grid, 128, 0, st>>>(A, ld, k0, c0, ld);
+
+	// factorisation with one-step look-ahead
+	{
+		const size_t n_cols = ld + CH_NB;
+		cudaStream_t sA = st, sB = ch.bulk_stream;
+		double *Rinv = ch.work.p();
+		int *info = ch.info.p();
+		bool bulk_in_flight = false;
+		for(size_t b = 0; b < n_blk; ++ b) {
+			const size_t k0 = b * CH_NB, c0 = k0 + CH_NB;
+			k_potrf128<<<1, PT, POTRF_SMEM, sA>>>(A, ld, k0, Rinv + b * (size_t)(CH_NB * CH_NB), info);
 			LAUNCH_CHECK(ctx);
+			k_gemm_tn<GEMM_TRSM, 128, 64><<<(unsigned)((n_cols - c0) / 64), 256, gemm_smem<128, 64>(), sA>>>(A, ld, k0, 0, c0,
+				Rinv + b * (size_t)(CH_NB * CH_NB));
+			LAUNCH_CHECK(ctx);
+			if(c0 >= ld)
+				break;
+			SPP_CUDA(cudaEventRecord(ch.ev_panel, sA)); // panel b is final
+			// the look-ahead below writes tile row c0, which the bulk update of step b - 1 also wrote
+			if(bulk_in_flight) {
+				SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_bulk, 0));
+				bulk_in_flight = false;
+			}
+			if(c0 + CH_NB < ld) { // bulk: tile rows below the next panel's row
+				SPP_CUDA(cudaStreamWaitEvent(sB, ch.ev_panel, 0));
+				dim3 grid((unsigned)((n_cols - (c0 + CH_NB)) / 128), (unsigned)((ld - (c0 + CH_NB)) / 128));
+				k_gemm_tn<GEMM_SYRK, 128, 128><<<grid, 512, gemm_smem<128, 128>(), sB>>>(A, ld, k0, c0 + CH_NB, c0 + CH_NB, 0);
+				LAUNCH_CHECK(ctx);
+				SPP_CUDA(cudaEventRecord(ch.ev_bulk, sB));
+				bulk_in_flight = true;
+			}
+			{ // look-ahead: tile row of the next panel, 64x64 tiles, critical stream
+				dim3 grid((unsigned)((n_cols - c0) / 64), 2);
+				k_gemm_tn<GEMM_SYRK, 64, 64><<<grid, 128, gemm_smem<64, 64>(), sA>>>(A, ld, k0, c0, c0, 0);
+				LAUNCH_CHECK(ctx);
+			}
 		}
+		if(bulk_in_flight)
+			SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_bulk, 0));
 	}
-	k_invert_diag<<<(unsigned)n_blk, CH_NB, 0, st>>>(A, ld, ch.work.p());
-	LAUNCH_CHECK(ctx);
-	k_backsolve<<<(unsigned)n_blk, CH_NB, 0, st>>>(A, ld, n_blk, ch.work.p(), rhs_col, ch.info.p() + 1);
+	k_backsolve<<<(unsigned)n_blk, 256, 0, st>>>(A, ld, n_blk, ch.work.p(), rhs_col, ch.info.p() + 1);
 	LAUNCH_CHECK(ctx);
 	k_copy_rhs<<<n_blocks(n, 256), 256, 0, st>>>(d_rhs_x, rhs_col, n);
 	LAUNCH_CHECK(ctx);

@@ -75,8 +75,11 @@ struct SchurSlot {
 };
 
 struct DenseChol {
-	DBuf<double> work;
-	DBuf<int> info;
+	DBuf<double> work;        // inverse diagonal blocks, [n_blk][128 x 128]
+	DBuf<int> info;           // [0] first non-positive pivot (1-based), [1..] block-row flags of the backsolve
+	cudaStream_t bulk_stream; // trailing updates that overlap the next panel
+	cudaEvent_t ev_panel, ev_bulk;
+	DenseChol() : bulk_stream(0), ev_panel(0), ev_bulk(0) {}
 };
 
 } // namespace spp
