@@ -24,6 +24,7 @@
 
 #include "spp_ctx.h"
 #include <cuda_pipeline_primitives.h>
+#include <stdlib.h>
 
 namespace spp {
 
@@ -47,53 +48,70 @@ __device__ __forceinline__ int xblk(int a, int b) { return a * 4 - a * (a - 1) /
 #define PW (PT / 32)
 
 __global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size_t ld, size_t k0,
-	double *__restrict__ Rinv_out, int *__restrict__ info)
+	double *__restrict__ Rinv_out, int *__restrict__ info, long long *__restrict__ dbg)
 {
+#define DBG_MARK(i) do { if(dbg && threadIdx.x == 0) dbg[i] = clock64(); } while(0)
 	extern __shared__ double smem[];
+	DBG_MARK(0);
 	double (*T)[CH_TP] = reinterpret_cast<double (*)[CH_TP]>(smem); // T[r][c], upper
 	double *Xs = smem + CH_NB * CH_TP;       // 10 packed 32x33 blocks of the inverse
 	double *rdinv = Xs + 10 * XB_SIZE;       // 128 reciprocal pivots
 	// scratch block g of the inversion lives in the (unused) strictly lower part of T: rows 96.., columns g*32..
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	double *Akk = A + k0 * ld + k0;
-	for(int idx = tid; idx < CH_NB * CH_NB; idx += PT) {
-		const int c = idx >> 7, r = idx & 127;
-		T[r][c] = (r <= c)? Akk[(size_t)c * ld + r] : 0.0;
+	{
+		// all loads of a thread are independent: issue them together, then fill the tile
+		constexpr int NQ = CH_NB * CH_NB / PT;
+		const int r = tid & 127, cb = tid >> 7;
+		double v[NQ];
+		#pragma unroll
+		for(int q = 0; q < NQ; ++ q) {
+			const int c = cb + (PT / CH_NB) * q;
+			v[q] = (r <= c)? Akk[(size_t)c * ld + r] : 0.0;
+		}
+		#pragma unroll
+		for(int q = 0; q < NQ; ++ q)
+			T[r][cb + (PT / CH_NB) * q] = v[q];
 	}
 	__syncthreads();
+	DBG_MARK(1);
 
 	for(int kb = 0; kb < 4; ++ kb) {
 		const int o = kb * 32;
+		if(kb == 0) DBG_MARK(2);
 		if(warp == 0) {
-			// lane r owns row r of L = R^T (column r of the block); left-looking register Cholesky
-			double a[32], L[32];
+			// lane r owns row r of L = R^T (column r of the block). Right-looking register Cholesky: after
+			// column j is final every later column is updated at once (independent FMAs), so the serial chain
+			// per pivot is shuffle -> rsqrt -> multiply -> shuffle -> FMA.
+			double a[32];
 			#pragma unroll
 			for(int c = 0; c < 32; ++ c)
 				a[c] = T[o + c][o + lane]; // zero for c > lane
 			bool bad = false;
 			#pragma unroll
 			for(int j = 0; j < 32; ++ j) {
-				double s = a[j];
-				#pragma unroll
-				for(int k = 0; k < j; ++ k)
-					s -= L[k] * __shfl_sync(0xffffffffu, L[k], j);
-				double piv = __shfl_sync(0xffffffffu, s, j);
+				double piv = __shfl_sync(0xffffffffu, a[j], j);
 				if(!(piv > 0)) { // Eigen's LLT stops at a non-positive pivot (NaN fails the test as well)
 					bad = true;
 					piv = 1;
 				}
-				const double d = sqrt(piv), rd = 1.0 / d;
-				L[j] = (lane == j)? d : ((lane > j)? s * rd : 0.0);
+				const double rd = rsqrt(piv), d = piv * rd;
+				const double l = (lane == j)? d : ((lane > j)? a[j] * rd : 0.0);
+				a[j] = l;
 				if(lane == j)
 					rdinv[o + j] = rd;
+				#pragma unroll
+				for(int c = j + 1; c < 32; ++ c)
+					a[c] -= l * __shfl_sync(0xffffffffu, l, c);
 			}
 			#pragma unroll
 			for(int c = 0; c < 32; ++ c)
-				if(c <= lane) T[o + c][o + lane] = L[c];
+				if(c <= lane) T[o + c][o + lane] = a[c];
 			if(bad && lane == 0 && *info == 0)
 				*info = int(k0) + o + 1;
 		}
 		__syncthreads();
+		if(kb == 0) DBG_MARK(3);
 		// sub-row: solve R_bb^T X = T[o..o+31][o+32..127], thread per column
 		const int nrem = CH_NB - o - 32;
 		if(tid < nrem) {
@@ -103,18 +121,19 @@ __global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size
 			for(int j = 0; j < 32; ++ j)
 				x[j] = T[o + j][c];
 			#pragma unroll
-			for(int j = 0; j < 32; ++ j) {
-				double s = x[j];
+			for(int j = 0; j < 32; ++ j) { // right-looking: independent updates, short serial chain
+				const double xj = x[j] * rdinv[o + j];
+				x[j] = xj;
 				#pragma unroll
-				for(int i = 0; i < j; ++ i)
-					s -= T[o + i][o + j] * x[i];
-				x[j] = s * rdinv[o + j];
+				for(int i = j + 1; i < 32; ++ i)
+					x[i] -= T[o + j][o + i] * xj;
 			}
 			#pragma unroll
 			for(int j = 0; j < 32; ++ j)
 				T[o + j][c] = x[j];
 		}
 		__syncthreads();
+		if(kb == 0) DBG_MARK(4);
 		// rank-32 update of the remaining upper sub-blocks; thread (ty, tx): rows ty + PW q, column tx
 		const int ty = tid >> 5, tx = lane;
 		for(int bi = kb + 1; bi < 4; ++ bi) {
@@ -136,7 +155,9 @@ __global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size
 			}
 		}
 		__syncthreads();
+		if(kb == 0) DBG_MARK(5);
 	}
+	DBG_MARK(6);
 	// R back to global (upper triangle)
 	for(int idx = tid; idx < CH_NB * CH_NB; idx += PT) {
 		const int c = idx >> 7, r = idx & 127;
@@ -144,18 +165,22 @@ __global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size
 			Akk[(size_t)c * ld + r] = T[r][c];
 	}
 
+	DBG_MARK(7);
 	// ---- inverse of the upper-triangular factor, 32x32 blocks ----
 	// phase A: diagonal blocks, warp a, lane c solves R_aa x = e_c (uniform formula, zeros above c stay zero)
 	if(warp < 4) {
 		const int o = warp * 32;
 		double x[32];
 		#pragma unroll
-		for(int r = 31; r >= 0; -- r) {
-			double s = (r == lane)? 1.0 : 0.0;
+		for(int r = 0; r < 32; ++ r)
+			x[r] = (r == lane)? 1.0 : 0.0;
+		#pragma unroll
+		for(int r = 31; r >= 0; -- r) { // right-looking back-substitution
+			const double xr = x[r] * rdinv[o + r];
+			x[r] = xr;
 			#pragma unroll
-			for(int k = r + 1; k < 32; ++ k)
-				s -= T[o + r][o + k] * x[k];
-			x[r] = s * rdinv[o + r];
+			for(int k = 0; k < r; ++ k)
+				x[k] -= T[o + k][o + r] * xr;
 		}
 		double *X = Xs + xblk(warp, warp) * XB_SIZE;
 		#pragma unroll
@@ -163,6 +188,7 @@ __global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size
 			X[r * XB_LD + lane] = x[r];
 	}
 	__syncthreads();
+	DBG_MARK(8);
 	// phase B: X_ab = -X_aa (sum_{m=a+1..b} R_am X_mb), by distance d = b - a; PW / 4 warps per block
 	for(int d = 1; d < 4; ++ d) {
 		constexpr int WG = PW / 4, RPW = 32 / WG; // warps per block, rows per warp
@@ -207,12 +233,15 @@ __global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size
 		}
 		__syncthreads();
 	}
+	DBG_MARK(9);
 	// column-major 128x128 inverse (zeros below the diagonal blocks)
 	for(int idx = tid; idx < CH_NB * CH_NB; idx += PT) {
 		const int c = idx >> 7, r = idx & 127;
 		const int a = r >> 5, b = c >> 5;
 		Rinv_out[idx] = (a <= b)? Xs[xblk(a, b) * XB_SIZE + (r & 31) * XB_LD + (c & 31)] : 0.0;
 	}
+	DBG_MARK(10);
+#undef DBG_MARK
 }
 
 static const size_t POTRF_SMEM = (size_t)(CH_NB * CH_TP + 10 * XB_SIZE + CH_NB) * sizeof(double);
@@ -271,17 +300,26 @@ __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_gemm_tn(double *
 	};
 
 	double acc[4][4][2];
-	#pragma unroll
-	for(int a = 0; a < 4; ++ a)
-		#pragma unroll
-		for(int b = 0; b < 4; ++ b)
-			acc[a][b][0] = acc[a][b][1] = 0;
 
 	constexpr int KT = CH_NB / CH_BK;
 	#pragma unroll
 	for(int s = 0; s < CH_STAGES - 1; ++ s) {
 		stage_load(s, s);
 		__pipeline_commit();
+	}
+	// SYRK: the accumulators start from the C tile (its loads overlap the pipeline fill) and the A fragments
+	// are negated, so the epilogue is a plain store instead of a read-modify-write
+	#pragma unroll
+	for(int a = 0; a < 4; ++ a) {
+		#pragma unroll
+		for(int b = 0; b < 4; ++ b) {
+			if(MODE == GEMM_SYRK) {
+				const size_t c = j0 + wj + b * 8 + 2 * t, r = i0 + wi + a * 8 + g;
+				acc[a][b][0] = A[c * ld + r];
+				acc[a][b][1] = A[(c + 1) * ld + r];
+			} else
+				acc[a][b][0] = acc[a][b][1] = 0;
+		}
 	}
 	for(int kt = 0; kt < KT; ++ kt) {
 		__pipeline_wait_prior(CH_STAGES - 2);
@@ -295,7 +333,7 @@ __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_gemm_tn(double *
 			double fa[4], fb[4];
 			#pragma unroll
 			for(int a = 0; a < 4; ++ a)
-				fa[a] = As[st][wi + a * 8 + g][k4 + t];
+				fa[a] = (MODE == GEMM_SYRK)? -As[st][wi + a * 8 + g][k4 + t] : As[st][wi + a * 8 + g][k4 + t];
 			#pragma unroll
 			for(int b = 0; b < 4; ++ b)
 				fb[b] = Bs[st][wj + b * 8 + g][k4 + t];
@@ -316,8 +354,8 @@ __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_gemm_tn(double *
 			const size_t c = j0 + wj + b * 8 + 2 * t;
 			if(MODE == GEMM_SYRK) {
 				const size_t r = i0 + wi + a * 8 + g;
-				A[c * ld + r] -= acc[a][b][0];
-				A[(c + 1) * ld + r] -= acc[a][b][1];
+				A[c * ld + r] = acc[a][b][0];
+				A[(c + 1) * ld + r] = acc[a][b][1];
 			} else {
 				const size_t r = k0 + wi + a * 8 + g;
 				A[c * ld + r] = acc[a][b][0];
@@ -427,6 +465,7 @@ static void chol_init_attributes()
 	if(done) return;
 	SPP_CUDA(cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 128>()));
+	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64, 64>()));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_TRSM, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
 	done = true;
@@ -442,8 +481,14 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 	cudaStream_t st = ctx->stream;
 	if(!ch.bulk_stream) {
 		SPP_CUDA(cudaStreamCreateWithFlags(&ch.bulk_stream, cudaStreamNonBlocking));
-		SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_panel, cudaEventDisableTiming));
-		SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_bulk, cudaEventDisableTiming));
+		SPP_CUDA(cudaStreamCreateWithFlags(&ch.row_stream, cudaStreamNonBlocking));
+		for(int i = 0; i < 2; ++ i) {
+			SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_panel[i], cudaEventDisableTiming));
+			SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_bulk[i], cudaEventDisableTiming));
+			SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_row[i], cudaEventDisableTiming));
+		}
+		ch.profile = getenv("SPP_CHOL_PROFILE") != 0;
+		ch.force_tile = getenv("SPP_CHOL_TILE")? atoi(getenv("SPP_CHOL_TILE")) : -1;
 	}
 	ch.info.resize(1 + n_blk);
 	SPP_CUDA(cudaMemsetAsync(ch.info.p(), 0, (1 + n_blk) * sizeof(int), st));
@@ -456,44 +501,118 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 	k_copy_rhs<<<n_blocks(n, 256), 256, 0, st>>>(rhs_col, d_rhs_x, n);
 	LAUNCH_CHECK(ctx);
 
-	// factorisation with one-step look-ahead
+	// factorisation with one-step look-ahead on three streams:
+	//   sA (critical): potrf(b) -> trsm(b) -> update of the next diagonal tile -> potrf(b+1) ...
+	//   sC           : update of the rest of the next panel's tile row (needed by trsm(b+1) only)
+	//   sB (bulk)    : update of everything below that row, overlapping potrf/trsm of the next panel
 	{
 		const size_t n_cols = ld + CH_NB;
-		cudaStream_t sA = st, sB = ch.bulk_stream;
+		cudaStream_t sA = st, sB = ch.bulk_stream, sC = ch.row_stream;
 		double *Rinv = ch.work.p();
 		int *info = ch.info.p();
-		bool bulk_in_flight = false;
+		const bool prof = ch.profile;
+		if(prof) {
+			sB = sC = sA;
+			ch.dbg.resize(16);
+		}
+		float t_acc[5] = {0, 0, 0, 0, 0};
+		auto tic = [&]() { if(prof) cudaEventRecord(ctx->ev[4], sA); };
+		auto toc = [&](int k) {
+			if(prof) {
+				cudaEventRecord(ctx->ev[5], sA);
+				cudaEventSynchronize(ctx->ev[5]);
+				float ms;
+				cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+				t_acc[k] += ms;
+			}
+		};
+		// C(rows r0.., cols c0..) -= P^T P on the upper tiles of a (n_r x n_c) region, tile shape by size
+		auto syrk = [&](cudaStream_t s, size_t k0, size_t r0, size_t c0, size_t n_r, size_t n_c, int tile) {
+			if(tile == 0) {
+				dim3 grid((unsigned)(n_c / 128), (unsigned)(n_r / 128));
+				k_gemm_tn<GEMM_SYRK, 128, 128><<<grid, 512, gemm_smem<128, 128>(), s>>>(A, ld, k0, r0, c0, 0);
+			} else if(tile == 1) {
+				dim3 grid((unsigned)(n_c / 64), (unsigned)(n_r / 128));
+				k_gemm_tn<GEMM_SYRK, 128, 64><<<grid, 256, gemm_smem<128, 64>(), s>>>(A, ld, k0, r0, c0, 0);
+			} else {
+				dim3 grid((unsigned)(n_c / 64), (unsigned)(n_r / 64));
+				k_gemm_tn<GEMM_SYRK, 64, 64><<<grid, 128, gemm_smem<64, 64>(), s>>>(A, ld, k0, r0, c0, 0);
+			}
+			LAUNCH_CHECK(ctx);
+		};
+		bool bulk_in_flight = false, row_in_flight = false;
 		for(size_t b = 0; b < n_blk; ++ b) {
 			const size_t k0 = b * CH_NB, c0 = k0 + CH_NB;
-			k_potrf128<<<1, PT, POTRF_SMEM, sA>>>(A, ld, k0, Rinv + b * (size_t)(CH_NB * CH_NB), info);
+			const int e = int(b & 1);
+			tic();
+			k_potrf128<<<1, PT, POTRF_SMEM, sA>>>(A, ld, k0, Rinv + b * (size_t)(CH_NB * CH_NB), info,
+				(prof && b == 1)? ch.dbg.p() : 0);
 			LAUNCH_CHECK(ctx);
+			toc(0);
+			if(row_in_flight && !prof) { // the rest of tile row b was updated on sC
+				SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_row[e ^ 1], 0));
+				row_in_flight = false;
+			}
+			tic();
 			k_gemm_tn<GEMM_TRSM, 128, 64><<<(unsigned)((n_cols - c0) / 64), 256, gemm_smem<128, 64>(), sA>>>(A, ld, k0, 0, c0,
 				Rinv + b * (size_t)(CH_NB * CH_NB));
 			LAUNCH_CHECK(ctx);
+			toc(1);
 			if(c0 >= ld)
 				break;
-			SPP_CUDA(cudaEventRecord(ch.ev_panel, sA)); // panel b is final
-			// the look-ahead below writes tile row c0, which the bulk update of step b - 1 also wrote
-			if(bulk_in_flight) {
-				SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_bulk, 0));
-				bulk_in_flight = false;
+			if(!prof) {
+				SPP_CUDA(cudaEventRecord(ch.ev_panel[e], sA)); // panel b is final
+				// the look-ahead updates write tile row b + 1, which the bulk update of step b - 1 also wrote
+				if(bulk_in_flight) {
+					SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_bulk[e ^ 1], 0));
+					SPP_CUDA(cudaStreamWaitEvent(sC, ch.ev_bulk[e ^ 1], 0));
+					bulk_in_flight = false;
+				}
 			}
-			if(c0 + CH_NB < ld) { // bulk: tile rows below the next panel's row
-				SPP_CUDA(cudaStreamWaitEvent(sB, ch.ev_panel, 0));
-				dim3 grid((unsigned)((n_cols - (c0 + CH_NB)) / 128), (unsigned)((ld - (c0 + CH_NB)) / 128));
-				k_gemm_tn<GEMM_SYRK, 128, 128><<<grid, 512, gemm_smem<128, 128>(), sB>>>(A, ld, k0, c0 + CH_NB, c0 + CH_NB, 0);
-				LAUNCH_CHECK(ctx);
-				SPP_CUDA(cudaEventRecord(ch.ev_bulk, sB));
+			const size_t r1 = c0 + CH_NB; // first row below the next panel's tile row
+			if(r1 < ld) {
+				if(!prof)
+					SPP_CUDA(cudaStreamWaitEvent(sB, ch.ev_panel[e], 0));
+				const size_t T = (ld - r1) / 128, n_tiles = T * (T + 1) / 2 + T;
+				int tile = (n_tiles >= 3 * 148)? 0 : ((n_tiles >= 74)? 1 : 2);
+				if(ch.force_tile >= 0) tile = ch.force_tile;
+				tic();
+				syrk(sB, k0, r1, r1, ld - r1, n_cols - r1, tile);
+				toc(2);
+				if(!prof)
+					SPP_CUDA(cudaEventRecord(ch.ev_bulk[e], sB));
 				bulk_in_flight = true;
 			}
-			{ // look-ahead: tile row of the next panel, 64x64 tiles, critical stream
-				dim3 grid((unsigned)((n_cols - c0) / 64), 2);
-				k_gemm_tn<GEMM_SYRK, 64, 64><<<grid, 128, gemm_smem<64, 64>(), sA>>>(A, ld, k0, c0, c0, 0);
-				LAUNCH_CHECK(ctx);
-			}
+			// look-ahead, critical part: the next diagonal tile
+			tic();
+			syrk(sA, k0, c0, c0, CH_NB, CH_NB, 2);
+			toc(3);
+			// look-ahead, rest of the next panel's tile row (rhs block included)
+			if(!prof)
+				SPP_CUDA(cudaStreamWaitEvent(sC, ch.ev_panel[e], 0));
+			tic();
+			syrk(sC, k0, c0, c0 + CH_NB, CH_NB, n_cols - (c0 + CH_NB), 2);
+			toc(4);
+			if(!prof)
+				SPP_CUDA(cudaEventRecord(ch.ev_row[e], sC));
+			row_in_flight = true;
 		}
-		if(bulk_in_flight)
-			SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_bulk, 0));
+		if(!prof) {
+			for(int i = 0; i < 2; ++ i) { // join: whatever is still in flight on the side streams
+				if(bulk_in_flight)
+					SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_bulk[i], 0));
+				if(row_in_flight)
+					SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_row[i], 0));
+			}
+		} else
+		{
+			long long h[16];
+			cudaMemcpy(h, ch.dbg.p(), sizeof(h), cudaMemcpyDeviceToHost);
+			fprintf(stderr, "[spp potrf clocks] load %lld | chol32 %lld | subrow %lld | update %lld | kb1-3 %lld | store %lld | invA %lld | invB %lld | storeinv %lld\n",
+				h[1] - h[0], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[8] - h[7], h[9] - h[8], h[10] - h[9]);
+		}
+			fprintf(stderr, "[spp chol profile] n=%zu potrf %.3f ms, trsm %.3f, bulk %.3f, la_diag %.3f, la_row %.3f (serialised)\n",
+				n, t_acc[0], t_acc[1], t_acc[2], t_acc[3], t_acc[4]);
 	}
 	k_backsolve<<<(unsigned)n_blk, 256, 0, st>>>(A, ld, n_blk, ch.work.p(), rhs_col, ch.info.p() + 1);
 	LAUNCH_CHECK(ctx);
