@@ -124,6 +124,12 @@ int spp_ba_linearise(spp_ctx_t ctx);
 int spp_ba_get_lambda(spp_ctx_t ctx, uint64_t *p_n_block_cols, uint64_t *p_n_blocks, uint64_t *p_n_values,
 	uint64_t *p_col_dims, uint64_t *p_col_ptr, uint64_t *p_row_idx, double *p_values, double *p_eta);
 
+/* The same linearised system as raw block arrays, for full-size checks where the column-ordered export above is
+ * unwieldy: p_U[36 * C] / p_V[9 * P] diagonal blocks in camera / point id order, p_W[18 * O] the camera x point
+ * block J_c^T Sigma^-1 J_p (6 x 3, column-major) of every observation in EDGE INSERTION order, p_eta_c[6 * C],
+ * p_eta_p[3 * P]. Undamped; any pointer may be NULL. (CUberBlockMatrix::t_Block_AtColumn, BlockMatrix.h:470-485) */
+int spp_ba_get_blocks(spp_ctx_t ctx, double *p_U, double *p_V, double *p_W, double *p_eta_c, double *p_eta_p);
+
 /* Replaces CNonlinearSolver_Lambda_LM::f_Chi_Squared_Error_Denorm (NonlinearSolver_Base.h:278-297 ->
  * CEdgeP2C3D::f_Chi_Squared_Error, BA_Types.h:511-531). */
 int spp_ba_chi2(spp_ctx_t ctx, double *p_chi2);

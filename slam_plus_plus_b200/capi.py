@@ -23,7 +23,7 @@ MAX_TRACE = 64
 EXPORTED_SYMBOLS = [
     "spp_create", "spp_destroy", "spp_last_error", "spp_describe", "spp_kernel_launches", "spp_stream",
     "spp_synchronize", "spp_set_allreduce", "spp_ba_set_graph", "spp_ba_set_states", "spp_ba_get_states",
-    "spp_ba_restore_initial", "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_chi2", "spp_ba_solve_step",
+    "spp_ba_restore_initial", "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_get_blocks", "spp_ba_chi2", "spp_ba_solve_step",
     "spp_ba_optimize", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_get_reduced_system",
     "spp_dense_posdef_solve",
 ]
@@ -86,6 +86,7 @@ def load_library() -> C.CDLL:
     lib.spp_ba_set_jacobian_mode.argtypes = [vp, C.c_int]
     lib.spp_ba_linearise.argtypes = [vp]
     lib.spp_ba_get_lambda.argtypes = [vp, u64p, u64p, u64p, u64p, u64p, u64p, dp, dp]
+    lib.spp_ba_get_blocks.argtypes = [vp, dp, dp, dp, dp, dp]
     lib.spp_ba_chi2.argtypes = [vp, dp]
     lib.spp_ba_solve_step.argtypes = [vp, C.c_double, dp]
     lib.spp_ba_optimize.argtypes = [vp, C.c_size_t, C.c_double, C.POINTER(Report)]
@@ -227,6 +228,14 @@ class Context:
         self._check(self.lib.spp_ba_get_lambda(self.h, None, None, None, _u64p(col_dims), _u64p(col_ptr), _u64p(row_idx),
                                                _dp(vals), _dp(eta)))
         return col_dims, col_ptr, row_idx, vals, eta
+
+    def ba_get_blocks(self):
+        """Returns U (C,36), V (P,9), W (O,18; edge insertion order), eta_c (C,6), eta_p (P,3)."""
+        c, p, o, _ = self._ba_dims
+        U, V, W = np.empty((c, 36)), np.empty((p, 9)), np.empty((o, 18))
+        gc, gp = np.empty((c, 6)), np.empty((p, 3))
+        self._check(self.lib.spp_ba_get_blocks(self.h, _dp(U), _dp(V), _dp(W), _dp(gc), _dp(gp)))
+        return U, V, W, gc, gp
 
     def ba_chi2(self) -> float:
         v = C.c_double()

@@ -544,6 +544,30 @@ int spp_ba_get_lambda(spp_ctx_t ctx, uint64_t *p_n_block_cols, uint64_t *p_n_blo
 	API_END(ctx)
 }
 
+int spp_ba_get_blocks(spp_ctx_t ctx, double *p_U, double *p_V, double *p_W, double *p_eta_c, double *p_eta_p)
+{
+	API_BEGIN(ctx)
+	BAProblem &ba = ctx->ba;
+	SchurSystem &s = ctx->sys;
+	if(!ba.valid) throw invalid_error("no BA graph");
+	if(!ba.linearised) throw invalid_error("spp_ba_linearise() has not been called");
+	if(p_U) s.U.download(p_U, s.C * 36, ctx->stream);
+	if(p_V) s.V.download(p_V, s.P * 9, ctx->stream);
+	if(p_eta_c) s.gc.download(p_eta_c, s.C * 6, ctx->stream);
+	if(p_eta_p) s.gp.download(p_eta_p, s.P * 3, ctx->stream);
+	std::vector<double> hW;
+	if(p_W) {
+		hW.resize(s.O * 18);
+		s.W.download(hW.data(), hW.size(), ctx->stream);
+	}
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	if(p_W) { // track order -> edge insertion order
+		for(size_t k = 0; k < s.O; ++ k)
+			memcpy(p_W + (size_t)ba.obs_orig[k] * 18, &hW[k * 18], 18 * sizeof(double));
+	}
+	API_END(ctx)
+}
+
 int spp_ba_chi2(spp_ctx_t ctx, double *p_chi2)
 {
 	API_BEGIN(ctx)
