@@ -34,7 +34,7 @@ if [ ! -d "$REF/include/slam" ]; then
 fi
 mkdir -p "$OBJ"
 DRIVERS=("$@")
-[ ${#DRIVERS[@]} -eq 0 ] && DRIVERS=(ba pose)
+[ ${#DRIVERS[@]} -eq 0 ] && DRIVERS=(ba dropin)
 
 compile_one() { # src obj compiler extra
 	local src="$1" obj="$2" comp="$3"; shift 3
@@ -50,7 +50,8 @@ for f in BlockMatrix Debug LinearSolver_Schur LinearSolver_Schur_GPU LinearSolve
 	echo "$REF/src/slam/$f.cpp $OBJ/slam_$f.o $CXX" >> "$LIST"
 done
 for d in "${DRIVERS[@]}"; do
-	echo "$HERE/ref_driver_$d.cpp $OBJ/ref_driver_$d.o $CXX" >> "$LIST"
+	# the drop-in driver also sees the product's public headers (C ABI + reference-side adapter)
+	echo "$HERE/ref_driver_$d.cpp $OBJ/ref_driver_$d.o $CXX -I$HERE/../include" >> "$LIST"
 done
 for f in "$REF"/src/csparse/*.c; do
 	echo "$f $OBJ/csparse_$(basename "$f" .c).o $CC -I$REF/include/csparse" >> "$LIST"
@@ -67,7 +68,11 @@ xargs -P "$JOBS" -L 1 bash -c 'compile_one "$@"' _ < "$LIST" || { echo "build_re
 LIBOBJ=$(ls "$OBJ"/slam_*.o "$OBJ"/csparse_*.o "$OBJ"/amd_*.o "$OBJ"/camd_*.o)
 rc=0
 for d in "${DRIVERS[@]}"; do
-	$CXX -fopenmp -o "$OUT/ref_driver_$d" "$OBJ/ref_driver_$d.o" $LIBOBJ -lrt || rc=1
+	EXTRA=""
+	if [ "$d" = "dropin" ]; then # links the product library; found at run time relative to the binary
+		EXTRA="-L$HERE/../slam_plus_plus_b200 -lspp_b200 -Wl,-rpath,\$ORIGIN/../../slam_plus_plus_b200"
+	fi
+	$CXX -fopenmp -o "$OUT/ref_driver_$d" "$OBJ/ref_driver_$d.o" $LIBOBJ -lrt $EXTRA || rc=1
 done
 [ $rc -eq 0 ] && echo "build_ref: ok -> $OUT" || echo "build_ref: link failed"
 exit $rc

@@ -604,15 +604,14 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 				if(row_in_flight)
 					SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_row[i], 0));
 			}
-		} else
-		{
+		} else {
 			long long h[16];
 			cudaMemcpy(h, ch.dbg.p(), sizeof(h), cudaMemcpyDeviceToHost);
 			fprintf(stderr, "[spp potrf clocks] load %lld | chol32 %lld | subrow %lld | update %lld | kb1-3 %lld | store %lld | invA %lld | invB %lld | storeinv %lld\n",
 				h[1] - h[0], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[8] - h[7], h[9] - h[8], h[10] - h[9]);
-		}
 			fprintf(stderr, "[spp chol profile] n=%zu potrf %.3f ms, trsm %.3f, bulk %.3f, la_diag %.3f, la_row %.3f (serialised)\n",
 				n, t_acc[0], t_acc[1], t_acc[2], t_acc[3], t_acc[4]);
+		}
 	}
 	k_backsolve<<<(unsigned)n_blk, 256, 0, st>>>(A, ld, n_blk, ch.work.p(), rhs_col, ch.info.p() + 1);
 	LAUNCH_CHECK(ctx);

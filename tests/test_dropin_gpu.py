@@ -1,0 +1,42 @@
+"""The drop-in test: the UNMODIFIED reference LM solver (oracle/_ref/ref_driver_dropin, compiled from
+/root/reference in the build container) with CLinearSolver_Schur_B200 (include/slam_b200/) plugged into its
+linear-solver slot -- i.e. the reference's own edges, Jacobians and LM loop, our Schur / Cholesky / back-substitution
+through the C ABI. Since the linearisation is the reference's own, the whole LM trace must reproduce the
+pure-reference golden run to the accuracy of the linear solves (1e-9)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+BIN = os.path.join(ROOT, "oracle", "_ref", "ref_driver_dropin")
+
+
+@pytest.mark.parametrize("name", ["ba_tiny", "ba_tiny_interleaved", "ba_small", "ba_small_hard"])
+def test_reference_lm_with_b200_linear_solver(name, tmp_path):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/ref_driver_dropin not built (needs /root/reference at build time)")
+    from slam_plus_plus_b200 import sppio
+    g, d = load_golden(name)
+    gp, dp = str(tmp_path / "g.bin"), str(tmp_path / "d.dump")
+    sppio.write_graph(gp, g)
+    subprocess.run([BIN, gp, dp, str(int(d["max_iter"][0])), "0"], check=True, stdout=subprocess.DEVNULL,
+                   env=dict(os.environ, OMP_NUM_THREADS="1"))
+    r = sppio.read_dump(dp)
+    assert abs(r["chi2_0"][0] - d["chi2_0"][0]) <= 1e-13 * d["chi2_0"][0]
+    tr, tg = r["lm_trace"].reshape(-1, 6), d["lm_trace"].reshape(-1, 6)
+    for k in range(min(len(tr), len(tg))):
+        if abs(tg[k, 1] - tg[k, 2]) <= 1e-9 * tg[k, 1]:
+            break  # chi2 no longer changes: the accept / reject decision is rounding noise from here on
+        assert int(tr[k, 4]) == int(tg[k, 4])
+        assert abs(tr[k, 2] - tg[k, 2]) <= 1e-9 * tg[k, 2]
+        assert abs(tr[k, 0] - tg[k, 0]) <= 1e-7 * tg[k, 0]  # damping history
+    assert abs(r["chi2"][0] - d["chi2"][0]) <= 1e-9 * d["chi2"][0]
+    # converged problems end with noise-decided accept / reject steps along nearly flat directions: the states
+    # agree less tightly than chi2 does
+    assert rel_err(r["states"], d["states"]) < 1e-4
