@@ -85,6 +85,15 @@ int spp_synchronize(spp_ctx_t ctx);
 typedef int (*spp_allreduce_fn)(void *p_user, void *p_device_doubles, size_t n_doubles);
 int spp_set_allreduce(spp_ctx_t ctx, spp_allreduce_fn fn, void *p_user, int rank, int world);
 
+/* Pure host helper (no context, no GPU): the landmark slices used by the multi-GPU path. p_track_length[p] = number
+ * of observations of landmark p; p_bounds[world + 1] receives the slice boundaries (rank r owns landmarks
+ * p_bounds[r] .. p_bounds[r + 1]), contiguous and balanced by the Schur-product work k (k + 1) / 2 + k. */
+int spp_partition_landmarks(size_t n_points, const uint32_t *p_track_length, int world, uint64_t *p_bounds);
+
+/* The landmark slice [*p_begin, *p_end) (indices into the point array given to spp_ba_set_graph) owned by this
+ * context; the whole range when world == 1. spp_ba_get_states / spp_ba_set_states touch only this slice. */
+int spp_ba_get_partition(spp_ctx_t ctx, uint64_t *p_begin, uint64_t *p_end);
+
 /* ---- slot 3: bundle adjustment system resident on the device --------------------------------------- */
 
 /* Replaces Add_CamVertex / Add_XYZVertex / Add_P2C3DEdge called in a loop (BAOptimizer.h:130-133;

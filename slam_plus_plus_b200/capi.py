@@ -22,7 +22,7 @@ MAX_TRACE = 64
 # every symbol include/spp_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "spp_create", "spp_destroy", "spp_last_error", "spp_describe", "spp_kernel_launches", "spp_stream",
-    "spp_synchronize", "spp_set_allreduce", "spp_ba_set_graph", "spp_ba_set_states", "spp_ba_get_states",
+    "spp_synchronize", "spp_set_allreduce", "spp_partition_landmarks", "spp_ba_get_partition", "spp_ba_set_graph", "spp_ba_set_states", "spp_ba_get_states",
     "spp_ba_restore_initial", "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_get_blocks", "spp_ba_chi2", "spp_ba_solve_step",
     "spp_ba_optimize", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_get_reduced_system",
     "spp_dense_posdef_solve",
@@ -79,6 +79,8 @@ def load_library() -> C.CDLL:
     lib.spp_stream.restype = vp
     lib.spp_synchronize.argtypes = [vp]
     lib.spp_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp, C.c_int, C.c_int]
+    lib.spp_partition_landmarks.argtypes = [C.c_size_t, C.POINTER(C.c_uint32), C.c_int, u64p]
+    lib.spp_ba_get_partition.argtypes = [vp, u64p, u64p]
     lib.spp_ba_set_graph.argtypes = [vp, C.c_size_t, u8p, dp, dp, C.c_size_t, u64p, u64p, dp, dp]
     lib.spp_ba_set_states.argtypes = [vp, dp, dp]
     lib.spp_ba_get_states.argtypes = [vp, dp, dp]
@@ -108,6 +110,16 @@ def _u64p(a):
 
 def _u8p(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def partition_landmarks(track_length, world: int) -> np.ndarray:
+    """Landmark slice boundaries of the multi-GPU path (pure host code in the library, no GPU needed)."""
+    tl = np.ascontiguousarray(track_length, np.uint32)
+    bounds = np.zeros(world + 1, np.uint64)
+    rc = load_library().spp_partition_landmarks(tl.shape[0], tl.ctypes.data_as(C.POINTER(C.c_uint32)), world, _u64p(bounds))
+    if rc != SPP_OK:
+        raise ValueError("spp_partition_landmarks: invalid arguments")
+    return bounds.astype(np.int64)
 
 
 class SppError(RuntimeError):
@@ -200,10 +212,17 @@ class Context:
         ps = None if pts is None else np.ascontiguousarray(pts, np.float64)
         self._check(self.lib.spp_ba_set_states(self.h, _dp(cs), _dp(ps)))
 
+    def ba_get_partition(self):
+        b, e = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.spp_ba_get_partition(self.h, C.byref(b), C.byref(e)))
+        return int(b.value), int(e.value)
+
     def ba_get_states(self):
+        """Camera states and landmark positions; on a partitioned context only this rank's landmark slice
+        (ba_get_partition) is filled, the rest is zero."""
         c, p, _, _ = self._ba_dims
         cs = np.empty((c, 6))
-        ps = np.empty((p, 3))
+        ps = np.zeros((p, 3))
         self._check(self.lib.spp_ba_get_states(self.h, _dp(cs), _dp(ps)))
         return cs, ps
 

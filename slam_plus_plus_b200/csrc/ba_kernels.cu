@@ -394,13 +394,13 @@ __global__ void __launch_bounds__(RED_THREADS) k_final_sum(const double *__restr
 
 // partial[0*G + b] = sum dx.dx ; partial[1*G + b] = sum dx.(alpha dx + eta) over this block's slice
 __global__ void __launch_bounds__(RED_THREADS) k_step_dots(size_t n, const double *__restrict__ dx,
-	const double *__restrict__ eta, double alpha, double *__restrict__ partial, size_t G, int accumulate)
+	const double *__restrict__ eta, double alpha, double w_norm, double *__restrict__ partial, size_t G, int accumulate)
 {
 	__shared__ double sred[2][RED_THREADS / 32];
 	double a0 = 0, a1 = 0;
 	for(size_t i = blockIdx.x * (size_t)RED_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * RED_THREADS) {
 		double d = dx[i];
-		a0 += d * d;
+		a0 += w_norm * d * d;
 		a1 += d * (alpha * d + eta[i]);
 	}
 	a0 = warp_sum(a0); a1 = warp_sum(a1);
@@ -500,9 +500,13 @@ void ba_step_dots_device(spp_ctx *ctx, double alpha, double *d_out)
 	SchurSystem &s = ctx->sys;
 	const unsigned G = 148 * 2;
 	ba.partial.resize(4 * 1024);
-	k_step_dots<<<G, RED_THREADS, 0, ctx->stream>>>(s.C * 6, s.dxc.p(), s.gc.p(), alpha, ba.partial.p(), G, 0);
+	// multi-GPU: the camera increments are replicated while eta_c is a per-rank partial sum: every rank adds
+	// dx_c . eta_c(partial), only rank 0 adds |dx_c|^2 and alpha |dx_c|^2; landmarks are disjoint
+	const bool first = ctx->rank == 0;
+	k_step_dots<<<G, RED_THREADS, 0, ctx->stream>>>(s.C * 6, s.dxc.p(), s.gc.p(), first? alpha : 0.0, first? 1.0 : 0.0,
+		ba.partial.p(), G, 0);
 	LAUNCH_CHECK(ctx);
-	k_step_dots<<<G, RED_THREADS, 0, ctx->stream>>>(s.P * 3, s.dxp.p(), s.gp.p(), alpha, ba.partial.p(), G, 1);
+	k_step_dots<<<G, RED_THREADS, 0, ctx->stream>>>(s.P * 3, s.dxp.p(), s.gp.p(), alpha, 1.0, ba.partial.p(), G, 1);
 	LAUNCH_CHECK(ctx);
 	k_final_sum<<<2, RED_THREADS, 0, ctx->stream>>>(ba.partial.p(), G, G, d_out);
 	LAUNCH_CHECK(ctx);

@@ -198,7 +198,9 @@ __global__ void k_backsubstitute(size_t P, const uint32_t *__restrict__ pt_ptr, 
 // ---------------------------------------------------------------------------------------------------
 
 // forms Cinv, Y, the dense upper-triangular reduced camera system S and its right-hand side b
-void schur_form_reduced_system(spp_ctx *ctx, double alpha)
+// alpha damps the landmark blocks of this rank; alpha_diag is what this rank adds to the camera diagonal (alpha on
+// rank 0, zero elsewhere: the partial systems are summed over ranks)
+void schur_form_reduced_system(spp_ctx *ctx, double alpha, double alpha_diag)
 {
 	SchurSystem &s = ctx->sys;
 	const size_t n = s.C * 6;
@@ -214,7 +216,7 @@ void schur_form_reduced_system(spp_ctx *ctx, double alpha)
 	}
 	s.S.zero(ctx->stream);
 	if(s.n_blocks) {
-		k_schur_blocks<<<n_blocks(s.n_blocks, SB_WARPS), SB_WARPS * 32, 0, ctx->stream>>>(s.n_blocks, ld, alpha,
+		k_schur_blocks<<<n_blocks(s.n_blocks, SB_WARPS), SB_WARPS * 32, 0, ctx->stream>>>(s.n_blocks, ld, alpha_diag,
 			s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), s.U.p(),
 			s.gc.p(), s.gp.p(), s.obs_pt.p(), s.S.p(), s.b.p());
 		LAUNCH_CHECK(ctx);

@@ -17,7 +17,7 @@ void ba_linearise(spp_ctx *ctx, bool b_want_maxdiag);
 void ba_chi2_device(spp_ctx *ctx, double *d_out);
 void ba_step_dots_device(spp_ctx *ctx, double alpha, double *d_out);
 void ba_apply_update(spp_ctx *ctx);
-void schur_form_reduced_system(spp_ctx *ctx, double alpha);
+void schur_form_reduced_system(spp_ctx *ctx, double alpha, double alpha_diag);
 void schur_backsubstitute(spp_ctx *ctx);
 size_t dense_chol_ld(size_t n);
 size_t dense_chol_storage(size_t n);
@@ -27,6 +27,23 @@ void slot_symbolic(spp_ctx *ctx, size_t n, const uint64_t *col_dims, const uint6
 int slot_solve(spp_ctx *ctx, const double *p_values, double *p_eta_dx);
 
 static thread_local std::string g_create_error;
+
+struct comm_error : std::runtime_error {
+	explicit comm_error(const std::string &t) : std::runtime_error(t) {}
+};
+
+// sums n doubles at d_ptr over the ranks through the hook installed by spp_set_allreduce (no-op on one rank).
+// The hook orders itself on the context's stream (slam_plus_plus_b200/parallel.py runs the collective with the
+// context stream as torch's current stream).
+void allreduce_device(spp_ctx *ctx, double *d_ptr, size_t n)
+{
+	if(ctx->world <= 1 || !n)
+		return;
+	if(!ctx->allreduce)
+		throw invalid_error("world > 1 but no all-reduce hook installed (spp_set_allreduce)");
+	if(ctx->allreduce(ctx->allreduce_user, d_ptr, n) != 0)
+		throw comm_error("the all-reduce hook failed");
+}
 
 struct EventTimer {
 	spp_ctx *ctx;
@@ -50,9 +67,11 @@ int schur_solve_current(spp_ctx *ctx, double alpha, spp_report_t *rep)
 	const size_t n = s.C * 6;
 	EventTimer tm(ctx);
 	tm.start();
-	schur_form_reduced_system(ctx, alpha); // S lives in the padded storage of the dense solver
-	if(ctx->allreduce && ctx->world > 1) {
-		// TODO(multi-GPU): pack [S_upper | b], all-reduce
+	schur_form_reduced_system(ctx, alpha, (ctx->rank == 0)? alpha : 0.0); // S lives in the padded storage of the dense solver
+	if(ctx->world > 1) { // sum the partial reduced camera systems and right-hand sides over the ranks
+		const size_t ld = dense_chol_ld(n);
+		allreduce_device(ctx, s.S.p(), ld * ld);
+		allreduce_device(ctx, s.b.p(), n);
 	}
 	if(s.keep_reduced) {
 		s.S_copy.resize(s.S.size());
@@ -90,6 +109,7 @@ static double ba_chi2_host(spp_ctx *ctx)
 	ba.partial.resize(4 * 1024);
 	double *d_out = ba.partial.p() + 2048;
 	ba_chi2_device(ctx, d_out);
+	allreduce_device(ctx, d_out, 1);
 	double v;
 	read_scalar(ctx, d_out, 1, &v);
 	return v;
@@ -133,6 +153,17 @@ static int ba_optimize(spp_ctx *ctx, size_t n_max_iteration_num, double f_min_dx
 	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
 	double f_max_diag;
 	memcpy(&f_max_diag, &bits, 8);
+	if(ctx->world > 1) { // max over ranks through the sum hook: every rank fills its own slot
+		std::vector<double> slots(ctx->world, 0.0);
+		slots[ctx->rank] = f_max_diag;
+		ba.partial.resize(4 * 1024);
+		double *d_slots = ba.partial.p() + 3072;
+		SPP_CUDA(cudaMemcpyAsync(d_slots, slots.data(), ctx->world * 8, cudaMemcpyHostToDevice, ctx->stream));
+		allreduce_device(ctx, d_slots, ctx->world);
+		SPP_CUDA(cudaMemcpyAsync(slots.data(), d_slots, ctx->world * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+		f_max_diag = *std::max_element(slots.begin(), slots.end());
+	}
 	double f_alpha = f_max_diag * 1e-3;
 	double f_nu = 2.0;
 	rep->alpha_initial = f_alpha;
@@ -166,6 +197,7 @@ static int ba_optimize(spp_ctx *ctx, size_t n_max_iteration_num, double f_min_dx
 		double dots[2];
 		ba.partial.resize(4 * 1024);
 		ba_step_dots_device(ctx, f_alpha, ba.partial.p() + 2048);
+		allreduce_device(ctx, ba.partial.p() + 2048, 2);
 		read_scalar(ctx, ba.partial.p() + 2048, 2, dots);
 		const double f_residual_norm = sqrt(dots[0]);
 		rep->last_dx_norm = f_residual_norm;
@@ -226,6 +258,7 @@ using namespace spp;
 #define API_BEGIN(ctx) if(!(ctx)) return SPP_ERR_INVALID; try { SPP_CUDA(cudaSetDevice((ctx)->device));
 #define API_END(ctx) } catch(const std::bad_alloc&) { (ctx)->last_error = "out of memory"; return SPP_ERR_NOMEM; } \
 	catch(const spp::invalid_error &e) { (ctx)->last_error = e.what(); return SPP_ERR_INVALID; } \
+	catch(const spp::comm_error &e) { (ctx)->last_error = e.what(); return SPP_ERR_COMM; } \
 	catch(const std::exception &e) { (ctx)->last_error = e.what(); return SPP_ERR_CUDA; } return SPP_OK;
 
 extern "C" {
@@ -373,7 +406,39 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 		h_cam[e] = ba.vertex_local[vc];
 		h_pt[e] = ba.vertex_local[vp];
 	}
-	build_schur_structure(ctx, C, P, h_cam, h_pt, ba.obs_orig, ba.h_obs_cam, ba.h_obs_pt);
+	// multi-GPU: this rank keeps a contiguous slice of the landmarks with all their observations; cameras are
+	// replicated. The slice bounds balance the Schur-product work sum k_p (k_p + 1) / 2 + k_p.
+	ba.P_global = P;
+	ba.pt_begin = 0;
+	ba.pt_end = P;
+	if(ctx->world > 1) {
+		std::vector<uint32_t> track_len(P, 0);
+		for(size_t e = 0; e < O; ++ e)
+			++ track_len[h_pt[e]];
+		std::vector<uint64_t> bounds(ctx->world + 1);
+		spp_partition_landmarks(P, P? &track_len[0] : 0, ctx->world, &bounds[0]);
+		ba.pt_begin = bounds[ctx->rank];
+		ba.pt_end = bounds[ctx->rank + 1];
+		std::vector<uint32_t> l_cam, l_pt, kept;
+		for(size_t e = 0; e < O; ++ e) {
+			if(h_pt[e] >= ba.pt_begin && h_pt[e] < ba.pt_end) {
+				l_cam.push_back(h_cam[e]);
+				l_pt.push_back(uint32_t(h_pt[e] - ba.pt_begin));
+				kept.push_back((uint32_t)e);
+			}
+		}
+		h_cam.swap(l_cam);
+		h_pt.swap(l_pt);
+		build_schur_structure(ctx, C, ba.pt_end - ba.pt_begin, h_cam, h_pt, ba.obs_orig, ba.h_obs_cam, ba.h_obs_pt);
+		for(size_t k = 0; k < ba.obs_orig.size(); ++ k)
+			ba.obs_orig[k] = kept[ba.obs_orig[k]]; // local track position -> original (global) edge index
+	} else
+		build_schur_structure(ctx, C, P, h_cam, h_pt, ba.obs_orig, ba.h_obs_cam, ba.h_obs_pt);
+	const size_t P_local = ba.pt_end - ba.pt_begin, O_local = ba.obs_orig.size();
+	if(!ba.uf_is_cam && n_vertices) // the unary factor sits on landmark 0: only its owner adds it
+		ba.uf_index = (ba.pt_begin == 0 && P_local)? 0 : -1;
+	else if(ctx->rank != 0)
+		ba.uf_index = -1; // camera 0: added once, by rank 0
 
 	cudaStream_t st = ctx->stream;
 	std::vector<double> cs(C * 6), ci(C * 5);
@@ -383,11 +448,11 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 	}
 	ba.cam_state.upload(cs, st);
 	ba.cam_intr.upload(ci, st);
-	ba.pts.upload(p_points, P * 3, st);
+	ba.pts.upload(p_points + ba.pt_begin * 3, P_local * 3, st);
 	ba.cam_state0.upload(cs, st);
-	ba.pts0.upload(p_points, P * 3, st);
-	std::vector<double> tz(O * 2), ti(O * 4);
-	for(size_t k = 0; k < O; ++ k) {
+	ba.pts0.upload(p_points + ba.pt_begin * 3, P_local * 3, st);
+	std::vector<double> tz(O_local * 2), ti(O_local * 4);
+	for(size_t k = 0; k < O_local; ++ k) {
 		size_t e = ba.obs_orig[k];
 		tz[k * 2] = p_z[e * 2]; tz[k * 2 + 1] = p_z[e * 2 + 1];
 		for(int q = 0; q < 4; ++ q) ti[k * 4 + q] = p_info[e * 4 + q];
@@ -410,11 +475,20 @@ int spp_ba_set_states(spp_ctx_t ctx, const double *p_cam_states, const double *p
 	if(!ctx->ba.valid) throw invalid_error("no BA graph");
 	if(p_cam_states)
 		SPP_CUDA(cudaMemcpyAsync(ctx->ba.cam_state.p(), p_cam_states, ctx->sys.C * 6 * 8, cudaMemcpyHostToDevice, ctx->stream));
-	if(p_points)
-		SPP_CUDA(cudaMemcpyAsync(ctx->ba.pts.p(), p_points, ctx->sys.P * 3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+	if(p_points) // p_points is the full point array; this context holds the slice [pt_begin, pt_end)
+		SPP_CUDA(cudaMemcpyAsync(ctx->ba.pts.p(), p_points + ctx->ba.pt_begin * 3, ctx->sys.P * 3 * 8, cudaMemcpyHostToDevice, ctx->stream));
 	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->ba.linearised = false;
 	API_END(ctx)
+}
+
+int spp_ba_get_partition(spp_ctx_t ctx, uint64_t *p_begin, uint64_t *p_end)
+{
+	if(!ctx || !ctx->ba.valid)
+		return SPP_ERR_INVALID;
+	if(p_begin) *p_begin = ctx->ba.pt_begin;
+	if(p_end) *p_end = ctx->ba.pt_end;
+	return SPP_OK;
 }
 
 int spp_ba_get_states(spp_ctx_t ctx, double *p_cam_states, double *p_points)
@@ -423,8 +497,8 @@ int spp_ba_get_states(spp_ctx_t ctx, double *p_cam_states, double *p_points)
 	if(!ctx->ba.valid) throw invalid_error("no BA graph");
 	if(p_cam_states)
 		ctx->ba.cam_state.download(p_cam_states, ctx->sys.C * 6, ctx->stream);
-	if(p_points)
-		ctx->ba.pts.download(p_points, ctx->sys.P * 3, ctx->stream);
+	if(p_points) // only this context's slice of the full point array is written
+		ctx->ba.pts.download(p_points + ctx->ba.pt_begin * 3, ctx->sys.P * 3, ctx->stream);
 	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
 	API_END(ctx)
 }
@@ -465,6 +539,7 @@ int spp_ba_get_lambda(spp_ctx_t ctx, uint64_t *p_n_block_cols, uint64_t *p_n_blo
 	BAProblem &ba = ctx->ba;
 	SchurSystem &s = ctx->sys;
 	if(!ba.valid) throw invalid_error("no BA graph");
+	if(ctx->world > 1) throw invalid_error("not available on a landmark-partitioned (multi-GPU) context");
 	const size_t NV = ba.n_vertices, O = s.O;
 	// structure in vertex id order: column v holds the off-diagonal blocks (row u < v) and the diagonal block last
 	std::vector<std::vector<std::pair<uint32_t, uint32_t> > > cols(NV); // (row vertex, track position)
@@ -550,6 +625,7 @@ int spp_ba_get_blocks(spp_ctx_t ctx, double *p_U, double *p_V, double *p_W, doub
 	BAProblem &ba = ctx->ba;
 	SchurSystem &s = ctx->sys;
 	if(!ba.valid) throw invalid_error("no BA graph");
+	if(ctx->world > 1) throw invalid_error("not available on a landmark-partitioned (multi-GPU) context");
 	if(!ba.linearised) throw invalid_error("spp_ba_linearise() has not been called");
 	if(p_U) s.U.download(p_U, s.C * 36, ctx->stream);
 	if(p_V) s.V.download(p_V, s.P * 9, ctx->stream);
@@ -601,6 +677,7 @@ int spp_ba_solve_step(spp_ctx_t ctx, double alpha, double *p_dx)
 	int rc = SPP_OK;
 	API_BEGIN(ctx)
 	if(!ctx->ba.valid) throw invalid_error("no BA graph");
+	if(ctx->world > 1) throw invalid_error("not available on a landmark-partitioned (multi-GPU) context");
 	if(!ctx->ba.linearised) ba_linearise(ctx, true);
 	rc = schur_solve_current(ctx, alpha, 0);
 	if(rc == SPP_OK && p_dx)

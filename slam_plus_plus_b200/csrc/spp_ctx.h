@@ -45,7 +45,8 @@ struct BAProblem {
 	std::vector<uint32_t> cam_vertex, pt_vertex; // local index -> vertex id
 	std::vector<uint32_t> obs_orig;      // track position -> original edge index
 	std::vector<uint32_t> h_obs_cam, h_obs_pt; // host copies (track order)
-	int uf_is_cam; long uf_index;        // vertex id 0 carries the unary factor
+	int uf_is_cam; long uf_index;        // vertex id 0 carries the unary factor (-1: added by another rank)
+	size_t P_global, pt_begin, pt_end;   // landmark slice of this rank (multi-GPU)
 	int jac_mode;
 	// device state
 	DBuf<double> cam_state, cam_intr, pts;        // [6C], [5C], [3P]
@@ -57,7 +58,8 @@ struct BAProblem {
 	DBuf<double> partial;                         // reduction scratch
 	DBuf<unsigned long long> maxdiag;             // [1] bits of the max per-edge Hessian diagonal
 	bool linearised;
-	BAProblem() : valid(false), n_vertices(0), uf_is_cam(1), uf_index(0), jac_mode(0), linearised(false) {}
+	BAProblem() : valid(false), n_vertices(0), uf_is_cam(1), uf_index(0), P_global(0), pt_begin(0), pt_end(0),
+		jac_mode(0), linearised(false) {}
 };
 
 // slot-1 state: map from the caller's lambda values to the SchurSystem arrays

@@ -199,3 +199,32 @@ void build_schur_structure(spp_ctx *ctx, size_t C, size_t P, const std::vector<u
 }
 
 } // namespace spp
+
+extern "C" int spp_partition_landmarks(size_t n_points, const uint32_t *p_track_length, int world, uint64_t *p_bounds)
+{
+	if(world < 1 || !p_bounds || (n_points && !p_track_length))
+		return SPP_ERR_INVALID;
+	long double total = 0;
+	for(size_t p = 0; p < n_points; ++ p) {
+		const long double k = p_track_length[p];
+		total += k * (k + 1) / 2 + k;
+	}
+	p_bounds[0] = 0;
+	long double acc = 0;
+	size_t p = 0;
+	for(int r = 1; r < world; ++ r) {
+		const long double target = total * r / world;
+		while(p < n_points) {
+			const long double k = p_track_length[p];
+			const long double w = k * (k + 1) / 2 + k;
+			if(acc + w / 2 > target)
+				break;
+			acc += w;
+			++ p;
+		}
+		p_bounds[r] = p;
+	}
+	p_bounds[world] = n_points;
+	return SPP_OK;
+}
+

@@ -1,0 +1,63 @@
+"""Multi-rank tests: world_size 2 over gloo on the CPU (host logic + sharding math on the oracle) and, on a box
+with >= 2 GPUs, the NCCL path against the single-GPU run."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+WORKER = os.path.join(ROOT, "tests", "mgpu_worker.py")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _launch(mode, world, env=None):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), WORKER, mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    return json.loads(line)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_schur_on_cpu_gloo(world):
+    out = _launch("cpu", world)
+    assert out["err_S"] < 1e-12 and out["err_b"] < 1e-12
+    assert out["bounds"][0] == 0 and sorted(out["bounds"]) == out["bounds"]
+    assert max(out["shares"]) < 1.25 / world  # the slices balance the Schur work
+
+
+def test_partition_edge_cases():
+    import numpy as np
+    from slam_plus_plus_b200 import capi
+    assert capi.partition_landmarks(np.zeros(0, np.uint32), 4).tolist() == [0, 0, 0, 0, 0]
+    assert capi.partition_landmarks(np.array([5], np.uint32), 1).tolist() == [0, 1]
+    b = capi.partition_landmarks(np.array([2, 2, 2, 2, 60, 2, 2, 2], np.uint32), 2)
+    assert b[0] == 0 and b[-1] == 8 and 0 < b[1] < 8
+    b = capi.partition_landmarks(np.full(1000, 3, np.uint32), 8)
+    assert np.all(np.diff(b) == 125)
+
+
+@pytest.mark.gpu
+def test_sharded_lm_on_two_gpus_matches_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = _launch("gpu", 2)
+    one = out["single"]
+    assert out["accepted"] == one["accepted"]
+    assert abs(out["alpha_initial"] - one["alpha_initial"]) <= 1e-12 * one["alpha_initial"]
+    for a, b in zip(out["trace_chi2"], one["trace_chi2"]):
+        assert abs(a - b) <= 1e-9 * b  # NCCL sums in a different order: 1e-9, not bitwise
+    assert out["err_cams"] < 1e-8 and out["err_pts"] < 1e-8
