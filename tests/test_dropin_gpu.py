@@ -30,12 +30,18 @@ def test_reference_lm_with_b200_linear_solver(name, tmp_path):
     r = sppio.read_dump(dp)
     assert abs(r["chi2_0"][0] - d["chi2_0"][0]) <= 1e-13 * d["chi2_0"][0]
     tr, tg = r["lm_trace"].reshape(-1, 6), d["lm_trace"].reshape(-1, 6)
+    # damping history: alpha_{k+1} = alpha_k * max(1/3, 1 - (2 rho - 1)^3) with rho = (chi2_last - chi2) / denominator
+    # (LM.h:204-223). chi2 is reproduced to 1e-9 RELATIVE TO CHI2, so rho carries a relative error of
+    # 1e-9 * chi2 / |chi2_last - chi2| (large once the steps stop reducing chi2), and |d factor / d rho| <= 6 with
+    # factor >= 1/3 turns that into <= 18x as much in alpha. The tolerance accumulates over the steps.
+    tol_alpha = 1e-7
     for k in range(min(len(tr), len(tg))):
         if abs(tg[k, 1] - tg[k, 2]) <= 1e-9 * tg[k, 1]:
             break  # chi2 no longer changes: the accept / reject decision is rounding noise from here on
         assert int(tr[k, 4]) == int(tg[k, 4])
         assert abs(tr[k, 2] - tg[k, 2]) <= 1e-9 * tg[k, 2]
-        assert abs(tr[k, 0] - tg[k, 0]) <= 1e-7 * tg[k, 0]  # damping history
+        assert abs(tr[k, 0] - tg[k, 0]) <= tol_alpha * tg[k, 0]
+        tol_alpha += 20 * 1e-9 * tg[k, 1] / abs(tg[k, 1] - tg[k, 2])
     assert abs(r["chi2"][0] - d["chi2"][0]) <= 1e-9 * d["chi2"][0]
     # converged problems end with noise-decided accept / reject steps along nearly flat directions: the states
     # agree less tightly than chi2 does
