@@ -34,225 +34,10 @@ namespace spp {
 #define CH_BK 16           // k-chunk staged in shared memory
 #define CH_LDS (CH_BK + 4) // padded row length: conflict-free DMMA fragment loads
 #define CH_STAGES 3
-#define CH_TP (CH_NB + 1)  // padded row of the potrf tile
 
-// ---- diagonal block: factor + invert -----------------------------------------------------------------
-
-// packed index of the 32x32 block (a, b), a <= b, of the 4x4 upper block grid
-__device__ __forceinline__ int xblk(int a, int b) { return a * 4 - a * (a - 1) / 2 + (b - a); }
-
-#define XB_LD 33
-#define XB_SIZE (32 * XB_LD)
-
-#define PT 256              // threads of k_potrf128
-#define PW (PT / 32)
-
-__global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size_t ld, size_t k0,
-	double *__restrict__ Rinv_out, int *__restrict__ info, long long *__restrict__ dbg)
-{
-#define DBG_MARK(i) do { if(dbg && threadIdx.x == 0) dbg[i] = clock64(); } while(0)
-	extern __shared__ double smem[];
-	DBG_MARK(0);
-	double (*T)[CH_TP] = reinterpret_cast<double (*)[CH_TP]>(smem); // T[r][c], upper
-	double *Xs = smem + CH_NB * CH_TP;       // 10 packed 32x33 blocks of the inverse
-	double *rdinv = Xs + 10 * XB_SIZE;       // 128 reciprocal pivots
-	// scratch block g of the inversion lives in the (unused) strictly lower part of T: rows 96.., columns g*32..
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	double *Akk = A + k0 * ld + k0;
-	{
-		// all loads of a thread are independent: issue them together, then fill the tile
-		constexpr int NQ = CH_NB * CH_NB / PT;
-		const int r = tid & 127, cb = tid >> 7;
-		double v[NQ];
-		#pragma unroll
-		for(int q = 0; q < NQ; ++ q) {
-			const int c = cb + (PT / CH_NB) * q;
-			v[q] = (r <= c)? Akk[(size_t)c * ld + r] : 0.0;
-		}
-		#pragma unroll
-		for(int q = 0; q < NQ; ++ q)
-			T[r][cb + (PT / CH_NB) * q] = v[q];
-	}
-	__syncthreads();
-	DBG_MARK(1);
-
-	for(int kb = 0; kb < 4; ++ kb) {
-		const int o = kb * 32;
-		if(kb == 0) DBG_MARK(2);
-		if(warp == 0) {
-			// lane r owns row r of L = R^T (column r of the block). Right-looking register Cholesky: after
-			// column j is final every later column is updated at once (independent FMAs), so the serial chain
-			// per pivot is shuffle -> rsqrt -> multiply -> shuffle -> FMA.
-			double a[32];
-			#pragma unroll
-			for(int c = 0; c < 32; ++ c)
-				a[c] = T[o + c][o + lane]; // zero for c > lane
-			bool bad = false;
-			#pragma unroll
-			for(int j = 0; j < 32; ++ j) {
-				double piv = __shfl_sync(0xffffffffu, a[j], j);
-				if(!(piv > 0)) { // Eigen's LLT stops at a non-positive pivot (NaN fails the test as well)
-					bad = true;
-					piv = 1;
-				}
-				const double rd = rsqrt(piv), d = piv * rd;
-				const double l = (lane == j)? d : ((lane > j)? a[j] * rd : 0.0);
-				a[j] = l;
-				if(lane == j)
-					rdinv[o + j] = rd;
-				#pragma unroll
-				for(int c = j + 1; c < 32; ++ c)
-					a[c] -= l * __shfl_sync(0xffffffffu, l, c);
-			}
-			#pragma unroll
-			for(int c = 0; c < 32; ++ c)
-				if(c <= lane) T[o + c][o + lane] = a[c];
-			if(bad && lane == 0 && *info == 0)
-				*info = int(k0) + o + 1;
-		}
-		__syncthreads();
-		if(kb == 0) DBG_MARK(3);
-		// sub-row: solve R_bb^T X = T[o..o+31][o+32..127], thread per column
-		const int nrem = CH_NB - o - 32;
-		if(tid < nrem) {
-			const int c = o + 32 + tid;
-			double x[32];
-			#pragma unroll
-			for(int j = 0; j < 32; ++ j)
-				x[j] = T[o + j][c];
-			#pragma unroll
-			for(int j = 0; j < 32; ++ j) { // right-looking: independent updates, short serial chain
-				const double xj = x[j] * rdinv[o + j];
-				x[j] = xj;
-				#pragma unroll
-				for(int i = j + 1; i < 32; ++ i)
-					x[i] -= T[o + j][o + i] * xj;
-			}
-			#pragma unroll
-			for(int j = 0; j < 32; ++ j)
-				T[o + j][c] = x[j];
-		}
-		__syncthreads();
-		if(kb == 0) DBG_MARK(4);
-		// rank-32 update of the remaining upper sub-blocks; thread (ty, tx): rows ty + PW q, column tx
-		const int ty = tid >> 5, tx = lane;
-		for(int bi = kb + 1; bi < 4; ++ bi) {
-			for(int bj = bi; bj < 4; ++ bj) {
-				const int i0 = bi * 32 + ty, j = bj * 32 + tx;
-				double s[32 / PW];
-				#pragma unroll
-				for(int q = 0; q < 32 / PW; ++ q) s[q] = 0;
-				#pragma unroll 8
-				for(int k = 0; k < 32; ++ k) {
-					const double tj = T[o + k][j];
-					#pragma unroll
-					for(int q = 0; q < 32 / PW; ++ q)
-						s[q] += T[o + k][i0 + PW * q] * tj;
-				}
-				#pragma unroll
-				for(int q = 0; q < 32 / PW; ++ q)
-					T[i0 + PW * q][j] -= s[q];
-			}
-		}
-		__syncthreads();
-		if(kb == 0) DBG_MARK(5);
-	}
-	DBG_MARK(6);
-	// R back to global (upper triangle)
-	for(int idx = tid; idx < CH_NB * CH_NB; idx += PT) {
-		const int c = idx >> 7, r = idx & 127;
-		if(r <= c)
-			Akk[(size_t)c * ld + r] = T[r][c];
-	}
-
-	DBG_MARK(7);
-	// ---- inverse of the upper-triangular factor, 32x32 blocks ----
-	// phase A: diagonal blocks, warp a, lane c solves R_aa x = e_c (uniform formula, zeros above c stay zero)
-	if(warp < 4) {
-		const int o = warp * 32;
-		double x[32];
-		#pragma unroll
-		for(int r = 0; r < 32; ++ r)
-			x[r] = (r == lane)? 1.0 : 0.0;
-		#pragma unroll
-		for(int r = 31; r >= 0; -- r) { // right-looking back-substitution
-			const double xr = x[r] * rdinv[o + r];
-			x[r] = xr;
-			#pragma unroll
-			for(int k = 0; k < r; ++ k)
-				x[k] -= T[o + k][o + r] * xr;
-		}
-		double *X = Xs + xblk(warp, warp) * XB_SIZE;
-		#pragma unroll
-		for(int r = 0; r < 32; ++ r)
-			X[r * XB_LD + lane] = x[r];
-	}
-	__syncthreads();
-	DBG_MARK(8);
-	// phase B: X_ab = -X_aa (sum_{m=a+1..b} R_am X_mb), by distance d = b - a; PW / 4 warps per block
-	for(int d = 1; d < 4; ++ d) {
-		constexpr int WG = PW / 4, RPW = 32 / WG; // warps per block, rows per warp
-		const int nblk_d = 4 - d, g = warp / WG, w4 = warp % WG; // block group / warp inside the group
-		if(g < nblk_d) {
-			const int a = g, b = g + d;
-			double acc[RPW];
-			#pragma unroll
-			for(int q = 0; q < RPW; ++ q) acc[q] = 0;
-			for(int m = a + 1; m <= b; ++ m) {
-				const double *Xm = Xs + xblk(m, b) * XB_SIZE;
-				#pragma unroll 4
-				for(int k = 0; k < 32; ++ k) {
-					const double xv = Xm[k * XB_LD + lane];
-					#pragma unroll
-					for(int q = 0; q < RPW; ++ q)
-						acc[q] += T[a * 32 + w4 * RPW + q][m * 32 + k] * xv;
-				}
-			}
-			#pragma unroll
-			for(int q = 0; q < RPW; ++ q)
-				T[96 + w4 * RPW + q][g * 32 + lane] = acc[q];
-		}
-		__syncthreads();
-		if(g < nblk_d) {
-			const int a = g, b = g + d;
-			const double *Xa = Xs + xblk(a, a) * XB_SIZE;
-			double acc[RPW];
-			#pragma unroll
-			for(int q = 0; q < RPW; ++ q) acc[q] = 0;
-			#pragma unroll 4
-			for(int k = 0; k < 32; ++ k) {
-				const double tv = T[96 + k][g * 32 + lane];
-				#pragma unroll
-				for(int q = 0; q < RPW; ++ q)
-					acc[q] += Xa[(w4 * RPW + q) * XB_LD + k] * tv;
-			}
-			double *X = Xs + xblk(a, b) * XB_SIZE;
-			#pragma unroll
-			for(int q = 0; q < RPW; ++ q)
-				X[(w4 * RPW + q) * XB_LD + lane] = -acc[q];
-		}
-		__syncthreads();
-	}
-	DBG_MARK(9);
-	// column-major 128x128 inverse (zeros below the diagonal blocks)
-	for(int idx = tid; idx < CH_NB * CH_NB; idx += PT) {
-		const int c = idx >> 7, r = idx & 127;
-		const int a = r >> 5, b = c >> 5;
-		Rinv_out[idx] = (a <= b)? Xs[xblk(a, b) * XB_SIZE + (r & 31) * XB_LD + (c & 31)] : 0.0;
-	}
-	DBG_MARK(10);
-#undef DBG_MARK
-}
-
-static const size_t POTRF_SMEM = (size_t)(CH_NB * CH_TP + 10 * XB_SIZE + CH_NB) * sizeof(double);
+#include "potrf128.cuh"
 
 // ---- FP64 tensor-core GEMM: C (op)= A^T B with K = 128, operands K-contiguous ---------------------------
-
-__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
-{
-	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-		: "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 enum { GEMM_SYRK = 0, GEMM_TRSM = 1 };
 
@@ -468,6 +253,7 @@ static void chol_init_attributes()
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64, 64>()));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_TRSM, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
+	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_TRSM, 128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 32>()));
 	done = true;
 }
 
@@ -480,9 +266,15 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 	const size_t ld = dense_chol_ld(n), n_blk = ld / CH_NB;
 	cudaStream_t st = ctx->stream;
 	if(!ch.bulk_stream) {
-		SPP_CUDA(cudaStreamCreateWithFlags(&ch.bulk_stream, cudaStreamNonBlocking));
-		SPP_CUDA(cudaStreamCreateWithFlags(&ch.row_stream, cudaStreamNonBlocking));
+		// the context stream carries the critical chain (created with the highest priority in spp_create); the
+		// look-ahead row is next, the bulk updates yield to both whenever an SM frees up
+		int prio_lo = 0, prio_hi = 0;
+		SPP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		SPP_CUDA(cudaStreamCreateWithPriority(&ch.bulk_stream, cudaStreamNonBlocking, prio_lo));
+		SPP_CUDA(cudaStreamCreateWithPriority(&ch.row_stream, cudaStreamNonBlocking, (prio_hi + 1 <= prio_lo)? prio_hi + 1 : prio_hi));
 		for(int i = 0; i < 2; ++ i) {
+			SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_potrf[i], cudaEventDisableTiming));
+			SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_first[i], cudaEventDisableTiming));
 			SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_panel[i], cudaEventDisableTiming));
 			SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_bulk[i], cudaEventDisableTiming));
 			SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_row[i], cudaEventDisableTiming));
@@ -492,7 +284,10 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 	}
 	ch.info.resize(1 + n_blk);
 	SPP_CUDA(cudaMemsetAsync(ch.info.p(), 0, (1 + n_blk) * sizeof(int), st));
-	ch.work.resize(n_blk * CH_NB * CH_NB);
+	if(ch.work.size() != n_blk * CH_NB * CH_NB) { // k_potrf128 writes the upper triangles only
+		ch.work.resize(n_blk * CH_NB * CH_NB);
+		ch.work.zero(st);
+	}
 	if(ld > n) {
 		k_pad_identity<<<n_blocks(ld - n, 64), 64, 0, st>>>(A, ld, n, ld);
 		LAUNCH_CHECK(ctx);
@@ -544,24 +339,37 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 		for(size_t b = 0; b < n_blk; ++ b) {
 			const size_t k0 = b * CH_NB, c0 = k0 + CH_NB;
 			const int e = int(b & 1);
+			double *Rinv_b = Rinv + b * (size_t)(CH_NB * CH_NB);
 			tic();
-			k_potrf128<<<1, PT, POTRF_SMEM, sA>>>(A, ld, k0, Rinv + b * (size_t)(CH_NB * CH_NB), info,
-				(prof && b == 1)? ch.dbg.p() : 0);
+			k_potrf128<<<1, PT, POTRF_SMEM, sA>>>(A, ld, k0, Rinv_b, info, (prof && b == 1)? ch.dbg.p() : 0);
 			LAUNCH_CHECK(ctx);
 			toc(0);
-			if(row_in_flight && !prof) { // the rest of tile row b was updated on sC
-				SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_row[e ^ 1], 0));
-				row_in_flight = false;
+			if(!prof) {
+				SPP_CUDA(cudaEventRecord(ch.ev_potrf[e], sA));
+				if(row_in_flight) { // tile row b was last updated by the look-ahead of panel b - 1 on sC
+					SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_row[e ^ 1], 0));
+					row_in_flight = false;
+				}
 			}
+			// panel solve, critical part: the tile right of the diagonal (the rhs block for the last panel)
 			tic();
-			k_gemm_tn<GEMM_TRSM, 128, 64><<<(unsigned)((n_cols - c0) / 64), 256, gemm_smem<128, 64>(), sA>>>(A, ld, k0, 0, c0,
-				Rinv + b * (size_t)(CH_NB * CH_NB));
+			k_gemm_tn<GEMM_TRSM, 128, 32><<<CH_NB / 32, 128, gemm_smem<128, 32>(), sA>>>(A, ld, k0, 0, c0, Rinv_b);
 			LAUNCH_CHECK(ctx);
 			toc(1);
 			if(c0 >= ld)
 				break;
 			if(!prof) {
-				SPP_CUDA(cudaEventRecord(ch.ev_panel[e], sA)); // panel b is final
+				SPP_CUDA(cudaEventRecord(ch.ev_first[e], sA));
+				SPP_CUDA(cudaStreamWaitEvent(sC, ch.ev_potrf[e], 0));
+			}
+			// panel solve, the rest of the block row (sC; its input was written by sC itself)
+			tic();
+			k_gemm_tn<GEMM_TRSM, 128, 64><<<(unsigned)((n_cols - c0 - CH_NB) / 64), 256, gemm_smem<128, 64>(), sC>>>(A, ld, k0, 0,
+				c0 + CH_NB, Rinv_b);
+			LAUNCH_CHECK(ctx);
+			toc(1);
+			if(!prof) {
+				SPP_CUDA(cudaEventRecord(ch.ev_panel[e], sC)); // panel b is final (together with ev_first)
 				// the look-ahead updates write tile row b + 1, which the bulk update of step b - 1 also wrote
 				if(bulk_in_flight) {
 					SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_bulk[e ^ 1], 0));
@@ -569,10 +377,25 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 					bulk_in_flight = false;
 				}
 			}
+			// look-ahead, critical part: the next diagonal tile
+			tic();
+			syrk(sA, k0, c0, c0, CH_NB, CH_NB, 2);
+			toc(3);
+			// look-ahead, rest of the next panel's tile row (rhs block included)
+			if(!prof)
+				SPP_CUDA(cudaStreamWaitEvent(sC, ch.ev_first[e], 0));
+			tic();
+			syrk(sC, k0, c0, c0 + CH_NB, CH_NB, n_cols - (c0 + CH_NB), 2);
+			toc(4);
+			if(!prof)
+				SPP_CUDA(cudaEventRecord(ch.ev_row[e], sC));
+			row_in_flight = true;
 			const size_t r1 = c0 + CH_NB; // first row below the next panel's tile row
 			if(r1 < ld) {
-				if(!prof)
+				if(!prof) {
 					SPP_CUDA(cudaStreamWaitEvent(sB, ch.ev_panel[e], 0));
+					SPP_CUDA(cudaStreamWaitEvent(sB, ch.ev_first[e], 0));
+				}
 				const size_t T = (ld - r1) / 128, n_tiles = T * (T + 1) / 2 + T;
 				int tile = (n_tiles >= 3 * 148)? 0 : ((n_tiles >= 74)? 1 : 2);
 				if(ch.force_tile >= 0) tile = ch.force_tile;
@@ -583,19 +406,6 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 					SPP_CUDA(cudaEventRecord(ch.ev_bulk[e], sB));
 				bulk_in_flight = true;
 			}
-			// look-ahead, critical part: the next diagonal tile
-			tic();
-			syrk(sA, k0, c0, c0, CH_NB, CH_NB, 2);
-			toc(3);
-			// look-ahead, rest of the next panel's tile row (rhs block included)
-			if(!prof)
-				SPP_CUDA(cudaStreamWaitEvent(sC, ch.ev_panel[e], 0));
-			tic();
-			syrk(sC, k0, c0, c0 + CH_NB, CH_NB, n_cols - (c0 + CH_NB), 2);
-			toc(4);
-			if(!prof)
-				SPP_CUDA(cudaEventRecord(ch.ev_row[e], sC));
-			row_in_flight = true;
 		}
 		if(!prof) {
 			for(int i = 0; i < 2; ++ i) { // join: whatever is still in flight on the side streams
@@ -607,8 +417,8 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 		} else {
 			long long h[16];
 			cudaMemcpy(h, ch.dbg.p(), sizeof(h), cudaMemcpyDeviceToHost);
-			fprintf(stderr, "[spp potrf clocks] load %lld | chol32 %lld | subrow %lld | update %lld | kb1-3 %lld | store %lld | invA %lld | invB %lld | storeinv %lld\n",
-				h[1] - h[0], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[8] - h[7], h[9] - h[8], h[10] - h[9]);
+			fprintf(stderr, "[spp potrf clocks] load %lld | leaf0+rowsolve %lld | rank8 update %lld | first 32 rows %lld | factor total %lld | store %lld | inverse %lld | storeinv %lld\n",
+				h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[1], h[5] - h[1], h[6] - h[5], h[7] - h[6], h[8] - h[7]);
 			fprintf(stderr, "[spp chol profile] n=%zu potrf %.3f ms, trsm %.3f, bulk %.3f, la_diag %.3f, la_row %.3f (serialised)\n",
 				n, t_acc[0], t_acc[1], t_acc[2], t_acc[3], t_acc[4]);
 		}

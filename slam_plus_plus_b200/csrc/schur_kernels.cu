@@ -15,6 +15,7 @@
 // -- so there are no floating-point atomics and the result is bit-reproducible.
 
 #include "spp_ctx.h"
+#include <stdlib.h>
 
 namespace spp {
 
@@ -23,135 +24,178 @@ size_t dense_chol_storage(size_t n);
 
 #define LAUNCH_CHECK(ctx) do { ++ (ctx)->n_launches; SPP_CUDA(cudaGetLastError()); } while(0)
 
-// thread per landmark: Cinv = (V + alpha I)^-1 by cofactors (what Eigen's fixed 3x3 inverse() does,
-// BlockMatrixBase.h:1256-1270), then Y_o = W_o Cinv along the track
-__global__ void k_landmark_inverse(size_t P, double alpha, const uint32_t *__restrict__ pt_ptr,
+// warp per 32 consecutive landmarks: lane l inverts landmark p0 + l, Cinv = (V + alpha I)^-1 by cofactors (what
+// Eigen's fixed 3x3 inverse() does, BlockMatrixBase.h:1256-1270); then the warp walks the CONTIGUOUS W range of its
+// 32 tracks element by element (coalesced) and writes Y_o = W_o Cinv.
+#define LI_WARPS 8
+
+__global__ void __launch_bounds__(LI_WARPS * 32) k_landmark_inverse(size_t P, double alpha, const uint32_t *__restrict__ pt_ptr,
 	const double *__restrict__ V, const double *__restrict__ W, double *__restrict__ Cinv, double *__restrict__ Y)
 {
-	size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-	if(p >= P) return;
-	const double *Vp = V + p * 9; // column-major
-	double m00 = Vp[0] + alpha, m10 = Vp[1], m20 = Vp[2];
-	double m01 = Vp[3], m11 = Vp[4] + alpha, m21 = Vp[5];
-	double m02 = Vp[6], m12 = Vp[7], m22 = Vp[8] + alpha;
-	// cofactors
-	double c00 = m11 * m22 - m12 * m21, c10 = m21 * m02 - m22 * m01, c20 = m01 * m12 - m02 * m11;
-	double det = c00 * m00 + c10 * m10 + c20 * m20;
-	double id = 1.0 / det;
-	double i00 = c00 * id, i01 = c10 * id, i02 = c20 * id;
-	double i10 = (m12 * m20 - m10 * m22) * id, i11 = (m22 * m00 - m20 * m02) * id, i12 = (m02 * m10 - m00 * m12) * id;
-	double i20 = (m10 * m21 - m11 * m20) * id, i21 = (m20 * m01 - m21 * m00) * id, i22 = (m00 * m11 - m01 * m10) * id;
-	double *Ci = Cinv + p * 9; // column-major
-	Ci[0] = i00; Ci[1] = i10; Ci[2] = i20;
-	Ci[3] = i01; Ci[4] = i11; Ci[5] = i21;
-	Ci[6] = i02; Ci[7] = i12; Ci[8] = i22;
-	const unsigned beg = pt_ptr[p], end = pt_ptr[p + 1];
-	for(unsigned o = beg; o < end; ++ o) {
-		const double *Wo = W + (size_t)o * 18;
-		double *Yo = Y + (size_t)o * 18;
-		double w[18];
+	__shared__ double sC[LI_WARPS][32][9];
+	__shared__ unsigned sPtr[LI_WARPS][33];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const size_t p0 = (blockIdx.x * (size_t)LI_WARPS + warp) * 32;
+	if(p0 >= P) return;
+	const size_t p = p0 + lane;
+	if(p < P) {
+		const double *Vp = V + p * 9; // column-major
+		double m00 = Vp[0] + alpha, m10 = Vp[1], m20 = Vp[2];
+		double m01 = Vp[3], m11 = Vp[4] + alpha, m21 = Vp[5];
+		double m02 = Vp[6], m12 = Vp[7], m22 = Vp[8] + alpha;
+		// cofactors
+		double c00 = m11 * m22 - m12 * m21, c10 = m21 * m02 - m22 * m01, c20 = m01 * m12 - m02 * m11;
+		double det = c00 * m00 + c10 * m10 + c20 * m20;
+		double id = 1.0 / det;
+		double inv[9]; // column-major
+		inv[0] = c00 * id; inv[3] = c10 * id; inv[6] = c20 * id;
+		inv[1] = (m12 * m20 - m10 * m22) * id; inv[4] = (m22 * m00 - m20 * m02) * id; inv[7] = (m02 * m10 - m00 * m12) * id;
+		inv[2] = (m10 * m21 - m11 * m20) * id; inv[5] = (m20 * m01 - m21 * m00) * id; inv[8] = (m00 * m11 - m01 * m10) * id;
+		double *Ci = Cinv + p * 9;
 		#pragma unroll
-		for(int i = 0; i < 18; i += 2) {
-			double2 t = *reinterpret_cast<const double2*>(Wo + i);
-			w[i] = t.x; w[i + 1] = t.y;
+		for(int i = 0; i < 9; ++ i) {
+			Ci[i] = inv[i];
+			sC[warp][lane][i] = inv[i];
 		}
-		double y[18];
-		#pragma unroll
-		for(int r = 0; r < 6; ++ r) {
-			y[r] = w[r] * i00 + w[6 + r] * i10 + w[12 + r] * i20;
-			y[6 + r] = w[r] * i01 + w[6 + r] * i11 + w[12 + r] * i21;
-			y[12 + r] = w[r] * i02 + w[6 + r] * i12 + w[12 + r] * i22;
-		}
-		#pragma unroll
-		for(int i = 0; i < 18; i += 2)
-			*reinterpret_cast<double2*>(Yo + i) = make_double2(y[i], y[i + 1]);
+	}
+	sPtr[warp][lane] = pt_ptr[(p < P)? p : P];
+	if(lane == 0)
+		sPtr[warp][32] = pt_ptr[(p0 + 32 < P)? p0 + 32 : P];
+	__syncwarp();
+	const size_t e_end = (size_t)sPtr[warp][32] * 18;
+	int pl = 0; // landmark (relative to p0) of the current observation; e grows monotonically per lane
+	for(size_t e = (size_t)sPtr[warp][0] * 18 + lane; e < e_end; e += 32) {
+		const unsigned o = (unsigned)(e / 18), q = (unsigned)(e - (size_t)o * 18);
+		const unsigned c = q / 6, r = q - c * 6;
+		while(sPtr[warp][pl + 1] <= o)
+			++ pl;
+		const double *Wo = W + (size_t)o * 18, *Ci = sC[warp][pl];
+		Y[e] = Wo[r] * Ci[c * 3] + Wo[6 + r] * Ci[c * 3 + 1] + Wo[12 + r] * Ci[c * 3 + 2];
 	}
 }
 
-// one warp per upper-triangular 6x6 block of the reduced camera system.
+// ---- the Schur product ---------------------------------------------------------------------------------
 // S(i,j) = [i == j] (U_i + alpha I) - sum_pairs Y_a W_b^T ; for i == j also b_i = gc_i - sum_a Y_a gp_{p(a)}
+//
+// Lane mapping: a warp is three groups of nine lanes (27 of 32 lanes work). Lane q = r3 + 3 c3 of a group owns the
+// 2 x 2 sub-block {r3, r3 + 3} x {c3, c3 + 3} of the 6 x 6 product: it needs two rows of Y_a and two rows of W_b
+// (12 scalar loads that the nine lanes of the group coalesce into the two 144-byte blocks) and does 12 FMAs per
+// pair; no accumulator ever crosses a lane until the three groups are summed at the end (fixed order, so the
+// result is bit-reproducible). Group g of a warp takes pairs g, g + 3 * n_warps, ... of the list.
 #define SB_WARPS 8
 
-__global__ void __launch_bounds__(SB_WARPS * 32) k_schur_blocks(size_t n_blocks_total, size_t ld, double alpha,
+struct SchurAcc {
+	double s00, s01, s10, s11, b0, b1;
+};
+
+template <bool RHS, int SB_UNROLL>
+__device__ __forceinline__ void schur_accumulate(uint64_t k0, uint64_t end, uint64_t stride, int r3, int c3,
+	const uint32_t *__restrict__ pair_a, const uint32_t *__restrict__ pair_b, const double *__restrict__ Y,
+	const double *__restrict__ W, const double *__restrict__ gp, const uint32_t *__restrict__ obs_pt, SchurAcc &acc)
+{
+	for(uint64_t k = k0; k < end; k += SB_UNROLL * stride) {
+		double y[SB_UNROLL][6], w[SB_UNROLL][6], g[SB_UNROLL][3];
+		#pragma unroll
+		for(int u = 0; u < SB_UNROLL; ++ u) {
+			const uint64_t kk = k + u * stride;
+			const bool ok = kk < end;
+			const unsigned oa = ok? pair_a[kk] : 0u, ob = RHS? oa : (ok? pair_b[kk] : 0u);
+			const double *Ya = Y + (size_t)oa * 18 + r3, *Wb = W + (size_t)ob * 18 + c3;
+			#pragma unroll
+			for(int q = 0; q < 3; ++ q) {
+				y[u][q] = ok? Ya[q * 6] : 0.0;
+				y[u][3 + q] = ok? Ya[q * 6 + 3] : 0.0;
+				w[u][q] = ok? Wb[q * 6] : 0.0;
+				w[u][3 + q] = ok? Wb[q * 6 + 3] : 0.0;
+			}
+			if(RHS) {
+				const unsigned p = ok? obs_pt[oa] : 0u;
+				#pragma unroll
+				for(int q = 0; q < 3; ++ q)
+					g[u][q] = ok? gp[(size_t)p * 3 + q] : 0.0;
+			}
+		}
+		#pragma unroll
+		for(int u = 0; u < SB_UNROLL; ++ u) {
+			acc.s00 += y[u][0] * w[u][0] + y[u][1] * w[u][1] + y[u][2] * w[u][2];
+			acc.s10 += y[u][3] * w[u][0] + y[u][4] * w[u][1] + y[u][5] * w[u][2];
+			acc.s01 += y[u][0] * w[u][3] + y[u][1] * w[u][4] + y[u][2] * w[u][5];
+			acc.s11 += y[u][3] * w[u][3] + y[u][4] * w[u][4] + y[u][5] * w[u][5];
+			if(RHS) {
+				acc.b0 += y[u][0] * g[u][0] + y[u][1] * g[u][1] + y[u][2] * g[u][2];
+				acc.b1 += y[u][3] * g[u][0] + y[u][4] * g[u][1] + y[u][5] * g[u][2];
+			}
+		}
+	}
+}
+
+// off-diagonal blocks (list entries first_blk ..): one warp per block
+template <int UNROLL>
+__global__ void __launch_bounds__(SB_WARPS * 32, (UNROLL >= 4)? 2 : 4) k_schur_blocks(size_t first_blk, size_t n_blocks_total, size_t ld,
 	const uint32_t *__restrict__ blk_row, const uint32_t *__restrict__ blk_col, const uint64_t *__restrict__ blk_ptr,
 	const uint32_t *__restrict__ pair_a, const uint32_t *__restrict__ pair_b, const double *__restrict__ Y,
-	const double *__restrict__ W, const double *__restrict__ U, const double *__restrict__ gc,
-	const double *__restrict__ gp, const uint32_t *__restrict__ obs_pt, double *__restrict__ S, double *__restrict__ b)
+	const double *__restrict__ W, double *__restrict__ S)
 {
 	const int lane = threadIdx.x & 31;
-	const size_t blk = blockIdx.x * (size_t)SB_WARPS + (threadIdx.x >> 5);
+	const size_t blk = first_blk + blockIdx.x * (size_t)SB_WARPS + (threadIdx.x >> 5);
 	if(blk >= n_blocks_total) return;
 	const unsigned bi = blk_row[blk], bj = blk_col[blk];
-	const bool diag = bi == bj;
-	double acc[36], accb[6];
+	const int grp = lane / 9, q9 = lane - grp * 9, r3 = q9 % 3, c3 = q9 / 3;
+	SchurAcc acc = {0, 0, 0, 0, 0, 0};
+	if(grp < 3)
+		schur_accumulate<false, UNROLL>(blk_ptr[blk] + grp, blk_ptr[blk + 1], 3, r3, c3, pair_a, pair_b, Y, W, 0, 0, acc);
+	// sum the three groups in a fixed order
+	double v[4] = {acc.s00, acc.s10, acc.s01, acc.s11};
 	#pragma unroll
-	for(int i = 0; i < 36; ++ i) acc[i] = 0;
-	#pragma unroll
-	for(int i = 0; i < 6; ++ i) accb[i] = 0;
-	const uint64_t beg = blk_ptr[blk], end = blk_ptr[blk + 1];
-	for(uint64_t k = beg + lane; k < end; k += 32) {
-		const unsigned oa = pair_a[k], ob = pair_b[k];
-		double y[18], w[18];
-		const double *Ya = Y + (size_t)oa * 18, *Wb = W + (size_t)ob * 18;
-		#pragma unroll
-		for(int i = 0; i < 18; i += 2) {
-			double2 t = *reinterpret_cast<const double2*>(Ya + i);
-			y[i] = t.x; y[i + 1] = t.y;
-			double2 s = *reinterpret_cast<const double2*>(Wb + i);
-			w[i] = s.x; w[i + 1] = s.y;
-		}
-		// (Y_a W_b^T)(r, c) = sum_k Y(r,k) W(c,k), column-major accumulators
-		#pragma unroll
-		for(int c = 0; c < 6; ++ c) {
+	for(int i = 0; i < 4; ++ i) {
+		const double v1 = __shfl_sync(0xffffffffu, v[i], (lane + 9) & 31), v2 = __shfl_sync(0xffffffffu, v[i], (lane + 18) & 31);
+		v[i] = (v[i] + v1) + v2;
+	}
+	if(lane < 9) {
+		double *Sb = S + ((size_t)bj * 6 + c3) * ld + (size_t)bi * 6 + r3;
+		Sb[0] = -v[0];
+		Sb[3] = -v[1];
+		Sb[3 * ld] = -v[2];
+		Sb[3 * ld + 3] = -v[3];
+	}
+}
+
+// diagonal blocks (list entries 0 .. C-1, pairs (a, a) = the camera's observations): one CTA per camera, every
+// warp group takes a strided share of the list, the 3 * SB_WARPS partial sums are added in a fixed order
+__global__ void __launch_bounds__(SB_WARPS * 32) k_schur_diag(size_t ld, double alpha, const uint64_t *__restrict__ blk_ptr,
+	const uint32_t *__restrict__ pair_a, const double *__restrict__ Y, const double *__restrict__ W,
+	const double *__restrict__ U, const double *__restrict__ gc, const double *__restrict__ gp,
+	const uint32_t *__restrict__ obs_pt, double *__restrict__ S, double *__restrict__ b)
+{
+	__shared__ double part[3 * SB_WARPS][9][6];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const size_t bi = blockIdx.x;
+	const int grp = lane / 9, q9 = lane - grp * 9, r3 = q9 % 3, c3 = q9 / 3;
+	SchurAcc acc = {0, 0, 0, 0, 0, 0};
+	if(grp < 3) {
+		schur_accumulate<true, 4>(blk_ptr[bi] + warp * 3 + grp, blk_ptr[bi + 1], 3 * SB_WARPS, r3, c3, pair_a, pair_a, Y, W,
+			gp, obs_pt, acc);
+		double *pp = part[warp * 3 + grp][q9];
+		pp[0] = acc.s00; pp[1] = acc.s10; pp[2] = acc.s01; pp[3] = acc.s11; pp[4] = acc.b0; pp[5] = acc.b1;
+	}
+	__syncthreads();
+	if(threadIdx.x < 9) {
+		double v[6] = {0, 0, 0, 0, 0, 0};
+		for(int s = 0; s < 3 * SB_WARPS; ++ s) {
 			#pragma unroll
-			for(int r = 0; r < 6; ++ r)
-				acc[c * 6 + r] += y[r] * w[c] + y[6 + r] * w[6 + c] + y[12 + r] * w[12 + c];
+			for(int i = 0; i < 6; ++ i)
+				v[i] += part[s][q9][i];
 		}
-		if(diag) {
-			const unsigned p = obs_pt[oa];
-			const double g0 = gp[(size_t)p * 3], g1 = gp[(size_t)p * 3 + 1], g2 = gp[(size_t)p * 3 + 2];
-			#pragma unroll
-			for(int r = 0; r < 6; ++ r)
-				accb[r] += y[r] * g0 + y[6 + r] * g1 + y[12 + r] * g2;
+		const double *Ub = U + bi * 36 + c3 * 6 + r3; // column-major 6x6
+		double *Sb = S + (bi * 6 + c3) * ld + bi * 6 + r3;
+		Sb[0] = (Ub[0] + ((r3 == c3)? alpha : 0.0)) - v[0];
+		Sb[3] = Ub[3] - v[1];
+		Sb[3 * ld] = Ub[18] - v[2];
+		Sb[3 * ld + 3] = (Ub[21] + ((r3 == c3)? alpha : 0.0)) - v[3];
+		if(c3 == 0) {
+			b[bi * 6 + r3] = gc[bi * 6 + r3] - v[4];
+			b[bi * 6 + r3 + 3] = gc[bi * 6 + r3 + 3] - v[5];
 		}
-	}
-	#pragma unroll
-	for(int i = 0; i < 36; ++ i) {
-		double v = acc[i];
-		#pragma unroll
-		for(int o = 16; o > 0; o >>= 1)
-			v += __shfl_xor_sync(0xffffffffu, v, o);
-		acc[i] = v;
-	}
-	if(diag) {
-		#pragma unroll
-		for(int i = 0; i < 6; ++ i) {
-			double v = accb[i];
-			#pragma unroll
-			for(int o = 16; o > 0; o >>= 1)
-				v += __shfl_xor_sync(0xffffffffu, v, o);
-			accb[i] = v;
-		}
-	}
-	// every lane holds the full sums; lanes 0..35 -> lane l writes entries l and (l + 32 < 36)
-	#pragma unroll
-	for(int i = 0; i < 36; ++ i) {
-		if((i & 31) == lane) {
-			const int c = i / 6, r = i % 6;
-			double v = -acc[i];
-			if(diag) {
-				v += U[(size_t)bi * 36 + i];
-				if(r == c) v += alpha;
-			}
-			S[((size_t)bj * 6 + c) * ld + (size_t)bi * 6 + r] = v;
-		}
-	}
-	if(diag && lane < 6) {
-		double v = 0;
-		#pragma unroll
-		for(int i = 0; i < 6; ++ i)
-			if(i == lane) v = accb[i];
-		b[(size_t)bi * 6 + lane] = gc[(size_t)bi * 6 + lane] - v;
 	}
 }
 
@@ -210,15 +254,24 @@ void schur_form_reduced_system(spp_ctx *ctx, double alpha, double alpha_diag)
 	s.S.resize(dense_chol_storage(n));
 	s.b.resize(n);
 	if(s.P) {
-		k_landmark_inverse<<<n_blocks(s.P, 128), 128, 0, ctx->stream>>>(s.P, alpha, s.pt_ptr.p(), s.V.p(), s.W.p(),
-			s.Cinv.p(), s.Y.p());
+		k_landmark_inverse<<<n_blocks(s.P, LI_WARPS * 32), LI_WARPS * 32, 0, ctx->stream>>>(s.P, alpha, s.pt_ptr.p(), s.V.p(),
+			s.W.p(), s.Cinv.p(), s.Y.p());
 		LAUNCH_CHECK(ctx);
 	}
 	s.S.zero(ctx->stream);
-	if(s.n_blocks) {
-		k_schur_blocks<<<n_blocks(s.n_blocks, SB_WARPS), SB_WARPS * 32, 0, ctx->stream>>>(s.n_blocks, ld, alpha_diag,
-			s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), s.U.p(),
-			s.gc.p(), s.gp.p(), s.obs_pt.p(), s.S.p(), s.b.p());
+	if(s.C) { // list entries 0 .. C-1 are the diagonal blocks
+		k_schur_diag<<<(unsigned)s.C, SB_WARPS * 32, 0, ctx->stream>>>(ld, alpha_diag, s.blk_ptr.p(), s.pair_a.p(), s.Y.p(),
+			s.W.p(), s.U.p(), s.gc.p(), s.gp.p(), s.obs_pt.p(), s.S.p(), s.b.p());
+		LAUNCH_CHECK(ctx);
+	}
+	if(s.n_blocks > s.C) {
+		static const int unroll = getenv("SPP_SCHUR_UNROLL")? atoi(getenv("SPP_SCHUR_UNROLL")) : 2;
+		if(unroll >= 4)
+			k_schur_blocks<4><<<n_blocks(s.n_blocks - s.C, SB_WARPS), SB_WARPS * 32, 0, ctx->stream>>>(s.C, s.n_blocks, ld,
+				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), s.S.p());
+		else
+			k_schur_blocks<2><<<n_blocks(s.n_blocks - s.C, SB_WARPS), SB_WARPS * 32, 0, ctx->stream>>>(s.C, s.n_blocks, ld,
+				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), s.S.p());
 		LAUNCH_CHECK(ctx);
 	}
 }

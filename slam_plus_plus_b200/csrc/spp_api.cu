@@ -296,7 +296,9 @@ int spp_create(int device, spp_ctx_t *p_ctx)
 	for(int i = 0; i < 16; ++ i) ctx->ev[i] = 0;
 	try {
 		SPP_CUDA(cudaSetDevice(device));
-		SPP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+		int prio_lo = 0, prio_hi = 0;
+		SPP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		SPP_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
 		for(int i = 0; i < 16; ++ i)
 			SPP_CUDA(cudaEventCreate(&ctx->ev[i]));
 		ctx->h_scalars.resize(16);

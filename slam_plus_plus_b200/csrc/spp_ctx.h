@@ -82,7 +82,7 @@ struct DenseChol {
 	DBuf<int> info;           // [0] first non-positive pivot (1-based), [1..] block-row flags of the backsolve
 	cudaStream_t bulk_stream; // trailing updates that overlap the next panel
 	cudaStream_t row_stream;  // look-ahead update of the next panel's tile row
-	cudaEvent_t ev_panel[2], ev_bulk[2], ev_row[2];
+	cudaEvent_t ev_potrf[2], ev_first[2], ev_panel[2], ev_bulk[2], ev_row[2];
 	bool profile;             // SPP_CHOL_PROFILE: serialised per-kernel timing to stderr
 	int force_tile;           // SPP_CHOL_TILE: force the bulk tile shape (0: 128x128, 1: 128x64, 2: 64x64)
 	DenseChol() : bulk_stream(0), row_stream(0), profile(false), force_tile(-1) {}

@@ -60,8 +60,11 @@ void build_schur_structure(spp_ctx *ctx, size_t C, size_t P, const std::vector<u
 			cam_obs[fill[h_cam[e]] ++] = pos_of_edge[e];
 	}
 
-	// reduced camera system: count the pairs of every upper block (i <= j)
-	// pass 1: histogram over block keys; dense table when C^2 is affordable, sorted keys otherwise
+	// reduced camera system: the upper blocks (i <= j) and the observation pairs of each.
+	// Block list layout: blocks 0 .. C-1 are the diagonal blocks (i, i) -- every camera owns one, with or without
+	// observations; their pair lists are the camera's own observations (a, a). The off-diagonal blocks follow,
+	// in 8 x 8 camera tiles when C^2 is affordable (the warps of a CTA then work on one block row of a tile and
+	// share the Y / W lines of its cameras through L1 / L2), in row-major key order otherwise.
 	std::vector<uint32_t> blk_row, blk_col;
 	std::vector<uint64_t> blk_ptr;
 	std::vector<uint32_t> pair_a, pair_b;
@@ -71,40 +74,47 @@ void build_schur_structure(spp_ctx *ctx, size_t C, size_t P, const std::vector<u
 		n_pairs += k * (k + 1) / 2;
 	}
 	const bool b_dense_table = C * C <= (size_t(1) << 28);
-	std::vector<uint64_t> keys; // sorted unique keys (sparse mode)
+	std::vector<uint64_t> keys; // sorted unique off-diagonal keys (sparse mode)
 	std::vector<uint32_t> table; // key -> block index + 1 (dense mode)
 	auto key_of = [C](uint32_t i, uint32_t j) { return (uint64_t)i * C + j; };
+	blk_ptr.push_back(0);
+	for(size_t i = 0; i < C; ++ i) {
+		blk_row.push_back((uint32_t)i);
+		blk_col.push_back((uint32_t)i);
+		blk_ptr.push_back(blk_ptr.back() + (cam_ptr[i + 1] - cam_ptr[i]));
+	}
+	const size_t SCHUR_TILE = 8;
 	if(b_dense_table) {
 		std::vector<uint32_t> count(C * C, 0);
 		for(size_t p = 0; p < P; ++ p) {
 			for(uint32_t a = pt_ptr[p]; a < pt_ptr[p + 1]; ++ a) {
 				for(uint32_t b = pt_ptr[p]; b < pt_ptr[p + 1]; ++ b) {
 					uint32_t ca = t_cam[a], cb = t_cam[b];
-					if(ca < cb || a == b)
+					if(ca < cb)
 						++ count[key_of(ca, cb)];
 					else if(ca == cb && a != b)
 						throw invalid_error("a landmark is observed twice by the same camera (duplicate edge)");
 				}
 			}
 		}
-		// cameras without observations still own their diagonal block
 		table.assign(C * C, 0);
-		blk_ptr.push_back(0);
-		for(size_t i = 0; i < C; ++ i) {
-			for(size_t j = i; j < C; ++ j) {
-				uint32_t n = count[i * C + j];
-				if(n || i == j) {
-					blk_row.push_back((uint32_t)i);
-					blk_col.push_back((uint32_t)j);
-					table[i * C + j] = (uint32_t)blk_row.size();
-					blk_ptr.push_back(blk_ptr.back() + n);
+		for(size_t ti = 0; ti < C; ti += SCHUR_TILE) {
+			for(size_t tj = ti; tj < C; tj += SCHUR_TILE) {
+				for(size_t i = ti; i < std::min(C, ti + SCHUR_TILE); ++ i) {
+					for(size_t j = std::max(tj, i + 1); j < std::min(C, tj + SCHUR_TILE); ++ j) {
+						uint32_t n = count[i * C + j];
+						if(n) {
+							blk_row.push_back((uint32_t)i);
+							blk_col.push_back((uint32_t)j);
+							table[i * C + j] = (uint32_t)blk_row.size();
+							blk_ptr.push_back(blk_ptr.back() + n);
+						}
+					}
 				}
 			}
 		}
 	} else {
-		keys.reserve(n_pairs + C);
-		for(size_t i = 0; i < C; ++ i)
-			keys.push_back(key_of((uint32_t)i, (uint32_t)i));
+		keys.reserve(n_pairs - O);
 		for(size_t p = 0; p < P; ++ p) {
 			for(uint32_t a = pt_ptr[p]; a < pt_ptr[p + 1]; ++ a) {
 				for(uint32_t b = pt_ptr[p]; b < pt_ptr[p + 1]; ++ b) {
@@ -118,37 +128,16 @@ void build_schur_structure(spp_ctx *ctx, size_t C, size_t P, const std::vector<u
 		}
 		std::sort(keys.begin(), keys.end());
 		std::vector<uint64_t> uniq;
-		std::vector<uint64_t> cnt;
 		for(size_t i = 0; i < keys.size();) {
 			size_t j = i;
 			while(j < keys.size() && keys[j] == keys[i]) ++ j;
 			uniq.push_back(keys[i]);
-			uint64_t n = j - i;
-			if(keys[i] / C == keys[i] % C)
-				-- n; // the seed entry of the diagonal
-			cnt.push_back(n);
+			blk_row.push_back((uint32_t)(keys[i] / C));
+			blk_col.push_back((uint32_t)(keys[i] % C));
+			blk_ptr.push_back(blk_ptr.back() + (j - i));
 			i = j;
 		}
 		keys.swap(uniq);
-		blk_ptr.push_back(0);
-		for(size_t i = 0; i < keys.size(); ++ i) {
-			blk_row.push_back((uint32_t)(keys[i] / C));
-			blk_col.push_back((uint32_t)(keys[i] % C));
-			blk_ptr.push_back(blk_ptr.back() + cnt[i]);
-		}
-		// diagonal pairs (a, a) were not emitted above: add their counts
-		std::vector<uint64_t> diag_extra(C, 0);
-		for(size_t k = 0; k < O; ++ k)
-			++ diag_extra[t_cam[k]];
-		std::vector<uint64_t> new_ptr(blk_ptr.size());
-		uint64_t shift = 0;
-		for(size_t i = 0; i < keys.size(); ++ i) {
-			new_ptr[i] = blk_ptr[i] + shift;
-			if(blk_row[i] == blk_col[i])
-				shift += diag_extra[blk_row[i]];
-		}
-		new_ptr[keys.size()] = blk_ptr[keys.size()] + shift;
-		blk_ptr.swap(new_ptr);
 	}
 	const size_t n_blk = blk_row.size();
 	if(blk_ptr.back() != n_pairs)
@@ -165,10 +154,12 @@ void build_schur_structure(spp_ctx *ctx, size_t C, size_t P, const std::vector<u
 					if(!(ca < cb || a == b))
 						continue;
 					size_t blk;
-					if(b_dense_table)
+					if(a == b)
+						blk = ca;
+					else if(b_dense_table)
 						blk = table[key_of(ca, cb)] - 1;
 					else
-						blk = std::lower_bound(keys.begin(), keys.end(), key_of(ca, cb)) - keys.begin();
+						blk = C + (std::lower_bound(keys.begin(), keys.end(), key_of(ca, cb)) - keys.begin());
 					uint64_t dst = fill[blk] ++;
 					pair_a[dst] = a;
 					pair_b[dst] = b;

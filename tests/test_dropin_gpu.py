@@ -17,32 +17,53 @@ pytestmark = pytest.mark.gpu
 BIN = os.path.join(ROOT, "oracle", "_ref", "ref_driver_dropin")
 
 
-@pytest.mark.parametrize("name", ["ba_tiny", "ba_tiny_interleaved", "ba_small", "ba_small_hard"])
-def test_reference_lm_with_b200_linear_solver(name, tmp_path):
-    if not os.path.exists(BIN):
-        pytest.skip("oracle/_ref/ref_driver_dropin not built (needs /root/reference at build time)")
-    from slam_plus_plus_b200 import sppio
-    g, d = load_golden(name)
-    gp, dp = str(tmp_path / "g.bin"), str(tmp_path / "d.dump")
-    sppio.write_graph(gp, g)
-    subprocess.run([BIN, gp, dp, str(int(d["max_iter"][0])), "0"], check=True, stdout=subprocess.DEVNULL,
-                   env=dict(os.environ, OMP_NUM_THREADS="1"))
-    r = sppio.read_dump(dp)
-    assert abs(r["chi2_0"][0] - d["chi2_0"][0]) <= 1e-13 * d["chi2_0"][0]
-    tr, tg = r["lm_trace"].reshape(-1, 6), d["lm_trace"].reshape(-1, 6)
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_driver_ba")
+
+
+def _compare_traces(tr, tg, tol_chi2, tol_first=None):
+    """LM traces [alpha, chi2_last, chi2, ., accepted, .] of two runs; tg is the reference one. tol_first, if given,
+    is the (tighter) chi2 tolerance of the first step, where both runs linearise at the same state."""
     # damping history: alpha_{k+1} = alpha_k * max(1/3, 1 - (2 rho - 1)^3) with rho = (chi2_last - chi2) / denominator
-    # (LM.h:204-223). chi2 is reproduced to 1e-9 RELATIVE TO CHI2, so rho carries a relative error of
-    # 1e-9 * chi2 / |chi2_last - chi2| (large once the steps stop reducing chi2), and |d factor / d rho| <= 6 with
+    # (LM.h:204-223). chi2 is reproduced to tol_chi2 RELATIVE TO CHI2, so rho carries a relative error of
+    # tol_chi2 * chi2 / |chi2_last - chi2| (large once the steps stop reducing chi2), and |d factor / d rho| <= 6 with
     # factor >= 1/3 turns that into <= 18x as much in alpha. The tolerance accumulates over the steps.
-    tol_alpha = 1e-7
+    tol_alpha = 100 * tol_chi2
     for k in range(min(len(tr), len(tg))):
-        if abs(tg[k, 1] - tg[k, 2]) <= 1e-9 * tg[k, 1]:
+        if abs(tg[k, 1] - tg[k, 2]) <= max(tol_chi2, 1e-9) * tg[k, 1]:
             break  # chi2 no longer changes: the accept / reject decision is rounding noise from here on
         assert int(tr[k, 4]) == int(tg[k, 4])
-        assert abs(tr[k, 2] - tg[k, 2]) <= 1e-9 * tg[k, 2]
+        assert abs(tr[k, 2] - tg[k, 2]) <= (tol_first if (k == 0 and tol_first) else tol_chi2) * tg[k, 2]
         assert abs(tr[k, 0] - tg[k, 0]) <= tol_alpha * tg[k, 0]
-        tol_alpha += 20 * 1e-9 * tg[k, 1] / abs(tg[k, 1] - tg[k, 2])
-    assert abs(r["chi2"][0] - d["chi2"][0]) <= 1e-9 * d["chi2"][0]
+        tol_alpha += 20 * tol_chi2 * tg[k, 1] / abs(tg[k, 1] - tg[k, 2])
+
+
+@pytest.mark.parametrize("name", ["ba_tiny", "ba_tiny_interleaved", "ba_small", "ba_small_hard"])
+def test_reference_lm_with_b200_linear_solver(name, tmp_path):
+    if not os.path.exists(BIN) or not os.path.exists(REF):
+        pytest.skip("oracle/_ref drivers not built (need /root/reference at build time)")
+    from slam_plus_plus_b200 import sppio
+    g, d = load_golden(name)
+    gp, dp, rp = str(tmp_path / "g.bin"), str(tmp_path / "d.dump"), str(tmp_path / "r.dump")
+    sppio.write_graph(gp, g)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    n_it = str(int(d["max_iter"][0]))
+    subprocess.run([BIN, gp, dp, n_it, "0"], check=True, stdout=subprocess.DEVNULL, env=env)
+    # the pure reference on THIS machine: its forward-difference Jacobians (delta = 1e-9) amplify last-bit libm
+    # differences between host CPUs to ~1e-6 (SURVEY F3), so the 1e-9 comparison must not cross machines
+    subprocess.run([REF, "dump", gp, rp, n_it, "0"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
+    r, ref = sppio.read_dump(dp), sppio.read_dump(rp)
+    assert abs(r["chi2_0"][0] - ref["chi2_0"][0]) <= 1e-13 * ref["chi2_0"][0]
+    # First step: same state, same Jacobians, so chi2 after the step shows the accuracy of the linear solve alone
+    # (1e-9). From the second step on the two runs linearise at states that differ in the last bits (our increment
+    # agrees with the reference's to ~1e-13, not bitwise), and the reference's forward-difference Jacobians turn
+    # that into ~1e-7 relative noise in J (rounding of h(x) over delta = 1e-9, SURVEY F3): the traces then agree at
+    # that noise floor -- 1e-6 on chi2, the north-star bound for the final chi2.
+    _compare_traces(r["lm_trace"].reshape(-1, 6), ref["lm_trace"].reshape(-1, 6), 1e-6, tol_first=1e-9)
+    assert abs(r["chi2"][0] - ref["chi2"][0]) <= 1e-6 * ref["chi2"][0]
     # converged problems end with noise-decided accept / reject steps along nearly flat directions: the states
     # agree less tightly than chi2 does
-    assert rel_err(r["states"], d["states"]) < 1e-4
+    assert rel_err(r["states"], ref["states"]) < 1e-4
+    # and against the committed golden run (another machine): FD noise floor
+    assert abs(r["chi2_0"][0] - d["chi2_0"][0]) <= 1e-11 * d["chi2_0"][0]
+    _compare_traces(r["lm_trace"].reshape(-1, 6), d["lm_trace"].reshape(-1, 6), 2e-5)
+    assert abs(r["chi2"][0] - d["chi2"][0]) <= 1e-6 * d["chi2"][0]
