@@ -6,6 +6,7 @@
 #include <string.h>
 #include <math.h>
 #include <algorithm>
+#include <stdlib.h>
 
 namespace spp {
 
@@ -13,6 +14,11 @@ namespace spp {
 void build_schur_structure(spp_ctx *ctx, size_t C, size_t P, const std::vector<uint32_t> &h_cam,
 	const std::vector<uint32_t> &h_pt, std::vector<uint32_t> &obs_orig, std::vector<uint32_t> &t_cam,
 	std::vector<uint32_t> &t_pt);
+bool schur_structure_device_supported(size_t C);
+void ba_upload_and_analyse_device(spp_ctx *ctx, size_t C, size_t P, size_t O, const uint64_t *p_obs_point,
+	const uint64_t *p_obs_camera, const double *p_z, const double *p_info);
+void ba_fetch_host_maps(spp_ctx *ctx);
+void schur_fetch_host_pattern(spp_ctx *ctx);
 void ba_linearise(spp_ctx *ctx, bool b_want_maxdiag);
 void ba_chi2_device(spp_ctx *ctx, double *d_out);
 void ba_step_dots_device(spp_ctx *ctx, double alpha, double *d_out);
@@ -400,67 +406,80 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 	ba.uf_is_cam = n_vertices? (p_vertex_type[0] == 0) : 1;
 	ba.uf_index = n_vertices? 0 : -1; // vertex id 0 is local index 0 of its type
 
-	std::vector<uint32_t> h_cam(O), h_pt(O);
-	for(size_t e = 0; e < O; ++ e) {
-		uint64_t vp = p_obs_point[e], vc = p_obs_camera[e];
-		if(vp >= n_vertices || vc >= n_vertices || p_vertex_type[vp] != 1 || p_vertex_type[vc] != 0)
-			throw invalid_error("observation references a vertex of the wrong type or out of range");
-		h_cam[e] = ba.vertex_local[vc];
-		h_pt[e] = ba.vertex_local[vp];
-	}
-	// multi-GPU: this rank keeps a contiguous slice of the landmarks with all their observations; cameras are
-	// replicated. The slice bounds balance the Schur-product work sum k_p (k_p + 1) / 2 + k_p.
-	ba.P_global = P;
-	ba.pt_begin = 0;
-	ba.pt_end = P;
-	if(ctx->world > 1) {
-		std::vector<uint32_t> track_len(P, 0);
-		for(size_t e = 0; e < O; ++ e)
-			++ track_len[h_pt[e]];
-		std::vector<uint64_t> bounds(ctx->world + 1);
-		spp_partition_landmarks(P, P? &track_len[0] : 0, ctx->world, &bounds[0]);
-		ba.pt_begin = bounds[ctx->rank];
-		ba.pt_end = bounds[ctx->rank + 1];
-		std::vector<uint32_t> l_cam, l_pt, kept;
-		for(size_t e = 0; e < O; ++ e) {
-			if(h_pt[e] >= ba.pt_begin && h_pt[e] < ba.pt_end) {
-				l_cam.push_back(h_cam[e]);
-				l_pt.push_back(uint32_t(h_pt[e] - ba.pt_begin));
-				kept.push_back((uint32_t)e);
-			}
-		}
-		h_cam.swap(l_cam);
-		h_pt.swap(l_pt);
-		build_schur_structure(ctx, C, ba.pt_end - ba.pt_begin, h_cam, h_pt, ba.obs_orig, ba.h_obs_cam, ba.h_obs_pt);
-		for(size_t k = 0; k < ba.obs_orig.size(); ++ k)
-			ba.obs_orig[k] = kept[ba.obs_orig[k]]; // local track position -> original (global) edge index
-	} else
-		build_schur_structure(ctx, C, P, h_cam, h_pt, ba.obs_orig, ba.h_obs_cam, ba.h_obs_pt);
-	const size_t P_local = ba.pt_end - ba.pt_begin, O_local = ba.obs_orig.size();
-	if(!ba.uf_is_cam && n_vertices) // the unary factor sits on landmark 0: only its owner adds it
-		ba.uf_index = (ba.pt_begin == 0 && P_local)? 0 : -1;
-	else if(ctx->rank != 0)
-		ba.uf_index = -1; // camera 0: added once, by rank 0
-
 	cudaStream_t st = ctx->stream;
 	std::vector<double> cs(C * 6), ci(C * 5);
 	for(size_t c = 0; c < C; ++ c) {
 		for(int k = 0; k < 6; ++ k) cs[c * 6 + k] = p_cam_params[c * 11 + k];
 		for(int k = 0; k < 5; ++ k) ci[c * 5 + k] = p_cam_params[c * 11 + 6 + k];
 	}
+	ba.P_global = P;
+	ba.pt_begin = 0;
+	ba.pt_end = P;
+	if(ctx->world == 1 && schur_structure_device_supported(C) && !getenv("SPP_HOST_SYMBOLIC")) {
+		// single GPU: the observation arrays go to the device as they are; local indices, tracks, camera lists, the
+		// block and pair lists of the reduced camera system and the track-ordered measurements are built there
+		ba_upload_and_analyse_device(ctx, C, P, O, p_obs_point, p_obs_camera, p_z, p_info);
+		ba.pts.upload(p_points, P * 3, st);
+		ba.pts0.upload(p_points, P * 3, st);
+	} else {
+		std::vector<uint32_t> h_cam(O), h_pt(O);
+		for(size_t e = 0; e < O; ++ e) {
+			uint64_t vp = p_obs_point[e], vc = p_obs_camera[e];
+			if(vp >= n_vertices || vc >= n_vertices || p_vertex_type[vp] != 1 || p_vertex_type[vc] != 0)
+				throw invalid_error("observation references a vertex of the wrong type or out of range");
+			h_cam[e] = ba.vertex_local[vc];
+			h_pt[e] = ba.vertex_local[vp];
+		}
+		// multi-GPU: this rank keeps a contiguous slice of the landmarks with all their observations; cameras are
+		// replicated. The slice bounds balance the Schur-product work sum k_p (k_p + 1) / 2 + k_p.
+		if(ctx->world > 1) {
+			std::vector<uint32_t> track_len(P, 0);
+			for(size_t e = 0; e < O; ++ e)
+				++ track_len[h_pt[e]];
+			std::vector<uint64_t> bounds(ctx->world + 1);
+			spp_partition_landmarks(P, P? &track_len[0] : 0, ctx->world, &bounds[0]);
+			ba.pt_begin = bounds[ctx->rank];
+			ba.pt_end = bounds[ctx->rank + 1];
+			std::vector<uint32_t> l_cam, l_pt, kept;
+			for(size_t e = 0; e < O; ++ e) {
+				if(h_pt[e] >= ba.pt_begin && h_pt[e] < ba.pt_end) {
+					l_cam.push_back(h_cam[e]);
+					l_pt.push_back(uint32_t(h_pt[e] - ba.pt_begin));
+					kept.push_back((uint32_t)e);
+				}
+			}
+			h_cam.swap(l_cam);
+			h_pt.swap(l_pt);
+			build_schur_structure(ctx, C, ba.pt_end - ba.pt_begin, h_cam, h_pt, ba.obs_orig, ba.h_obs_cam, ba.h_obs_pt);
+			for(size_t k = 0; k < ba.obs_orig.size(); ++ k)
+				ba.obs_orig[k] = kept[ba.obs_orig[k]]; // local track position -> original (global) edge index
+		} else
+			build_schur_structure(ctx, C, P, h_cam, h_pt, ba.obs_orig, ba.h_obs_cam, ba.h_obs_pt);
+		ba.host_maps_valid = true;
+		ba.d_obs_orig.upload(ba.obs_orig, st);
+		const size_t P_local = ba.pt_end - ba.pt_begin, O_local = ba.obs_orig.size();
+		ba.pts.upload(p_points + ba.pt_begin * 3, P_local * 3, st);
+		ba.pts0.upload(p_points + ba.pt_begin * 3, P_local * 3, st);
+		std::vector<double> tz(O_local * 2), ti(O_local * 4);
+		for(size_t k = 0; k < O_local; ++ k) {
+			size_t e = ba.obs_orig[k];
+			tz[k * 2] = p_z[e * 2]; tz[k * 2 + 1] = p_z[e * 2 + 1];
+			for(int q = 0; q < 4; ++ q) ti[k * 4 + q] = p_info[e * 4 + q];
+		}
+		ba.z.upload(tz, st);
+		ba.info.upload(ti, st);
+		SPP_CUDA(cudaStreamSynchronize(st)); // the host vectors go out of scope
+	}
+	{
+		const size_t P_local = ba.pt_end - ba.pt_begin;
+		if(!ba.uf_is_cam && n_vertices) // the unary factor sits on landmark 0: only its owner adds it
+			ba.uf_index = (ba.pt_begin == 0 && P_local)? 0 : -1;
+		else if(ctx->rank != 0)
+			ba.uf_index = -1; // camera 0: added once, by rank 0
+	}
 	ba.cam_state.upload(cs, st);
 	ba.cam_intr.upload(ci, st);
-	ba.pts.upload(p_points + ba.pt_begin * 3, P_local * 3, st);
 	ba.cam_state0.upload(cs, st);
-	ba.pts0.upload(p_points + ba.pt_begin * 3, P_local * 3, st);
-	std::vector<double> tz(O_local * 2), ti(O_local * 4);
-	for(size_t k = 0; k < O_local; ++ k) {
-		size_t e = ba.obs_orig[k];
-		tz[k * 2] = p_z[e * 2]; tz[k * 2 + 1] = p_z[e * 2 + 1];
-		for(int q = 0; q < 4; ++ q) ti[k * 4 + q] = p_info[e * 4 + q];
-	}
-	ba.z.upload(tz, st);
-	ba.info.upload(ti, st);
 	ba.camRt.resize(C * 84);
 	ba.camK.resize(C * 5);
 	ba.partial.resize(4 * 1024);
@@ -543,6 +562,7 @@ int spp_ba_get_lambda(spp_ctx_t ctx, uint64_t *p_n_block_cols, uint64_t *p_n_blo
 	if(!ba.valid) throw invalid_error("no BA graph");
 	if(ctx->world > 1) throw invalid_error("not available on a landmark-partitioned (multi-GPU) context");
 	const size_t NV = ba.n_vertices, O = s.O;
+	ba_fetch_host_maps(ctx);
 	// structure in vertex id order: column v holds the off-diagonal blocks (row u < v) and the diagonal block last
 	std::vector<std::vector<std::pair<uint32_t, uint32_t> > > cols(NV); // (row vertex, track position)
 	for(size_t k = 0; k < O; ++ k) {
@@ -639,6 +659,8 @@ int spp_ba_get_blocks(spp_ctx_t ctx, double *p_U, double *p_V, double *p_W, doub
 		s.W.download(hW.data(), hW.size(), ctx->stream);
 	}
 	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	if(p_W)
+		ba_fetch_host_maps(ctx);
 	if(p_W) { // track order -> edge insertion order
 		for(size_t k = 0; k < s.O; ++ k)
 			memcpy(p_W + (size_t)ba.obs_orig[k] * 18, &hW[k * 18], 18 * sizeof(double));
@@ -733,6 +755,7 @@ int spp_schur_get_reduced_system(spp_ctx_t ctx, uint64_t *p_n, double *p_S, doub
 		SPP_CUDA(cudaStreamSynchronize(ctx->stream));
 	}
 	if(p_block_pattern) {
+		schur_fetch_host_pattern(ctx);
 		memset(p_block_pattern, 0, s.C * s.C);
 		for(size_t i = 0; i < s.h_blk_row.size(); ++ i)
 			p_block_pattern[(size_t)s.h_blk_row[i] * s.C + s.h_blk_col[i]] = 1;

@@ -43,8 +43,10 @@ struct BAProblem {
 	std::vector<uint8_t> vtype;          // per vertex id
 	std::vector<uint32_t> vertex_local;  // vertex id -> camera / point index
 	std::vector<uint32_t> cam_vertex, pt_vertex; // local index -> vertex id
-	std::vector<uint32_t> obs_orig;      // track position -> original edge index
-	std::vector<uint32_t> h_obs_cam, h_obs_pt; // host copies (track order)
+	std::vector<uint32_t> obs_orig;      // track position -> original edge index (host copy, fetched on demand)
+	std::vector<uint32_t> h_obs_cam, h_obs_pt; // host copies (track order, fetched on demand)
+	DBuf<uint32_t> d_obs_orig;           // the same map on the device
+	bool host_maps_valid;
 	int uf_is_cam; long uf_index;        // vertex id 0 carries the unary factor (-1: added by another rank)
 	size_t P_global, pt_begin, pt_end;   // landmark slice of this rank (multi-GPU)
 	int jac_mode;
@@ -58,8 +60,8 @@ struct BAProblem {
 	DBuf<double> partial;                         // reduction scratch
 	DBuf<unsigned long long> maxdiag;             // [1] bits of the max per-edge Hessian diagonal
 	bool linearised;
-	BAProblem() : valid(false), n_vertices(0), uf_is_cam(1), uf_index(0), P_global(0), pt_begin(0), pt_end(0),
-		jac_mode(0), linearised(false) {}
+	BAProblem() : valid(false), n_vertices(0), host_maps_valid(false), uf_is_cam(1), uf_index(0), P_global(0), pt_begin(0),
+		pt_end(0), jac_mode(0), linearised(false) {}
 };
 
 // slot-1 state: map from the caller's lambda values to the SchurSystem arrays
@@ -74,6 +76,18 @@ struct SchurSlot {
 	DBuf<uint8_t> w_transposed;           // W block stored 3x6 in lambda (point id < camera id)
 	DBuf<uint64_t> cam_eta_off, pt_eta_off; // scalar offsets in eta
 	SchurSlot() : valid(false), n_bcols(0), n_scalars(0), n_values(0), cut(0) {}
+};
+
+// scratch of the device-side symbolic analysis (symbolic_gpu.cu); grows only
+struct SymbolicScratch {
+	DBuf<uint8_t> cub_temp;
+	DBuf<int> err;
+	DBuf<uint32_t> iota, pos_of_edge, cnt, keys_out, cnt_lin, flag, rank, blk_of_lin, pkey, pkey_out;
+	DBuf<uint64_t> cnt64, before, n_off, pair_off, pval, pval_out;
+	DBuf<uint32_t> ocam, opt, vlocal;   // per-edge local indices (edge insertion order), vertex id -> local index
+	DBuf<uint64_t> obs_pt_id, obs_cam_id; // staging of the caller's vertex ids
+	DBuf<uint8_t> vtype;
+	DBuf<double> z_in, info_in;         // staging of the caller's measurements (edge insertion order)
 };
 
 struct DenseChol {
@@ -103,6 +117,7 @@ struct spp_ctx {
 	spp::BAProblem ba;
 	spp::SchurSlot slot;
 	spp::DenseChol chol;
+	spp::SymbolicScratch sym;
 	spp::HPinned<double> h_scalars;
 	cudaEvent_t ev[16];
 };
