@@ -37,6 +37,8 @@ namespace spp {
 
 #include "potrf128.cuh"
 
+static const size_t POTRF_SMEM_EXCLUSIVE = 227 * 1024; // the opt-in maximum per CTA: nothing else fits on the SM
+
 // ---- FP64 tensor-core GEMM: C (op)= A^T B with K = 128, operands K-contiguous ---------------------------
 
 enum { GEMM_SYRK = 0, GEMM_TRSM = 1 };
@@ -44,11 +46,13 @@ enum { GEMM_SYRK = 0, GEMM_TRSM = 1 };
 // SYRK: C(i0.., j0..) -= P(:, i0..)^T P(:, j0..), P = rows k0..k0+127 of A; tiles with i0 > j0 are skipped.
 //       grid.x = column tile (from column cbase), grid.y = row tile (from row rbase).
 // TRSM: P(:, j0..) <- Rinv^T P(:, j0..) in place; BM must be 128 (a CTA owns whole columns of the panel).
-template <int MODE, int BM, int BN>
-__global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_gemm_tn(double *__restrict__ A, size_t ld, size_t k0,
+// WM x WN is the warp tile (multiples of 8): 32 x 32 for the bulk updates, smaller for the few tiles on the critical
+// chain, where more warps with shorter DMMA chains finish sooner.
+template <int MODE, int BM, int BN, int WM = 32, int WN = 32, int STAGES = CH_STAGES>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) k_gemm_tn(double *__restrict__ A, size_t ld, size_t k0,
 	size_t rbase, size_t cbase, const double *__restrict__ Rinv)
 {
-	constexpr int WARPS_N = BN / 32, NT = (BM / 32) * (BN / 32) * 32;
+	constexpr int WARPS_N = BN / WN, NT = (BM / WM) * (BN / WN) * 32, MA = WM / 8, NB = WN / 8;
 	size_t i0, j0;
 	if(MODE == GEMM_SYRK) {
 		i0 = rbase + blockIdx.y * (size_t)BM;
@@ -61,9 +65,9 @@ __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_gemm_tn(double *
 	}
 	extern __shared__ double smem[];
 	double (*As)[BM][CH_LDS] = reinterpret_cast<double (*)[BM][CH_LDS]>(smem);
-	double (*Bs)[BN][CH_LDS] = reinterpret_cast<double (*)[BN][CH_LDS]>(smem + CH_STAGES * BM * CH_LDS);
+	double (*Bs)[BN][CH_LDS] = reinterpret_cast<double (*)[BN][CH_LDS]>(smem + STAGES * BM * CH_LDS);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const int wi = (warp / WARPS_N) * 32, wj = (warp % WARPS_N) * 32;
+	const int wi = (warp / WARPS_N) * WM, wj = (warp % WARPS_N) * WN;
 	const int g = lane >> 2, t = lane & 3;
 
 	// operand pointers: element (k, m) at base[m * stride + k]
@@ -84,20 +88,20 @@ __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_gemm_tn(double *
 		}
 	};
 
-	double acc[4][4][2];
+	double acc[MA][NB][2];
 
 	constexpr int KT = CH_NB / CH_BK;
 	#pragma unroll
-	for(int s = 0; s < CH_STAGES - 1; ++ s) {
+	for(int s = 0; s < STAGES - 1; ++ s) {
 		stage_load(s, s);
 		__pipeline_commit();
 	}
 	// SYRK: the accumulators start from the C tile (its loads overlap the pipeline fill) and the A fragments
 	// are negated, so the epilogue is a plain store instead of a read-modify-write
 	#pragma unroll
-	for(int a = 0; a < 4; ++ a) {
+	for(int a = 0; a < MA; ++ a) {
 		#pragma unroll
-		for(int b = 0; b < 4; ++ b) {
+		for(int b = 0; b < NB; ++ b) {
 			if(MODE == GEMM_SYRK) {
 				const size_t c = j0 + wj + b * 8 + 2 * t, r = i0 + wi + a * 8 + g;
 				acc[a][b][0] = A[c * ld + r];
@@ -107,25 +111,25 @@ __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_gemm_tn(double *
 		}
 	}
 	for(int kt = 0; kt < KT; ++ kt) {
-		__pipeline_wait_prior(CH_STAGES - 2);
+		__pipeline_wait_prior(STAGES - 2);
 		__syncthreads();
-		if(kt + CH_STAGES - 1 < KT)
-			stage_load((kt + CH_STAGES - 1) % CH_STAGES, kt + CH_STAGES - 1);
+		if(kt + STAGES - 1 < KT)
+			stage_load((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
 		__pipeline_commit();
-		const int st = kt % CH_STAGES;
+		const int st = kt % STAGES;
 		#pragma unroll
 		for(int k4 = 0; k4 < CH_BK; k4 += 4) {
-			double fa[4], fb[4];
+			double fa[MA], fb[NB];
 			#pragma unroll
-			for(int a = 0; a < 4; ++ a)
+			for(int a = 0; a < MA; ++ a)
 				fa[a] = (MODE == GEMM_SYRK)? -As[st][wi + a * 8 + g][k4 + t] : As[st][wi + a * 8 + g][k4 + t];
 			#pragma unroll
-			for(int b = 0; b < 4; ++ b)
+			for(int b = 0; b < NB; ++ b)
 				fb[b] = Bs[st][wj + b * 8 + g][k4 + t];
 			#pragma unroll
-			for(int a = 0; a < 4; ++ a)
+			for(int a = 0; a < MA; ++ a)
 				#pragma unroll
-				for(int b = 0; b < 4; ++ b)
+				for(int b = 0; b < NB; ++ b)
 					dmma_m8n8k4(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
 		}
 	}
@@ -133,9 +137,9 @@ __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_gemm_tn(double *
 	if(MODE == GEMM_TRSM)
 		__syncthreads(); // every warp is done reading the panel (through smem) before anyone overwrites it
 	#pragma unroll
-	for(int a = 0; a < 4; ++ a) {
+	for(int a = 0; a < MA; ++ a) {
 		#pragma unroll
-		for(int b = 0; b < 4; ++ b) {
+		for(int b = 0; b < NB; ++ b) {
 			const size_t c = j0 + wj + b * 8 + 2 * t;
 			if(MODE == GEMM_SYRK) {
 				const size_t r = i0 + wi + a * 8 + g;
@@ -150,8 +154,8 @@ __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_gemm_tn(double *
 	}
 }
 
-template <int BM, int BN>
-constexpr size_t gemm_smem() { return (size_t)CH_STAGES * (BM + BN) * CH_LDS * sizeof(double); }
+template <int BM, int BN, int STAGES = CH_STAGES>
+constexpr size_t gemm_smem() { return (size_t)STAGES * (BM + BN) * CH_LDS * sizeof(double); }
 
 // ---- backward solve R x = y ---------------------------------------------------------------------------
 
@@ -248,12 +252,13 @@ static void chol_init_attributes()
 {
 	static bool done = false;
 	if(done) return;
-	SPP_CUDA(cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+	SPP_CUDA(cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM_EXCLUSIVE));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 128>()));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64, 64>()));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_TRSM, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
-	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_TRSM, 128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 32>()));
+	SPP_CUDA(cudaFuncSetAttribute((k_gemm_tn<GEMM_TRSM, 128, 16, 32, 16, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 16, 8>()));
+	SPP_CUDA(cudaFuncSetAttribute((k_gemm_tn<GEMM_SYRK, 32, 32, 16, 16, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<32, 32, 8>()));
 	done = true;
 }
 
@@ -281,6 +286,7 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 		}
 		ch.profile = getenv("SPP_CHOL_PROFILE") != 0;
 		ch.force_tile = getenv("SPP_CHOL_TILE")? atoi(getenv("SPP_CHOL_TILE")) : -1;
+		ch.potrf_exclusive = getenv("SPP_CHOL_SHARED_SM") == 0;
 	}
 	ch.info.resize(1 + n_blk);
 	SPP_CUDA(cudaMemsetAsync(ch.info.p(), 0, (1 + n_blk) * sizeof(int), st));
@@ -311,6 +317,18 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 			ch.dbg.resize(16);
 		}
 		float t_acc[5] = {0, 0, 0, 0, 0};
+		// SPP_CHOL_TIMELINE: time stamps on the critical stream only (no serialisation): per panel, before potrf, after
+		// potrf, after the first-tile solve, after the diagonal look-ahead update
+		static const bool timeline = getenv("SPP_CHOL_TIMELINE") != 0;
+		std::vector<cudaEvent_t> tl;
+		auto stamp = [&]() {
+			if(timeline && !prof) {
+				cudaEvent_t e;
+				cudaEventCreate(&e);
+				cudaEventRecord(e, sA);
+				tl.push_back(e);
+			}
+		};
 		auto tic = [&]() { if(prof) cudaEventRecord(ctx->ev[4], sA); };
 		auto toc = [&](int k) {
 			if(prof) {
@@ -340,10 +358,15 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 			const size_t k0 = b * CH_NB, c0 = k0 + CH_NB;
 			const int e = int(b & 1);
 			double *Rinv_b = Rinv + b * (size_t)(CH_NB * CH_NB);
+			stamp();
 			tic();
-			k_potrf128<<<1, PT, POTRF_SMEM, sA>>>(A, ld, k0, Rinv_b, info, (prof && b == 1)? ch.dbg.p() : 0);
+			// the diagonal block asks for a whole SM's shared memory: co-resident update CTAs would compete for the FP64
+			// pipe and stretch the critical chain (measured: 33 -> 45 us)
+			k_potrf128<<<1, PT, ch.potrf_exclusive? POTRF_SMEM_EXCLUSIVE : POTRF_SMEM, sA>>>(A, ld, k0, Rinv_b, info,
+				(prof && b == 1)? ch.dbg.p() : 0);
 			LAUNCH_CHECK(ctx);
 			toc(0);
+			stamp();
 			if(!prof) {
 				SPP_CUDA(cudaEventRecord(ch.ev_potrf[e], sA));
 				if(row_in_flight) { // tile row b was last updated by the look-ahead of panel b - 1 on sC
@@ -353,9 +376,10 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 			}
 			// panel solve, critical part: the tile right of the diagonal (the rhs block for the last panel)
 			tic();
-			k_gemm_tn<GEMM_TRSM, 128, 32><<<CH_NB / 32, 128, gemm_smem<128, 32>(), sA>>>(A, ld, k0, 0, c0, Rinv_b);
+			k_gemm_tn<GEMM_TRSM, 128, 16, 32, 16, 8><<<CH_NB / 16, 128, gemm_smem<128, 16, 8>(), sA>>>(A, ld, k0, 0, c0, Rinv_b);
 			LAUNCH_CHECK(ctx);
 			toc(1);
+			stamp();
 			if(c0 >= ld)
 				break;
 			if(!prof) {
@@ -377,10 +401,12 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 					bulk_in_flight = false;
 				}
 			}
-			// look-ahead, critical part: the next diagonal tile
+			// look-ahead, critical part: the next diagonal tile (32 x 32 tiles of four 16 x 16 warps: short chains)
 			tic();
-			syrk(sA, k0, c0, c0, CH_NB, CH_NB, 2);
+			k_gemm_tn<GEMM_SYRK, 32, 32, 16, 16, 8><<<dim3(CH_NB / 32, CH_NB / 32), 128, gemm_smem<32, 32, 8>(), sA>>>(A, ld, k0, c0, c0, 0);
+			LAUNCH_CHECK(ctx);
 			toc(3);
+			stamp();
 			// look-ahead, rest of the next panel's tile row (rhs block included)
 			if(!prof)
 				SPP_CUDA(cudaStreamWaitEvent(sC, ch.ev_first[e], 0));
@@ -406,6 +432,27 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 					SPP_CUDA(cudaEventRecord(ch.ev_bulk[e], sB));
 				bulk_in_flight = true;
 			}
+		}
+		if(timeline && !prof && !tl.empty()) {
+			cudaEventSynchronize(tl.back());
+			double t_potrf = 0, t_wait_trsm = 0, t_diag = 0, t_gap = 0;
+			size_t np = 0;
+			for(size_t i = 0; i + 3 < tl.size(); i += 4, ++ np) {
+				float a, b2, c, d = 0;
+				cudaEventElapsedTime(&a, tl[i], tl[i + 1]);
+				cudaEventElapsedTime(&b2, tl[i + 1], tl[i + 2]);
+				cudaEventElapsedTime(&c, tl[i + 2], tl[i + 3]);
+				if(i + 4 < tl.size()) cudaEventElapsedTime(&d, tl[i + 3], tl[i + 4]);
+				t_potrf += a; t_wait_trsm += b2; t_diag += c; t_gap += d;
+				if(np < 3 || np % 10 == 0)
+					fprintf(stderr, "[spp chol timeline] panel %zu: potrf %.1f us, wait+trsm_first %.1f, wait+la_diag %.1f, to next %.1f\n",
+						np, a * 1e3, b2 * 1e3, c * 1e3, d * 1e3);
+			}
+			float total;
+			cudaEventElapsedTime(&total, tl.front(), tl.back());
+			fprintf(stderr, "[spp chol timeline] %zu panels, chain total %.3f ms: potrf %.3f, wait+trsm_first %.3f, wait+la_diag %.3f, gaps %.3f\n",
+				np, total, t_potrf, t_wait_trsm, t_diag, t_gap);
+			for(size_t i = 0; i < tl.size(); ++ i) cudaEventDestroy(tl[i]);
 		}
 		if(!prof) {
 			for(int i = 0; i < 2; ++ i) { // join: whatever is still in flight on the side streams

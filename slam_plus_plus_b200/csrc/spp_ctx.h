@@ -98,8 +98,9 @@ struct DenseChol {
 	cudaStream_t row_stream;  // look-ahead update of the next panel's tile row
 	cudaEvent_t ev_potrf[2], ev_first[2], ev_panel[2], ev_bulk[2], ev_row[2];
 	bool profile;             // SPP_CHOL_PROFILE: serialised per-kernel timing to stderr
+	bool potrf_exclusive;     // the diagonal-block kernel takes a whole SM (default; SPP_CHOL_SHARED_SM turns it off)
 	int force_tile;           // SPP_CHOL_TILE: force the bulk tile shape (0: 128x128, 1: 128x64, 2: 64x64)
-	DenseChol() : bulk_stream(0), row_stream(0), profile(false), force_tile(-1) {}
+	DenseChol() : bulk_stream(0), row_stream(0), profile(false), potrf_exclusive(true), force_tile(-1) {}
 };
 
 } // namespace spp
