@@ -182,6 +182,64 @@ int spp_schur_get_reduced_system(spp_ctx_t ctx, uint64_t *p_n, double *p_S, doub
  * solves; p_rhs_x is the right-hand side on input, the solution on output. Host pointers. */
 int spp_dense_posdef_solve(spp_ctx_t ctx, size_t n, const double *p_A, double *p_rhs_x);
 
+/* ---- block-sparse FP64 Cholesky (pose graphs; sparse reduced camera systems) ------------------------------ */
+
+/* Replaces CLinearSolver_UberBlock::SymbolicDecomposition_Blocky (include/slam/LinearSolver_UberBlock.h:272-296):
+ * takes the block structure of an upper block-triangular matrix whose block columns are all block_size wide (2, 3
+ * or 6; the reference's fbs_ut lists) and prepares the factorisation: ordering, elimination tree, factor pattern.
+ *   p_col_ptr[n + 1], p_row_idx[nnzb]   block CSC, rows ascending, diagonal block present
+ *   p_order_in[n] or NULL   the fill-reducing block ordering to use (new position -> original block column). The
+ *                           reference-side adapter passes the reference's own AMD ordering
+ *                           (CMatrixOrdering::p_BlockOrdering, src/slam/OrderingMagic.cpp:701-1033) so that the
+ *                           elimination order is the reference's, bit for bit; with NULL a minimum-degree ordering is
+ *                           computed by the library.
+ *   p_order_out[n] or NULL  receives the ordering in use. */
+int spp_chol_symbolic(spp_ctx_t ctx, size_t n_block_cols, size_t block_size, const uint64_t *p_col_ptr,
+	const uint64_t *p_row_idx, const uint64_t *p_order_in, uint64_t *p_order_out);
+
+/* Replaces CLinearSolver_UberBlock::Solve_PosDef_Blocky (LinearSolver_UberBlock.h:312-426): permutation, block
+ * Cholesky (CUberBlockMatrix::CholeskyOf_FBS, include/slam/BlockMatrixFBS.inl:2341-2513) and the two triangular
+ * solves (:2136-2275). p_values: the blocks in the order of the structure (column-major blocks; of the diagonal
+ * blocks the full symmetric block is read); p_eta_dx: right-hand side in, solution out.
+ * Returns SPP_NOT_POSDEF where the reference returns false. */
+int spp_chol_solve(spp_ctx_t ctx, const double *p_values, double *p_eta_dx);
+
+/* The factor of the last spp_chol_solve / spp_pose_* solve in the reference's form, the upper factor R with
+ * R^T R = P lambda P^T (block CSC in the permuted order, rows ascending, diagonal last; column-major blocks), for the
+ * parity tests: with the reference's ordering the block pattern of R must be the reference's, bit for bit.
+ * Call with NULL arrays to obtain the block count. */
+int spp_chol_get_factor(spp_ctx_t ctx, uint64_t *p_n_blocks, uint64_t *p_col_ptr, uint64_t *p_row_idx, double *p_values);
+
+/* ---- pose graphs resident on the device (SE(2); Gauss-Newton) ----------------------------------------------- */
+
+/* Replaces r_Get_Vertex<CVertexPose2D> / r_Add_Edge(CEdgePose2D(...)) called in a loop (src/slam_simple_example/
+ * Main.cpp; include/slam/SE2_Types.h:178-260) plus the structure build of CLambdaOps2::Extend_Lambda
+ * (include/slam/NonlinearSolver_Lambda_Base.h:1634, 1853-1931).
+ *   dim            3 = SE(2) poses [x, y, theta]
+ *   p_states[dim * n_poses], p_from / p_to[n_edges] vertex ids (any order; duplicates allowed)
+ *   p_z[dim * n_edges] relative pose measurements, p_info[dim * dim * n_edges] information matrices (symmetric)
+ * Vertex 0 receives the reference's automatic unary factor (identity). */
+int spp_pose_set_graph(spp_ctx_t ctx, int dim, size_t n_poses, const double *p_states, size_t n_edges,
+	const uint64_t *p_from, const uint64_t *p_to, const double *p_z, const double *p_info);
+/* optional: the block ordering for the factorisation (see spp_chol_symbolic); NULL = computed by the library */
+int spp_pose_set_ordering(spp_ctx_t ctx, const uint64_t *p_order);
+int spp_pose_set_states(spp_ctx_t ctx, const double *p_states);
+int spp_pose_get_states(spp_ctx_t ctx, double *p_states);
+int spp_pose_restore_initial(spp_ctx_t ctx);
+/* CLambdaOps2::Refresh_Lambda + Collect_RightHandSide_Vector for CEdgePose2D (SE2_Types.h:308-319; analytic
+ * Jacobians include/slam/2DSolverBase.h:373-430; BaseTypes_Binary.h:759-848) */
+int spp_pose_linearise(spp_ctx_t ctx);
+/* lambda / eta of the last linearisation in the reference's layout (upper block CSC in vertex order, rows ascending,
+ * diagonal last, column-major blocks). Call with NULL arrays for the sizes. */
+int spp_pose_get_lambda(spp_ctx_t ctx, uint64_t *p_n_block_cols, uint64_t *p_n_blocks, uint64_t *p_col_ptr,
+	uint64_t *p_row_idx, double *p_values, double *p_eta);
+/* f_Chi_Squared_Error_Denorm (NonlinearSolver_Base.h:278-297 -> CEdgePose2D::f_Chi_Squared_Error, SE2_Types.h:325-335) */
+int spp_pose_chi2(spp_ctx_t ctx, double *p_chi2);
+/* one Gauss-Newton increment on the current linearisation: lambda dx = eta; does not move the vertices */
+int spp_pose_solve_step(spp_ctx_t ctx, double *p_dx);
+/* Replaces CNonlinearSolver_Lambda::Optimize(max_iter, min_dx_norm) (include/slam/NonlinearSolver_Lambda.h:476-667) */
+int spp_pose_optimize(spp_ctx_t ctx, size_t n_max_iterations, double f_min_dx_norm, spp_report_t *p_report);
+
 #ifdef __cplusplus
 }
 #endif

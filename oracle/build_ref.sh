@@ -34,7 +34,7 @@ if [ ! -d "$REF/include/slam" ]; then
 fi
 mkdir -p "$OBJ"
 DRIVERS=("$@")
-[ ${#DRIVERS[@]} -eq 0 ] && DRIVERS=(ba dropin)
+[ ${#DRIVERS[@]} -eq 0 ] && DRIVERS=(ba dropin pose)
 
 compile_one() { # src obj compiler extra
 	local src="$1" obj="$2" comp="$3"; shift 3

@@ -130,3 +130,41 @@ def lambda_blocks_to_reference_layout(g, U, V, W):
         vals.append(d.ravel())  # symmetric: row/column-major agree
         col_ptr.append(len(row_idx))
     return col_dims, np.array(col_ptr, np.uint64), np.array(row_idx, np.uint64), np.concatenate(vals)
+
+
+# ---- SE(2) pose graphs ------------------------------------------------------------------------------------------
+
+def _pose_args(g, poses=None):
+    st = np.ascontiguousarray(g.poses if poses is None else poses, np.float64).copy()
+    ef = np.ascontiguousarray(g.e_from, np.uint64)
+    et = np.ascontiguousarray(g.e_to, np.uint64)
+    z = np.ascontiguousarray(g.z, np.float64)
+    info = np.ascontiguousarray(g.info, np.float64)
+    keep = (st, ef, et, z, info)
+    args = [C.c_size_t(st.shape[0]), _p(st, C.c_double), C.c_size_t(ef.shape[0]), _p(ef, C.c_uint64), _p(et, C.c_uint64),
+            _p(z, C.c_double), _p(info, C.c_double)]
+    return args, keep
+
+
+def se2_chi2(g, poses=None) -> float:
+    args, keep = _pose_args(g, poses)
+    v = C.c_double()
+    assert lib().spo_se2_chi2(*args, C.byref(v)) == 0
+    return v.value
+
+
+def se2_linearise_dense(g, poses=None):
+    """Dense lambda (n x n, symmetric) and eta of the SE(2) graph at the given poses."""
+    args, keep = _pose_args(g, poses)
+    n = keep[0].shape[0] * 3
+    lam, eta = np.zeros((n, n)), np.zeros(n)
+    assert lib().spo_se2_linearise_dense(*args, _p(lam, C.c_double), _p(eta, C.c_double)) == 0
+    return lam, eta  # symmetric: row/column-major agree
+
+
+def se2_optimize(g, max_iter=5, min_dx=0.0):
+    args, keep = _pose_args(g)
+    out, norms = np.zeros(3), np.zeros(max(max_iter, 1))
+    rc = lib().spo_se2_optimize(*args, C.c_size_t(max_iter), C.c_double(min_dx), _p(out, C.c_double), _p(norms, C.c_double))
+    return dict(status=rc, chi2_initial=out[0], chi2_final=out[1], n_solves=int(out[2]), dx_norms=norms[:int(out[2])],
+                poses=keep[0])

@@ -16,10 +16,15 @@
  * Where the reference calls Eigen (quaternion product, _transformVector, toRotationMatrix, 3x3 inverse,
  * LLT<Upper>) the published Eigen algorithm is written out.
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
 
 #define SPO_API __attribute__((visibility("default")))
 
@@ -565,4 +570,148 @@ SPO_API int spo_ba_optimize(size_t nv, const uint8_t *vtype, const double *cams1
 	free(U); free(V); free(W); free(gc); free(gp); free(dxc); free(dxp); free(cam_saved); free(pt_saved); free(oc); free(op);
 	ba_free(&g);
 	return 0;
+}
+
+/* ---- SE(2) pose graphs --------------------------------------------------------------
+ *   2D  = include/slam/2DSolverBase.h      SE2 = include/slam/SE2_Types.h     GN = include/slam/NonlinearSolver_Lambda.h
+ *   UB  = include/slam/LinearSolver_UberBlock.h */
+
+/* C2DJacobians::f_ClampAngle_2Pi / f_ClampAngularError_2Pi, 2D:44-95 */
+static double clamp_angle_2pi(double a)
+{
+	return isfinite(a)? fmod(a, M_PI * 2) : 0.0;
+}
+
+static double clamp_angular_error_2pi(double e)
+{
+	e = clamp_angle_2pi(e);
+	double a = e, b = e - 2 * M_PI, c = e + 2 * M_PI;
+	double m = (fabs(a) < fabs(b))? a : b;
+	return (fabs(m) < fabs(c))? m : c;
+}
+
+/* C2DJacobians::Absolute_to_Relative with Jacobians, 2D:373-430 (row-major 3x3) */
+static void se2_absolute_to_relative(const double *v1, const double *v2, double *d, double *J1, double *J2)
+{
+	double p1e = v1[0], p1n = v1[1], p1a = v1[2], p2e = v2[0], p2n = v2[1], p2a = v2[2];
+	double de = p2e - p1e, dn = p2n - p1n, da = p2a - p1a;
+	double o = -p1a, co = cos(o), so = sin(o);
+	d[0] = co * de - so * dn;
+	d[1] = so * de + co * dn;
+	d[2] = clamp_angle_2pi(da);
+	if(J1) {
+		double cp1a = cos(p1a), sp1a = sin(p1a);
+		J1[0] = -cp1a; J1[1] = -sp1a; J1[2] = sp1a * (p1e - p2e) - cp1a * (p1n - p2n);
+		J1[3] = sp1a; J1[4] = -cp1a; J1[5] = cp1a * (p1e - p2e) + sp1a * (p1n - p2n);
+		J1[6] = 0; J1[7] = 0; J1[8] = -1;
+		J2[0] = cp1a; J2[1] = sp1a; J2[2] = 0;
+		J2[3] = -sp1a; J2[4] = cp1a; J2[5] = 0;
+		J2[6] = 0; J2[7] = 0; J2[8] = 1;
+	}
+}
+
+/* CEdgePose2D::Calculate_Jacobians_Expectation_Error, SE2:308-319 */
+static void se2_edge(const double *states, uint64_t a, uint64_t b, const double *z, double *J0, double *J1, double *r)
+{
+	double d[3];
+	se2_absolute_to_relative(states + a * 3, states + b * 3, d, J0, J1);
+	r[0] = z[0] - d[0];
+	r[1] = z[1] - d[1];
+	r[2] = clamp_angular_error_2pi(z[2] - d[2]);
+}
+
+/* f_Chi_Squared_Error_Denorm: serial sum over the edges, SE2:325-335 */
+SPO_API int spo_se2_chi2(size_t N, const double *states, size_t E, const uint64_t *from, const uint64_t *to, const double *z,
+	const double *info, double *chi2)
+{
+	(void)N;
+	double s = 0;
+	for(size_t e = 0; e < E; ++ e) {
+		double r[3];
+		se2_edge(states, from[e], to[e], z + e * 3, 0, 0, r);
+		const double *W = info + e * 9;
+		for(int i = 0; i < 3; ++ i)
+			s += r[i] * (W[i * 3] * r[0] + W[i * 3 + 1] * r[1] + W[i * 3 + 2] * r[2]);
+	}
+	*chi2 = s;
+	return 0;
+}
+
+/* Refresh_Lambda for a pose graph into a DENSE n x n lambda (column-major, full symmetric) and eta: per edge the
+ * blocks of Calculate_Hessians_v2 (BIN:759-848: vertex blocks mirrored from the upper triangle, off-diagonal block
+ * J0^T W J1 at (min id, max id), transposed if id0 > id1), summed in edge order, the unary factor I on vertex 0 last
+ * (LB:1903-1923) */
+SPO_API int spo_se2_linearise_dense(size_t N, const double *states, size_t E, const uint64_t *from, const uint64_t *to,
+	const double *z, const double *info, double *lambda, double *eta)
+{
+	const size_t n = N * 3;
+	memset(lambda, 0, n * n * sizeof(double));
+	memset(eta, 0, n * sizeof(double));
+	for(size_t e = 0; e < E; ++ e) {
+		double J0[9], J1[9], r[3], T[9], WJ1[9], Wr[3];
+		se2_edge(states, from[e], to[e], z + e * 3, J0, J1, r);
+		const double *W = info + e * 9;
+		for(int i = 0; i < 3; ++ i)
+			for(int j = 0; j < 3; ++ j)
+				T[i * 3 + j] = J0[0 * 3 + i] * W[0 * 3 + j] + J0[1 * 3 + i] * W[1 * 3 + j] + J0[2 * 3 + i] * W[2 * 3 + j];
+		for(int i = 0; i < 3; ++ i) {
+			for(int j = 0; j < 3; ++ j)
+				WJ1[i * 3 + j] = W[i * 3 + 0] * J1[0 * 3 + j] + W[i * 3 + 1] * J1[1 * 3 + j] + W[i * 3 + 2] * J1[2 * 3 + j];
+			Wr[i] = W[i * 3 + 0] * r[0] + W[i * 3 + 1] * r[1] + W[i * 3 + 2] * r[2];
+		}
+		const size_t a = from[e] * 3, b = to[e] * 3;
+		for(int c = 0; c < 3; ++ c) {
+			for(int rr = 0; rr < 3; ++ rr) {
+				int p = (rr <= c)? rr : c, q = (rr <= c)? c : rr;
+				double h00 = T[p * 3 + 0] * J0[0 * 3 + q] + T[p * 3 + 1] * J0[1 * 3 + q] + T[p * 3 + 2] * J0[2 * 3 + q];
+				double h11 = J1[0 * 3 + p] * WJ1[0 * 3 + q] + J1[1 * 3 + p] * WJ1[1 * 3 + q] + J1[2 * 3 + p] * WJ1[2 * 3 + q];
+				double h01 = T[rr * 3 + 0] * J1[0 * 3 + c] + T[rr * 3 + 1] * J1[1 * 3 + c] + T[rr * 3 + 2] * J1[2 * 3 + c];
+				lambda[(a + c) * n + a + rr] += h00;
+				lambda[(b + c) * n + b + rr] += h11;
+				lambda[(b + c) * n + a + rr] += h01; /* block (v0, v1) */
+				lambda[(a + rr) * n + b + c] += h01; /* and its mirror */
+			}
+		}
+		for(int i = 0; i < 3; ++ i) {
+			eta[a + i] += T[i * 3 + 0] * r[0] + T[i * 3 + 1] * r[1] + T[i * 3 + 2] * r[2];
+			eta[b + i] += J1[0 * 3 + i] * Wr[0] + J1[1 * 3 + i] * Wr[1] + J1[2 * 3 + i] * Wr[2];
+		}
+	}
+	if(N)
+		for(int i = 0; i < 3; ++ i)
+			lambda[i * n + i] += 1.0;
+	return 0;
+}
+
+/* CNonlinearSolver_Lambda::Optimize (GN:476-667) with a dense LLT standing in for the block-sparse one (the
+ * Cholesky factor is unique: CLinearSolver_UberBlock, UB:312-426, yields the same increment up to rounding).
+ * out[0] = chi2 before, out[1] = chi2 after, out[2] = number of solves; dx_norms[k] per solve. */
+SPO_API int spo_se2_optimize(size_t N, double *states, size_t E, const uint64_t *from, const uint64_t *to, const double *z,
+	const double *info, size_t max_iter, double min_dx, double *out, double *dx_norms)
+{
+	const size_t n = N * 3;
+	double *lambda = (double*)malloc(n * n * sizeof(double)), *eta = (double*)malloc(n * sizeof(double));
+	if(!lambda || !eta) return -1;
+	spo_se2_chi2(N, states, E, from, to, z, info, &out[0]);
+	size_t n_solves = 0;
+	int rc = 0;
+	for(size_t it = 0; it < max_iter; ++ it) {
+		spo_se2_linearise_dense(N, states, E, from, to, z, info, lambda, eta);
+		if(dense_llt_upper(n, lambda)) { rc = 1; ++ n_solves; break; }
+		dense_llt_solve(n, lambda, eta);
+		double s = 0;
+		for(size_t i = 0; i < n; ++ i) s += eta[i] * eta[i];
+		dx_norms[n_solves ++] = sqrt(s);
+		if(sqrt(s) <= min_dx)
+			break;
+		for(size_t v = 0; v < N; ++ v) { /* CVertexPose2D::Operator_Plus, SE2:70-74 */
+			states[v * 3] += eta[v * 3];
+			states[v * 3 + 1] += eta[v * 3 + 1];
+			states[v * 3 + 2] = clamp_angle_2pi(states[v * 3 + 2] + eta[v * 3 + 2]);
+		}
+	}
+	spo_se2_chi2(N, states, E, from, to, z, info, &out[1]);
+	out[2] = (double)n_solves;
+	free(lambda); free(eta);
+	return rc;
 }

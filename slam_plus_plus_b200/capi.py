@@ -26,6 +26,9 @@ EXPORTED_SYMBOLS = [
     "spp_ba_restore_initial", "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_get_blocks", "spp_ba_chi2", "spp_ba_solve_step",
     "spp_ba_optimize", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_get_reduced_system",
     "spp_dense_posdef_solve",
+    "spp_chol_symbolic", "spp_chol_solve", "spp_chol_get_factor",
+    "spp_pose_set_graph", "spp_pose_set_ordering", "spp_pose_set_states", "spp_pose_get_states", "spp_pose_restore_initial",
+    "spp_pose_linearise", "spp_pose_get_lambda", "spp_pose_chi2", "spp_pose_solve_step", "spp_pose_optimize",
 ]
 
 
@@ -96,6 +99,19 @@ def load_library() -> C.CDLL:
     lib.spp_schur_solve.argtypes = [vp, dp, dp]
     lib.spp_schur_get_reduced_system.argtypes = [vp, u64p, dp, dp, u8p]
     lib.spp_dense_posdef_solve.argtypes = [vp, C.c_size_t, dp, dp]
+    lib.spp_chol_symbolic.argtypes = [vp, C.c_size_t, C.c_size_t, u64p, u64p, u64p, u64p]
+    lib.spp_chol_solve.argtypes = [vp, dp, dp]
+    lib.spp_chol_get_factor.argtypes = [vp, u64p, u64p, u64p, dp]
+    lib.spp_pose_set_graph.argtypes = [vp, C.c_int, C.c_size_t, dp, C.c_size_t, u64p, u64p, dp, dp]
+    lib.spp_pose_set_ordering.argtypes = [vp, u64p]
+    lib.spp_pose_set_states.argtypes = [vp, dp]
+    lib.spp_pose_get_states.argtypes = [vp, dp]
+    lib.spp_pose_restore_initial.argtypes = [vp]
+    lib.spp_pose_linearise.argtypes = [vp]
+    lib.spp_pose_get_lambda.argtypes = [vp, u64p, u64p, u64p, u64p, dp, dp]
+    lib.spp_pose_chi2.argtypes = [vp, dp]
+    lib.spp_pose_solve_step.argtypes = [vp, dp]
+    lib.spp_pose_optimize.argtypes = [vp, C.c_size_t, C.c_double, C.POINTER(Report)]
     _lib = lib
     return lib
 
@@ -309,3 +325,86 @@ class Context:
         x = np.array(b, np.float64, copy=True)
         self._check(self.lib.spp_dense_posdef_solve(self.h, A.shape[0], A.ctypes.data_as(C.POINTER(C.c_double)), _dp(x)))
         return x
+
+    # ---- block-sparse Cholesky (slot: CLinearSolver_UberBlock) -------------------------------------
+    def chol_symbolic(self, block_size: int, col_ptr, row_idx, order=None) -> np.ndarray:
+        """Returns the block ordering in use (new position -> original block column)."""
+        cp = np.ascontiguousarray(col_ptr, np.uint64)
+        ri = np.ascontiguousarray(row_idx, np.uint64)
+        oi = None if order is None else np.ascontiguousarray(order, np.uint64)
+        n = cp.shape[0] - 1
+        out = np.empty(n, np.uint64)
+        self._check(self.lib.spp_chol_symbolic(self.h, n, block_size, _u64p(cp), _u64p(ri), _u64p(oi), _u64p(out)))
+        self._chol_dims = (n, block_size)
+        return out.astype(np.int64)
+
+    def chol_solve(self, values, eta) -> np.ndarray:
+        v = np.ascontiguousarray(values, np.float64)
+        x = np.array(eta, np.float64, copy=True)
+        self._check(self.lib.spp_chol_solve(self.h, _dp(v), _dp(x)))
+        return x
+
+    def chol_get_factor(self, n: int, block_size: int):
+        """The upper factor R (R^T R = P lambda P^T) as block CSC: col_ptr, row_idx, values (column-major blocks)."""
+        nb = C.c_uint64()
+        self._check(self.lib.spp_chol_get_factor(self.h, C.byref(nb), None, None, None))
+        cp = np.empty(n + 1, np.uint64)
+        ri = np.empty(nb.value, np.uint64)
+        vals = np.empty(nb.value * block_size * block_size)
+        self._check(self.lib.spp_chol_get_factor(self.h, None, _u64p(cp), _u64p(ri), _dp(vals)))
+        return cp, ri, vals
+
+    # ---- pose graphs -------------------------------------------------------------------------------
+    def pose_set_graph(self, g, order=None):
+        poses = np.ascontiguousarray(g.poses, np.float64)
+        ef = np.ascontiguousarray(g.e_from, np.uint64)
+        et = np.ascontiguousarray(g.e_to, np.uint64)
+        z = np.ascontiguousarray(g.z, np.float64)
+        info = np.ascontiguousarray(g.info, np.float64)
+        self._pose_dims = (int(poses.shape[0]), int(poses.shape[1]))
+        self._check(self.lib.spp_pose_set_graph(self.h, poses.shape[1], poses.shape[0], _dp(poses), ef.shape[0], _u64p(ef),
+                                                _u64p(et), _dp(z), _dp(info)))
+        if order is not None:
+            self._check(self.lib.spp_pose_set_ordering(self.h, _u64p(np.ascontiguousarray(order, np.uint64))))
+
+    def pose_set_states(self, poses):
+        self._check(self.lib.spp_pose_set_states(self.h, _dp(np.ascontiguousarray(poses, np.float64))))
+
+    def pose_get_states(self) -> np.ndarray:
+        out = np.empty(self._pose_dims)
+        self._check(self.lib.spp_pose_get_states(self.h, _dp(out)))
+        return out
+
+    def pose_restore_initial(self):
+        self._check(self.lib.spp_pose_restore_initial(self.h))
+
+    def pose_linearise(self):
+        self._check(self.lib.spp_pose_linearise(self.h))
+
+    def pose_get_lambda(self):
+        """Returns (col_ptr, row_idx, values, eta) in the reference's block layout."""
+        n, d = self._pose_dims
+        nbc, nb = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.spp_pose_get_lambda(self.h, C.byref(nbc), C.byref(nb), None, None, None, None))
+        cp = np.empty(nbc.value + 1, np.uint64)
+        ri = np.empty(nb.value, np.uint64)
+        vals = np.empty(nb.value * d * d)
+        eta = np.empty(n * d)
+        self._check(self.lib.spp_pose_get_lambda(self.h, None, None, _u64p(cp), _u64p(ri), _dp(vals), _dp(eta)))
+        return cp, ri, vals, eta
+
+    def pose_chi2(self) -> float:
+        v = C.c_double()
+        self._check(self.lib.spp_pose_chi2(self.h, C.byref(v)))
+        return v.value
+
+    def pose_solve_step(self) -> np.ndarray:
+        n, d = self._pose_dims
+        dx = np.empty(n * d)
+        self._check(self.lib.spp_pose_solve_step(self.h, _dp(dx)))
+        return dx
+
+    def pose_optimize(self, max_iterations: int = 5, min_dx_norm: float = 0.01) -> dict:
+        rep = Report()
+        self._check(self.lib.spp_pose_optimize(self.h, max_iterations, min_dx_norm, C.byref(rep)))
+        return rep.as_dict()

@@ -32,6 +32,16 @@ void slot_symbolic(spp_ctx *ctx, size_t n, const uint64_t *col_dims, const uint6
 	uint64_t *p_order, uint64_t *p_cut);
 int slot_solve(spp_ctx *ctx, const double *p_values, double *p_eta_dx);
 
+void sparse_chol_symbolic(spp_ctx *ctx, size_t n, size_t B, const uint64_t *col_ptr, const uint64_t *row_idx,
+	const uint64_t *p_order_in);
+int sparse_chol_solve_device(spp_ctx *ctx, const double *d_A, const double *d_rhs, double *d_x);
+void pose_set_graph(spp_ctx *ctx, int dim, size_t N, const double *p_states, size_t E, const uint64_t *p_from,
+	const uint64_t *p_to, const double *p_z, const double *p_info);
+void pose_linearise(spp_ctx *ctx);
+double pose_chi2(spp_ctx *ctx);
+int pose_solve(spp_ctx *ctx);
+int pose_optimize(spp_ctx *ctx, size_t n_max_iteration_num, double f_min_dx_norm, spp_report_t *rep);
+
 static thread_local std::string g_create_error;
 
 struct comm_error : std::runtime_error {
@@ -779,6 +789,189 @@ int spp_dense_posdef_solve(spp_ctx_t ctx, size_t n, const double *p_A, double *p
 	b.download(p_rhs_x, n, ctx->stream);
 	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
 	if(rc != SPP_OK) return rc;
+	API_END(ctx)
+}
+
+// ---- block-sparse Cholesky slot ---------------------------------------------------------------------
+
+int spp_chol_symbolic(spp_ctx_t ctx, size_t n_block_cols, size_t block_size, const uint64_t *p_col_ptr,
+	const uint64_t *p_row_idx, const uint64_t *p_order_in, uint64_t *p_order_out)
+{
+	API_BEGIN(ctx)
+	if(!n_block_cols || !p_col_ptr || !p_row_idx) throw invalid_error("null argument");
+	if(block_size != 2 && block_size != 3 && block_size != 6) throw invalid_error("block size must be 2, 3 or 6");
+	sparse_chol_symbolic(ctx, n_block_cols, block_size, p_col_ptr, p_row_idx, p_order_in);
+	if(p_order_out)
+		for(size_t i = 0; i < n_block_cols; ++ i) p_order_out[i] = ctx->schol.h_order[i];
+	API_END(ctx)
+}
+
+int spp_chol_solve(spp_ctx_t ctx, const double *p_values, double *p_eta_dx)
+{
+	int rc = SPP_OK;
+	API_BEGIN(ctx)
+	SparseChol &sc = ctx->schol;
+	if(!sc.valid) throw invalid_error("spp_chol_symbolic() has not been called");
+	if(!p_values || !p_eta_dx) throw invalid_error("null argument");
+	const size_t nv = sc.n_a_blocks * sc.B * sc.B, ns = sc.n * sc.B;
+	sc.slot_vals.upload(p_values, nv, ctx->stream);
+	sc.slot_rhs.upload(p_eta_dx, ns, ctx->stream);
+	sc.slot_x.resize(ns);
+	rc = sparse_chol_solve_device(ctx, sc.slot_vals.p(), sc.slot_rhs.p(), sc.slot_x.p());
+	sc.slot_x.download(p_eta_dx, ns, ctx->stream);
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	if(rc != SPP_OK) return rc;
+	API_END(ctx)
+}
+
+int spp_chol_get_factor(spp_ctx_t ctx, uint64_t *p_n_blocks, uint64_t *p_col_ptr, uint64_t *p_row_idx, double *p_values)
+{
+	API_BEGIN(ctx)
+	SparseChol &sc = ctx->schol;
+	if(!sc.valid) throw invalid_error("no block-sparse factorisation");
+	const size_t n = sc.n, BB = sc.B * sc.B, B = sc.B, nb = sc.n_l_blocks;
+	if(p_n_blocks) *p_n_blocks = nb;
+	if(p_col_ptr || p_row_idx || p_values) {
+		// L is stored by columns (rows >= column); R = L^T by columns = L by rows
+		std::vector<uint64_t> cnt(n + 1, 0);
+		for(size_t j = 0; j < n; ++ j)
+			for(uint64_t b = sc.h_lptr[j]; b < sc.h_lptr[j + 1]; ++ b)
+				++ cnt[sc.h_lrow[b] + 1];
+		for(size_t j = 0; j < n; ++ j) cnt[j + 1] += cnt[j];
+		if(p_col_ptr) std::copy(cnt.begin(), cnt.end(), p_col_ptr);
+		std::vector<double> hL;
+		if(p_values) {
+			hL.resize(nb * BB);
+			sc.d_L.download(hL.data(), nb * BB, ctx->stream);
+			SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+		}
+		std::vector<uint64_t> fill(cnt.begin(), cnt.end() - 1);
+		for(size_t j = 0; j < n; ++ j) { // ascending j = ascending row of R inside every column
+			for(uint64_t b = sc.h_lptr[j]; b < sc.h_lptr[j + 1]; ++ b) {
+				const uint64_t dst = fill[sc.h_lrow[b]] ++;
+				if(p_row_idx) p_row_idx[dst] = j;
+				if(p_values)
+					for(size_t c = 0; c < B; ++ c)
+						for(size_t r = 0; r < B; ++ r)
+							p_values[dst * BB + c * B + r] = hL[b * BB + r * B + c]; // R(j, i) = L(i, j)^T
+			}
+		}
+	}
+	API_END(ctx)
+}
+
+// ---- pose graphs ---------------------------------------------------------------------------------------
+
+int spp_pose_set_graph(spp_ctx_t ctx, int dim, size_t n_poses, const double *p_states, size_t n_edges,
+	const uint64_t *p_from, const uint64_t *p_to, const double *p_z, const double *p_info)
+{
+	API_BEGIN(ctx)
+	if((n_poses && !p_states) || (n_edges && (!p_from || !p_to || !p_z || !p_info))) throw invalid_error("null argument");
+	ctx->pose.h_order_in.clear();
+	pose_set_graph(ctx, dim, n_poses, p_states, n_edges, p_from, p_to, p_z, p_info);
+	API_END(ctx)
+}
+
+int spp_pose_set_ordering(spp_ctx_t ctx, const uint64_t *p_order)
+{
+	API_BEGIN(ctx)
+	PoseProblem &pp = ctx->pose;
+	if(!pp.valid) throw invalid_error("no pose graph");
+	if(p_order) pp.h_order_in.assign(p_order, p_order + pp.N);
+	else pp.h_order_in.clear();
+	pp.symbolic_done = false;
+	API_END(ctx)
+}
+
+int spp_pose_set_states(spp_ctx_t ctx, const double *p_states)
+{
+	API_BEGIN(ctx)
+	PoseProblem &pp = ctx->pose;
+	if(!pp.valid || !p_states) throw invalid_error("no pose graph");
+	SPP_CUDA(cudaMemcpyAsync(pp.states.p(), p_states, pp.N * pp.dim * 8, cudaMemcpyHostToDevice, ctx->stream));
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	pp.linearised = false;
+	API_END(ctx)
+}
+
+int spp_pose_get_states(spp_ctx_t ctx, double *p_states)
+{
+	API_BEGIN(ctx)
+	PoseProblem &pp = ctx->pose;
+	if(!pp.valid || !p_states) throw invalid_error("no pose graph");
+	pp.states.download(p_states, pp.N * pp.dim, ctx->stream);
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	API_END(ctx)
+}
+
+int spp_pose_restore_initial(spp_ctx_t ctx)
+{
+	API_BEGIN(ctx)
+	PoseProblem &pp = ctx->pose;
+	if(!pp.valid) throw invalid_error("no pose graph");
+	SPP_CUDA(cudaMemcpyAsync(pp.states.p(), pp.states0.p(), pp.N * pp.dim * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	pp.linearised = false;
+	API_END(ctx)
+}
+
+int spp_pose_linearise(spp_ctx_t ctx)
+{
+	API_BEGIN(ctx)
+	if(!ctx->pose.valid) throw invalid_error("no pose graph");
+	pose_linearise(ctx);
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	API_END(ctx)
+}
+
+int spp_pose_get_lambda(spp_ctx_t ctx, uint64_t *p_n_block_cols, uint64_t *p_n_blocks, uint64_t *p_col_ptr,
+	uint64_t *p_row_idx, double *p_values, double *p_eta)
+{
+	API_BEGIN(ctx)
+	PoseProblem &pp = ctx->pose;
+	if(!pp.valid) throw invalid_error("no pose graph");
+	if(p_n_block_cols) *p_n_block_cols = pp.N;
+	if(p_n_blocks) *p_n_blocks = pp.n_blocks;
+	if(p_col_ptr) std::copy(pp.h_col_ptr.begin(), pp.h_col_ptr.end(), p_col_ptr);
+	if(p_row_idx) std::copy(pp.h_row_idx.begin(), pp.h_row_idx.end(), p_row_idx);
+	if(p_values || p_eta) {
+		if(!pp.linearised) throw invalid_error("spp_pose_linearise() has not been called");
+		if(p_values) pp.vals.download(p_values, pp.n_blocks * pp.dim * pp.dim, ctx->stream);
+		if(p_eta) pp.eta.download(p_eta, pp.N * pp.dim, ctx->stream);
+		SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	API_END(ctx)
+}
+
+int spp_pose_chi2(spp_ctx_t ctx, double *p_chi2)
+{
+	API_BEGIN(ctx)
+	if(!ctx->pose.valid || !p_chi2) throw invalid_error("no pose graph");
+	*p_chi2 = pose_chi2(ctx);
+	API_END(ctx)
+}
+
+int spp_pose_solve_step(spp_ctx_t ctx, double *p_dx)
+{
+	int rc = SPP_OK;
+	API_BEGIN(ctx)
+	PoseProblem &pp = ctx->pose;
+	if(!pp.valid) throw invalid_error("no pose graph");
+	if(!pp.linearised) pose_linearise(ctx);
+	rc = pose_solve(ctx);
+	if(rc == SPP_OK && p_dx) {
+		pp.dx.download(p_dx, pp.N * pp.dim, ctx->stream);
+		SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	if(rc != SPP_OK) return rc;
+	API_END(ctx)
+}
+
+int spp_pose_optimize(spp_ctx_t ctx, size_t n_max_iterations, double f_min_dx_norm, spp_report_t *p_report)
+{
+	API_BEGIN(ctx)
+	if(!ctx->pose.valid) throw invalid_error("no pose graph");
+	spp_report_t local;
+	pose_optimize(ctx, n_max_iterations, f_min_dx_norm, p_report? p_report : &local);
 	API_END(ctx)
 }
 

@@ -90,6 +90,37 @@ struct SymbolicScratch {
 	DBuf<double> z_in, info_in;         // staging of the caller's measurements (edge insertion order)
 };
 
+// block-sparse Cholesky (sparse_chol.cu): symbolic structures and the factor
+struct SparseChol {
+	bool valid;
+	size_t n, B, n_a_blocks, n_l_blocks;
+	uint32_t n_levels, tail_level;
+	int max_coop_ctas;
+	std::vector<uint32_t> h_order;   // new position -> caller's block column
+	std::vector<uint64_t> h_lptr;    // column pointers of L
+	std::vector<uint32_t> h_lrow, h_parent;
+	DBuf<uint32_t> d_order, d_lrow, d_lcolof, d_rblk, d_ua, d_ub, d_lvl_ptr, d_lvl_cols, d_lvl_off_blk;
+	DBuf<uint64_t> d_lptr, d_rptr, d_uptr, d_lvl_off_ptr;
+	DBuf<int64_t> d_src;
+	DBuf<double> d_L, d_Linv, d_y;
+	DBuf<int> d_info;
+	DBuf<double> slot_vals, slot_rhs, slot_x; // staging of the caller's arrays (slot use)
+	SparseChol() : valid(false), n(0), B(0), n_a_blocks(0), n_l_blocks(0), n_levels(0), tail_level(0), max_coop_ctas(0) {}
+};
+
+// pose graph resident on the device (pose_kernels.cu)
+struct PoseProblem {
+	bool valid, symbolic_done, linearised;
+	int dim;
+	size_t N, E, n_blocks;
+	long uf_block;                          // diagonal block of vertex 0 (unary factor)
+	std::vector<uint64_t> h_col_ptr, h_row_idx, h_order_in; // structure of lambda (upper block CSC), optional ordering
+	DBuf<double> states, states0, z, info, rec, vals, eta, dx, scratch;
+	DBuf<uint32_t> e_from, e_to;
+	DBuf<uint64_t> blk_src_ptr, blk_src, vec_src_ptr, vec_src;
+	PoseProblem() : valid(false), symbolic_done(false), linearised(false), dim(0), N(0), E(0), n_blocks(0), uf_block(-1) {}
+};
+
 struct DenseChol {
 	DBuf<double> work;        // inverse diagonal blocks, [n_blk][128 x 128]
 	DBuf<long long> dbg;      // clock64 marks of k_potrf128 (profile mode)
@@ -119,6 +150,8 @@ struct spp_ctx {
 	spp::SchurSlot slot;
 	spp::DenseChol chol;
 	spp::SymbolicScratch sym;
+	spp::SparseChol schol;
+	spp::PoseProblem pose;
 	spp::HPinned<double> h_scalars;
 	cudaEvent_t ev[16];
 };

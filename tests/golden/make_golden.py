@@ -54,7 +54,42 @@ def run_ba(name, spec):
           f"accepted={d['lm_trace'].reshape(-1, 6)[:, 4].astype(int).tolist()}")
 
 
+REF_POSE = os.path.join(ROOT, "oracle", "_ref", "ref_driver_pose")
+
+POSE_CASES = {
+    # name: (generator, kwargs, max_iter)
+    "se2_tiny": ("make_manhattan", dict(n_poses=120, n_loops=40, seed=1), 5),
+    "se2_small": ("make_manhattan", dict(n_poses=600, n_loops=400, seed=11), 5),
+}
+
+
+def run_pose(name, spec):
+    gen, kw, max_iter = spec
+    g = getattr(graphs, gen)(**kw)
+    with tempfile.TemporaryDirectory() as td:
+        gp = os.path.join(td, "g.bin")
+        dp = os.path.join(td, "d.dump")
+        sppio.write_graph(gp, g)
+        subprocess.run([REF_POSE, "dump", gp, dp, str(max_iter), "0"], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1"))
+        d = sppio.read_dump(dp)
+    out = dict(g_kind=np.array([g.kind]), g_poses=g.poses, g_from=g.e_from, g_to=g.e_to, g_z=g.z, g_info=g.info,
+               max_iter=np.array([max_iter]))
+    for k, v in d.items():
+        if k[0] == "L" and k[1].isdigit() and int(k[1:].split(".")[0]) != 0 and not k.endswith(".dx"):
+            continue  # full lambda only for the first solve
+        out[k] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: N={g.poses.shape[0]} E={g.e_from.shape[0]} solves={int(d['n_solves'][0])} "
+          f"chi2 {d['chi2_0'][0]:.6g} -> {d['chi2'][0]:.6g} R blocks {d['R.row_idx'].shape[0]}")
+
+
 if __name__ == "__main__":
+    if os.path.exists(REF_POSE) and (len(sys.argv) < 2 or sys.argv[1] == "pose"):
+        for name, spec in POSE_CASES.items():
+            run_pose(name, spec)
+        if len(sys.argv) > 1:
+            sys.exit(0)
     if not os.path.exists(REF_BA):
         sys.exit("oracle/_ref/ref_driver_ba missing: run oracle/build_ref.sh (needs /root/reference)")
     for name, spec in BA_CASES.items():

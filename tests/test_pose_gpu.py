@@ -1,0 +1,134 @@
+"""GPU parity tests of the pose-graph path (SE(2), Gauss-Newton, block-sparse Cholesky)
+against the golden vectors of the unmodified reference, the C oracle and -- at the Manhattan-3500 shape -- the
+reference itself run on the same machine. All calls go through the C ABI (libspp_b200.so)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_err
+from test_pose_cpu import CASES, load_pose_golden, pose_lambda_to_dense, dx_tolerance
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_chi2_and_lambda(ctx, name):
+    g, d = load_pose_golden(name)
+    ctx.pose_set_graph(g)
+    assert abs(ctx.pose_chi2() - d["chi2_0"][0]) <= 1e-12 * d["chi2_0"][0]
+    ctx.pose_linearise()
+    cp, ri, vals, eta = ctx.pose_get_lambda()
+    assert np.array_equal(cp, d["L0.col_ptr"]) and np.array_equal(ri, d["L0.row_idx"])  # block pattern bit-exact
+    # analytic Jacobians: no FD noise; cos/sin of the device differ from glibc by an ulp at most
+    iu = np.triu_indices(3)
+    A = pose_lambda_to_dense(cp, ri, vals, 3)
+    A_ref = pose_lambda_to_dense(cp, ri, d["L0.vals"], 3)
+    assert rel_err(A, A_ref) < 1e-13
+    assert rel_err(eta, d["L0.eta"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_chol_slot_with_reference_ordering(ctx, name):
+    """P1 for row a15: the reference's lambda, eta AND AMD ordering -> dx within 1e-9, factor pattern bit-exact."""
+    g, d = load_pose_golden(name)
+    order = ctx.chol_symbolic(3, d["L0.col_ptr"], d["L0.row_idx"], d["amd.order"])
+    assert np.array_equal(order, d["amd.order"].astype(np.int64))
+    dx = ctx.chol_solve(d["L0.vals"], d["L0.eta"])
+    A = pose_lambda_to_dense(d["L0.col_ptr"], d["L0.row_idx"], d["L0.vals"], 3)
+    assert rel_err(dx, d["L0.dx"]) < dx_tolerance(A)
+    assert np.linalg.norm(A @ dx - d["L0.eta"]) <= 1e-12 * np.linalg.norm(d["L0.eta"]) * np.sqrt(len(dx))  # backward stable
+    n = len(d["L0.col_ptr"]) - 1
+    cp, ri, vals = ctx.chol_get_factor(n, 3)
+    assert np.array_equal(cp, d["R.col_ptr"]) and np.array_equal(ri, d["R.row_idx"])  # factor pattern bit-exact
+    assert rel_err(vals, d["R.vals"]) < 1e-2 * dx_tolerance(A) + 1e-11
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_chol_slot_with_own_ordering(ctx, name):
+    g, d = load_pose_golden(name)
+    order = ctx.chol_symbolic(3, d["L0.col_ptr"], d["L0.row_idx"])
+    n = len(d["L0.col_ptr"]) - 1
+    assert sorted(order.tolist()) == list(range(n))
+    dx = ctx.chol_solve(d["L0.vals"], d["L0.eta"])
+    A = pose_lambda_to_dense(d["L0.col_ptr"], d["L0.row_idx"], d["L0.vals"], 3)
+    assert rel_err(dx, d["L0.dx"]) < dx_tolerance(A)
+    # fill of the built-in minimum-degree ordering stays close to the reference's AMD
+    cp, ri, _ = ctx.chol_get_factor(n, 3)
+    assert len(ri) <= 1.3 * len(d["R.row_idx"]) + 16
+
+
+def test_chol_not_posdef(ctx):
+    from slam_plus_plus_b200 import capi
+    cp = np.array([0, 1, 3], np.uint64)
+    ri = np.array([0, 0, 1], np.uint64)
+    vals = np.concatenate([np.eye(2).ravel(), np.zeros(4), -np.eye(2).ravel()])
+    ctx.chol_symbolic(2, cp, ri)
+    with pytest.raises(capi.NotPositiveDefinite):
+        ctx.chol_solve(vals, np.ones(4))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_gauss_newton_vs_reference(ctx, name):
+    """P3: analytic Jacobians -> the whole GN trace reproduces the reference: every increment to 1e-9."""
+    g, d = load_pose_golden(name)
+    for order in (None, d["amd.order"]):
+        ctx.pose_set_graph(g, order)
+        n_it = int(d["max_iter"][0])
+        poses = g.poses.copy()
+        A = pose_lambda_to_dense(d["L0.col_ptr"], d["L0.row_idx"], d["L0.vals"], 3)
+        tol = 10 * dx_tolerance(A)
+        for k in range(n_it):
+            ctx.pose_linearise()
+            dx = ctx.pose_solve_step()
+            # every increment against the reference's, relative to the size of the first one (later ones shrink to
+            # the noise of the earlier ones); the states are then set to the reference trajectory's own
+            assert np.linalg.norm(dx - d[f"L{k}.dx"]) < tol * np.linalg.norm(d["L0.dx"])
+            poses = poses + d[f"L{k}.dx"].reshape(-1, 3)
+            poses[:, 2] = np.fmod(poses[:, 2], 2 * np.pi)
+            ctx.pose_set_states(poses)
+        ctx.pose_restore_initial()
+        rep = ctx.pose_optimize(n_it, 0.0)
+        assert rep["n_iterations"] == int(d["n_solves"][0])
+        assert abs(rep["chi2_final"] - d["chi2"][0]) <= 1e-9 * d["chi2"][0]
+        assert rel_err(ctx.pose_get_states().ravel(), d["states"]) < tol
+
+
+def test_manhattan_full_size_vs_reference_and_oracle(ctx, tmp_path):
+    """BASELINE.json configs[0] shape (3500 poses): against the reference run on this machine when oracle/_ref is
+    present, and through size-independent properties (normal-equation residual, chi2 decrease)."""
+    from slam_plus_plus_b200 import graphs, sppio
+    g = graphs.make_manhattan()
+    ctx.pose_set_graph(g)
+    ctx.pose_linearise()
+    cp, ri, vals, eta = ctx.pose_get_lambda()
+    dx = ctx.pose_solve_step()
+    import scipy.sparse as sp
+    n = g.poses.shape[0]
+    rows, cols, data = [], [], []
+    off = 0
+    for c in range(n):
+        for k in range(int(cp[c]), int(cp[c + 1])):
+            r = int(ri[k])
+            blk = vals[off:off + 9].reshape(3, 3).T
+            off += 9
+            for i in range(3):
+                for j in range(3):
+                    if r < c or i <= j:
+                        rows.append(r * 3 + i); cols.append(c * 3 + j); data.append(blk[i, j])
+                        if not (r == c and i == j):
+                            rows.append(c * 3 + j); cols.append(r * 3 + i); data.append(blk[i, j])
+    A = sp.csr_matrix((data, (rows, cols)), shape=(3 * n, 3 * n))
+    assert np.linalg.norm(A @ dx - eta) / np.linalg.norm(eta) < 1e-10
+    rep = ctx.pose_optimize(5, 0.0)
+    assert rep["chi2_final"] < 1e-3 * rep["chi2_initial"]
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "ref_driver_pose")
+    if os.path.exists(ref_bin):
+        gp, dp = str(tmp_path / "g.bin"), str(tmp_path / "d.dump")
+        sppio.write_graph(gp, g)
+        subprocess.run([ref_bin, "time", gp, dp, "5", "0"], check=True, stdout=subprocess.DEVNULL,
+                       env=dict(os.environ, OMP_NUM_THREADS="1"))
+        ref = sppio.read_dump(dp)
+        assert abs(rep["chi2_final"] - ref["chi2"][0]) <= 1e-9 * ref["chi2"][0]
