@@ -26,13 +26,19 @@
 #include <algorithm>
 #include <numeric>
 #include <set>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
 namespace spp {
 
+size_t dense_chol_ld(size_t n);
+size_t dense_chol_storage(size_t n);
+int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x);
+
 #define LAUNCH_CHECK(ctx) do { ++ (ctx)->n_launches; SPP_CUDA(cudaGetLastError()); } while(0)
 #define SC_WARPS 8
+#define SC_ROOT_MAX_SCALARS 6144 // the dense root front is at most this wide
 
 // ---- host: ordering ------------------------------------------------------------------------------------
 
@@ -218,20 +224,41 @@ void sparse_chol_symbolic(spp_ctx *ctx, size_t n, size_t B, const uint64_t *col_
 			uptr[b + 1] = ua.size();
 		}
 	}
-	// levels of the elimination tree
+	// The top of the elimination tree is a long chain of wide columns (the top-level separators): level by level it
+	// costs a barrier per column. Columns t0 .. n-1 (everything from the first column of a narrow level on) are
+	// instead assembled into ONE dense front and factored by the dense DMMA Cholesky (dense_chol.cu).
 	std::vector<uint32_t> level(n, 0);
-	uint32_t n_levels = 0;
+	uint32_t n_levels_all = 0;
 	for(size_t j = 0; j < n; ++ j) {
 		if(parent[j] != 0xffffffffu)
 			level[parent[j]] = std::max(level[parent[j]], level[j] + 1);
-		n_levels = std::max(n_levels, level[j] + 1);
+		n_levels_all = std::max(n_levels_all, level[j] + 1);
 	}
-	std::vector<uint32_t> lvl_ptr(n_levels + 1, 0), lvl_cols(n);
-	for(size_t j = 0; j < n; ++ j) ++ lvl_ptr[level[j] + 1];
+	// root set: the columns of the narrow top levels (upward closed in the tree: the row structure of a root column
+	// lies in the root set); ridx = dense index of a root column
+	std::vector<uint32_t> ridx(n, 0xffffffffu);
+	size_t m = 0;
+	uint32_t narrow = n_levels_all; // first level of the narrow tail
+	{
+		std::vector<uint32_t> width(n_levels_all, 0);
+		for(size_t j = 0; j < n; ++ j) ++ width[level[j]];
+		while(narrow > 0 && width[narrow - 1] <= 2 * SC_WARPS) -- narrow;
+		size_t cnt = 0;
+		for(size_t j = 0; j < n; ++ j) cnt += level[j] >= narrow;
+		if(n_levels_all - narrow < 8 || cnt * B > SC_ROOT_MAX_SCALARS || getenv("SPP_SPARSE_NO_ROOT"))
+			narrow = n_levels_all; // not worth it / too large: everything level by level
+		for(size_t j = 0; j < n; ++ j)
+			if(level[j] >= narrow) ridx[j] = (uint32_t)m ++;
+	}
+	sc.n_root = m;
+	// levels over the other columns
+	const uint32_t n_levels = narrow;
+	std::vector<uint32_t> lvl_ptr(n_levels + 1, 0), lvl_cols(n - m);
+	for(size_t j = 0; j < n; ++ j) if(level[j] < narrow) ++ lvl_ptr[level[j] + 1];
 	for(uint32_t l = 0; l < n_levels; ++ l) lvl_ptr[l + 1] += lvl_ptr[l];
 	{
 		std::vector<uint32_t> fill(lvl_ptr.begin(), lvl_ptr.end() - 1);
-		for(size_t j = 0; j < n; ++ j) lvl_cols[fill[level[j]] ++] = (uint32_t)j;
+		for(size_t j = 0; j < n; ++ j) if(level[j] < narrow) lvl_cols[fill[level[j]] ++] = (uint32_t)j;
 	}
 	// off-diagonal blocks grouped by the level of their column (for the one-warp-per-block phase)
 	std::vector<uint64_t> lvl_off_ptr(n_levels + 1, 0);
@@ -245,10 +272,33 @@ void sparse_chol_symbolic(spp_ctx *ctx, size_t n, size_t B, const uint64_t *col_
 		}
 		lvl_off_ptr[l + 1] = lvl_off_blk.size();
 	}
-	// the tail of the tree (levels narrower than one CTA's warps) runs on a single CTA
+	// the tail of what is left (levels narrower than one CTA's warps) runs on a single CTA
 	uint32_t tail = n_levels;
 	while(tail > 0 && lvl_ptr[tail] - lvl_ptr[tail - 1] <= SC_WARPS && lvl_off_ptr[tail] - lvl_off_ptr[tail - 1] <= 4 * SC_WARPS)
 		-- tail;
+	// root front: its blocks with the update pairs that come from the other columns, and the row lists of the root
+	// rows restricted to the other columns
+	std::vector<uint32_t> root_blk, root_ua, root_ub, root_rblk, root_cols;
+	std::vector<uint64_t> root_uptr(1, 0), root_rptr(1, 0);
+	for(size_t j = 0; j < n; ++ j) {
+		if(ridx[j] == 0xffffffffu)
+			continue;
+		root_cols.push_back((uint32_t)j);
+		for(uint64_t b = lptr[j]; b < lptr[j + 1]; ++ b) {
+			root_blk.push_back((uint32_t)b);
+			for(uint64_t q = uptr[b]; q < uptr[b + 1]; ++ q) {
+				if(ridx[lcolof[ub[q]]] == 0xffffffffu) {
+					root_ua.push_back(ua[q]);
+					root_ub.push_back(ub[q]);
+				}
+			}
+			root_uptr.push_back(root_ua.size());
+		}
+		for(uint64_t q = rptr[j]; q < rptr[j + 1]; ++ q)
+			if(ridx[lcolof[rblk[q]]] == 0xffffffffu) root_rblk.push_back(rblk[q]);
+		root_rptr.push_back(root_rblk.size());
+	}
+	sc.h_ridx = ridx;
 	sc.n_levels = n_levels;
 	sc.tail_level = tail;
 	sc.n_l_blocks = nb;
@@ -272,6 +322,19 @@ void sparse_chol_symbolic(spp_ctx *ctx, size_t n, size_t B, const uint64_t *col_
 	sc.d_lvl_cols.upload(lvl_cols, st);
 	sc.d_lvl_off_ptr.upload(lvl_off_ptr, st);
 	sc.d_lvl_off_blk.upload(lvl_off_blk, st);
+	sc.n_root_blocks = root_blk.size();
+	sc.d_root_blk.upload(root_blk, st);
+	sc.d_root_uptr.upload(root_uptr, st);
+	sc.d_root_ua.upload(root_ua, st);
+	sc.d_root_ub.upload(root_ub, st);
+	sc.d_root_rptr.upload(root_rptr, st);
+	sc.d_root_rblk.upload(root_rblk, st);
+	sc.d_root_cols.upload(root_cols, st);
+	sc.d_ridx.upload(ridx, st);
+	if(m) {
+		sc.d_root_S.resize(dense_chol_storage(m * B));
+		sc.d_root_rhs.resize(m * B);
+	}
 	sc.d_L.resize(nb * BB);
 	sc.d_Linv.resize(n * BB);
 	sc.d_y.resize(n * B);
@@ -313,7 +376,8 @@ struct SparseCholArgs {
 // one warp: T(r, c) = A-part - sum over the update pairs of La(r, :) . Lb(c, :); lane e = r + B c (lanes >= B*B idle;
 // B = 6 uses lanes 0..17 with two elements each: e and e + 18)
 template <int B>
-__device__ __forceinline__ void block_update(const SparseCholArgs &a, uint32_t blk, int lane, double (&t)[2])
+__device__ __forceinline__ void block_update(const SparseCholArgs &a, uint32_t blk, int lane, double (&t)[2],
+	const uint32_t *pa = 0, const uint32_t *pb = 0, uint64_t pbeg = 0, uint64_t pend = 0)
 {
 	constexpr int BB = B * B, NE = (BB > 32)? 2 : 1, STEP = (BB > 32)? BB / 2 : 0;
 	const int64_t s = a.src[blk];
@@ -327,9 +391,10 @@ __device__ __forceinline__ void block_update(const SparseCholArgs &a, uint32_t b
 			t[u] = (s > 0)? Ab[e] : Ab[c + B * r]; // transposed source
 		}
 	}
-	const uint64_t beg = a.uptr[blk], end = a.uptr[blk + 1];
+	const uint32_t *ua = pa? pa : a.ua, *ub = pa? pb : a.ub;
+	const uint64_t beg = pa? pbeg : a.uptr[blk], end = pa? pend : a.uptr[blk + 1];
 	for(uint64_t q = beg; q < end; ++ q) {
-		const double *La = a.L + (size_t)a.ua[q] * BB, *Lb = a.L + (size_t)a.ub[q] * BB;
+		const double *La = a.L + (size_t)ua[q] * BB, *Lb = a.L + (size_t)ub[q] * BB;
 		#pragma unroll
 		for(int u = 0; u < NE; ++ u) {
 			const int e = lane + u * STEP;
@@ -517,6 +582,73 @@ __global__ void __launch_bounds__(SC_WARPS * 32) k_sparse_backsolve(SparseCholAr
 	}
 }
 
+struct SparseRootArgs {
+	size_t n_blocks, m;
+	const uint32_t *blk;        // [n_blocks] the root's blocks
+	const uint64_t *uptr;       // [n_blocks + 1] update pairs from the non-root columns
+	const uint32_t *ua, *ub;
+	const uint64_t *rptr;       // [m + 1] per root row: its blocks in non-root columns
+	const uint32_t *rblk;
+	const uint32_t *cols;       // [m] root index -> column
+	const uint32_t *ridx;       // [n] column -> root index
+	double *S;                  // dense storage of the dense solver (upper triangle, column-major)
+	size_t ld;
+	double *rhs;                // [m * B]
+};
+
+// root front assembly: warp per block (i, j) of the root, S_upper(j, i) = (A_ij - sum_{k not in root} L_ik L_jk^T)^T
+template <int B>
+__global__ void __launch_bounds__(SC_WARPS * 32) k_root_assemble(SparseCholArgs a, SparseRootArgs ra)
+{
+	constexpr int BB = B * B, NE = (BB > 32)? 2 : 1, STEP = (BB > 32)? BB / 2 : 0;
+	const int lane = threadIdx.x & 31;
+	const size_t q = blockIdx.x * (size_t)SC_WARPS + (threadIdx.x >> 5);
+	if(q >= ra.n_blocks) return;
+	const uint32_t blk = ra.blk[q];
+	const size_t i = ra.ridx[a.lrow[blk]], j = ra.ridx[a.lcolof[blk]];
+	double t[2];
+	block_update<B>(a, blk, lane, t, ra.ua, ra.ub, ra.uptr[q], ra.uptr[q + 1]);
+	#pragma unroll
+	for(int u = 0; u < NE; ++ u) {
+		const int e = lane + u * STEP;
+		if(e < BB && (NE == 1 || lane < STEP)) {
+			const int r = e % B, c = e / B; // element (r, c) of block (i, j) -> S(j B + c, i B + r)
+			ra.S[(i * B + r) * ra.ld + j * B + c] = t[u];
+		}
+	}
+}
+
+// right-hand side of the root: thread per scalar row, rhs_i - sum_{k not in root} L(i, k) y_k
+template <int B>
+__global__ void k_root_rhs(SparseCholArgs a, SparseRootArgs ra)
+{
+	constexpr int BB = B * B;
+	const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(idx >= ra.m * B) return;
+	const size_t ri = idx / B, i = ra.cols[ri];
+	const int r = int(idx % B);
+	double v = a.rhs[(size_t)a.order[i] * B + r];
+	for(uint64_t p = ra.rptr[ri]; p < ra.rptr[ri + 1]; ++ p) {
+		const uint32_t b = ra.rblk[p];
+		const double *Lb = a.L + (size_t)b * BB, *yk = a.y + (size_t)a.lcolof[b] * B;
+		#pragma unroll
+		for(int k = 0; k < B; ++ k)
+			v -= Lb[r + B * k] * yk[k];
+	}
+	ra.rhs[idx] = v;
+}
+
+template <int B>
+__global__ void k_root_scatter(SparseCholArgs a, SparseRootArgs ra)
+{
+	const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(idx >= ra.m * B) return;
+	const size_t i = ra.cols[idx / B];
+	const int r = int(idx % B);
+	a.y[i * B + r] = ra.rhs[idx];
+	a.x[(size_t)a.order[i] * B + r] = ra.rhs[idx];
+}
+
 template <int B>
 static int sparse_chol_numeric_t(spp_ctx *ctx, SparseCholArgs &a)
 {
@@ -539,6 +671,26 @@ static int sparse_chol_numeric_t(spp_ctx *ctx, SparseCholArgs &a)
 	if(tail < nl) {
 		k_sparse_chol<B, false><<<1, SC_WARPS * 32, 0, st>>>(a, tail, nl);
 		LAUNCH_CHECK(ctx);
+	}
+	const size_t m = sc.n_root;
+	if(m) { // the dense root front: assemble, factor + solve on the dense DMMA Cholesky, scatter
+		const size_t nd = m * B;
+		SparseRootArgs ra;
+		ra.n_blocks = sc.n_root_blocks; ra.m = m; ra.blk = sc.d_root_blk.p(); ra.uptr = sc.d_root_uptr.p();
+		ra.ua = sc.d_root_ua.p(); ra.ub = sc.d_root_ub.p(); ra.rptr = sc.d_root_rptr.p(); ra.rblk = sc.d_root_rblk.p();
+		ra.cols = sc.d_root_cols.p(); ra.ridx = sc.d_ridx.p(); ra.S = sc.d_root_S.p(); ra.ld = dense_chol_ld(nd);
+		ra.rhs = sc.d_root_rhs.p();
+		sc.d_root_S.zero(st);
+		k_root_assemble<B><<<n_blocks(sc.n_root_blocks, SC_WARPS), SC_WARPS * 32, 0, st>>>(a, ra);
+		LAUNCH_CHECK(ctx);
+		k_root_rhs<B><<<n_blocks(nd, 128), 128, 0, st>>>(a, ra);
+		LAUNCH_CHECK(ctx);
+		if(dense_chol_solve_device(ctx, sc.d_root_S.p(), nd, sc.d_root_rhs.p()) != SPP_OK)
+			return SPP_NOT_POSDEF;
+		k_root_scatter<B><<<n_blocks(nd, 128), 128, 0, st>>>(a, ra);
+		LAUNCH_CHECK(ctx);
+	}
+	if(tail < nl) {
 		k_sparse_backsolve<B, false><<<1, SC_WARPS * 32, 0, st>>>(a, tail, nl);
 		LAUNCH_CHECK(ctx);
 	}

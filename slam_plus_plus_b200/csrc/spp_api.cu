@@ -844,6 +844,23 @@ int spp_chol_get_factor(spp_ctx_t ctx, uint64_t *p_n_blocks, uint64_t *p_col_ptr
 			hL.resize(nb * BB);
 			sc.d_L.download(hL.data(), nb * BB, ctx->stream);
 			SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+			if(sc.n_root) { // the blocks of the dense root front live in the dense factor (upper, column-major)
+				const size_t nd = sc.n_root * B, ld = dense_chol_ld(nd);
+				std::vector<double> hS(ld * nd);
+				sc.d_root_S.download(hS.data(), ld * nd, ctx->stream);
+				SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+				for(size_t j = 0; j < n; ++ j) {
+					if(sc.h_ridx[j] == 0xffffffffu)
+						continue;
+					const size_t rj = sc.h_ridx[j];
+					for(uint64_t b = sc.h_lptr[j]; b < sc.h_lptr[j + 1]; ++ b) {
+						const size_t i = sc.h_lrow[b], ri = sc.h_ridx[i];
+						for(size_t c = 0; c < B; ++ c)
+							for(size_t r = 0; r < B; ++ r) // L(i, j)(r, c) = R(rj B + c, ri B + r)
+								hL[b * BB + c * B + r] = (i > j || r >= c)? hS[(ri * B + r) * ld + rj * B + c] : 0.0;
+					}
+				}
+			}
 		}
 		std::vector<uint64_t> fill(cnt.begin(), cnt.end() - 1);
 		for(size_t j = 0; j < n; ++ j) { // ascending j = ascending row of R inside every column

@@ -105,7 +105,13 @@ struct SparseChol {
 	DBuf<double> d_L, d_Linv, d_y;
 	DBuf<int> d_info;
 	DBuf<double> slot_vals, slot_rhs, slot_x; // staging of the caller's arrays (slot use)
-	SparseChol() : valid(false), n(0), B(0), n_a_blocks(0), n_l_blocks(0), n_levels(0), tail_level(0), max_coop_ctas(0) {}
+	size_t n_root, n_root_blocks;              // the columns of the narrow top levels form one dense root front
+	std::vector<uint32_t> h_ridx;              // column -> index in the root front (0xffffffff: not in it)
+	DBuf<uint32_t> d_root_blk, d_root_ua, d_root_ub, d_root_rblk, d_root_cols, d_ridx;
+	DBuf<uint64_t> d_root_uptr, d_root_rptr;
+	DBuf<double> d_root_S, d_root_rhs;
+	SparseChol() : valid(false), n(0), B(0), n_a_blocks(0), n_l_blocks(0), n_levels(0), tail_level(0), max_coop_ctas(0),
+		n_root(0), n_root_blocks(0) {}
 };
 
 // pose graph resident on the device (pose_kernels.cu)
