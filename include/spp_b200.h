@@ -175,6 +175,40 @@ int spp_schur_solve(spp_ctx_t ctx, const double *p_values, double *p_eta_dx);
  * 6x6 blocks of the upper triangle (row-major bitmap, C*C bytes). Any pointer may be NULL. */
 int spp_schur_get_reduced_system(spp_ctx_t ctx, uint64_t *p_n, double *p_S, double *p_rhs, uint8_t *p_block_pattern);
 
+/* ---- solver of the reduced camera system (RCS) ------------------------------------------------------------ */
+
+/* Replaces the reference's choice between CLinearSolver_DenseEigen and, when the dense matrix cannot be allocated
+ * (std::bad_alloc), CLinearSolver_UberBlock on the block-sparse Schur complement (include/slam/LinearSolver_Schur.h:
+ * 1427-1435, 1836-1847). SPP_RCS_AUTO: dense up to 16 384 unknowns, supernodal block-sparse above. Applies to the
+ * spp_ba_* and spp_schur_* entry points of this context. */
+#define SPP_RCS_AUTO 0
+#define SPP_RCS_DENSE 1
+#define SPP_RCS_SPARSE 2
+int spp_schur_set_rcs_solver(spp_ctx_t ctx, int mode);
+
+/* The fill-reducing ordering of the cameras used by the block-sparse RCS solver: p_order[new position] = camera index
+ * (position among the 6-wide vertices in id order). The reference-side adapter passes the reference's own AMD
+ * permutation (CMatrixOrdering::p_BlockOrdering on the Schur complement, src/slam/OrderingMagic.cpp:701-1033, called
+ * from LinearSolver_UberBlock.h:272-296) so that the elimination order is the reference's bit for bit; with NULL (the
+ * default) the library computes an approximate-minimum-degree ordering itself (spp_block_ordering). */
+int spp_schur_set_rcs_ordering(spp_ctx_t ctx, size_t n_cameras, const uint64_t *p_order);
+
+/* After a solve on the block-sparse path: the ordering in use (p_order[C], may be NULL) and p_stats[8] = cameras,
+ * non-zero 6x6 blocks of the upper RCS, supernodes, blocks of the exact factor, blocks of the factor as stored
+ * (amalgamation zeros included), flops of one numeric factorisation, bytes of factor storage, supernode updates. */
+int spp_schur_get_rcs_info(spp_ctx_t ctx, uint64_t *p_order, double *p_stats);
+
+/* Pure host helpers (no context, no GPU). spp_block_ordering: the library's fill-reducing ordering (approximate
+ * minimum degree on the block graph of A + A^T, then a postorder of the elimination tree) of an upper block-triangular
+ * structure in block CSC (rows ascending, diagonal present) -- what CMatrixOrdering::p_BlockOrdering / amd_l2 does in
+ * the reference; same quality of fill, not the same permutation. spp_block_symbolic_stats: symbolic Cholesky under an
+ * ordering (NULL = natural): p_col_count[n] blocks per column of the factor, p_parent[n] elimination tree
+ * (UINT64_MAX = root), p_stats[3] = blocks of the factor, sum of count^2, maximal supernodes. Any output may be NULL.
+ * (CUberBlockMatrix::Build_EliminationTree, src/slam/BlockMatrix.cpp:9403.) */
+int spp_block_ordering(size_t n_block_cols, const uint64_t *p_col_ptr, const uint64_t *p_row_idx, uint64_t *p_order);
+int spp_block_symbolic_stats(size_t n_block_cols, const uint64_t *p_col_ptr, const uint64_t *p_row_idx,
+	const uint64_t *p_order, uint64_t *p_col_count, uint64_t *p_parent, double *p_stats);
+
 /* ---- dense FP64 Cholesky (the reduced camera system solver) ----------------------------------------- */
 
 /* Replaces CLinearSolver_DenseEigen::Solve_PosDef (src/slam/LinearSolver_Schur.cpp:2314-2333): Eigen::LLT<MatrixXd,

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libspp_b200.so")
 SPP_OK, SPP_NOT_POSDEF = 0, 1
 SPP_ERR_INVALID, SPP_ERR_CUDA, SPP_ERR_NOMEM, SPP_ERR_COMM = -1, -2, -3, -4
 JAC_FD_REFERENCE, JAC_ANALYTIC = 0, 1
+RCS_AUTO, RCS_DENSE, RCS_SPARSE = 0, 1, 2
 MAX_TRACE = 64
 
 # every symbol include/spp_b200.h declares (tests check that the library exports all of them)
@@ -25,7 +26,8 @@ EXPORTED_SYMBOLS = [
     "spp_synchronize", "spp_set_allreduce", "spp_partition_landmarks", "spp_ba_get_partition", "spp_ba_set_graph", "spp_ba_set_states", "spp_ba_get_states",
     "spp_ba_restore_initial", "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_get_blocks", "spp_ba_chi2", "spp_ba_solve_step",
     "spp_ba_optimize", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_get_reduced_system",
-    "spp_dense_posdef_solve",
+    "spp_schur_set_rcs_solver", "spp_schur_set_rcs_ordering", "spp_schur_get_rcs_info", "spp_block_ordering",
+    "spp_block_symbolic_stats", "spp_dense_posdef_solve",
     "spp_chol_symbolic", "spp_chol_solve", "spp_chol_get_factor",
     "spp_pose_set_graph", "spp_pose_set_ordering", "spp_pose_set_states", "spp_pose_get_states", "spp_pose_restore_initial",
     "spp_pose_linearise", "spp_pose_get_lambda", "spp_pose_chi2", "spp_pose_solve_step", "spp_pose_optimize",
@@ -99,6 +101,11 @@ def load_library() -> C.CDLL:
     lib.spp_schur_solve.argtypes = [vp, dp, dp]
     lib.spp_schur_get_reduced_system.argtypes = [vp, u64p, dp, dp, u8p]
     lib.spp_dense_posdef_solve.argtypes = [vp, C.c_size_t, dp, dp]
+    lib.spp_schur_set_rcs_solver.argtypes = [vp, C.c_int]
+    lib.spp_schur_set_rcs_ordering.argtypes = [vp, C.c_size_t, u64p]
+    lib.spp_schur_get_rcs_info.argtypes = [vp, u64p, dp]
+    lib.spp_block_ordering.argtypes = [C.c_size_t, u64p, u64p, u64p]
+    lib.spp_block_symbolic_stats.argtypes = [C.c_size_t, u64p, u64p, u64p, u64p, u64p, dp]
     lib.spp_chol_symbolic.argtypes = [vp, C.c_size_t, C.c_size_t, u64p, u64p, u64p, u64p]
     lib.spp_chol_solve.argtypes = [vp, dp, dp]
     lib.spp_chol_get_factor.argtypes = [vp, u64p, u64p, u64p, dp]
@@ -136,6 +143,33 @@ def partition_landmarks(track_length, world: int) -> np.ndarray:
     if rc != SPP_OK:
         raise ValueError("spp_partition_landmarks: invalid arguments")
     return bounds.astype(np.int64)
+
+
+def block_ordering(col_ptr, row_idx) -> np.ndarray:
+    """Pure host helper: the library's fill-reducing block ordering (order[new position] = block column)."""
+    lib = load_library()
+    col_ptr = np.ascontiguousarray(col_ptr, np.uint64)
+    row_idx = np.ascontiguousarray(row_idx, np.uint64)
+    n = len(col_ptr) - 1
+    order = np.empty(n, np.uint64)
+    rc = lib.spp_block_ordering(n, _u64p(col_ptr), _u64p(row_idx), _u64p(order))
+    if rc != SPP_OK:
+        raise RuntimeError(f"spp_block_ordering failed: {rc}")
+    return order
+
+
+def block_symbolic_stats(col_ptr, row_idx, order=None) -> dict:
+    """Pure host helper: symbolic block Cholesky under an ordering (None = natural)."""
+    lib = load_library()
+    col_ptr = np.ascontiguousarray(col_ptr, np.uint64)
+    row_idx = np.ascontiguousarray(row_idx, np.uint64)
+    n = len(col_ptr) - 1
+    o = None if order is None else np.ascontiguousarray(order, np.uint64)
+    cnt, par, st = np.empty(n, np.uint64), np.empty(n, np.uint64), np.zeros(3)
+    rc = lib.spp_block_symbolic_stats(n, _u64p(col_ptr), _u64p(row_idx), _u64p(o), _u64p(cnt), _u64p(par), _dp(st))
+    if rc != SPP_OK:
+        raise RuntimeError(f"spp_block_symbolic_stats failed: {rc}")
+    return dict(col_count=cnt, parent=par, nnzb_factor=int(st[0]), sum_count_sq=float(st[1]), supernodes=int(st[2]))
 
 
 class SppError(RuntimeError):
@@ -320,6 +354,24 @@ class Context:
         return None, None, pat
 
     # ---- dense Cholesky --------------------------------------------------------------------------
+    def schur_set_rcs_solver(self, mode: int):
+        self._check(self.lib.spp_schur_set_rcs_solver(self.h, mode))
+
+    def schur_set_rcs_ordering(self, order=None):
+        if order is None:
+            self._check(self.lib.spp_schur_set_rcs_ordering(self.h, 0, None))
+        else:
+            o = np.ascontiguousarray(order, np.uint64)
+            self._check(self.lib.spp_schur_set_rcs_ordering(self.h, len(o), _u64p(o)))
+
+    def schur_get_rcs_info(self) -> dict:
+        st = np.zeros(8)
+        self._check(self.lib.spp_schur_get_rcs_info(self.h, None, _dp(st)))
+        order = np.empty(int(st[0]), np.uint64)
+        self._check(self.lib.spp_schur_get_rcs_info(self.h, _u64p(order), None))
+        return dict(order=order, cameras=int(st[0]), rcs_blocks=int(st[1]), supernodes=int(st[2]), factor_blocks_exact=int(st[3]),
+                    factor_blocks_stored=int(st[4]), factor_flops=float(st[5]), factor_bytes=float(st[6]), updates=int(st[7]))
+
     def dense_posdef_solve(self, A, b) -> np.ndarray:
         A = np.asfortranarray(A, np.float64)
         x = np.array(b, np.float64, copy=True)

@@ -1,0 +1,426 @@
+// block_ordering.cpp -- see block_ordering.h. Pure host code (integer work, one-time per structure).
+
+#include "block_ordering.h"
+#include "../../include/spp_b200.h"
+#include <algorithm>
+#include <stdexcept>
+#include <math.h>
+
+namespace spp {
+
+// ---- approximate minimum degree -------------------------------------------------------------------------
+
+namespace {
+
+enum { ST_VAR = 0, ST_ELEM = 1, ST_DEAD = 2, ST_DENSE = 3 };
+
+struct DegreeLists { // doubly linked bucket lists, LIFO within a bucket
+	std::vector<int32_t> head, next, prev;
+	size_t min_deg;
+	DegreeLists(size_t n) : head(n + 1, -1), next(n, -1), prev(n, -1), min_deg(0) {}
+	void insert(uint32_t i, size_t d)
+	{
+		next[i] = head[d];
+		prev[i] = -1;
+		if(head[d] >= 0) prev[head[d]] = (int32_t)i;
+		head[d] = (int32_t)i;
+		if(d < min_deg) min_deg = d;
+	}
+	void remove(uint32_t i, size_t d)
+	{
+		if(prev[i] >= 0) next[prev[i]] = next[i];
+		else head[d] = next[i];
+		if(next[i] >= 0) prev[next[i]] = prev[i];
+	}
+	uint32_t pop_min()
+	{
+		while(head[min_deg] < 0) ++ min_deg;
+		const uint32_t p = (uint32_t)head[min_deg];
+		remove(p, min_deg);
+		return p;
+	}
+};
+
+} // namespace
+
+void amd_block_ordering(size_t n, const uint64_t *col_ptr, const uint64_t *row_idx, std::vector<uint32_t> &order)
+{
+	order.clear();
+	order.reserve(n);
+	if(!n) return;
+	std::vector<std::vector<uint32_t> > adjv(n), adje(n), elem(n);
+	{
+		std::vector<uint32_t> cnt(n, 0);
+		for(size_t c = 0; c < n; ++ c)
+			for(uint64_t k = col_ptr[c]; k < col_ptr[c + 1]; ++ k)
+				if(row_idx[k] != c) { ++ cnt[c]; ++ cnt[row_idx[k]]; }
+		for(size_t i = 0; i < n; ++ i) adjv[i].reserve(cnt[i]);
+		for(size_t c = 0; c < n; ++ c) {
+			for(uint64_t k = col_ptr[c]; k < col_ptr[c + 1]; ++ k) {
+				const size_t r = row_idx[k];
+				if(r >= n) throw std::runtime_error("block ordering: row index out of range");
+				if(r != c) { adjv[r].push_back((uint32_t)c); adjv[c].push_back((uint32_t)r); }
+			}
+		}
+		for(size_t i = 0; i < n; ++ i) {
+			std::sort(adjv[i].begin(), adjv[i].end());
+			adjv[i].erase(std::unique(adjv[i].begin(), adjv[i].end()), adjv[i].end());
+		}
+	}
+	std::vector<uint8_t> state(n, ST_VAR);
+	// rows much denser than the rest are ordered last (they would fill whatever they touch anyway)
+	const size_t dense_thr = std::max<size_t>(16, (size_t)(10.0 * sqrt((double)n)));
+	std::vector<uint32_t> dense;
+	for(size_t i = 0; i < n; ++ i)
+		if(adjv[i].size() > dense_thr) { state[i] = ST_DENSE; dense.push_back((uint32_t)i); }
+	if(!dense.empty()) {
+		for(size_t i = 0; i < n; ++ i) {
+			if(state[i] == ST_DENSE) continue;
+			std::vector<uint32_t> &a = adjv[i];
+			a.erase(std::remove_if(a.begin(), a.end(), [&](uint32_t v) { return state[v] == ST_DENSE; }), a.end());
+		}
+	}
+	const size_t n_live = n - dense.size();
+	std::vector<uint32_t> degree(n, 0), mark(n, 0), wmark(n, 0), Lp;
+	std::vector<int64_t> w(n, 0);
+	DegreeLists lists(n);
+	lists.min_deg = n;
+	for(size_t i = 0; i < n; ++ i) {
+		if(state[i] != ST_VAR) continue;
+		degree[i] = (uint32_t)adjv[i].size();
+		lists.insert((uint32_t)i, degree[i]);
+	}
+	uint32_t stamp = 0;
+	for(size_t k = 0; k < n_live; ++ k) {
+		const uint32_t p = lists.pop_min();
+		++ stamp;
+		mark[p] = stamp;
+		Lp.clear();
+		for(uint32_t v : adjv[p])
+			if(state[v] == ST_VAR && mark[v] != stamp) { mark[v] = stamp; Lp.push_back(v); }
+		for(uint32_t e : adje[p]) {
+			if(state[e] != ST_ELEM) continue;
+			for(uint32_t v : elem[e])
+				if(state[v] == ST_VAR && mark[v] != stamp) { mark[v] = stamp; Lp.push_back(v); }
+			state[e] = ST_DEAD; // absorbed into the new element
+			std::vector<uint32_t>().swap(elem[e]);
+		}
+		state[p] = ST_ELEM;
+		order.push_back(p);
+		std::vector<uint32_t>().swap(adjv[p]);
+		std::vector<uint32_t>().swap(adje[p]);
+		// w[e] = |L_e \ L_p| for every element adjacent to a variable of L_p
+		for(uint32_t i : Lp) {
+			for(uint32_t e : adje[i]) {
+				if(state[e] != ST_ELEM) continue;
+				if(wmark[e] != stamp) { wmark[e] = stamp; w[e] = (int64_t)elem[e].size(); }
+				-- w[e];
+			}
+		}
+		const size_t lp = Lp.size(), remaining = n_live - k - 1;
+		for(uint32_t i : Lp) {
+			lists.remove(i, degree[i]);
+			std::vector<uint32_t> &ei = adje[i];
+			size_t out = 0;
+			uint64_t sum = 0;
+			for(uint32_t e : ei) {
+				if(state[e] != ST_ELEM) continue;
+				if(w[e] == 0) { // L_e is a subset of L_p: aggressive absorption
+					state[e] = ST_DEAD;
+					std::vector<uint32_t>().swap(elem[e]);
+					continue;
+				}
+				ei[out ++] = e;
+				sum += (uint64_t)w[e];
+			}
+			ei.resize(out);
+			ei.push_back(p);
+			std::vector<uint32_t> &vi = adjv[i];
+			out = 0;
+			for(uint32_t v : vi)
+				if(state[v] == ST_VAR && mark[v] != stamp) vi[out ++] = v; // members of L_p are reached through element p now
+			vi.resize(out);
+			uint64_t d = std::min<uint64_t>(remaining, (uint64_t)degree[i] + lp - 1);
+			d = std::min<uint64_t>(d, vi.size() + (lp - 1) + sum);
+			degree[i] = (uint32_t)d;
+			lists.insert(i, d);
+		}
+		elem[p] = Lp;
+	}
+	std::stable_sort(dense.begin(), dense.end(), [&](uint32_t a, uint32_t b) { return adjv[a].size() < adjv[b].size(); });
+	order.insert(order.end(), dense.begin(), dense.end());
+}
+
+// ---- elimination tree ---------------------------------------------------------------------------------------
+
+// for every permuted column j, the permuted rows i < j of the symmetric pattern (unsorted)
+static void permuted_upper(size_t n, const uint64_t *col_ptr, const uint64_t *row_idx, const std::vector<uint32_t> &inv,
+	std::vector<uint64_t> &ptr, std::vector<uint32_t> &idx)
+{
+	ptr.assign(n + 1, 0);
+	for(size_t c = 0; c < n; ++ c) {
+		for(uint64_t k = col_ptr[c]; k < col_ptr[c + 1]; ++ k) {
+			const size_t r = row_idx[k];
+			if(r >= n) throw std::runtime_error("block ordering: row index out of range");
+			if(r == c) continue;
+			++ ptr[std::max(inv[r], inv[c]) + 1];
+		}
+	}
+	for(size_t j = 0; j < n; ++ j) ptr[j + 1] += ptr[j];
+	idx.resize(ptr[n]);
+	std::vector<uint64_t> fill(ptr.begin(), ptr.end() - 1);
+	for(size_t c = 0; c < n; ++ c) {
+		for(uint64_t k = col_ptr[c]; k < col_ptr[c + 1]; ++ k) {
+			const size_t r = row_idx[k];
+			if(r == c) continue;
+			const uint32_t a = inv[r], b = inv[c];
+			idx[fill[std::max(a, b)] ++] = std::min(a, b);
+		}
+	}
+}
+
+static void elimination_tree(size_t n, const std::vector<uint64_t> &ptr, const std::vector<uint32_t> &idx,
+	std::vector<uint32_t> &parent)
+{
+	const uint32_t none = 0xffffffffu;
+	parent.assign(n, none);
+	std::vector<uint32_t> ancestor(n, none);
+	for(size_t j = 0; j < n; ++ j) {
+		for(uint64_t k = ptr[j]; k < ptr[j + 1]; ++ k) {
+			uint32_t i = idx[k];
+			while(i != none && i < j) { // walk to the root of i's subtree, compressing the path to j
+				const uint32_t nxt = ancestor[i];
+				ancestor[i] = (uint32_t)j;
+				if(nxt == none) parent[i] = (uint32_t)j;
+				i = nxt;
+			}
+		}
+	}
+}
+
+void etree_postorder(size_t n, const uint64_t *col_ptr, const uint64_t *row_idx, std::vector<uint32_t> &order)
+{
+	if(order.size() != n) throw std::runtime_error("etree_postorder: bad ordering");
+	std::vector<uint32_t> inv(n);
+	for(size_t i = 0; i < n; ++ i) inv[order[i]] = (uint32_t)i;
+	std::vector<uint64_t> ptr;
+	std::vector<uint32_t> idx, parent;
+	permuted_upper(n, col_ptr, row_idx, inv, ptr, idx);
+	elimination_tree(n, ptr, idx, parent);
+	const uint32_t none = 0xffffffffu;
+	// children lists in ascending order
+	std::vector<int32_t> head(n, -1), next(n, -1);
+	for(size_t jj = n; jj > 0; -- jj) {
+		const size_t j = jj - 1;
+		if(parent[j] != none) { next[j] = head[parent[j]]; head[parent[j]] = (int32_t)j; }
+	}
+	std::vector<uint32_t> post;
+	post.reserve(n);
+	std::vector<uint32_t> stack;
+	for(size_t r = 0; r < n; ++ r) {
+		if(parent[r] != none) continue;
+		stack.push_back((uint32_t)r);
+		while(!stack.empty()) {
+			const uint32_t v = stack.back();
+			if(head[v] >= 0) { // descend into the next unvisited child
+				const uint32_t c = (uint32_t)head[v];
+				head[v] = next[c];
+				stack.push_back(c);
+			} else {
+				post.push_back(v);
+				stack.pop_back();
+			}
+		}
+	}
+	std::vector<uint32_t> composed(n);
+	for(size_t k = 0; k < n; ++ k) composed[k] = order[post[k]];
+	order.swap(composed);
+}
+
+// ---- symbolic factorisation, supernodes -------------------------------------------------------------------
+
+void supernodal_symbolic(size_t n, const uint64_t *col_ptr, const uint64_t *row_idx, const std::vector<uint32_t> &order,
+	double relax_zeros, size_t relax_small, size_t max_width, Supernodes &out)
+{
+	const uint32_t none = 0xffffffffu;
+	if(order.size() != n) throw std::runtime_error("supernodal_symbolic: bad ordering");
+	std::vector<uint32_t> inv(n, none);
+	for(size_t i = 0; i < n; ++ i) {
+		if(order[i] >= n || inv[order[i]] != none) throw std::runtime_error("supernodal_symbolic: the ordering is not a permutation");
+		inv[order[i]] = (uint32_t)i;
+	}
+	// permuted lower pattern by column: rows > j of column j
+	std::vector<std::vector<uint32_t> > lcol(n);
+	{
+		std::vector<uint32_t> cnt(n, 0);
+		for(size_t c = 0; c < n; ++ c) {
+			bool diag = false;
+			for(uint64_t k = col_ptr[c]; k < col_ptr[c + 1]; ++ k) {
+				const size_t r = row_idx[k];
+				if(r > c || r >= n) throw std::runtime_error("supernodal_symbolic: the matrix must be upper block-triangular");
+				if(r == c) { diag = true; continue; }
+				++ cnt[std::min(inv[r], inv[c])];
+			}
+			if(!diag) throw std::runtime_error("supernodal_symbolic: missing diagonal block");
+		}
+		for(size_t j = 0; j < n; ++ j) lcol[j].reserve(cnt[j] + 1);
+		for(size_t j = 0; j < n; ++ j) lcol[j].push_back((uint32_t)j);
+		for(size_t c = 0; c < n; ++ c) {
+			for(uint64_t k = col_ptr[c]; k < col_ptr[c + 1]; ++ k) {
+				const size_t r = row_idx[k];
+				if(r == c) continue;
+				const uint32_t a = inv[r], b = inv[c];
+				lcol[std::min(a, b)].push_back(std::max(a, b));
+			}
+		}
+		for(size_t j = 0; j < n; ++ j) {
+			std::sort(lcol[j].begin() + 1, lcol[j].end());
+			lcol[j].erase(std::unique(lcol[j].begin(), lcol[j].end()), lcol[j].end());
+		}
+	}
+	// column structures of the factor: struct(j) = pattern(A_j) U (struct(children) \ {child}); the structure of a column
+	// that is not the first of its maximal supernode is dropped as soon as its parent has consumed it
+	out.n = n;
+	out.col_parent.assign(n, none);
+	out.col_count.assign(n, 0);
+	std::vector<uint8_t> starts(n, 1); // column j starts a maximal supernode
+	{
+		std::vector<std::vector<uint32_t> > children(n);
+		std::vector<uint32_t> tmp;
+		for(size_t j = 0; j < n; ++ j) {
+			std::vector<uint32_t> &s = lcol[j];
+			for(uint32_t c : children[j]) {
+				const std::vector<uint32_t> &cs = lcol[c];
+				tmp.clear();
+				std::set_union(s.begin(), s.end(), cs.begin() + 1, cs.end(), std::back_inserter(tmp));
+				s.swap(tmp);
+			}
+			out.col_count[j] = (uint32_t)s.size();
+			if(s.size() > 1) {
+				out.col_parent[j] = s[1];
+				children[s[1]].push_back((uint32_t)j);
+			}
+			if(j > 0 && out.col_parent[j - 1] == j && out.col_count[j - 1] == out.col_count[j] + 1)
+				starts[j] = 0;
+			for(uint32_t c : children[j])
+				if(!starts[c] || true) { /* kept: amalgamation below may need any supernode's first column */ }
+			std::vector<uint32_t>().swap(children[j]);
+		}
+	}
+	out.nnzb_exact = 0;
+	out.flops_blocks = 0;
+	for(size_t j = 0; j < n; ++ j) {
+		out.nnzb_exact += out.col_count[j];
+		out.flops_blocks += (double)out.col_count[j] * out.col_count[j];
+	}
+	// maximal supernodes, then relaxed amalgamation of contiguous child -> parent chains
+	std::vector<uint32_t> sfirst; // first column of every (maximal) supernode
+	for(size_t j = 0; j < n; ++ j)
+		if(starts[j]) sfirst.push_back((uint32_t)j);
+	const size_t ns0 = sfirst.size();
+	sfirst.push_back((uint32_t)n);
+	std::vector<uint8_t> merge_next(ns0, 0); // supernode s is merged with s + 1
+	{
+		size_t gw = 0; // width and explicit zeros of the group that ends with supernode s
+		double gz = 0;
+		for(size_t s = 0; s + 1 < ns0; ++ s) {
+			const size_t w = sfirst[s + 1] - sfirst[s];
+			if(s == 0 || !merge_next[s - 1]) { gw = 0; gz = 0; }
+			gw += w;
+			const size_t last = sfirst[s + 1] - 1;           // last column of s
+			if(out.col_parent[last] != sfirst[s + 1])
+				continue;                                       // the next supernode is not the parent
+			const size_t h = out.col_count[last] - 1;          // rows below the group
+			const size_t wp = sfirst[s + 2] - sfirst[s + 1];
+			const size_t hp = out.col_count[sfirst[s + 2] - 1] - 1;
+			if(gw + wp > max_width)
+				continue;
+			const double zeros = gz + (double)gw * (double)(wp + hp - h);
+			const double total = (double)(gw + wp) * (double)(gw + wp + hp);
+			if(gw + wp <= relax_small || zeros <= relax_zeros * total) {
+				merge_next[s] = 1;
+				gz = zeros;
+			}
+		}
+	}
+	out.first.clear();
+	std::vector<uint32_t> top_first; // first column of the top (last) member of every final supernode
+	for(size_t s = 0; s < ns0; ++ s) {
+		if(s == 0 || !merge_next[s - 1]) out.first.push_back(sfirst[s]);
+		if(!merge_next[s] || s + 1 == ns0) top_first.push_back(sfirst[s]);
+	}
+	out.first.push_back((uint32_t)n);
+	const size_t ns = out.first.size() - 1;
+	out.col_super.assign(n, 0);
+	for(size_t s = 0; s < ns; ++ s)
+		for(size_t j = out.first[s]; j < out.first[s + 1]; ++ j) out.col_super[j] = (uint32_t)s;
+	out.row_ptr.assign(ns + 1, 0);
+	out.rows.clear();
+	out.parent.assign(ns, none);
+	out.level.assign(ns, 0);
+	out.nnzb_factor = 0;
+	for(size_t s = 0; s < ns; ++ s) {
+		const std::vector<uint32_t> &cs = lcol[top_first[s]];
+		const uint32_t end = out.first[s + 1];
+		std::vector<uint32_t>::const_iterator it = std::lower_bound(cs.begin(), cs.end(), end);
+		out.rows.insert(out.rows.end(), it, cs.end());
+		out.row_ptr[s + 1] = out.rows.size();
+		const uint64_t wdt = end - out.first[s], h = out.row_ptr[s + 1] - out.row_ptr[s];
+		out.nnzb_factor += wdt * (wdt + 1) / 2 + wdt * h;
+		if(h) out.parent[s] = out.col_super[out.rows[out.row_ptr[s]]];
+	}
+	for(size_t s = 0; s < ns; ++ s)
+		if(out.parent[s] != none)
+			out.level[out.parent[s]] = std::max(out.level[out.parent[s]], out.level[s] + 1);
+}
+
+} // namespace spp
+
+// ---- C ABI: pure host helpers (no context, no GPU) ------------------------------------------------------------
+
+extern "C" int spp_block_ordering(size_t n_block_cols, const uint64_t *p_col_ptr, const uint64_t *p_row_idx, uint64_t *p_order)
+{
+	if(!p_col_ptr || !p_row_idx || !p_order)
+		return SPP_ERR_INVALID;
+	try {
+		std::vector<uint32_t> order;
+		spp::amd_block_ordering(n_block_cols, p_col_ptr, p_row_idx, order);
+		spp::etree_postorder(n_block_cols, p_col_ptr, p_row_idx, order);
+		for(size_t i = 0; i < n_block_cols; ++ i) p_order[i] = order[i];
+	} catch(const std::bad_alloc&) {
+		return SPP_ERR_NOMEM;
+	} catch(const std::exception&) {
+		return SPP_ERR_INVALID;
+	}
+	return SPP_OK;
+}
+
+extern "C" int spp_block_symbolic_stats(size_t n_block_cols, const uint64_t *p_col_ptr, const uint64_t *p_row_idx,
+	const uint64_t *p_order, uint64_t *p_col_count, uint64_t *p_parent, double *p_stats)
+{
+	if(!p_col_ptr || !p_row_idx)
+		return SPP_ERR_INVALID;
+	try {
+		std::vector<uint32_t> order(n_block_cols);
+		for(size_t i = 0; i < n_block_cols; ++ i) {
+			if(p_order && p_order[i] >= n_block_cols) return SPP_ERR_INVALID;
+			order[i] = p_order? (uint32_t)p_order[i] : (uint32_t)i;
+		}
+		spp::Supernodes sn;
+		spp::supernodal_symbolic(n_block_cols, p_col_ptr, p_row_idx, order, 0.0, 0, (size_t)1 << 30, sn);
+		for(size_t j = 0; j < n_block_cols; ++ j) {
+			if(p_col_count) p_col_count[j] = sn.col_count[j];
+			if(p_parent) p_parent[j] = (sn.col_parent[j] == 0xffffffffu)? UINT64_MAX : sn.col_parent[j];
+		}
+		if(p_stats) {
+			p_stats[0] = (double)sn.nnzb_exact;
+			p_stats[1] = sn.flops_blocks;
+			p_stats[2] = (double)sn.n_super();
+		}
+	} catch(const std::bad_alloc&) {
+		return SPP_ERR_NOMEM;
+	} catch(const std::exception&) {
+		return SPP_ERR_INVALID;
+	}
+	return SPP_OK;
+}

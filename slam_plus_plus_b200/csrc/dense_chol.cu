@@ -262,55 +262,50 @@ static void chol_init_attributes()
 	done = true;
 }
 
-// A: device, augmented storage (upper triangle of the n x n matrix filled, everything else zero, rhs NOT yet
-// placed). d_rhs_x: device vector of n doubles, rhs in, solution out. Returns SPP_OK / SPP_NOT_POSDEF.
-int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
+static void chol_init_streams(spp_ctx *ctx)
 {
 	DenseChol &ch = ctx->chol;
 	chol_init_attributes();
-	const size_t ld = dense_chol_ld(n), n_blk = ld / CH_NB;
-	cudaStream_t st = ctx->stream;
-	if(!ch.bulk_stream) {
-		// the context stream carries the critical chain (created with the highest priority in spp_create); the
-		// look-ahead row is next, the bulk updates yield to both whenever an SM frees up
-		int prio_lo = 0, prio_hi = 0;
-		SPP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-		SPP_CUDA(cudaStreamCreateWithPriority(&ch.bulk_stream, cudaStreamNonBlocking, prio_lo));
-		SPP_CUDA(cudaStreamCreateWithPriority(&ch.row_stream, cudaStreamNonBlocking, (prio_hi + 1 <= prio_lo)? prio_hi + 1 : prio_hi));
-		for(int i = 0; i < 2; ++ i) {
-			SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_potrf[i], cudaEventDisableTiming));
-			SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_first[i], cudaEventDisableTiming));
-			SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_panel[i], cudaEventDisableTiming));
-			SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_bulk[i], cudaEventDisableTiming));
-			SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_row[i], cudaEventDisableTiming));
-		}
-		ch.profile = getenv("SPP_CHOL_PROFILE") != 0;
-		ch.force_tile = getenv("SPP_CHOL_TILE")? atoi(getenv("SPP_CHOL_TILE")) : -1;
-		ch.potrf_exclusive = getenv("SPP_CHOL_SHARED_SM") == 0;
+	if(ch.bulk_stream)
+		return;
+	// the context stream carries the critical chain (created with the highest priority in spp_create); the
+	// look-ahead row is next, the bulk updates yield to both whenever an SM frees up
+	int prio_lo = 0, prio_hi = 0;
+	SPP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+	SPP_CUDA(cudaStreamCreateWithPriority(&ch.bulk_stream, cudaStreamNonBlocking, prio_lo));
+	SPP_CUDA(cudaStreamCreateWithPriority(&ch.row_stream, cudaStreamNonBlocking, (prio_hi + 1 <= prio_lo)? prio_hi + 1 : prio_hi));
+	for(int i = 0; i < 2; ++ i) {
+		SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_potrf[i], cudaEventDisableTiming));
+		SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_first[i], cudaEventDisableTiming));
+		SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_panel[i], cudaEventDisableTiming));
+		SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_bulk[i], cudaEventDisableTiming));
+		SPP_CUDA(cudaEventCreateWithFlags(&ch.ev_row[i], cudaEventDisableTiming));
 	}
-	ch.info.resize(1 + n_blk);
-	SPP_CUDA(cudaMemsetAsync(ch.info.p(), 0, (1 + n_blk) * sizeof(int), st));
-	if(ch.work.size() != n_blk * CH_NB * CH_NB) { // k_potrf128 writes the upper triangles only
-		ch.work.resize(n_blk * CH_NB * CH_NB);
-		ch.work.zero(st);
-	}
-	if(ld > n) {
-		k_pad_identity<<<n_blocks(ld - n, 64), 64, 0, st>>>(A, ld, n, ld);
-		LAUNCH_CHECK(ctx);
-	}
-	double *rhs_col = A + ld * ld; // first column of the rhs block
-	k_copy_rhs<<<n_blocks(n, 256), 256, 0, st>>>(rhs_col, d_rhs_x, n);
-	LAUNCH_CHECK(ctx);
+	ch.profile = getenv("SPP_CHOL_PROFILE") != 0;
+	ch.force_tile = getenv("SPP_CHOL_TILE")? atoi(getenv("SPP_CHOL_TILE")) : -1;
+	ch.potrf_exclusive = getenv("SPP_CHOL_SHARED_SM") == 0;
+}
 
+// Partial right-looking factorisation of a block ROW panel: A is column-major with ld rows (a multiple of 128) and
+// n_cols >= ld + 128 columns (a multiple of 128). The leading ld x ld upper triangle is factored (R11), the columns
+// right of it receive R11^-T A12 (block row of the factor / forward-solved right-hand sides). A dense matrix with its
+// right-hand side block is the case n_cols = ld + 128; a supernode of the block-sparse factorisation
+// (supernodal_chol.cu) is the case "ld = its own columns, n_cols - ld = its row structure + right-hand side".
+// Rinv receives the inverses of the ld / 128 diagonal blocks of R11; *info the first non-positive pivot (1-based).
+// Asynchronous: everything is ordered on (or joined back into) the context's stream.
+void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols, double *Rinv, int *info)
+{
+	DenseChol &ch = ctx->chol;
+	chol_init_streams(ctx);
+	const size_t n_blk = ld / CH_NB;
+	const size_t n = ld; // for the profile print
+	cudaStream_t st = ctx->stream;
 	// factorisation with one-step look-ahead on three streams:
 	//   sA (critical): potrf(b) -> trsm(b) -> update of the next diagonal tile -> potrf(b+1) ...
 	//   sC           : update of the rest of the next panel's tile row (needed by trsm(b+1) only)
 	//   sB (bulk)    : update of everything below that row, overlapping potrf/trsm of the next panel
 	{
-		const size_t n_cols = ld + CH_NB;
 		cudaStream_t sA = st, sB = ch.bulk_stream, sC = ch.row_stream;
-		double *Rinv = ch.work.p();
-		int *info = ch.info.p();
 		const bool prof = ch.profile;
 		if(prof) {
 			sB = sC = sA;
@@ -380,8 +375,14 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 			LAUNCH_CHECK(ctx);
 			toc(1);
 			stamp();
-			if(c0 >= ld)
+			if(c0 >= ld) { // last diagonal block: what is left of its block row (more than the first tile only for a panel)
+				if(n_cols > c0 + CH_NB) {
+					k_gemm_tn<GEMM_TRSM, 128, 64><<<(unsigned)((n_cols - c0 - CH_NB) / 64), 256, gemm_smem<128, 64>(), sA>>>(A, ld, k0, 0,
+						c0 + CH_NB, Rinv_b);
+					LAUNCH_CHECK(ctx);
+				}
 				break;
+			}
 			if(!prof) {
 				SPP_CUDA(cudaEventRecord(ch.ev_first[e], sA));
 				SPP_CUDA(cudaStreamWaitEvent(sC, ch.ev_potrf[e], 0));
@@ -470,6 +471,37 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 				n, t_acc[0], t_acc[1], t_acc[2], t_acc[3], t_acc[4]);
 		}
 	}
+}
+
+// Backward solve R11 x = y on a factored panel (see dense_chol_factor_panel): y (ld doubles, in place) must not alias the
+// panel's first ld columns; flags: ld / 128 ints, zero on entry.
+void dense_chol_backsolve_panel(spp_ctx *ctx, const double *A, size_t ld, const double *Rinv, double *y, int *flags)
+{
+	k_backsolve<<<(unsigned)(ld / CH_NB), 256, 0, ctx->stream>>>(A, ld, ld / CH_NB, Rinv, y, flags);
+	LAUNCH_CHECK(ctx);
+}
+
+// A: device, augmented storage (upper triangle of the n x n matrix filled, everything else zero, rhs NOT yet
+// placed). d_rhs_x: device vector of n doubles, rhs in, solution out. Returns SPP_OK / SPP_NOT_POSDEF.
+int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
+{
+	DenseChol &ch = ctx->chol;
+	const size_t ld = dense_chol_ld(n), n_blk = ld / CH_NB;
+	cudaStream_t st = ctx->stream;
+	ch.info.resize(1 + n_blk);
+	SPP_CUDA(cudaMemsetAsync(ch.info.p(), 0, (1 + n_blk) * sizeof(int), st));
+	if(ch.work.size() != n_blk * CH_NB * CH_NB) { // k_potrf128 writes the upper triangles only
+		ch.work.resize(n_blk * CH_NB * CH_NB);
+		ch.work.zero(st);
+	}
+	if(ld > n) {
+		k_pad_identity<<<n_blocks(ld - n, 64), 64, 0, st>>>(A, ld, n, ld);
+		LAUNCH_CHECK(ctx);
+	}
+	double *rhs_col = A + ld * ld; // first column of the rhs block
+	k_copy_rhs<<<n_blocks(n, 256), 256, 0, st>>>(rhs_col, d_rhs_x, n);
+	LAUNCH_CHECK(ctx);
+	dense_chol_factor_panel(ctx, A, ld, ld + CH_NB, ch.work.p(), ch.info.p());
 	k_backsolve<<<(unsigned)n_blk, 256, 0, st>>>(A, ld, n_blk, ch.work.p(), rhs_col, ch.info.p() + 1);
 	LAUNCH_CHECK(ctx);
 	k_copy_rhs<<<n_blocks(n, 256), 256, 0, st>>>(d_rhs_x, rhs_col, n);

@@ -151,12 +151,13 @@ __global__ void __launch_bounds__(SB_WARPS * 32, (UNROLL >= 4)? 2 : 4) k_schur_b
 		const double v1 = __shfl_sync(0xffffffffu, v[i], (lane + 9) & 31), v2 = __shfl_sync(0xffffffffu, v[i], (lane + 18) & 31);
 		v[i] = (v[i] + v1) + v2;
 	}
-	if(lane < 9) {
-		double *Sb = S + ((size_t)bj * 6 + c3) * ld + (size_t)bi * 6 + r3;
+	if(lane < 9) { // ld == 0: compact block list (block blk at S + 36 blk), else the dense matrix
+		const size_t ldo = ld? ld : 6;
+		double *Sb = ld? S + ((size_t)bj * 6 + c3) * ld + (size_t)bi * 6 + r3 : S + blk * 36 + c3 * 6 + r3;
 		Sb[0] = -v[0];
 		Sb[3] = -v[1];
-		Sb[3 * ld] = -v[2];
-		Sb[3 * ld + 3] = -v[3];
+		Sb[3 * ldo] = -v[2];
+		Sb[3 * ldo + 3] = -v[3];
 	}
 }
 
@@ -187,11 +188,12 @@ __global__ void __launch_bounds__(SB_WARPS * 32) k_schur_diag(size_t ld, double 
 				v[i] += part[s][q9][i];
 		}
 		const double *Ub = U + bi * 36 + c3 * 6 + r3; // column-major 6x6
-		double *Sb = S + (bi * 6 + c3) * ld + bi * 6 + r3;
+		const size_t ldo = ld? ld : 6; // ld == 0: compact block list
+		double *Sb = ld? S + (bi * 6 + c3) * ld + bi * 6 + r3 : S + bi * 36 + c3 * 6 + r3;
 		Sb[0] = (Ub[0] + ((r3 == c3)? alpha : 0.0)) - v[0];
 		Sb[3] = Ub[3] - v[1];
-		Sb[3 * ld] = Ub[18] - v[2];
-		Sb[3 * ld + 3] = (Ub[21] + ((r3 == c3)? alpha : 0.0)) - v[3];
+		Sb[3 * ldo] = Ub[18] - v[2];
+		Sb[3 * ldo + 3] = (Ub[21] + ((r3 == c3)? alpha : 0.0)) - v[3];
 		if(c3 == 0) {
 			b[bi * 6 + r3] = gc[bi * 6 + r3] - v[4];
 			b[bi * 6 + r3 + 3] = gc[bi * 6 + r3 + 3] - v[5];
@@ -244,34 +246,40 @@ __global__ void k_backsubstitute(size_t P, const uint32_t *__restrict__ pt_ptr, 
 // forms Cinv, Y, the dense upper-triangular reduced camera system S and its right-hand side b
 // alpha damps the landmark blocks of this rank; alpha_diag is what this rank adds to the camera diagonal (alpha on
 // rank 0, zero elsewhere: the partial systems are summed over ranks)
-void schur_form_reduced_system(spp_ctx *ctx, double alpha, double alpha_diag)
+// sparse_rcs: S goes to the compact block list s.Sblk (the supernodal solver scatters it into its panels)
+void schur_form_reduced_system(spp_ctx *ctx, double alpha, double alpha_diag, bool sparse_rcs)
 {
 	SchurSystem &s = ctx->sys;
 	const size_t n = s.C * 6;
-	const size_t ld = dense_chol_ld(n); // S is written straight into the dense solver's padded storage
+	const size_t ld = sparse_rcs? 0 : dense_chol_ld(n); // S is written straight into the dense solver's padded storage
 	s.Cinv.resize(s.P * 9);
 	s.Y.resize(s.O * 18);
-	s.S.resize(dense_chol_storage(n));
+	if(sparse_rcs)
+		s.Sblk.resize(s.n_blocks * 36);
+	else
+		s.S.resize(dense_chol_storage(n));
+	double *S_out = sparse_rcs? s.Sblk.p() : s.S.p();
 	s.b.resize(n);
 	if(s.P) {
 		k_landmark_inverse<<<n_blocks(s.P, LI_WARPS * 32), LI_WARPS * 32, 0, ctx->stream>>>(s.P, alpha, s.pt_ptr.p(), s.V.p(),
 			s.W.p(), s.Cinv.p(), s.Y.p());
 		LAUNCH_CHECK(ctx);
 	}
-	s.S.zero(ctx->stream);
+	if(!sparse_rcs)
+		s.S.zero(ctx->stream);
 	if(s.C) { // list entries 0 .. C-1 are the diagonal blocks
 		k_schur_diag<<<(unsigned)s.C, SB_WARPS * 32, 0, ctx->stream>>>(ld, alpha_diag, s.blk_ptr.p(), s.pair_a.p(), s.Y.p(),
-			s.W.p(), s.U.p(), s.gc.p(), s.gp.p(), s.obs_pt.p(), s.S.p(), s.b.p());
+			s.W.p(), s.U.p(), s.gc.p(), s.gp.p(), s.obs_pt.p(), S_out, s.b.p());
 		LAUNCH_CHECK(ctx);
 	}
 	if(s.n_blocks > s.C) {
 		static const int unroll = getenv("SPP_SCHUR_UNROLL")? atoi(getenv("SPP_SCHUR_UNROLL")) : 2;
 		if(unroll >= 4)
 			k_schur_blocks<4><<<n_blocks(s.n_blocks - s.C, SB_WARPS), SB_WARPS * 32, 0, ctx->stream>>>(s.C, s.n_blocks, ld,
-				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), s.S.p());
+				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), S_out);
 		else
 			k_schur_blocks<2><<<n_blocks(s.n_blocks - s.C, SB_WARPS), SB_WARPS * 32, 0, ctx->stream>>>(s.C, s.n_blocks, ld,
-				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), s.S.p());
+				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), S_out);
 		LAUNCH_CHECK(ctx);
 	}
 }

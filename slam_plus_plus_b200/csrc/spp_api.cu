@@ -23,7 +23,9 @@ void ba_linearise(spp_ctx *ctx, bool b_want_maxdiag);
 void ba_chi2_device(spp_ctx *ctx, double *d_out);
 void ba_step_dots_device(spp_ctx *ctx, double alpha, double *d_out);
 void ba_apply_update(spp_ctx *ctx);
-void schur_form_reduced_system(spp_ctx *ctx, double alpha, double alpha_diag);
+void schur_form_reduced_system(spp_ctx *ctx, double alpha, double alpha_diag, bool sparse_rcs);
+void snode_symbolic(spp_ctx *ctx, size_t n, const std::vector<uint32_t> &blk_row, const std::vector<uint32_t> &blk_col);
+int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, double *d_dx);
 void schur_backsubstitute(spp_ctx *ctx);
 size_t dense_chol_ld(size_t n);
 size_t dense_chol_storage(size_t n);
@@ -76,28 +78,67 @@ struct EventTimer {
 	}
 };
 
+// scatters the compact block list of S into a dense column-major n x n matrix (upper blocks; diagnostics only)
+__global__ void k_blocks_to_dense(size_t n_vals, const double *__restrict__ Sblk, const uint32_t *__restrict__ blk_row,
+	const uint32_t *__restrict__ blk_col, size_t ld, double *__restrict__ S)
+{
+	const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(e >= n_vals) return;
+	const size_t b = e / 36;
+	const unsigned q = (unsigned)(e - b * 36), c = q / 6, r = q - c * 6;
+	S[((size_t)blk_col[b] * 6 + c) * ld + (size_t)blk_row[b] * 6 + r] = Sblk[e];
+}
+
+// The reference tries the dense solver on the reduced camera system first and falls back to the block-sparse one when
+// the dense matrix cannot be allocated (LinearSolver_Schur.h:1836-1847). Here the choice is explicit: SPP_RCS_AUTO takes
+// the dense path up to 16 384 unknowns (2 GiB of FP64, n^3 / 3 = 1.5e12 flop) and the supernodal one above.
+static bool rcs_is_sparse(spp_ctx *ctx)
+{
+	const int mode = ctx->snode.mode;
+	if(mode == SPP_RCS_DENSE) return false;
+	if(mode == SPP_RCS_SPARSE) return true;
+	return ctx->sys.C * 6 > 16384;
+}
+
 // Solves the damped Schur system on the current (U, V, W, gc, gp): dxc, dxp. Returns SPP_OK / SPP_NOT_POSDEF.
 int schur_solve_current(spp_ctx *ctx, double alpha, spp_report_t *rep)
 {
 	SchurSystem &s = ctx->sys;
 	const size_t n = s.C * 6;
+	const bool sparse = rcs_is_sparse(ctx);
+	if(sparse && ctx->world > 1)
+		throw invalid_error("the block-sparse reduced camera system is single-GPU in this version (use SPP_RCS_DENSE with several ranks)");
+	if(sparse && !ctx->snode.valid) { // one-time symbolic analysis of the structure (host)
+		schur_fetch_host_pattern(ctx);
+		snode_symbolic(ctx, s.C, s.h_blk_row, s.h_blk_col);
+	}
 	EventTimer tm(ctx);
 	tm.start();
-	schur_form_reduced_system(ctx, alpha, (ctx->rank == 0)? alpha : 0.0); // S lives in the padded storage of the dense solver
+	schur_form_reduced_system(ctx, alpha, (ctx->rank == 0)? alpha : 0.0, sparse); // S lives in the padded storage of the dense solver
 	if(ctx->world > 1) { // sum the partial reduced camera systems and right-hand sides over the ranks
 		const size_t ld = dense_chol_ld(n);
 		allreduce_device(ctx, s.S.p(), ld * ld);
 		allreduce_device(ctx, s.b.p(), n);
 	}
 	if(s.keep_reduced) {
-		s.S_copy.resize(s.S.size());
 		s.b_copy.resize(n);
-		SPP_CUDA(cudaMemcpyAsync(s.S_copy.p(), s.S.p(), s.S.size() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+		if(sparse) {
+			const size_t ld = dense_chol_ld(n);
+			s.S_copy.resize(dense_chol_storage(n));
+			s.S_copy.zero(ctx->stream);
+			k_blocks_to_dense<<<n_blocks(s.n_blocks * 36, 256), 256, 0, ctx->stream>>>(s.n_blocks * 36, s.Sblk.p(), s.blk_row.p(),
+				s.blk_col.p(), ld, s.S_copy.p());
+			++ ctx->n_launches;
+			SPP_CUDA(cudaGetLastError());
+		} else {
+			s.S_copy.resize(s.S.size());
+			SPP_CUDA(cudaMemcpyAsync(s.S_copy.p(), s.S.p(), s.S.size() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+		}
 		SPP_CUDA(cudaMemcpyAsync(s.b_copy.p(), s.b.p(), n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
 	}
 	if(rep) rep->ms_schur += tm.stop_ms();
 	tm.start();
-	int rc = dense_chol_solve_device(ctx, s.S.p(), n, s.b.p());
+	int rc = sparse? snode_factor_solve(ctx, s.Sblk.p(), s.b.p(), s.b.p()) : dense_chol_solve_device(ctx, s.S.p(), n, s.b.p());
 	if(rep) rep->ms_factor += tm.stop_ms();
 	if(rc != SPP_OK)
 		return rc;
@@ -393,6 +434,7 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 	BAProblem &ba = ctx->ba;
 	ba.valid = false;
 	ctx->slot.valid = false;
+	ctx->snode.valid = false;
 	if(!p_vertex_type || (n_observations && (!p_obs_point || !p_obs_camera || !p_z || !p_info)))
 		throw invalid_error("null argument");
 	ba.n_vertices = n_vertices;
@@ -734,6 +776,7 @@ int spp_schur_symbolic(spp_ctx_t ctx, size_t n_block_cols, const uint64_t *p_col
 {
 	API_BEGIN(ctx)
 	if(!n_block_cols || !p_col_dims || !p_col_ptr || !p_row_idx) throw invalid_error("null argument");
+	ctx->snode.valid = false;
 	slot_symbolic(ctx, n_block_cols, p_col_dims, p_col_ptr, p_row_idx, p_order, p_cut);
 	API_END(ctx)
 }
@@ -771,6 +814,51 @@ int spp_schur_get_reduced_system(spp_ctx_t ctx, uint64_t *p_n, double *p_S, doub
 			p_block_pattern[(size_t)s.h_blk_row[i] * s.C + s.h_blk_col[i]] = 1;
 	}
 	s.keep_reduced = true;
+	API_END(ctx)
+}
+
+int spp_schur_set_rcs_solver(spp_ctx_t ctx, int mode)
+{
+	API_BEGIN(ctx)
+	if(mode != SPP_RCS_AUTO && mode != SPP_RCS_DENSE && mode != SPP_RCS_SPARSE) throw invalid_error("unknown reduced-camera-system solver");
+	ctx->snode.mode = mode;
+	API_END(ctx)
+}
+
+int spp_schur_set_rcs_ordering(spp_ctx_t ctx, size_t n_cameras, const uint64_t *p_order)
+{
+	API_BEGIN(ctx)
+	SupernodalChol &sc = ctx->snode;
+	sc.valid = false;
+	sc.user_order.clear();
+	if(p_order) {
+		std::vector<char> seen(n_cameras, 0);
+		for(size_t i = 0; i < n_cameras; ++ i) {
+			if(p_order[i] >= n_cameras || seen[p_order[i]]) throw invalid_error("the ordering is not a permutation");
+			seen[p_order[i]] = 1;
+		}
+		sc.user_order.assign(p_order, p_order + n_cameras);
+	}
+	API_END(ctx)
+}
+
+int spp_schur_get_rcs_info(spp_ctx_t ctx, uint64_t *p_order, double *p_stats)
+{
+	API_BEGIN(ctx)
+	SupernodalChol &sc = ctx->snode;
+	if(!sc.valid) throw invalid_error("no block-sparse factorisation of a reduced camera system yet");
+	if(p_order)
+		for(size_t i = 0; i < sc.n; ++ i) p_order[i] = sc.h_order[i];
+	if(p_stats) {
+		p_stats[0] = (double)sc.n;
+		p_stats[1] = (double)sc.n_s_blocks;
+		p_stats[2] = (double)sc.sn.n_super();
+		p_stats[3] = (double)sc.sn.nnzb_exact;
+		p_stats[4] = (double)sc.sn.nnzb_factor;
+		p_stats[5] = sc.factor_flops;
+		p_stats[6] = (double)sc.d_L.size() * 8.0;
+		p_stats[7] = (double)sc.updates.size();
+	}
 	API_END(ctx)
 }
 

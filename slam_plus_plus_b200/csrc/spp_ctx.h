@@ -2,6 +2,7 @@
 #pragma once
 
 #include "spp_common.cuh"
+#include "block_ordering.h"
 
 namespace spp {
 
@@ -30,6 +31,7 @@ struct SchurSystem {
 	DBuf<double> Cinv; // [P*9]  (V + alpha I)^-1
 	DBuf<double> Y;    // [O*18] W C^-1
 	DBuf<double> S;    // [n*n] dense column-major reduced camera system, n = 6C (upper triangle valid)
+	DBuf<double> Sblk; // [n_blocks*36] the same as a compact block list (sparse reduced camera system), order of blk_row/col
 	DBuf<double> S_copy; // optional copy kept for spp_schur_get_reduced_system
 	DBuf<double> b, b_copy; // [n] reduced right-hand side / camera increment
 	DBuf<double> dxc, dxp; // [6C], [3P] increments
@@ -127,6 +129,36 @@ struct PoseProblem {
 	PoseProblem() : valid(false), symbolic_done(false), linearised(false), dim(0), N(0), E(0), n_blocks(0), uf_block(-1) {}
 };
 
+// supernodal block Cholesky of a reduced camera system that is too large to be dense (supernodal_chol.cu): every
+// supernode owns a dense block-ROW panel of the upper factor R (R^T R = P S P^T), column-major, ld = its own columns
+// rounded up to 128 (identity padding), followed by the columns of its row structure and one right-hand-side column
+struct SnodeUpdate { // contribution of supernode s to its ancestor t: panel_t -= R_s[:, J]^T R_s[:, J..end]
+	uint32_t s, t;
+	uint32_t col0;    // first column of panel s of the suffix of its structure that starts inside t
+	uint32_t M, N;    // scalar rows (the part of the suffix inside t's own columns) and columns (whole suffix + rhs)
+	uint64_t map_off; // block positions in panel t of the suffix blocks, then of the rhs column
+};
+
+struct SupernodalChol {
+	bool valid;
+	int mode;                              // SPP_RCS_*
+	size_t n;                              // block columns (cameras)
+	std::vector<uint64_t> user_order;      // ordering given by the caller (spp_schur_set_rcs_ordering), may be empty
+	std::vector<uint32_t> h_order;         // new position -> camera
+	Supernodes sn;
+	std::vector<uint64_t> panel_off;       // [ns] offset of panel s in d_L (doubles)
+	std::vector<uint32_t> panel_ld, panel_cols, rinv_first;
+	std::vector<SnodeUpdate> updates;      // grouped by s
+	std::vector<uint64_t> upd_ptr;         // [ns + 1]
+	size_t n_rinv_blocks, n_s_blocks, max_part;
+	DBuf<uint32_t> d_cmap, d_rows, d_asm_ld, d_pad_ld, d_pad_n0, d_order;
+	DBuf<uint64_t> d_asm_dst, d_rhs_dst, d_pad_off;
+	DBuf<double> d_L, d_Rinv, d_x, d_part;
+	DBuf<int> d_info;                      // [0] first non-positive pivot, [1..] backsolve flags
+	double factor_flops;                   // of the numeric phase as executed (amalgamation zeros included)
+	SupernodalChol() : valid(false), mode(0), n(0), n_rinv_blocks(0), n_s_blocks(0), max_part(0), factor_flops(0) {}
+};
+
 struct DenseChol {
 	DBuf<double> work;        // inverse diagonal blocks, [n_blk][128 x 128]
 	DBuf<long long> dbg;      // clock64 marks of k_potrf128 (profile mode)
@@ -157,6 +189,7 @@ struct spp_ctx {
 	spp::DenseChol chol;
 	spp::SymbolicScratch sym;
 	spp::SparseChol schol;
+	spp::SupernodalChol snode;
 	spp::PoseProblem pose;
 	spp::HPinned<double> h_scalars;
 	cudaEvent_t ev[16];
