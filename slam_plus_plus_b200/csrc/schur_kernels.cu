@@ -134,7 +134,7 @@ template <int UNROLL>
 __global__ void __launch_bounds__(SB_WARPS * 32, (UNROLL >= 4)? 2 : 4) k_schur_blocks(size_t first_blk, size_t n_blocks_total, size_t ld,
 	const uint32_t *__restrict__ blk_row, const uint32_t *__restrict__ blk_col, const uint64_t *__restrict__ blk_ptr,
 	const uint32_t *__restrict__ pair_a, const uint32_t *__restrict__ pair_b, const double *__restrict__ Y,
-	const double *__restrict__ W, double *__restrict__ S)
+	const double *__restrict__ W, double *__restrict__ S, const uint32_t *__restrict__ slot)
 {
 	const int lane = threadIdx.x & 31;
 	const size_t blk = first_blk + blockIdx.x * (size_t)SB_WARPS + (threadIdx.x >> 5);
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32, (UNROLL >= 4)? 2 : 4) k_schur_b
 	}
 	if(lane < 9) { // ld == 0: compact block list (block blk at S + 36 blk), else the dense matrix
 		const size_t ldo = ld? ld : 6;
-		double *Sb = ld? S + ((size_t)bj * 6 + c3) * ld + (size_t)bi * 6 + r3 : S + blk * 36 + c3 * 6 + r3;
+		double *Sb = ld? S + ((size_t)bj * 6 + c3) * ld + (size_t)bi * 6 + r3 : S + (size_t)(slot? slot[blk] : blk) * 36 + c3 * 6 + r3;
 		Sb[0] = -v[0];
 		Sb[3] = -v[1];
 		Sb[3 * ldo] = -v[2];
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32, (UNROLL >= 4)? 2 : 4) k_schur_b
 __global__ void __launch_bounds__(SB_WARPS * 32) k_schur_diag(size_t ld, double alpha, const uint64_t *__restrict__ blk_ptr,
 	const uint32_t *__restrict__ pair_a, const double *__restrict__ Y, const double *__restrict__ W,
 	const double *__restrict__ U, const double *__restrict__ gc, const double *__restrict__ gp,
-	const uint32_t *__restrict__ obs_pt, double *__restrict__ S, double *__restrict__ b)
+	const uint32_t *__restrict__ obs_pt, double *__restrict__ S, double *__restrict__ b, const uint32_t *__restrict__ slot)
 {
 	__shared__ double part[3 * SB_WARPS][9][6];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32) k_schur_diag(size_t ld, double 
 		}
 		const double *Ub = U + bi * 36 + c3 * 6 + r3; // column-major 6x6
 		const size_t ldo = ld? ld : 6; // ld == 0: compact block list
-		double *Sb = ld? S + (bi * 6 + c3) * ld + bi * 6 + r3 : S + bi * 36 + c3 * 6 + r3;
+		double *Sb = ld? S + (bi * 6 + c3) * ld + bi * 6 + r3 : S + (size_t)(slot? slot[bi] : bi) * 36 + c3 * 6 + r3;
 		Sb[0] = (Ub[0] + ((r3 == c3)? alpha : 0.0)) - v[0];
 		Sb[3] = Ub[3] - v[1];
 		Sb[3 * ldo] = Ub[18] - v[2];
@@ -254,9 +254,12 @@ void schur_form_reduced_system(spp_ctx *ctx, double alpha, double alpha_diag, bo
 	const size_t ld = sparse_rcs? 0 : dense_chol_ld(n); // S is written straight into the dense solver's padded storage
 	s.Cinv.resize(s.P * 9);
 	s.Y.resize(s.O * 18);
-	if(sparse_rcs)
-		s.Sblk.resize(s.n_blocks * 36);
-	else
+	const uint32_t *slot = (sparse_rcs && s.n_blocks_global)? s.blk_slot.p() : 0; // several ranks: the global block list
+	if(sparse_rcs) {
+		s.Sblk.resize((s.n_blocks_global? s.n_blocks_global : s.n_blocks) * 36);
+		if(slot)
+			s.Sblk.zero(ctx->stream); // blocks no landmark of this rank contributes to
+	} else
 		s.S.resize(dense_chol_storage(n));
 	double *S_out = sparse_rcs? s.Sblk.p() : s.S.p();
 	s.b.resize(n);
@@ -269,17 +272,17 @@ void schur_form_reduced_system(spp_ctx *ctx, double alpha, double alpha_diag, bo
 		s.S.zero(ctx->stream);
 	if(s.C) { // list entries 0 .. C-1 are the diagonal blocks
 		k_schur_diag<<<(unsigned)s.C, SB_WARPS * 32, 0, ctx->stream>>>(ld, alpha_diag, s.blk_ptr.p(), s.pair_a.p(), s.Y.p(),
-			s.W.p(), s.U.p(), s.gc.p(), s.gp.p(), s.obs_pt.p(), S_out, s.b.p());
+			s.W.p(), s.U.p(), s.gc.p(), s.gp.p(), s.obs_pt.p(), S_out, s.b.p(), slot);
 		LAUNCH_CHECK(ctx);
 	}
 	if(s.n_blocks > s.C) {
 		static const int unroll = getenv("SPP_SCHUR_UNROLL")? atoi(getenv("SPP_SCHUR_UNROLL")) : 2;
 		if(unroll >= 4)
 			k_schur_blocks<4><<<n_blocks(s.n_blocks - s.C, SB_WARPS), SB_WARPS * 32, 0, ctx->stream>>>(s.C, s.n_blocks, ld,
-				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), S_out);
+				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), S_out, slot);
 		else
 			k_schur_blocks<2><<<n_blocks(s.n_blocks - s.C, SB_WARPS), SB_WARPS * 32, 0, ctx->stream>>>(s.C, s.n_blocks, ld,
-				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), S_out);
+				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), S_out, slot);
 		LAUNCH_CHECK(ctx);
 	}
 }

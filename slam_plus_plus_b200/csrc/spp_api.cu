@@ -19,6 +19,10 @@ void ba_upload_and_analyse_device(spp_ctx *ctx, size_t C, size_t P, size_t O, co
 	const uint64_t *p_obs_camera, const double *p_z, const double *p_info);
 void ba_fetch_host_maps(spp_ctx *ctx);
 void schur_fetch_host_pattern(spp_ctx *ctx);
+void build_global_rcs_pattern(size_t C, size_t P, const std::vector<uint32_t> &h_cam, const std::vector<uint32_t> &h_pt,
+	std::vector<uint32_t> &g_row, std::vector<uint32_t> &g_col);
+void map_blocks_to_global(size_t C, const std::vector<uint32_t> &l_row, const std::vector<uint32_t> &l_col,
+	const std::vector<uint32_t> &g_row, const std::vector<uint32_t> &g_col, std::vector<uint32_t> &slot);
 void ba_linearise(spp_ctx *ctx, bool b_want_maxdiag);
 void ba_chi2_device(spp_ctx *ctx, double *d_out);
 void ba_step_dots_device(spp_ctx *ctx, double alpha, double *d_out);
@@ -92,12 +96,12 @@ __global__ void k_blocks_to_dense(size_t n_vals, const double *__restrict__ Sblk
 // The reference tries the dense solver on the reduced camera system first and falls back to the block-sparse one when
 // the dense matrix cannot be allocated (LinearSolver_Schur.h:1836-1847). Here the choice is explicit: SPP_RCS_AUTO takes
 // the dense path up to 16 384 unknowns (2 GiB of FP64, n^3 / 3 = 1.5e12 flop) and the supernodal one above.
-static bool rcs_is_sparse(spp_ctx *ctx)
+static bool rcs_is_sparse(spp_ctx *ctx, size_t C)
 {
 	const int mode = ctx->snode.mode;
 	if(mode == SPP_RCS_DENSE) return false;
 	if(mode == SPP_RCS_SPARSE) return true;
-	return ctx->sys.C * 6 > 16384;
+	return C * 6 > 16384;
 }
 
 // Solves the damped Schur system on the current (U, V, W, gc, gp): dxc, dxp. Returns SPP_OK / SPP_NOT_POSDEF.
@@ -105,19 +109,26 @@ int schur_solve_current(spp_ctx *ctx, double alpha, spp_report_t *rep)
 {
 	SchurSystem &s = ctx->sys;
 	const size_t n = s.C * 6;
-	const bool sparse = rcs_is_sparse(ctx);
-	if(sparse && ctx->world > 1)
-		throw invalid_error("the block-sparse reduced camera system is single-GPU in this version (use SPP_RCS_DENSE with several ranks)");
+	const bool sparse = rcs_is_sparse(ctx, s.C);
+	if(sparse && ctx->world > 1 && !s.n_blocks_global)
+		throw invalid_error("several ranks: select the block-sparse reduced-camera-system solver before spp_ba_set_graph");
 	if(sparse && !ctx->snode.valid) { // one-time symbolic analysis of the structure (host)
-		schur_fetch_host_pattern(ctx);
-		snode_symbolic(ctx, s.C, s.h_blk_row, s.h_blk_col);
+		if(ctx->world > 1) // the block list of the whole graph: every rank derives the same ordering and supernodes
+			snode_symbolic(ctx, s.C, s.h_gblk_row, s.h_gblk_col);
+		else {
+			schur_fetch_host_pattern(ctx);
+			snode_symbolic(ctx, s.C, s.h_blk_row, s.h_blk_col);
+		}
 	}
 	EventTimer tm(ctx);
 	tm.start();
 	schur_form_reduced_system(ctx, alpha, (ctx->rank == 0)? alpha : 0.0, sparse); // S lives in the padded storage of the dense solver
 	if(ctx->world > 1) { // sum the partial reduced camera systems and right-hand sides over the ranks
 		const size_t ld = dense_chol_ld(n);
-		allreduce_device(ctx, s.S.p(), ld * ld);
+		if(sparse)
+			allreduce_device(ctx, s.Sblk.p(), s.n_blocks_global * 36);
+		else
+			allreduce_device(ctx, s.S.p(), ld * ld);
 		allreduce_device(ctx, s.b.p(), n);
 	}
 	if(s.keep_reduced) {
@@ -126,6 +137,8 @@ int schur_solve_current(spp_ctx *ctx, double alpha, spp_report_t *rep)
 			const size_t ld = dense_chol_ld(n);
 			s.S_copy.resize(dense_chol_storage(n));
 			s.S_copy.zero(ctx->stream);
+			if(s.n_blocks_global)
+				throw invalid_error("spp_schur_get_reduced_system is not available with several ranks on the block-sparse path");
 			k_blocks_to_dense<<<n_blocks(s.n_blocks * 36, 256), 256, 0, ctx->stream>>>(s.n_blocks * 36, s.Sblk.p(), s.blk_row.p(),
 				s.blk_col.p(), ld, s.S_copy.p());
 			++ ctx->n_launches;
@@ -435,6 +448,7 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 	ba.valid = false;
 	ctx->slot.valid = false;
 	ctx->snode.valid = false;
+	ctx->sys.n_blocks_global = 0;
 	if(!p_vertex_type || (n_observations && (!p_obs_point || !p_obs_camera || !p_z || !p_info)))
 		throw invalid_error("null argument");
 	ba.n_vertices = n_vertices;
@@ -484,6 +498,11 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 		}
 		// multi-GPU: this rank keeps a contiguous slice of the landmarks with all their observations; cameras are
 		// replicated. The slice bounds balance the Schur-product work sum k_p (k_p + 1) / 2 + k_p.
+		ctx->sys.n_blocks_global = 0;
+		std::vector<uint32_t> g_row, g_col;
+		const bool b_global_pattern = ctx->world > 1 && rcs_is_sparse(ctx, C);
+		if(b_global_pattern)
+			build_global_rcs_pattern(C, P, h_cam, h_pt, g_row, g_col);
 		if(ctx->world > 1) {
 			std::vector<uint32_t> track_len(P, 0);
 			for(size_t e = 0; e < O; ++ e)
@@ -505,6 +524,15 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 			build_schur_structure(ctx, C, ba.pt_end - ba.pt_begin, h_cam, h_pt, ba.obs_orig, ba.h_obs_cam, ba.h_obs_pt);
 			for(size_t k = 0; k < ba.obs_orig.size(); ++ k)
 				ba.obs_orig[k] = kept[ba.obs_orig[k]]; // local track position -> original (global) edge index
+			if(b_global_pattern) {
+				std::vector<uint32_t> slot;
+				map_blocks_to_global(C, ctx->sys.h_blk_row, ctx->sys.h_blk_col, g_row, g_col, slot);
+				ctx->sys.blk_slot.upload(slot, st);
+				ctx->sys.n_blocks_global = g_row.size();
+				ctx->sys.h_gblk_row.swap(g_row);
+				ctx->sys.h_gblk_col.swap(g_col);
+				SPP_CUDA(cudaStreamSynchronize(st));
+			}
 		} else
 			build_schur_structure(ctx, C, P, h_cam, h_pt, ba.obs_orig, ba.h_obs_cam, ba.h_obs_pt);
 		ba.host_maps_valid = true;
@@ -777,6 +805,7 @@ int spp_schur_symbolic(spp_ctx_t ctx, size_t n_block_cols, const uint64_t *p_col
 	API_BEGIN(ctx)
 	if(!n_block_cols || !p_col_dims || !p_col_ptr || !p_row_idx) throw invalid_error("null argument");
 	ctx->snode.valid = false;
+	ctx->sys.n_blocks_global = 0;
 	slot_symbolic(ctx, n_block_cols, p_col_dims, p_col_ptr, p_row_idx, p_order, p_cut);
 	API_END(ctx)
 }

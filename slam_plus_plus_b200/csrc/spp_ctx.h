@@ -23,6 +23,11 @@ struct SchurSystem {
 	DBuf<uint64_t> blk_ptr;          // [n_blocks+1]
 	DBuf<uint32_t> pair_a, pair_b;   // [n_pairs]
 	std::vector<uint32_t> h_blk_row, h_blk_col; // host copy of the block pattern
+	// several ranks + block-sparse reduced camera system: the block list of the WHOLE graph (identical on every rank)
+	// and the position of this rank's blocks in it; n_blocks_global == 0 otherwise
+	size_t n_blocks_global;
+	std::vector<uint32_t> h_gblk_row, h_gblk_col;
+	DBuf<uint32_t> blk_slot;         // [n_blocks] local block -> global block
 	// values (device)
 	DBuf<double> U;    // [C*36] camera diagonal blocks (column-major 6x6, undamped, incl. unary factor)
 	DBuf<double> V;    // [P*9]  point diagonal blocks
@@ -36,7 +41,7 @@ struct SchurSystem {
 	DBuf<double> b, b_copy; // [n] reduced right-hand side / camera increment
 	DBuf<double> dxc, dxp; // [6C], [3P] increments
 	bool keep_reduced;
-	SchurSystem() : C(0), P(0), O(0), n_blocks(0), n_pairs(0), keep_reduced(false) {}
+	SchurSystem() : C(0), P(0), O(0), n_blocks(0), n_pairs(0), n_blocks_global(0), keep_reduced(false) {}
 };
 
 struct BAProblem {

@@ -77,7 +77,7 @@ void snode_symbolic(spp_ctx *ctx, size_t n, const std::vector<uint32_t> &blk_row
 		amd_block_ordering(n, col_ptr.data(), row_idx.data(), sc.h_order);
 		etree_postorder(n, col_ptr.data(), row_idx.data(), sc.h_order);
 	}
-	static const double relax_zeros = getenv("SPP_SNODE_RELAX")? atof(getenv("SPP_SNODE_RELAX")) : 0.15;
+	static const double relax_zeros = getenv("SPP_SNODE_RELAX")? atof(getenv("SPP_SNODE_RELAX")) : 0.05;
 	static const size_t relax_small = getenv("SPP_SNODE_SMALL")? (size_t)atoi(getenv("SPP_SNODE_SMALL")) : 16;
 	supernodal_symbolic(n, col_ptr.data(), row_idx.data(), sc.h_order, relax_zeros, relax_small, (size_t)1 << 30, sc.sn);
 	const Supernodes &sn = sc.sn;

@@ -189,6 +189,61 @@ void build_schur_structure(spp_ctx *ctx, size_t C, size_t P, const std::vector<u
 	SPP_CUDA(cudaStreamSynchronize(st)); // the host vectors go out of scope
 }
 
+// Several ranks + block-sparse reduced camera system: the upper block list of the WHOLE graph (every rank sees all
+// observations in spp_ba_set_graph and computes the same list): diagonal blocks 0 .. C-1 first, then the off-diagonal
+// blocks in row-major order. h_cam / h_pt: local camera / point index of every observation of the whole graph.
+void build_global_rcs_pattern(size_t C, size_t P, const std::vector<uint32_t> &h_cam, const std::vector<uint32_t> &h_pt,
+	std::vector<uint32_t> &g_row, std::vector<uint32_t> &g_col)
+{
+	const size_t O = h_cam.size();
+	std::vector<uint32_t> pt_ptr(P + 1, 0), t_cam(O);
+	for(size_t e = 0; e < O; ++ e) ++ pt_ptr[h_pt[e] + 1];
+	for(size_t p = 0; p < P; ++ p) pt_ptr[p + 1] += pt_ptr[p];
+	{
+		std::vector<uint32_t> fill(pt_ptr.begin(), pt_ptr.end() - 1);
+		for(size_t e = 0; e < O; ++ e) t_cam[fill[h_pt[e]] ++] = h_cam[e];
+	}
+	std::vector<uint64_t> bits((C * C + 63) / 64, 0);
+	for(size_t p = 0; p < P; ++ p) {
+		for(uint32_t a = pt_ptr[p]; a < pt_ptr[p + 1]; ++ a) {
+			for(uint32_t b = a + 1; b < pt_ptr[p + 1]; ++ b) {
+				const uint32_t ca = std::min(t_cam[a], t_cam[b]), cb = std::max(t_cam[a], t_cam[b]);
+				const uint64_t k = (uint64_t)ca * C + cb;
+				bits[k >> 6] |= (uint64_t)1 << (k & 63);
+			}
+		}
+	}
+	g_row.clear();
+	g_col.clear();
+	for(size_t i = 0; i < C; ++ i) { g_row.push_back((uint32_t)i); g_col.push_back((uint32_t)i); }
+	for(size_t i = 0; i < C; ++ i) {
+		for(size_t j = i + 1; j < C; ++ j) {
+			const uint64_t k = (uint64_t)i * C + j;
+			if(!(k & 63) && j + 64 <= C && !bits[k >> 6]) { j += 63; continue; } // skip an empty word
+			if(bits[k >> 6] >> (k & 63) & 1) { g_row.push_back((uint32_t)i); g_col.push_back((uint32_t)j); }
+		}
+	}
+}
+
+// position of every block of this rank's list in the global list built above
+void map_blocks_to_global(size_t C, const std::vector<uint32_t> &l_row, const std::vector<uint32_t> &l_col,
+	const std::vector<uint32_t> &g_row, const std::vector<uint32_t> &g_col, std::vector<uint32_t> &slot)
+{
+	std::vector<uint64_t> row_start(C + 1, 0); // off-diagonal blocks of the global list, by row
+	for(size_t b = C; b < g_row.size(); ++ b) ++ row_start[g_row[b] + 1];
+	for(size_t i = 0; i < C; ++ i) row_start[i + 1] += row_start[i];
+	slot.resize(l_row.size());
+	for(size_t b = 0; b < l_row.size(); ++ b) {
+		const uint32_t i = l_row[b], j = l_col[b];
+		if(i == j) { slot[b] = i; continue; }
+		const uint32_t *beg = &g_col[C + row_start[i]], *end = &g_col[0] + C + row_start[i + 1];
+		const uint32_t *it = std::lower_bound(beg, end, j);
+		if(it == end || *it != j)
+			throw invalid_error("internal error: a block of this rank is missing from the global block list");
+		slot[b] = (uint32_t)(it - &g_col[0]);
+	}
+}
+
 } // namespace spp
 
 extern "C" int spp_partition_landmarks(size_t n_points, const uint32_t *p_track_length, int world, uint64_t *p_bounds)

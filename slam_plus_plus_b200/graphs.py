@@ -132,7 +132,8 @@ def make_ba(n_cams: int, n_pts: int, seed: int, mean_extra_track: float = 3.35, 
 BA_SHAPES = {
     # name: (n_cams, n_pts, seed, kwargs)
     "venice871": (871, 530304, 871, dict(mean_extra_track=3.35, max_track=60, max_stride=11)),
-    "bal13682": (13682, 4456117, 13682, dict(mean_extra_track=4.5, max_track=120, max_stride=24, loops=3)),
+    # max_stride 12: the reduced camera system has 2.4 % non-zero blocks ("locality window so that S fill is 1-3 %")
+    "bal13682": (13682, 4456117, 13682, dict(mean_extra_track=4.5, max_track=120, max_stride=12, loops=3)),
     "mid": (100, 20000, 100, dict(mean_extra_track=3.0, max_track=30, max_stride=3)),
     "small": (24, 1500, 24, dict(mean_extra_track=3.0, max_track=12, max_stride=2)),
     "tiny": (6, 40, 6, dict(mean_extra_track=2.0, max_track=5, max_stride=1)),
@@ -238,3 +239,39 @@ def make_sphere(n_rings: int = 50, n_per_ring: int = 50, seed: int = 2500, radiu
         Re[i] = Re[i - 1] @ Rrel[i - 1]
     poses = np.concatenate([te, _rotmat_to_axis_angle(Re)], 1)
     return PoseGraph(GRAPH_SE3, poses, e_from, e_to, z, info)
+
+
+def rcs_block_pattern(g: BAGraph):
+    """Upper block structure (block CSC: col_ptr, row_idx, rows ascending, diagonal last) of the reduced camera system of
+    a BA graph: cameras i <= j share a block when some landmark is seen by both (LinearSolver_Schur.h:1757-1767)."""
+    vtype = np.asarray(g.vtype)
+    cam_local = np.cumsum(vtype == 0) - 1
+    n_cams = int((vtype == 0).sum())
+    oc = cam_local[np.asarray(g.obs_cam, np.int64)]
+    op = np.asarray(g.obs_pt, np.int64)
+    order = np.argsort(op, kind="stable")
+    oc, op = oc[order], op[order]
+    _, start, k = np.unique(op, return_index=True, return_counts=True)
+    j = np.arange(len(oc)) - np.repeat(start, k)
+    kk = np.repeat(k, k)
+    keys = [np.arange(n_cams, dtype=np.int64) * n_cams + np.arange(n_cams)]
+    for dj in range(1, int(k.max()) if len(k) else 1):
+        m = np.flatnonzero(j + dj < kk)
+        a, b = oc[m], oc[m + dj]
+        keys.append(np.unique(np.maximum(a, b) * n_cams + np.minimum(a, b)))  # key = col * C + row
+    keys = np.unique(np.concatenate(keys))
+    col, row = keys // n_cams, keys % n_cams
+    col_ptr = np.zeros(n_cams + 1, np.uint64)
+    np.add.at(col_ptr, col + 1, 1)
+    return np.cumsum(col_ptr).astype(np.uint64), row.astype(np.uint64)
+
+
+def pose_block_pattern(g: PoseGraph):
+    """Upper block structure of lambda of a pose graph (one block per edge + the diagonal)."""
+    n = len(g.poses)
+    a, b = np.asarray(g.e_from, np.int64), np.asarray(g.e_to, np.int64)
+    keys = np.unique(np.concatenate([np.arange(n, dtype=np.int64) * n + np.arange(n), np.maximum(a, b) * n + np.minimum(a, b)]))
+    col, row = keys // n, keys % n
+    col_ptr = np.zeros(n + 1, np.uint64)
+    np.add.at(col_ptr, col + 1, 1)
+    return np.cumsum(col_ptr).astype(np.uint64), row.astype(np.uint64)

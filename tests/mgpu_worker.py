@@ -77,6 +77,8 @@ def run_gpu(rank, world):
     g = graphs.ba_shape(shape)
     ctx = capi.Context(local)
     parallel.attach_torch_allreduce(ctx, rank, world)
+    if os.environ.get("SPP_TEST_RCS") == "sparse":  # block-sparse reduced camera system: the global block list is summed
+        ctx.schur_set_rcs_solver(capi.RCS_SPARSE)
     ctx.ba_set_graph(g)
     rep = ctx.ba_optimize(5, 0.0)
     cs, ps = ctx.ba_get_states()

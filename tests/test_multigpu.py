@@ -50,11 +50,12 @@ def test_partition_edge_cases():
 
 
 @pytest.mark.gpu
-def test_sharded_lm_on_two_gpus_matches_single_gpu():
+@pytest.mark.parametrize("rcs", ["dense", "sparse"])
+def test_sharded_lm_on_two_gpus_matches_single_gpu(rcs):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    out = _launch("gpu", 2)
+    out = _launch("gpu", 2, env=dict(SPP_TEST_RCS=rcs))
     one = out["single"]
     assert out["accepted"] == one["accepted"]
     assert abs(out["alpha_initial"] - one["alpha_initial"]) <= 1e-12 * one["alpha_initial"]
