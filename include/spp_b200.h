@@ -244,12 +244,15 @@ int spp_chol_solve(spp_ctx_t ctx, const double *p_values, double *p_eta_dx);
  * Call with NULL arrays to obtain the block count. */
 int spp_chol_get_factor(spp_ctx_t ctx, uint64_t *p_n_blocks, uint64_t *p_col_ptr, uint64_t *p_row_idx, double *p_values);
 
-/* ---- pose graphs resident on the device (SE(2); Gauss-Newton) ----------------------------------------------- */
+/* ---- pose graphs resident on the device (SE(2) and SE(3); Gauss-Newton) ---------------------------------------- */
 
 /* Replaces r_Get_Vertex<CVertexPose2D> / r_Add_Edge(CEdgePose2D(...)) called in a loop (src/slam_simple_example/
  * Main.cpp; include/slam/SE2_Types.h:178-260) plus the structure build of CLambdaOps2::Extend_Lambda
  * (include/slam/NonlinearSolver_Lambda_Base.h:1634, 1853-1931).
- *   dim            3 = SE(2) poses [x, y, theta]
+ *   dim            3 = SE(2) poses [x, y, theta] (CVertexPose2D / CEdgePose2D, analytic Jacobians);
+ *                  6 = SE(3) poses [t, axis-angle] (CVertexPose3D / CEdgePose3D, include/slam/SE3_Types.h:45-48, 128-129,
+ *                  265-288: forward-difference Jacobians with delta = 1e-9 in the reference's operation order, Huber
+ *                  weight on |r| / 0.3 applied exactly as the reference's robust Calculate_Hessians_v2 does)
  *   p_states[dim * n_poses], p_from / p_to[n_edges] vertex ids (any order; duplicates allowed)
  *   p_z[dim * n_edges] relative pose measurements, p_info[dim * dim * n_edges] information matrices (symmetric)
  * Vertex 0 receives the reference's automatic unary factor (identity). */

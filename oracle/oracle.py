@@ -146,25 +146,32 @@ def _pose_args(g, poses=None):
     return args, keep
 
 
-def se2_chi2(g, poses=None) -> float:
+def _fn(g, name):
+    return getattr(lib(), ("spo_se2_" if g.dim == 3 else "spo_se3_") + name)
+
+
+def pose_chi2(g, poses=None) -> float:
     args, keep = _pose_args(g, poses)
     v = C.c_double()
-    assert lib().spo_se2_chi2(*args, C.byref(v)) == 0
+    assert _fn(g, "chi2")(*args, C.byref(v)) == 0
     return v.value
 
 
-def se2_linearise_dense(g, poses=None):
-    """Dense lambda (n x n, symmetric) and eta of the SE(2) graph at the given poses."""
+def pose_linearise_dense(g, poses=None):
+    """Dense lambda (n x n, symmetric) and eta of the SE(2) / SE(3) graph at the given poses."""
     args, keep = _pose_args(g, poses)
-    n = keep[0].shape[0] * 3
+    n = keep[0].shape[0] * g.dim
     lam, eta = np.zeros((n, n)), np.zeros(n)
-    assert lib().spo_se2_linearise_dense(*args, _p(lam, C.c_double), _p(eta, C.c_double)) == 0
+    assert _fn(g, "linearise_dense")(*args, _p(lam, C.c_double), _p(eta, C.c_double)) == 0
     return lam, eta  # symmetric: row/column-major agree
 
 
-def se2_optimize(g, max_iter=5, min_dx=0.0):
+def pose_optimize(g, max_iter=5, min_dx=0.0):
     args, keep = _pose_args(g)
     out, norms = np.zeros(3), np.zeros(max(max_iter, 1))
-    rc = lib().spo_se2_optimize(*args, C.c_size_t(max_iter), C.c_double(min_dx), _p(out, C.c_double), _p(norms, C.c_double))
+    rc = _fn(g, "optimize")(*args, C.c_size_t(max_iter), C.c_double(min_dx), _p(out, C.c_double), _p(norms, C.c_double))
     return dict(status=rc, chi2_initial=out[0], chi2_final=out[1], n_solves=int(out[2]), dx_norms=norms[:int(out[2])],
                 poses=keep[0])
+
+
+se2_chi2, se2_linearise_dense, se2_optimize = pose_chi2, pose_linearise_dense, pose_optimize

@@ -715,3 +715,174 @@ SPO_API int spo_se2_optimize(size_t N, double *states, size_t E, const uint64_t 
 	free(lambda); free(eta);
 	return rc;
 }
+
+/* ---- SE(3) pose graphs ----------------------------------------------------------------------
+ *   3D  = include/slam/3DSolverBase.h    SE3 = include/slam/SE3_Types.h    ROB = include/slam/RobustUtils.h,
+ *   include/geometry/RobustLoss.h        BIN = include/slam/BaseTypes_Binary.h */
+
+/* C3DJacobians::Absolute_to_Relative (value), 3D:892-946 */
+static void absolute_to_relative(const double *v1, const double *v2, double *dest)
+{
+	quat_t q1, q2, q1i, q;
+	double d[3], t[6];
+	axis_angle_to_quat(v1 + 3, &q1);
+	axis_angle_to_quat(v2 + 3, &q2);
+	q1i.w = q1.w; q1i.x = -q1.x; q1i.y = -q1.y; q1i.z = -q1.z;
+	d[0] = v2[0] - v1[0]; d[1] = v2[1] - v1[1]; d[2] = v2[2] - v1[2];
+	quat_rotate(&q1i, d, t);
+	q = quat_mul(&q1i, &q2);
+	quat_to_axis_angle(&q, t + 3);
+	memcpy(dest, t, sizeof(t));
+}
+
+/* CEdgePose3D::Calculate_Jacobians_Expectation_Error, SE3:265-288: expectation + forward-difference Jacobians
+ * (delta = 1e-9, 3D:1043-1059, 1332-1370), error = [t_meas - t_exp, axis-angle of q_meas * conj(q_exp)].
+ * J0, J1 row-major 6 x 6 (may be NULL). */
+static void se3_edge(const double *states, uint64_t a, uint64_t b, const double *z, double *J0, double *J1, double *r)
+{
+	const double *v0 = states + a * 6, *v1 = states + b * 6;
+	double d[6];
+	absolute_to_relative(v0, v1, d);
+	if(J0) {
+		const double delta = 1e-9, scalar = 1.0 / delta;
+		for(int j = 0; j < 6; ++ j) {
+			double eps[6] = {0, 0, 0, 0, 0, 0}, p[6], d1[6];
+			eps[j] = delta;
+			relative_to_absolute(v0, eps, p);
+			absolute_to_relative(p, v1, d1);
+			for(int i = 0; i < 6; ++ i) J0[i * 6 + j] = (d1[i] - d[i]) * scalar;
+			relative_to_absolute(v1, eps, p);
+			absolute_to_relative(v0, p, d1);
+			for(int i = 0; i < 6; ++ i) J1[i * 6 + j] = (d1[i] - d[i]) * scalar;
+		}
+	}
+	quat_t pq, dq, dqc, e;
+	r[0] = z[0] - d[0]; r[1] = z[1] - d[1]; r[2] = z[2] - d[2];
+	axis_angle_to_quat(z + 3, &pq);
+	axis_angle_to_quat(d + 3, &dq);
+	dqc.w = dq.w; dqc.x = -dq.x; dqc.y = -dq.y; dqc.z = -dq.z;
+	e = quat_mul(&pq, &dqc);
+	quat_to_axis_angle(&e, r + 3);
+}
+
+/* CRobustify_ErrorNorm_Default<CCTFraction<30, 100>, CHuberLossd>::f_RobustWeight, SE3:128-129, ROB:412-438, Huber weight
+ * with the default parameter 1.345 (RobustLoss.h:63,100-104) */
+static double se3_robust_weight(const double *r)
+{
+	double s = 0;
+	for(int i = 0; i < 6; ++ i) s += r[i] * r[i];
+	double e = sqrt(s) / (30.0 / 100.0);
+	return (e <= 1.345)? 1.0 : 1.345 / e;
+}
+
+/* f_Chi_Squared_Error_Denorm: serial sum of the UNWEIGHTED r^T Sigma^-1 r, SE3:318-327 */
+SPO_API int spo_se3_chi2(size_t N, const double *states, size_t E, const uint64_t *from, const uint64_t *to, const double *z,
+	const double *info, double *chi2)
+{
+	(void)N;
+	double s = 0;
+	for(size_t e = 0; e < E; ++ e) {
+		double r[6];
+		se3_edge(states, from[e], to[e], z + e * 6, 0, 0, r);
+		const double *W = info + e * 36;
+		for(int i = 0; i < 6; ++ i) {
+			double t = 0;
+			for(int k = 0; k < 6; ++ k) t += W[i * 6 + k] * r[k];
+			s += r[i] * t;
+		}
+	}
+	*chi2 = s;
+	return 0;
+}
+
+/* Refresh_Lambda into a dense lambda (column-major, full symmetric) and eta. Calculate_Hessians_v2 for a ROBUST edge
+ * (BIN:759-848): T = J0^T Sigma^-1 w; H01 = T J1; H00 = sym_U(T J0); H11 = sym_U(J1^T Sigma^-1 J1 w);
+ * g0 = T r w (the weight enters twice, as in the reference, BIN:820-821); g1 = J1^T (Sigma^-1 r) w. */
+SPO_API int spo_se3_linearise_dense(size_t N, const double *states, size_t E, const uint64_t *from, const uint64_t *to,
+	const double *z, const double *info, double *lambda, double *eta)
+{
+	const size_t n = N * 6;
+	memset(lambda, 0, n * n * sizeof(double));
+	memset(eta, 0, n * sizeof(double));
+	for(size_t e = 0; e < E; ++ e) {
+		double J0[36], J1[36], r[6], T[36], WJ1[36], Wr[6];
+		se3_edge(states, from[e], to[e], z + e * 6, J0, J1, r);
+		const double w = se3_robust_weight(r);
+		const double *W = info + e * 36;
+		for(int i = 0; i < 6; ++ i)
+			for(int j = 0; j < 6; ++ j) {
+				double t = 0;
+				for(int k = 0; k < 6; ++ k) t += J0[k * 6 + i] * W[k * 6 + j];
+				T[i * 6 + j] = t * w;
+			}
+		for(int i = 0; i < 6; ++ i) {
+			for(int j = 0; j < 6; ++ j) {
+				double t = 0;
+				for(int k = 0; k < 6; ++ k) t += W[i * 6 + k] * J1[k * 6 + j];
+				WJ1[i * 6 + j] = t;
+			}
+			double t = 0;
+			for(int k = 0; k < 6; ++ k) t += W[i * 6 + k] * r[k];
+			Wr[i] = t;
+		}
+		const size_t a = from[e] * 6, b = to[e] * 6;
+		for(int c = 0; c < 6; ++ c) {
+			for(int rr = 0; rr < 6; ++ rr) {
+				int p = (rr <= c)? rr : c, q = (rr <= c)? c : rr;
+				double h00 = 0, h11 = 0, h01 = 0;
+				for(int k = 0; k < 6; ++ k) {
+					h00 += T[p * 6 + k] * J0[k * 6 + q];
+					h11 += J1[k * 6 + p] * WJ1[k * 6 + q];
+					h01 += T[rr * 6 + k] * J1[k * 6 + c];
+				}
+				h11 *= w;
+				lambda[(a + c) * n + a + rr] += h00;
+				lambda[(b + c) * n + b + rr] += h11;
+				lambda[(b + c) * n + a + rr] += h01;
+				lambda[(a + rr) * n + b + c] += h01;
+			}
+		}
+		for(int i = 0; i < 6; ++ i) {
+			double g0 = 0, g1 = 0;
+			for(int k = 0; k < 6; ++ k) {
+				g0 += T[i * 6 + k] * r[k];
+				g1 += J1[k * 6 + i] * Wr[k];
+			}
+			eta[a + i] += g0 * w;
+			eta[b + i] += g1 * w;
+		}
+	}
+	if(N)
+		for(int i = 0; i < 6; ++ i)
+			lambda[i * n + i] += 1.0;
+	return 0;
+}
+
+/* CNonlinearSolver_Lambda::Optimize (GN:476-667) on an SE(3) graph; CVertexPose3D::Operator_Plus = Relative_to_Absolute
+ * (SE3:45-48). Dense LLT stands in for the block-sparse factorisation, as in spo_se2_optimize. */
+SPO_API int spo_se3_optimize(size_t N, double *states, size_t E, const uint64_t *from, const uint64_t *to, const double *z,
+	const double *info, size_t max_iter, double min_dx, double *out, double *dx_norms)
+{
+	const size_t n = N * 6;
+	double *lambda = (double*)malloc(n * n * sizeof(double)), *eta = (double*)malloc(n * sizeof(double));
+	if(!lambda || !eta) return -1;
+	spo_se3_chi2(N, states, E, from, to, z, info, &out[0]);
+	size_t n_solves = 0;
+	int rc = 0;
+	for(size_t it = 0; it < max_iter; ++ it) {
+		spo_se3_linearise_dense(N, states, E, from, to, z, info, lambda, eta);
+		if(dense_llt_upper(n, lambda)) { rc = 1; ++ n_solves; break; }
+		dense_llt_solve(n, lambda, eta);
+		double s = 0;
+		for(size_t i = 0; i < n; ++ i) s += eta[i] * eta[i];
+		dx_norms[n_solves ++] = sqrt(s);
+		if(sqrt(s) <= min_dx)
+			break;
+		for(size_t v = 0; v < N; ++ v)
+			relative_to_absolute(states + v * 6, eta + v * 6, states + v * 6);
+	}
+	spo_se3_chi2(N, states, E, from, to, z, info, &out[1]);
+	out[2] = (double)n_solves;
+	free(lambda); free(eta);
+	return rc;
+}

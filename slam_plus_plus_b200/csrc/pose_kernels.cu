@@ -19,6 +19,7 @@
 // block-sparse Cholesky (sparse_chol.cu) consumes.
 
 #include "spp_ctx.h"
+#include "ba_geometry.cuh"
 #include <math.h>
 #include <algorithm>
 #include <map>
@@ -116,6 +117,175 @@ __global__ void k_se2_edges(size_t E, const double *__restrict__ states, const u
 		out[27 + i] = T[i * 3 + 0] * r[0] + T[i * 3 + 1] * r[1] + T[i * 3 + 2] * r[2];
 		out[30 + i] = J1[0 * 3 + i] * Wr[0] + J1[1 * 3 + i] * Wr[1] + J1[2 * 3 + i] * Wr[2];
 	}
+}
+
+// ---- SE(3) --------------------------------------------------------------------------------------
+//   CEdgePose3D::Calculate_Jacobians_Expectation_Error   include/slam/SE3_Types.h:265-288
+//   C3DJacobians::Absolute_to_Relative, forward differences, delta = 1e-9: 13 Absolute_to_Relative and 12
+//   Relative_to_Absolute evaluations per edge            include/slam/3DSolverBase.h:892-946, 1043-1059, 1332-1370
+//   Huber weight, CRobustify_ErrorNorm_Default<30/100>   include/slam/SE3_Types.h:128-129, RobustUtils.h:412-438,
+//                                                        include/geometry/RobustLoss.h:63,100-104
+//   robust Calculate_Hessians_v2                         include/slam/BaseTypes_Binary.h:759-848 (the weight enters the
+//                                                        gradient of vertex 0 twice and that of vertex 1 once, :820-843)
+//   CVertexPose3D::Operator_Plus = Relative_to_Absolute  include/slam/SE3_Types.h:45-48
+
+// error of an SE(3) edge given the expectation d
+__device__ __forceinline__ void se3_error(const double *z, const double *d, double *r)
+{
+	r[0] = z[0] - d[0]; r[1] = z[1] - d[1]; r[2] = z[2] - d[2];
+	Quat pq, dq;
+	axis_angle_to_quat(z[3], z[4], z[5], pq);
+	axis_angle_to_quat(d[3], d[4], d[5], dq);
+	const Quat e = quat_mul(pq, quat_conj(dq));
+	quat_to_axis_angle(e, r[3], r[4], r[5]);
+}
+
+__device__ __forceinline__ double se3_robust_weight(const double *r)
+{
+	double s = 0;
+	#pragma unroll
+	for(int i = 0; i < 6; ++ i) s += r[i] * r[i];
+	const double e = sqrt(s) / (30.0 / 100.0);
+	return (e <= 1.345)? 1.0 : 1.345 / e;
+}
+
+// per-edge record: H00 (36), H01 (36), H11 (36), g0 (6), g1 (6); blocks column-major
+#define SE3_REC 120
+#define SE3_EDGES_PER_CTA 8
+
+// 16 lanes per edge: lane 0 evaluates the expectation, lanes 1..6 / 7..12 the perturbed expectations for the columns of
+// J0 / J1 (the 25 pose compositions of an edge run side by side instead of one after the other); the 6 x 6 products are
+// then spread over the 16 lanes through shared memory.
+__global__ void __launch_bounds__(SE3_EDGES_PER_CTA * 16) k_se3_edges(size_t E, const double *__restrict__ states,
+	const uint32_t *__restrict__ e_from, const uint32_t *__restrict__ e_to, const double *__restrict__ z,
+	const double *__restrict__ info, double *__restrict__ rec)
+{
+	__shared__ double sD[SE3_EDGES_PER_CTA][13][6]; // expectation and the 12 perturbed expectations
+	__shared__ double sJ[SE3_EDGES_PER_CTA][2][36]; // J0, J1 row-major
+	__shared__ double sT[SE3_EDGES_PER_CTA][2][36]; // T = J0^T W w, WJ1 = W J1
+	__shared__ double sR[SE3_EDGES_PER_CTA][16];    // r (6), W r (6), w
+	const int sub = threadIdx.x & 15, le = threadIdx.x >> 4;
+	const size_t e = blockIdx.x * (size_t)SE3_EDGES_PER_CTA + le;
+	const bool live = e < E;
+	const size_t ee = live? e : 0;
+	const double *v0 = states + (size_t)e_from[ee] * 6, *v1 = states + (size_t)e_to[ee] * 6;
+	if(sub < 13) {
+		double a[6], b[6], eps[6] = {0, 0, 0, 0, 0, 0}, d[6];
+		#pragma unroll
+		for(int i = 0; i < 6; ++ i) { a[i] = v0[i]; b[i] = v1[i]; }
+		if(sub >= 1 && sub <= 6) {
+			eps[sub - 1] = 1e-9;
+			relative_to_absolute(a, eps, a);
+		} else if(sub >= 7) {
+			eps[sub - 7] = 1e-9;
+			relative_to_absolute(b, eps, b);
+		}
+		absolute_to_relative(a, b, d);
+		#pragma unroll
+		for(int i = 0; i < 6; ++ i) sD[le][sub][i] = d[i];
+	}
+	__syncthreads();
+	// Jacobians: J(i, j) = (d_j(i) - d(i)) * (1 / delta); 72 entries over 16 lanes
+	const double scalar = 1.0 / 1e-9;
+	for(int k = sub; k < 72; k += 16) {
+		const int m = k / 36, q = k - m * 36, i = q / 6, j = q - i * 6;
+		sJ[le][m][i * 6 + j] = (sD[le][1 + m * 6 + j][i] - sD[le][0][i]) * scalar;
+	}
+	if(sub == 0) {
+		double r[6];
+		se3_error(z + ee * 6, sD[le][0], r);
+		#pragma unroll
+		for(int i = 0; i < 6; ++ i) sR[le][i] = r[i];
+		sR[le][12] = se3_robust_weight(r);
+	}
+	__syncthreads();
+	const double *W = info + ee * 36; // row-major
+	const double w = sR[le][12];
+	const double *J0 = sJ[le][0], *J1 = sJ[le][1];
+	for(int k = sub; k < 72; k += 16) {
+		const int m = k / 36, q = k - m * 36, i = q / 6, j = q - i * 6;
+		double t = 0;
+		if(m == 0) { // T(i, j) = (sum_k J0(k, i) W(k, j)) * w
+			#pragma unroll
+			for(int c = 0; c < 6; ++ c) t += J0[c * 6 + i] * W[c * 6 + j];
+			t *= w;
+		} else {     // WJ1(i, j) = sum_k W(i, k) J1(k, j)
+			#pragma unroll
+			for(int c = 0; c < 6; ++ c) t += W[i * 6 + c] * J1[c * 6 + j];
+		}
+		sT[le][m][q] = t;
+	}
+	if(sub < 6) {
+		double t = 0;
+		#pragma unroll
+		for(int c = 0; c < 6; ++ c) t += W[sub * 6 + c] * sR[le][c];
+		sR[le][6 + sub] = t;
+	}
+	__syncthreads();
+	if(!live) return;
+	const double *T = sT[le][0], *WJ1 = sT[le][1];
+	double *out = rec + e * SE3_REC;
+	for(int k = sub; k < 120; k += 16) {
+		double v = 0;
+		if(k < 108) {
+			const int part = k / 36, q = k - part * 36, c = q / 6, rr = q - c * 6; // column-major block element (rr, c)
+			const int a = (rr <= c)? rr : c, b = (rr <= c)? c : rr; // vertex blocks are mirrored from the upper triangle
+			if(part == 0) {
+				#pragma unroll
+				for(int i = 0; i < 6; ++ i) v += T[a * 6 + i] * J0[i * 6 + b];
+			} else if(part == 1) {
+				#pragma unroll
+				for(int i = 0; i < 6; ++ i) v += T[rr * 6 + i] * J1[i * 6 + c];
+			} else {
+				#pragma unroll
+				for(int i = 0; i < 6; ++ i) v += J1[i * 6 + a] * WJ1[i * 6 + b];
+				v *= w;
+			}
+		} else if(k < 114) {
+			const int i = k - 108;
+			#pragma unroll
+			for(int c = 0; c < 6; ++ c) v += T[i * 6 + c] * sR[le][c];
+			v *= w;
+		} else {
+			const int i = k - 114;
+			#pragma unroll
+			for(int c = 0; c < 6; ++ c) v += J1[c * 6 + i] * sR[le][6 + c];
+			v *= w;
+		}
+		out[k] = v;
+	}
+}
+
+__global__ void k_se3_chi2(size_t E, const double *__restrict__ states, const uint32_t *__restrict__ e_from,
+	const uint32_t *__restrict__ e_to, const double *__restrict__ z, const double *__restrict__ info, double *__restrict__ out)
+{
+	size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(e >= E) return;
+	double d[6], r[6];
+	absolute_to_relative(states + (size_t)e_from[e] * 6, states + (size_t)e_to[e] * 6, d);
+	se3_error(z + e * 6, d, r);
+	const double *W = info + e * 36;
+	double s = 0;
+	#pragma unroll
+	for(int i = 0; i < 6; ++ i) {
+		double t = 0;
+		#pragma unroll
+		for(int k = 0; k < 6; ++ k) t += W[i * 6 + k] * r[k];
+		s += r[i] * t;
+	}
+	out[e] = s; // unweighted, as the reference's f_Chi_Squared_Error (SE3_Types.h:318-327)
+}
+
+__global__ void k_se3_update(size_t N, double *__restrict__ states, const double *__restrict__ dx)
+{
+	size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(v >= N) return;
+	double a[6], d[6];
+	#pragma unroll
+	for(int i = 0; i < 6; ++ i) { a[i] = states[v * 6 + i]; d[i] = dx[v * 6 + i]; }
+	relative_to_absolute(a, d, a);
+	#pragma unroll
+	for(int i = 0; i < 6; ++ i) states[v * 6 + i] = a[i];
 }
 
 // thread per scalar of lambda / eta: sum of the sources in edge insertion order.
@@ -222,8 +392,8 @@ void pose_set_graph(spp_ctx *ctx, int dim, size_t N, const double *p_states, siz
 {
 	PoseProblem &pp = ctx->pose;
 	pp.valid = false;
-	if(dim != 3)
-		throw invalid_error("pose graphs: only SE(2) (dim = 3) is implemented");
+	if(dim != 3 && dim != 6)
+		throw invalid_error("pose graphs: dim must be 3 (SE(2)) or 6 (SE(3))");
 	if(N >= 0x7fffffffu || E >= 0x3fffffffu)
 		throw invalid_error("pose graph too large for 32-bit indices");
 	pp.dim = dim; pp.N = N; pp.E = E;
@@ -284,7 +454,7 @@ void pose_set_graph(spp_ctx *ctx, int dim, size_t N, const double *p_states, siz
 	pp.blk_src.upload(bflat, st);
 	pp.vec_src_ptr.upload(vptr, st);
 	pp.vec_src.upload(vflat, st);
-	pp.rec.resize(E * SE2_REC);
+	pp.rec.resize(E * (dim == 3? SE2_REC : SE3_REC));
 	pp.vals.resize(nb * B * B);
 	pp.eta.resize(N * B);
 	pp.dx.resize(N * B);
@@ -299,6 +469,19 @@ void pose_linearise(spp_ctx *ctx)
 {
 	PoseProblem &pp = ctx->pose;
 	cudaStream_t st = ctx->stream;
+	if(pp.dim == 6) {
+		if(pp.E) {
+			k_se3_edges<<<n_blocks(pp.E, SE3_EDGES_PER_CTA), SE3_EDGES_PER_CTA * 16, 0, st>>>(pp.E, pp.states.p(), pp.e_from.p(),
+				pp.e_to.p(), pp.z.p(), pp.info.p(), pp.rec.p());
+			LAUNCH_CHECK(ctx);
+		}
+		const size_t total = pp.n_blocks * 36 + pp.N * 6;
+		k_pose_reduce<6, SE3_REC><<<n_blocks(total, 256), 256, 0, st>>>(pp.n_blocks, pp.N, pp.blk_src_ptr.p(), pp.blk_src.p(),
+			pp.vec_src_ptr.p(), pp.vec_src.p(), pp.rec.p(), pp.uf_block, pp.vals.p(), pp.eta.p());
+		LAUNCH_CHECK(ctx);
+		pp.linearised = true;
+		return;
+	}
 	if(pp.E) {
 		k_se2_edges<<<n_blocks(pp.E, 128), 128, 0, st>>>(pp.E, pp.states.p(), pp.e_from.p(), pp.e_to.p(), pp.z.p(), pp.info.p(), pp.rec.p());
 		LAUNCH_CHECK(ctx);
@@ -316,7 +499,10 @@ double pose_chi2(spp_ctx *ctx)
 	cudaStream_t st = ctx->stream;
 	if(!pp.E)
 		return 0;
-	k_se2_chi2<<<n_blocks(pp.E, 128), 128, 0, st>>>(pp.E, pp.states.p(), pp.e_from.p(), pp.e_to.p(), pp.z.p(), pp.info.p(), pp.scratch.p());
+	if(pp.dim == 6)
+		k_se3_chi2<<<n_blocks(pp.E, 64), 64, 0, st>>>(pp.E, pp.states.p(), pp.e_from.p(), pp.e_to.p(), pp.z.p(), pp.info.p(), pp.scratch.p());
+	else
+		k_se2_chi2<<<n_blocks(pp.E, 128), 128, 0, st>>>(pp.E, pp.states.p(), pp.e_from.p(), pp.e_to.p(), pp.z.p(), pp.info.p(), pp.scratch.p());
 	LAUNCH_CHECK(ctx);
 	k_sum_fixed<<<1, 1024, 0, st>>>(pp.E, pp.scratch.p(), 0, 0, pp.scratch.p() + pp.E);
 	LAUNCH_CHECK(ctx);
@@ -394,7 +580,10 @@ int pose_optimize(spp_ctx *ctx, size_t n_max_iteration_num, double f_min_dx_norm
 		if(f_norm <= f_min_dx_norm)
 			break;
 		cudaEventRecord(a, st);
-		k_se2_update<<<n_blocks(pp.N, 128), 128, 0, st>>>(pp.N, pp.states.p(), pp.dx.p()); // PushValuesInGraphSystem
+		if(pp.dim == 6)
+			k_se3_update<<<n_blocks(pp.N, 64), 64, 0, st>>>(pp.N, pp.states.p(), pp.dx.p());
+		else
+			k_se2_update<<<n_blocks(pp.N, 128), 128, 0, st>>>(pp.N, pp.states.p(), pp.dx.p()); // PushValuesInGraphSystem
 		LAUNCH_CHECK(ctx);
 		cudaEventRecord(b, st);
 		cudaEventSynchronize(b);

@@ -60,6 +60,12 @@ POSE_CASES = {
     # name: (generator, kwargs, max_iter)
     "se2_tiny": ("make_manhattan", dict(n_poses=120, n_loops=40, seed=1), 5),
     "se2_small": ("make_manhattan", dict(n_poses=600, n_loops=400, seed=11), 5),
+    # radius 5: the reference's robust SE(3) edges weight the two gradient halves differently (w^2 on vertex 0, w on vertex 1,
+    # BaseTypes_Binary.h:820-843), so its Gauss-Newton diverges once many Huber weights are active (large lever arms)
+    "se3_tiny": ("make_sphere", dict(n_rings=5, n_per_ring=8, seed=3, sigma_t=0.03, sigma_r=0.005, radius=5.0), 5),
+    "se3_small": ("make_sphere", dict(n_rings=12, n_per_ring=25, seed=33, sigma_t=0.02, sigma_r=0.002, radius=5.0), 5),
+    # larger noise: about half of the edges carry an active Huber weight; two iterations only (see the note above)
+    "se3_huber": ("make_sphere", dict(n_rings=5, n_per_ring=8, seed=7, sigma_t=0.1, sigma_r=0.02, radius=5.0), 2),
 }
 
 
@@ -87,7 +93,8 @@ def run_pose(name, spec):
 if __name__ == "__main__":
     if os.path.exists(REF_POSE) and (len(sys.argv) < 2 or sys.argv[1] == "pose"):
         for name, spec in POSE_CASES.items():
-            run_pose(name, spec)
+            if len(sys.argv) < 3 or name.startswith(sys.argv[2]):
+                run_pose(name, spec)
         if len(sys.argv) > 1:
             sys.exit(0)
     if not os.path.exists(REF_BA):

@@ -33,3 +33,24 @@ if os.path.exists(ref):
             out = subprocess.run([ref, "time", td + "/g.bin", td + "/d.dump", "5", "0"], capture_output=True, text=True,
                                  env=dict(os.environ, OMP_NUM_THREADS=thr)).stdout
             print("reference:", out.strip())
+
+# SE(3): sphere2500 shape (radius / noise chosen so that the reference's Gauss-Newton converges, see tests/golden/make_golden.py)
+g3 = graphs.make_sphere(n_rings=50, n_per_ring=50, seed=2500, sigma_t=0.004, sigma_r=0.0004, radius=5.0)
+t = time.time()
+ctx.pose_set_graph(g3)
+print(f"sphere2500: N={g3.poses.shape[0]} E={g3.e_from.shape[0]}; set_graph {time.time() - t:.4f}s", flush=True)
+for r in range(4):
+    ctx.pose_restore_initial()
+    l0 = ctx.kernel_launches
+    t = time.time()
+    rep = ctx.pose_optimize(5, 0.0)
+    wall = time.time() - t
+    print(json.dumps(dict(run=r, wall_s=round(wall, 5), launches=ctx.kernel_launches - l0, n=rep["n_iterations"],
+                          chi2=(rep["chi2_initial"], rep["chi2_final"]), ms=rep["ms"])), flush=True)
+if os.path.exists(ref):
+    with tempfile.TemporaryDirectory() as td:
+        sppio.write_graph(td + "/g.bin", g3)
+        for thr in ("1", str(os.cpu_count())):
+            out = subprocess.run([ref, "time", td + "/g.bin", td + "/d.dump", "5", "0"], capture_output=True, text=True,
+                                 env=dict(os.environ, OMP_NUM_THREADS=thr)).stdout
+            print("reference:", out.strip())
