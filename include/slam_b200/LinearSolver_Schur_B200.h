@@ -39,6 +39,7 @@
 
 #include "slam/LinearSolverTags.h" // reference
 #include "slam/BlockMatrix.h"      // reference: CUberBlockMatrix
+#include "slam/OrderingMagic.h"    // reference: CMatrixOrdering (AMD), for a block-sparse reduced camera system
 #include "spp_b200.h"
 
 class CLinearSolver_Schur_B200 {
@@ -102,10 +103,40 @@ public:
 	bool SymbolicDecomposition_Blocky(const CUberBlockMatrix &r_lambda) // throw(std::bad_alloc, std::runtime_error)
 	{
 		Flatten_Structure(r_lambda);
+		uint64_t n_cut = 0;
 		Check(spp_schur_symbolic(p_Context(), m_col_dims.size(), &m_col_dims[0], &m_col_ptr[0],
-			m_row_idx.empty()? 0 : &m_row_idx[0], 0, 0));
+			m_row_idx.empty()? 0 : &m_row_idx[0], 0, &n_cut));
+		if(n_cut * 6 > 16384)
+			Set_Reference_RCS_Ordering(size_t(n_cut));
 		m_b_have_symbolic = true;
 		return true;
+	}
+
+	/**
+	 *	A reduced camera system this large is factored block-sparse (SPP_RCS_AUTO), the path the reference takes when
+	 *	its dense solver throws std::bad_alloc (LinearSolver_Schur.h:1836-1847): CLinearSolver_UberBlock on the Schur
+	 *	complement, under the AMD ordering of its block structure. This gives the library that same permutation:
+	 *	the block pattern of S comes back from the library, the ordering from the reference's own CMatrixOrdering.
+	 */
+	void Set_Reference_RCS_Ordering(size_t n_camera_num) // throw(std::bad_alloc, std::runtime_error)
+	{
+		std::vector<uint8_t> pattern(n_camera_num * n_camera_num);
+		Check(spp_schur_get_reduced_system(p_Context(), 0, 0, 0, &pattern[0]));
+		CUberBlockMatrix S_structure; // 1 x 1 blocks: only the block graph matters to p_BlockOrdering
+		Eigen::Matrix<double, 1, 1> t_one;
+		t_one(0, 0) = 1;
+		for(size_t i = 0; i < n_camera_num; ++ i)
+			S_structure.Append_Block(t_one, i, i);
+		for(size_t c = 0; c < n_camera_num; ++ c) {
+			for(size_t r = 0; r < c; ++ r) {
+				if(pattern[r * n_camera_num + c])
+					S_structure.Append_Block(t_one, r, c);
+			}
+		}
+		CMatrixOrdering ordering;
+		const size_t *p_order = ordering.p_BlockOrdering(S_structure, true);
+		std::vector<uint64_t> order(p_order, p_order + n_camera_num);
+		Check(spp_schur_set_rcs_ordering(p_Context(), n_camera_num, &order[0]));
 	}
 
 	/** CLinearSolver_Schur::Solve_PosDef_Blocky (LinearSolver_Schur.h:1623-1935); r_v_eta: rhs in, solution out */

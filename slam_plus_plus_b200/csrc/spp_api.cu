@@ -137,8 +137,8 @@ int schur_solve_current(spp_ctx *ctx, double alpha, spp_report_t *rep)
 			const size_t ld = dense_chol_ld(n);
 			s.S_copy.resize(dense_chol_storage(n));
 			s.S_copy.zero(ctx->stream);
-			if(s.n_blocks_global)
-				throw invalid_error("spp_schur_get_reduced_system is not available with several ranks on the block-sparse path");
+			if(s.n_blocks_global || n > 32768)
+				throw invalid_error("spp_schur_get_reduced_system: no dense copy of a block-sparse reduced camera system this large / on several ranks");
 			k_blocks_to_dense<<<n_blocks(s.n_blocks * 36, 256), 256, 0, ctx->stream>>>(s.n_blocks * 36, s.Sblk.p(), s.blk_row.p(),
 				s.blk_col.p(), ld, s.S_copy.p());
 			++ ctx->n_launches;
@@ -842,7 +842,8 @@ int spp_schur_get_reduced_system(spp_ctx_t ctx, uint64_t *p_n, double *p_S, doub
 		for(size_t i = 0; i < s.h_blk_row.size(); ++ i)
 			p_block_pattern[(size_t)s.h_blk_row[i] * s.C + s.h_blk_col[i]] = 1;
 	}
-	s.keep_reduced = true;
+	if(p_S || p_rhs || !p_block_pattern)
+		s.keep_reduced = true; // a pattern-only query does not make the following solves keep a dense copy
 	API_END(ctx)
 }
 

@@ -419,11 +419,25 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 	LAUNCH_CHECK(ctx);
 	k_snode_assemble_rhs<<<n_blocks(n * 6, 256), 256, 0, st>>>(n * 6, d_b, sc.d_rhs_dst.p(), L);
 	LAUNCH_CHECK(ctx);
+	// SPP_SNODE_PROFILE: serialised per-supernode timing of the two parts of the numeric phase (diagnostics)
+	static const bool profile = getenv("SPP_SNODE_PROFILE") != 0;
+	std::vector<float> t_factor(profile? ns : 0), t_update(profile? ns : 0);
+	auto lap = [&](float *acc) {
+		if(!profile) return;
+		cudaEventRecord(ctx->ev[5], st);
+		cudaEventSynchronize(ctx->ev[5]);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+		if(acc) *acc = ms;
+		cudaEventRecord(ctx->ev[4], st);
+	};
+	lap(0);
 	// factorisation, elimination order (a postorder: every descendant of t precedes t)
 	for(size_t s = 0; s < ns; ++ s) {
 		double *Ps = L + sc.panel_off[s];
 		const size_t ld = sc.panel_ld[s], cols = sc.panel_cols[s];
 		dense_chol_factor_panel(ctx, Ps, ld, cols, sc.d_Rinv.p() + (size_t)sc.rinv_first[s] * SN_NB * SN_NB, sc.d_info.p());
+		if(profile) lap(&t_factor[s]);
 		const size_t w = 6 * (size_t)(sn.first[s + 1] - sn.first[s]);
 		const uint32_t n_kt = (uint32_t)(round_up(w, SN_BK) / SN_BK);
 		for(uint64_t q = sc.upd_ptr[s]; q < sc.upd_ptr[s + 1]; ++ q) {
@@ -440,6 +454,30 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 					n_kt, Pt, sc.panel_ld[u.t], sc.d_cmap.p() + u.map_off);
 			}
 			LAUNCH_CHECK(ctx);
+		}
+		if(profile) lap(&t_update[s]);
+	}
+	if(profile) {
+		double tf = 0, tu = 0, ff = 0, fu = 0, tf_small = 0, tu_small = 0;
+		size_t n_small = 0;
+		for(size_t s = 0; s < ns; ++ s) {
+			const double w = 6.0 * (sn.first[s + 1] - sn.first[s]), h = 6.0 * (sn.row_ptr[s + 1] - sn.row_ptr[s]);
+			tf += t_factor[s]; tu += t_update[s];
+			ff += w * w * w / 3 + w * w * h; fu += w * h * h;
+			if(w < 512) { tf_small += t_factor[s]; tu_small += t_update[s]; ++ n_small; }
+		}
+		fprintf(stderr, "[spp snode profile] %zu supernodes: panel factor %.2f ms (%.2f TFLOP/s), updates %.2f ms (%.2f TFLOP/s); "
+			"%zu supernodes narrower than 512: factor %.2f ms, updates %.2f ms\n", ns, tf, ff / tf * 1e-9, tu, fu / tu * 1e-9,
+			n_small, tf_small, tu_small);
+		std::vector<size_t> idx(ns);
+		std::iota(idx.begin(), idx.end(), 0);
+		std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return t_factor[a] + t_update[a] > t_factor[b] + t_update[b]; });
+		for(size_t k = 0; k < std::min<size_t>(ns, 12); ++ k) {
+			const size_t s = idx[k];
+			const double w = 6.0 * (sn.first[s + 1] - sn.first[s]), h = 6.0 * (sn.row_ptr[s + 1] - sn.row_ptr[s]);
+			fprintf(stderr, "[spp snode profile]   s %zu: w %.0f h %.0f, %llu targets: factor %.3f ms (%.1f TFLOP/s), updates %.3f ms (%.1f TFLOP/s)\n",
+				s, w, h, (unsigned long long)(sc.upd_ptr[s + 1] - sc.upd_ptr[s]), t_factor[s], (w * w * w / 3 + w * w * h) / t_factor[s] * 1e-9,
+				t_update[s], w * h * h / std::max(t_update[s], 1e-6f) * 1e-9);
 		}
 	}
 	// backward solve, root to leaves; y_s sits in the rhs column of panel s
@@ -461,6 +499,11 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 			sc.d_info.p() + 1 + sc.rinv_first[s]);
 		k_snode_store_x<<<n_blocks(w, 128), 128, 0, st>>>(w, 6 * (size_t)sn.first[s], y, sc.d_order.p(), sc.d_x.p(), d_dx);
 		LAUNCH_CHECK(ctx);
+	}
+	if(profile) {
+		float t_back = 0;
+		lap(&t_back);
+		fprintf(stderr, "[spp snode profile] backward solve %.2f ms\n", t_back);
 	}
 	ctx->h_scalars.resize(16);
 	int *h_info = reinterpret_cast<int*>(ctx->h_scalars.p());

@@ -68,3 +68,33 @@ def test_reference_lm_with_b200_linear_solver(name, tmp_path):
     assert abs(r["chi2_0"][0] - d["chi2_0"][0]) <= 1e-11 * d["chi2_0"][0]
     _compare_traces(r["lm_trace"].reshape(-1, 6), d["lm_trace"].reshape(-1, 6), 2e-5)
     assert abs(r["chi2"][0] - d["chi2"][0]) <= 1e-6 * d["chi2"][0]
+
+
+# ---- pose graphs: CLinearSolver_UberBlock_B200 in the reference's Gauss-Newton solver --------------------------------
+
+BIN_POSE = os.path.join(ROOT, "oracle", "_ref", "ref_driver_dropin_pose")
+REF_POSE = os.path.join(ROOT, "oracle", "_ref", "ref_driver_pose")
+
+
+@pytest.mark.parametrize("name", ["se2_tiny", "se2_small", "se3_tiny", "se3_small"])
+def test_reference_gauss_newton_with_b200_block_cholesky(name, tmp_path):
+    """the UNMODIFIED reference (its vertices, edges, Jacobians, GN loop and AMD ordering) with the GPU block Cholesky
+    in its linear-solver slot reproduces the pure-reference run on the same machine"""
+    if not os.path.exists(BIN_POSE) or not os.path.exists(REF_POSE):
+        pytest.skip("oracle/_ref drivers not built (need /root/reference at build time)")
+    from slam_plus_plus_b200 import sppio
+    from test_pose_cpu import load_pose_golden
+    g, d = load_pose_golden(name)
+    gp, dp, rp = str(tmp_path / "g.bin"), str(tmp_path / "d.dump"), str(tmp_path / "r.dump")
+    sppio.write_graph(gp, g)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    n_it = str(int(d["max_iter"][0]))
+    subprocess.run([BIN_POSE, gp, dp, n_it, "0"], check=True, stdout=subprocess.DEVNULL, env=env)
+    subprocess.run([REF_POSE, "time", gp, rp, n_it, "0"], check=True, stdout=subprocess.DEVNULL, env=env)
+    r, ref = sppio.read_dump(dp), sppio.read_dump(rp)
+    assert abs(r["chi2_0"][0] - d["chi2_0"][0]) <= 1e-12 * d["chi2_0"][0]
+    # SE(2): analytic Jacobians, the whole trajectory follows to the accuracy of the linear solves; SE(3): the
+    # reference's forward-difference Jacobians amplify the last-bit differences of the increments (see test_pose_gpu.py)
+    tol = 1e-9 if name.startswith("se2") else 1e-5
+    assert abs(r["chi2"][0] - ref["chi2"][0]) <= tol * ref["chi2"][0]
+    assert abs(r["chi2"][0] - d["chi2"][0]) <= tol * d["chi2"][0]
