@@ -475,9 +475,9 @@ void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols, 
 
 // Backward solve R11 x = y on a factored panel (see dense_chol_factor_panel): y (ld doubles, in place) must not alias the
 // panel's first ld columns; flags: ld / 128 ints, zero on entry.
-void dense_chol_backsolve_panel(spp_ctx *ctx, const double *A, size_t ld, const double *Rinv, double *y, int *flags)
+void dense_chol_backsolve_panel(spp_ctx *ctx, cudaStream_t stream, const double *A, size_t ld, const double *Rinv, double *y, int *flags)
 {
-	k_backsolve<<<(unsigned)(ld / CH_NB), 256, 0, ctx->stream>>>(A, ld, ld / CH_NB, Rinv, y, flags);
+	k_backsolve<<<(unsigned)(ld / CH_NB), 256, 0, stream>>>(A, ld, ld / CH_NB, Rinv, y, flags);
 	LAUNCH_CHECK(ctx);
 }
 

@@ -161,7 +161,15 @@ struct SupernodalChol {
 	DBuf<double> d_L, d_Rinv, d_x, d_part;
 	DBuf<int> d_info;                      // [0] first non-positive pivot, [1..] backsolve flags
 	double factor_flops;                   // of the numeric phase as executed (amalgamation zeros included)
-	SupernodalChol() : valid(false), mode(0), n(0), n_rinv_blocks(0), n_s_blocks(0), max_part(0), factor_flops(0) {}
+	// side streams: the updates into one target panel all go to the same stream (fixed order: deterministic), the
+	// updates of one supernode into different targets and the independent subtrees of the backward solve run side by side
+	enum { N_STREAMS = 8 };
+	cudaStream_t side[N_STREAMS];
+	std::vector<cudaEvent_t> ev_factor, ev_target, ev_x;
+	SupernodalChol() : valid(false), mode(0), n(0), n_rinv_blocks(0), n_s_blocks(0), max_part(0), factor_flops(0)
+	{
+		for(int i = 0; i < N_STREAMS; ++ i) side[i] = 0;
+	}
 };
 
 struct DenseChol {

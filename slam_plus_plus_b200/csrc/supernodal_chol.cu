@@ -32,7 +32,7 @@
 namespace spp {
 
 void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols, double *Rinv, int *info);
-void dense_chol_backsolve_panel(spp_ctx *ctx, const double *A, size_t ld, const double *Rinv, double *y, int *flags);
+void dense_chol_backsolve_panel(spp_ctx *ctx, cudaStream_t stream, const double *A, size_t ld, const double *Rinv, double *y, int *flags);
 void schur_fetch_host_pattern(spp_ctx *ctx);
 
 #define LAUNCH_CHECK(ctx) do { ++ (ctx)->n_launches; SPP_CUDA(cudaGetLastError()); } while(0)
@@ -188,7 +188,7 @@ void snode_symbolic(spp_ctx *ctx, size_t n, const std::vector<uint32_t> &blk_row
 	sc.d_Rinv.resize(n_rinv * SN_NB * SN_NB);
 	sc.d_Rinv.zero(st); // the diagonal-block kernel writes upper triangles only
 	sc.d_x.resize(n * 6);
-	sc.d_part.resize(std::max<size_t>(sc.max_part, 1));
+	sc.d_part.resize(std::max<size_t>(sc.max_part, 1) * SupernodalChol::N_STREAMS);
 	sc.d_info.resize(1 + n_rinv);
 	SPP_CUDA(cudaStreamSynchronize(st));
 	if(getenv("SPP_SNODE_VERBOSE"))
@@ -283,16 +283,29 @@ __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_snode_update(con
 	};
 
 	double acc[4][4][2];
-	#pragma unroll
-	for(int a = 0; a < 4; ++ a)
-		#pragma unroll
-		for(int b = 0; b < 4; ++ b)
-			acc[a][b][0] = acc[a][b][1] = 0;
 	const int KT = (int)n_kt;
 	#pragma unroll
 	for(int s = 0; s < SN_STAGES - 1; ++ s) {
 		if(s < KT) stage_load(s, s);
 		__pipeline_commit();
+	}
+	// the accumulators start from the target entries (gathered through the map while the pipeline fills) and the A
+	// fragments are negated below, so the epilogue is a plain scattered store instead of a read-modify-write
+	__syncthreads(); // rpos / cpos
+	#pragma unroll
+	for(int a = 0; a < 4; ++ a) {
+		const int mi = wi + a * 8 + g;
+		const uint32_t rp = rpos[mi], i = i0 + mi;
+		#pragma unroll
+		for(int b = 0; b < 4; ++ b) {
+			#pragma unroll
+			for(int h = 0; h < 2; ++ h) {
+				const int mj = wj + b * 8 + 2 * t + h;
+				const uint32_t cp = cpos[mj];
+				const bool ok = rp != 0xffffffffu && cp != 0xffffffffu && i <= j0 + mj;
+				acc[a][b][h] = ok? Pt[(size_t)cp * ld_t + rp] : 0.0;
+			}
+		}
 	}
 	for(int kt = 0; kt < KT; ++ kt) {
 		__pipeline_wait_prior(SN_STAGES - 2);
@@ -306,7 +319,7 @@ __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_snode_update(con
 			double fa[4], fb[4];
 			#pragma unroll
 			for(int a = 0; a < 4; ++ a)
-				fa[a] = As[st][wi + a * 8 + g][k4 + t];
+				fa[a] = -As[st][wi + a * 8 + g][k4 + t];
 			#pragma unroll
 			for(int b = 0; b < 4; ++ b)
 				fb[b] = Bs[st][wj + b * 8 + g][k4 + t];
@@ -330,10 +343,8 @@ __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_snode_update(con
 			for(int h = 0; h < 2; ++ h) {
 				const int mj = wj + b * 8 + 2 * t + h;
 				const uint32_t cp = cpos[mj];
-				if(cp != 0xffffffffu && i <= j0 + mj) {
-					double *p = Pt + (size_t)cp * ld_t + rp;
-					*p -= acc[a][b][h];
-				}
+				if(cp != 0xffffffffu && i <= j0 + mj)
+					Pt[(size_t)cp * ld_t + rp] = acc[a][b][h];
 			}
 		}
 	}
@@ -407,6 +418,24 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 	const Supernodes &sn = sc.sn;
 	const size_t ns = sn.n_super(), n = sc.n;
 	cudaStream_t st = ctx->stream;
+	static const bool profile = getenv("SPP_SNODE_PROFILE") != 0;
+	static const bool single_stream = profile || getenv("SPP_SNODE_SINGLE_STREAM") != 0;
+	if(!sc.side[0]) {
+		int prio_lo = 0, prio_hi = 0;
+		SPP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		for(int i = 0; i < SupernodalChol::N_STREAMS; ++ i)
+			SPP_CUDA(cudaStreamCreateWithPriority(&sc.side[i], cudaStreamNonBlocking, prio_lo));
+	}
+	if(sc.ev_factor.size() < ns) {
+		const size_t old = sc.ev_factor.size();
+		sc.ev_factor.resize(ns); sc.ev_target.resize(ns); sc.ev_x.resize(ns);
+		for(size_t i = old; i < ns; ++ i) {
+			SPP_CUDA(cudaEventCreateWithFlags(&sc.ev_factor[i], cudaEventDisableTiming));
+			SPP_CUDA(cudaEventCreateWithFlags(&sc.ev_target[i], cudaEventDisableTiming));
+			SPP_CUDA(cudaEventCreateWithFlags(&sc.ev_x[i], cudaEventDisableTiming));
+		}
+	}
+	std::vector<char> pending(ns, 0); // updates into panel t are in flight on its side stream
 	double *L = sc.d_L.p();
 	sc.d_L.zero(st);
 	SPP_CUDA(cudaMemsetAsync(sc.d_info.p(), 0, sc.d_info.size() * sizeof(int), st));
@@ -420,7 +449,6 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 	k_snode_assemble_rhs<<<n_blocks(n * 6, 256), 256, 0, st>>>(n * 6, d_b, sc.d_rhs_dst.p(), L);
 	LAUNCH_CHECK(ctx);
 	// SPP_SNODE_PROFILE: serialised per-supernode timing of the two parts of the numeric phase (diagnostics)
-	static const bool profile = getenv("SPP_SNODE_PROFILE") != 0;
 	std::vector<float> t_factor(profile? ns : 0), t_update(profile? ns : 0);
 	auto lap = [&](float *acc) {
 		if(!profile) return;
@@ -436,27 +464,40 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 	for(size_t s = 0; s < ns; ++ s) {
 		double *Ps = L + sc.panel_off[s];
 		const size_t ld = sc.panel_ld[s], cols = sc.panel_cols[s];
+		if(pending[s]) // every update into this panel went to one side stream, in elimination order
+			SPP_CUDA(cudaStreamWaitEvent(st, sc.ev_target[s], 0));
 		dense_chol_factor_panel(ctx, Ps, ld, cols, sc.d_Rinv.p() + (size_t)sc.rinv_first[s] * SN_NB * SN_NB, sc.d_info.p());
 		if(profile) lap(&t_factor[s]);
+		if(!single_stream && sc.upd_ptr[s + 1] > sc.upd_ptr[s])
+			SPP_CUDA(cudaEventRecord(sc.ev_factor[s], st));
 		const size_t w = 6 * (size_t)(sn.first[s + 1] - sn.first[s]);
 		const uint32_t n_kt = (uint32_t)(round_up(w, SN_BK) / SN_BK);
 		for(uint64_t q = sc.upd_ptr[s]; q < sc.upd_ptr[s + 1]; ++ q) {
 			const SnodeUpdate &u = sc.updates[q];
 			double *Pt = L + sc.panel_off[u.t];
+			cudaStream_t su = single_stream? st : sc.side[u.t % SupernodalChol::N_STREAMS];
+			if(!single_stream)
+				SPP_CUDA(cudaStreamWaitEvent(su, sc.ev_factor[s], 0));
 			const size_t tiles = (size_t)((u.M + 127) / 128) * ((u.N + 127) / 128);
 			if(tiles >= 96) {
 				dim3 grid((u.N + 127) / 128, (u.M + 127) / 128);
-				k_snode_update<128, 128><<<grid, 512, snode_update_smem<128, 128>(), st>>>(Ps, ld, u.col0, (uint32_t)(cols - 1), u.M, u.N,
+				k_snode_update<128, 128><<<grid, 512, snode_update_smem<128, 128>(), su>>>(Ps, ld, u.col0, (uint32_t)(cols - 1), u.M, u.N,
 					n_kt, Pt, sc.panel_ld[u.t], sc.d_cmap.p() + u.map_off);
 			} else {
 				dim3 grid((u.N + 63) / 64, (u.M + 63) / 64);
-				k_snode_update<64, 64><<<grid, 128, snode_update_smem<64, 64>(), st>>>(Ps, ld, u.col0, (uint32_t)(cols - 1), u.M, u.N,
+				k_snode_update<64, 64><<<grid, 128, snode_update_smem<64, 64>(), su>>>(Ps, ld, u.col0, (uint32_t)(cols - 1), u.M, u.N,
 					n_kt, Pt, sc.panel_ld[u.t], sc.d_cmap.p() + u.map_off);
 			}
 			LAUNCH_CHECK(ctx);
+			if(!single_stream) {
+				SPP_CUDA(cudaEventRecord(sc.ev_target[u.t], su));
+				pending[u.t] = 1;
+			}
 		}
 		if(profile) lap(&t_update[s]);
 	}
+	if(!single_stream)
+		SPP_CUDA(cudaEventRecord(sc.ev_factor[ns - 1], st)); // the last supernode (a root) has no updates: its event is free
 	if(profile) {
 		double tf = 0, tu = 0, ff = 0, fu = 0, tf_small = 0, tu_small = 0;
 		size_t n_small = 0;
@@ -480,25 +521,44 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 				t_update[s], w * h * h / std::max(t_update[s], 1e-6f) * 1e-9);
 		}
 	}
-	// backward solve, root to leaves; y_s sits in the rhs column of panel s
+	// backward solve, root to leaves; y_s sits in the rhs column of panel s. A supernode needs the x of its ancestors
+	// only: supernodes go round-robin to the side streams and wait for their parent's event (which implies the
+	// grandparents'), so independent subtrees are solved side by side
 	for(size_t ss = ns; ss > 0; -- ss) {
 		const size_t s = ss - 1;
 		double *Ps = L + sc.panel_off[s];
 		const size_t ld = sc.panel_ld[s], w = 6 * (size_t)(sn.first[s + 1] - sn.first[s]);
 		const size_t h = 6 * (size_t)(sn.row_ptr[s + 1] - sn.row_ptr[s]);
 		double *y = Ps + (ld + h) * ld;
+		const int lane = int(s % SupernodalChol::N_STREAMS);
+		cudaStream_t sb = single_stream? st : sc.side[lane];
+		double *part = sc.d_part.p() + (single_stream? 0 : (size_t)lane * std::max<size_t>(sc.max_part, 1));
+		if(!single_stream) {
+			if(sn.parent[s] != 0xffffffffu)
+				SPP_CUDA(cudaStreamWaitEvent(sb, sc.ev_x[sn.parent[s]], 0));
+			else
+				SPP_CUDA(cudaStreamWaitEvent(sb, sc.ev_factor[ns - 1], 0)); // the factorisation is complete (recorded below)
+		}
 		if(h) {
 			const size_t n_chunks = (h + SN_GEMV_COLS - 1) / SN_GEMV_COLS;
-			k_snode_gemv<<<dim3((unsigned)(ld / 128), (unsigned)n_chunks), 128, 0, st>>>(Ps, ld, h, sc.d_rows.p() + sn.row_ptr[s],
-				sc.d_x.p(), sc.d_part.p());
+			k_snode_gemv<<<dim3((unsigned)(ld / 128), (unsigned)n_chunks), 128, 0, sb>>>(Ps, ld, h, sc.d_rows.p() + sn.row_ptr[s],
+				sc.d_x.p(), part);
 			LAUNCH_CHECK(ctx);
-			k_snode_gemv_reduce<<<n_blocks(ld, 128), 128, 0, st>>>(ld, n_chunks, sc.d_part.p(), y);
+			k_snode_gemv_reduce<<<n_blocks(ld, 128), 128, 0, sb>>>(ld, n_chunks, part, y);
 			LAUNCH_CHECK(ctx);
 		}
-		dense_chol_backsolve_panel(ctx, Ps, ld, sc.d_Rinv.p() + (size_t)sc.rinv_first[s] * SN_NB * SN_NB, y,
+		dense_chol_backsolve_panel(ctx, sb, Ps, ld, sc.d_Rinv.p() + (size_t)sc.rinv_first[s] * SN_NB * SN_NB, y,
 			sc.d_info.p() + 1 + sc.rinv_first[s]);
-		k_snode_store_x<<<n_blocks(w, 128), 128, 0, st>>>(w, 6 * (size_t)sn.first[s], y, sc.d_order.p(), sc.d_x.p(), d_dx);
+		k_snode_store_x<<<n_blocks(w, 128), 128, 0, sb>>>(w, 6 * (size_t)sn.first[s], y, sc.d_order.p(), sc.d_x.p(), d_dx);
 		LAUNCH_CHECK(ctx);
+		if(!single_stream)
+			SPP_CUDA(cudaEventRecord(sc.ev_x[s], sb));
+	}
+	if(!single_stream) { // join the side streams
+		for(int i = 0; i < SupernodalChol::N_STREAMS; ++ i) {
+			SPP_CUDA(cudaEventRecord(sc.ev_target[i % ns], sc.side[i]));
+			SPP_CUDA(cudaStreamWaitEvent(st, sc.ev_target[i % ns], 0));
+		}
 	}
 	if(profile) {
 		float t_back = 0;
