@@ -11,7 +11,7 @@
 # (mixing -march settings breaks Eigen's alignment ABI), /usr/bin/g++ (the image's $CC gcc
 # has no libgomp spec).
 #
-# usage: oracle/build_ref.sh [driver ...]      (default drivers: ba dropin pose order dropin_pose)
+# usage: oracle/build_ref.sh [driver ...]      (default drivers: ba dropin pose order dropin_pose parse)
 set -u
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${SPP_REFERENCE:-/root/reference}"
@@ -34,7 +34,7 @@ if [ ! -d "$REF/include/slam" ]; then
 fi
 mkdir -p "$OBJ"
 DRIVERS=("$@")
-[ ${#DRIVERS[@]} -eq 0 ] && DRIVERS=(ba dropin pose order dropin_pose)
+[ ${#DRIVERS[@]} -eq 0 ] && DRIVERS=(ba dropin pose order dropin_pose parse)
 
 compile_one() { # src obj compiler extra
 	local src="$1" obj="$2" comp="$3"; shift 3

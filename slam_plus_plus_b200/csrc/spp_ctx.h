@@ -28,6 +28,7 @@ struct SchurSystem {
 	size_t n_blocks_global;
 	std::vector<uint32_t> h_gblk_row, h_gblk_col;
 	DBuf<uint32_t> blk_slot;         // [n_blocks] local block -> global block
+	DBuf<uint32_t> gblk_row, gblk_col; // [n_blocks_global] the global block list on the device
 	// values (device)
 	DBuf<double> U;    // [C*36] camera diagonal blocks (column-major 6x6, undamped, incl. unary factor)
 	DBuf<double> V;    // [P*9]  point diagonal blocks

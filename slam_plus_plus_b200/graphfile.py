@@ -1,0 +1,212 @@
+"""Graph-file ingest: the reference's text formats -> the SoA arrays the C ABI takes.
+
+Replaces, for the BA and SE(2) formats, the reference's parser front end:
+    CParserTemplate / CParserBase            include/slam/Parser.h:1137-..., TEdge2D :166-205, TEdgeP2C3D :625-664
+    CVertex2DParsePrimitive                  include/slam_app/ParsePrimitives.h:409-460   VERTEX2 / VERTEX_SE2 / VERTEX
+    CEdge2DParsePrimitive                    include/slam_app/ParsePrimitives.h:75-258    EDGE2 / EDGE_SE2 / EDGE / ODOMETRY
+    CVertexXYZParsePrimitive                 include/slam_app/ParsePrimitives.h:809-856   VERTEX_XYZ
+    CVertexCam3DParsePrimitive               include/slam_app/ParsePrimitives.h:861-927   VERTEX_CAM
+    CEdgeP2C3DParsePrimitive                 include/slam_app/ParsePrimitives.h:1123-1183 EDGE_PROJECT_P2MC / EDGE_P2MC / EDGE_P2C
+including what the parser does to the numbers before the optimizer sees them:
+  * VERTEX_CAM holds the camera-to-world pose as t, quaternion (x y z w); the state is the INVERSE pose
+    [q^-1 (-t), axis-angle(q^-1)] (ParsePrimitives.h:898-912, Quat_to_AxisAngle 3DSolverBase.h:556-649), and the
+    distortion coefficient is multiplied by (fx + fy) / 2 (TVertexCam3D, Parser.h:512-519);
+  * 2D edges written with from > to (Manhattan datasets) are inverted: ids swapped, measurement replaced by
+    Absolute_to_Relative(z, 0) (2DSolverBase.h:373-430) and the information matrix read in the "french" order
+    |0 1 5; . 2 4; . . 3| unless its zeros say it is in the usual upper-triangular order (ParsePrimitives.h:171-246);
+  * information matrices come as upper triangles, row by row.
+Pinned against the reference's own parser: tests/golden/parse_ref.npz (oracle/ref_driver_parse.cpp),
+tests/test_graphfile_cpu.py. Host-side plumbing only: no numerics of the hot path live here.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .sppio import GRAPH_SE2, BAGraph, PoseGraph
+
+_V2 = ("VERTEX2", "VERTEX_SE2", "VERTEX")
+_E2 = ("EDGE2", "EDGE_SE2", "EDGE", "ODOMETRY")
+_P2C = ("EDGE_PROJECT_P2MC", "EDGE_P2MC", "EDGE_P2C")
+
+
+def _quat_to_axis_angle(w, x, y, z):
+    """C3DJacobians::Quat_to_AxisAngle, include/slam/3DSolverBase.h:556-649 (the atan / atan2 variant)"""
+    f_norm = math.sqrt(x * x + y * y + z * z)
+    f_abs_w = abs(w)
+    f_abs_half = math.atan(f_norm / f_abs_w) if f_abs_w > 1e-3 else math.atan2(f_norm, f_abs_w)
+    f_half = math.copysign(f_abs_half, w)
+    if f_norm < 1e-12:
+        return 2.0 * x, 2.0 * y, 2.0 * z
+    f_s = f_half * 2 / f_norm
+    return x * f_s, y * f_s, z * f_s
+
+
+def _quat_rotate(w, x, y, z, v):
+    """Eigen::QuaternionBase::_transformVector"""
+    ux, uy, uz = y * v[2] - z * v[1], z * v[0] - x * v[2], x * v[1] - y * v[0]
+    ux, uy, uz = ux + ux, uy + uy, uz + uz
+    return (v[0] + w * ux + (y * uz - z * uy), v[1] + w * uy + (z * ux - x * uz), v[2] + w * uz + (x * uy - y * ux))
+
+
+def _clamp_angle_2pi(a):
+    return math.fmod(a, 2 * math.pi) if math.isfinite(a) else 0.0
+
+
+def _se2_absolute_to_relative(v1, v2):
+    """C2DJacobians::Absolute_to_Relative (value), include/slam/2DSolverBase.h:373-430"""
+    de, dn, da = v2[0] - v1[0], v2[1] - v1[1], v2[2] - v1[2]
+    o = -v1[2]
+    co, so = math.cos(o), math.sin(o)
+    return co * de - so * dn, so * de + co * dn, _clamp_angle_2pi(da)
+
+
+class ParsedGraph:
+    """What the reference's parse loop would receive, in file order."""
+
+    def __init__(self):
+        self.vertex2d, self.vertex_xyz, self.vertex_cam = [], [], []  # (id, state...)
+        self.edge2d, self.edge_p2c = [], []                          # (id0, id1, z..., info row-major...)
+        self.n_ignored = 0
+
+
+def parse(path) -> ParsedGraph:
+    out = ParsedGraph()
+    with open(path) as f:
+        for line_no, line in enumerate(f):
+            tok = line.split()
+            if not tok or tok[0].startswith("#") or tok[0].startswith("%"):
+                continue
+            name, a = tok[0].upper(), tok[1:]
+            try:
+                if name in _V2:
+                    out.vertex2d.append((int(a[0]), float(a[1]), float(a[2]), float(a[3])))
+                elif name == "VERTEX_XYZ":
+                    out.vertex_xyz.append((int(a[0]), float(a[1]), float(a[2]), float(a[3])))
+                elif name == "VERTEX_CAM":
+                    v = [float(x) for x in a[1:13]]
+                    if len(v) != 12:
+                        raise ValueError
+                    qx, qy, qz, qw = v[3], v[4], v[5], v[6]
+                    n = math.sqrt(qx * qx + qy * qy + qz * qz + qw * qw)
+                    qx, qy, qz, qw = qx / n, qy / n, qz / n, qw / n      # quat.normalize()
+                    n2 = qw * qw + qx * qx + qy * qy + qz * qz           # quat.inverse() = conjugate / squaredNorm
+                    iw, ix, iy, iz = qw / n2, -qx / n2, -qy / n2, -qz / n2
+                    c = _quat_rotate(iw, ix, iy, iz, (-v[0], -v[1], -v[2]))
+                    ax = _quat_to_axis_angle(iw, ix, iy, iz)
+                    d = v[11] * (.5 * (v[7] + v[8]))  # the distortion is scaled by the focal length internally (Parser.h:512-519)
+                    out.vertex_cam.append((int(a[0]), c[0], c[1], c[2], ax[0], ax[1], ax[2], v[7], v[8], v[9], v[10], d))
+                elif name in _E2:
+                    i0, i1 = int(a[0]), int(a[1])
+                    z = [float(x) for x in a[2:5]]
+                    m = [float(x) for x in a[5:11]]
+                    if len(m) != 6:
+                        raise ValueError
+                    if i0 < i1:
+                        up = m
+                    else:  # descending edge: invert it (ParsePrimitives.h:171-246)
+                        g2o = False
+                        if abs(m[0]) < 1e-5 or abs(m[2]) < 1e-5 or abs(m[3]) < 1e-5:
+                            if abs(m[0]) > 1e-5 and abs(m[3]) > 1e-5 and abs(m[5]) > 1e-5:
+                                g2o = True
+                        up = m if g2o else [m[0], m[1], m[5], m[2], m[4], m[3]]
+                        i0, i1 = i1, i0
+                        z = list(_se2_absolute_to_relative(z, (0.0, 0.0, 0.0)))
+                    info = (up[0], up[1], up[2], up[1], up[3], up[4], up[2], up[4], up[5])
+                    out.edge2d.append((i0, i1, z[0], z[1], z[2]) + info)
+                elif name in _P2C:
+                    m = [float(x) for x in a[4:7]]
+                    if len(m) != 3:
+                        raise ValueError
+                    out.edge_p2c.append((int(a[0]), int(a[1]), float(a[2]), float(a[3]), m[0], m[1], m[1], m[2]))
+                else:
+                    out.n_ignored += 1  # CONSISTENCY_MARKER and the primitives of other problem types
+            except (ValueError, IndexError):
+                raise ValueError(f"{path}: line {line_no + 1}: line is truncated") from None
+    return out
+
+
+def load_ba(path) -> BAGraph:
+    """A BA file (VERTEX_CAM / VERTEX_XYZ / EDGE_PROJECT_P2MC) as the arrays spp_ba_set_graph takes. Vertex ids must be
+    0 .. n-1 (any interleaving of cameras and points); edges keep their file order (= edge insertion order)."""
+    p = parse(path)
+    ids = sorted([(v[0], 0, k) for k, v in enumerate(p.vertex_cam)] + [(v[0], 1, k) for k, v in enumerate(p.vertex_xyz)])
+    if [i for i, _, _ in ids] != list(range(len(ids))):
+        raise ValueError(f"{path}: vertex ids must be 0 .. n-1 without gaps or repeats")
+    vtype = np.array([t for _, t, _ in ids], np.int64)
+    cams = np.array([p.vertex_cam[k][1:] for _, t, k in ids if t == 0], np.float64).reshape(-1, 11)
+    pts = np.array([p.vertex_xyz[k][1:] for _, t, k in ids if t == 1], np.float64).reshape(-1, 3)
+    e = np.array(p.edge_p2c, np.float64).reshape(-1, 8)
+    return BAGraph(vtype, cams, pts, e[:, 0].astype(np.int64), e[:, 1].astype(np.int64), e[:, 2:4].copy(),
+                   e[:, 4:8].reshape(-1, 2, 2).copy())
+
+
+def load_se2(path) -> PoseGraph:
+    """A 2D pose graph (VERTEX2 / EDGE2 ...). Poses without a VERTEX line are initialised from the first edge that
+    reaches them, as the reference does (CEdgePose2D constructor, SE2_Types.h:225-238: Relative_to_Absolute)."""
+    p = parse(path)
+    e = np.array(p.edge2d, np.float64).reshape(-1, 14)
+    n = int(max([v[0] for v in p.vertex2d] + ([int(e[:, :2].max())] if len(e) else []) + [-1])) + 1
+    poses = np.zeros((n, 3))
+    known = np.zeros(n, bool)
+    for v in p.vertex2d:
+        poses[v[0]] = v[1:]
+        known[v[0]] = True
+    if n and not known[0]:
+        known[0] = True  # the first vertex starts at the origin
+    for k in range(len(e)):
+        a, b = int(e[k, 0]), int(e[k, 1])
+        if known[a] and not known[b]:
+            c, s = math.cos(poses[a, 2]), math.sin(poses[a, 2])
+            poses[b] = (poses[a, 0] + c * e[k, 2] - s * e[k, 3], poses[a, 1] + s * e[k, 2] + c * e[k, 3],
+                        _clamp_angle_2pi(poses[a, 2] + e[k, 4]))
+            known[b] = True
+    if not known.all():
+        raise ValueError(f"{path}: pose {int(np.flatnonzero(~known)[0])} is neither given nor reachable from an initialised pose")
+    return PoseGraph(GRAPH_SE2, poses, e[:, 0].astype(np.int64), e[:, 1].astype(np.int64), e[:, 2:5].copy(),
+                     e[:, 5:14].reshape(-1, 3, 3).copy())
+
+
+# ---- writers (synthetic graphs -> the reference's text formats) ------------------------------------------------------
+
+def _axis_angle_to_quat(a):
+    """C3DJacobians::AxisAngle_to_Quat, include/slam/3DSolverBase.h:476-519 -> (w, x, y, z)"""
+    ang = math.sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2])
+    if ang < 1e-12:
+        return 1.0, a[0] * .5, a[1] * .5, a[2] * .5
+    s = math.sin(ang * .5) / ang
+    return math.cos(ang * .5), a[0] * s, a[1] * s, a[2] * s
+
+
+def write_ba(path, g: BAGraph):
+    """Writes the file whose parse gives g back (camera states are stored inverted in the file, as in the datasets)."""
+    ci = pi = 0
+    with open(path, "w") as f:
+        for vid, t in enumerate(g.vtype):
+            if t == 0:
+                c = g.cams[ci]
+                ci += 1
+                w, x, y, z = _axis_angle_to_quat(c[3:6])     # state rotation q^-1 -> file rotation q
+                tw = _quat_rotate(w, -x, -y, -z, (-c[0], -c[1], -c[2]))  # t = -(q c) with q = conj(state quaternion)
+                f.write("VERTEX_CAM %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n"
+                        % ((vid,) + tuple(tw) + (-x, -y, -z, w) + tuple(c[6:10]) + (c[10] / (.5 * (c[6] + c[7])),)))
+            else:
+                q = g.pts[pi]
+                pi += 1
+                f.write("VERTEX_XYZ %d %.17g %.17g %.17g\n" % (vid, q[0], q[1], q[2]))
+        for k in range(len(g.obs_pt)):
+            m = g.info[k]
+            f.write("EDGE_PROJECT_P2MC %d %d %.17g %.17g %.17g %.17g %.17g\n"
+                    % (g.obs_pt[k], g.obs_cam[k], g.z[k, 0], g.z[k, 1], m[0, 0], m[0, 1], m[1, 1]))
+
+
+def write_se2(path, g: PoseGraph, with_vertices: bool = True):
+    with open(path, "w") as f:
+        if with_vertices:
+            for i, v in enumerate(g.poses):
+                f.write("VERTEX2 %d %.17g %.17g %.17g\n" % (i, v[0], v[1], v[2]))
+        for k in range(len(g.e_from)):
+            m = g.info[k]
+            f.write("EDGE2 %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n"
+                    % (g.e_from[k], g.e_to[k], g.z[k, 0], g.z[k, 1], g.z[k, 2], m[0, 0], m[0, 1], m[0, 2], m[1, 1], m[1, 2], m[2, 2]))

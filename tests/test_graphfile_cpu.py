@@ -1,0 +1,67 @@
+"""Graph-file ingest (slam_plus_plus_b200/graphfile.py) against the UNMODIFIED reference's own parser: the golden
+tests/golden/parse_ref.npz holds what CParserTemplate + the parse primitives of include/slam_app/ParsePrimitives.h hand
+to the parse loop for the committed text files (tests/golden/make_golden_parse.py, oracle/ref_driver_parse.cpp)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_err
+from slam_plus_plus_b200 import graphfile, graphs
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return np.load(os.path.join(GOLDEN, "parse_ref.npz"))
+
+
+def test_ba_file_matches_reference_parser(ref):
+    p = graphfile.parse(os.path.join(GOLDEN, "parse_ba.txt"))
+    cam = np.array(p.vertex_cam).reshape(-1, 12)
+    r_cam = ref["parse_ba.vertex_cam"].reshape(-1, 12)
+    assert np.array_equal(cam[:, 0], r_cam[:, 0])
+    # the camera state is the inverted pose: q^-1 (-t) and the axis-angle of q^-1 -- libm-level agreement
+    assert np.max(np.abs(cam[:, 1:] - r_cam[:, 1:])) <= 1e-15 * max(1.0, np.abs(r_cam).max())
+    assert np.array_equal(np.array(p.vertex_xyz).reshape(-1, 4), ref["parse_ba.vertex_xyz"].reshape(-1, 4))
+    assert np.array_equal(np.array(p.edge_p2c).reshape(-1, 8), ref["parse_ba.edge_p2c"].reshape(-1, 8))
+
+
+def test_ba_file_round_trip():
+    g = graphs.ba_shape("tiny", interleave_ids=True, shuffle_edges=True, distortion=-0.03)
+    g.info[:, 0, 1] = g.info[:, 1, 0] = 0.25
+    h = graphfile.load_ba(os.path.join(GOLDEN, "parse_ba.txt"))
+    assert np.array_equal(h.vtype, g.vtype) and np.array_equal(h.obs_pt, g.obs_pt) and np.array_equal(h.obs_cam, g.obs_cam)
+    assert np.array_equal(h.pts, g.pts) and np.array_equal(h.z, g.z) and np.array_equal(h.info, g.info)
+    assert rel_err(h.cams, g.cams) < 1e-14  # pose -> file -> pose goes through a quaternion twice
+
+
+@pytest.mark.parametrize("name", ["parse_se2", "parse_se2_mixed"])
+def test_se2_file_matches_reference_parser(ref, name):
+    p = graphfile.parse(os.path.join(GOLDEN, name + ".txt"))
+    assert np.array_equal(np.array(p.vertex2d).reshape(-1, 4), ref[name + ".vertex2d"].reshape(-1, 4))
+    e, r = np.array(p.edge2d).reshape(-1, 14), ref[name + ".edge2d"].reshape(-1, 14)
+    assert e.shape == r.shape
+    assert np.array_equal(e[:, :2], r[:, :2])                      # ids, descending edges swapped
+    assert np.max(np.abs(e[:, 2:5] - r[:, 2:5])) <= 1e-15          # measurements, inverted where needed
+    assert np.array_equal(e[:, 5:], r[:, 5:])                      # information matrices, both storage orders
+
+
+def test_se2_load_initialises_missing_poses(tmp_path):
+    g = graphs.make_manhattan(30, 8, seed=2)
+    path = str(tmp_path / "g.txt")
+    graphfile.write_se2(path, g, with_vertices=False)
+    h = graphfile.load_se2(path)
+    assert h.poses.shape == g.poses.shape and np.array_equal(h.e_from, g.e_from)
+    assert np.allclose(h.poses[0], 0)
+    with open(path, "a") as f:
+        f.write("EDGE2 40 41 1 0 0 1 0 0 1 0 1\n")  # an island
+    with pytest.raises(ValueError):
+        graphfile.load_se2(path)
+
+
+def test_truncated_line_is_an_error(tmp_path):
+    path = str(tmp_path / "bad.txt")
+    with open(path, "w") as f:
+        f.write("VERTEX_XYZ 0 1 2\n")
+    with pytest.raises(ValueError):
+        graphfile.parse(path)
