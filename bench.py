@@ -278,7 +278,11 @@ def gpu_arm(args):
                                                    % (n, rcs_info["supernodes"])) if sparse_rcs else
                      "dense Cholesky %d^2 (k_potrf128 + k_gemm_tn<TRSM> + k_gemm_tn<SYRK> DMMA)" % n,
                      "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                     "traffic": None, "flops_per_launch": chol_flops,
+                     # DRAM bytes of one factorisation + solves of the Venice-shape system, summed over its kernels from the
+                     # ncu pass recorded in profiles/r1g_chol_traffic.csv (dram__bytes_read.sum + dram__bytes_write.sum)
+                     "traffic": 2396.9e6 if (not sparse_rcs and args.shape == "venice871") else None,
+                     "traffic_source": "profiles/r1g_chol_traffic.csv" if (not sparse_rcs and args.shape == "venice871") else None,
+                     "flops_per_launch": chol_flops,
                      "peak_source": "FP64: cuBLAS DGEMM 4096^3 via torch.matmul measured in this run (no FP64 entry in MEASURED_PEAKS.json)",
                      "hbm_stage": {"kernel": "linearise (k_linearise_cams + k_linearise_points)",
                                    "achieved_gbs": bytes_lin / (phase["linearise"] / max(n_iters, 1) * 1e-3) / 1e9,
