@@ -401,6 +401,22 @@ void spp_destroy(spp_ctx_t ctx)
 	}
 	for(int i = 0; i < 16; ++ i)
 		if(ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+	// side streams and events of the two Cholesky drivers
+	spp::DenseChol &ch = ctx->chol;
+	if(ch.bulk_stream) {
+		cudaStreamDestroy(ch.bulk_stream);
+		cudaStreamDestroy(ch.row_stream);
+		for(int i = 0; i < 2; ++ i) {
+			cudaEventDestroy(ch.ev_potrf[i]); cudaEventDestroy(ch.ev_first[i]); cudaEventDestroy(ch.ev_panel[i]);
+			cudaEventDestroy(ch.ev_bulk[i]); cudaEventDestroy(ch.ev_row[i]);
+		}
+	}
+	spp::SupernodalChol &sc = ctx->snode;
+	for(int i = 0; i < spp::SupernodalChol::N_STREAMS; ++ i)
+		if(sc.side[i]) cudaStreamDestroy(sc.side[i]);
+	for(size_t i = 0; i < sc.ev_factor.size(); ++ i) {
+		cudaEventDestroy(sc.ev_factor[i]); cudaEventDestroy(sc.ev_target[i]); cudaEventDestroy(sc.ev_x[i]);
+	}
 	delete ctx;
 }
 
