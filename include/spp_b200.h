@@ -90,6 +90,15 @@ int spp_set_allreduce(spp_ctx_t ctx, spp_allreduce_fn fn, void *p_user, int rank
  * p_bounds[r] .. p_bounds[r + 1]), contiguous and balanced by the Schur-product work k (k + 1) / 2 + k. */
 int spp_partition_landmarks(size_t n_points, const uint32_t *p_track_length, int world, uint64_t *p_bounds);
 
+/* Pure host helper (no context, no GPU): the upper block list of the reduced camera system of a whole BA graph --
+ * cameras i <= j share a block when some landmark is seen by both (the structure of schur_compl,
+ * include/slam/LinearSolver_Schur.h:1757-1767): the C diagonal blocks first, then the off-diagonal blocks in row-major
+ * order. This is the list under which several ranks sum their partial reduced camera systems. p_obs_camera /
+ * p_obs_point: camera / point index (not vertex id) of every observation. Call with NULL arrays for the count;
+ * *p_n_blocks is the capacity on input, the count on output. */
+int spp_rcs_block_pattern(size_t n_cameras, size_t n_points, size_t n_observations, const uint32_t *p_obs_camera,
+	const uint32_t *p_obs_point, uint64_t *p_n_blocks, uint32_t *p_block_row, uint32_t *p_block_col);
+
 /* The landmark slice [*p_begin, *p_end) (indices into the point array given to spp_ba_set_graph) owned by this
  * context; the whole range when world == 1. spp_ba_get_states / spp_ba_set_states touch only this slice. */
 int spp_ba_get_partition(spp_ctx_t ctx, uint64_t *p_begin, uint64_t *p_end);

@@ -23,7 +23,7 @@ MAX_TRACE = 64
 # every symbol include/spp_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "spp_create", "spp_destroy", "spp_last_error", "spp_describe", "spp_kernel_launches", "spp_stream",
-    "spp_synchronize", "spp_set_allreduce", "spp_partition_landmarks", "spp_ba_get_partition", "spp_ba_set_graph", "spp_ba_set_states", "spp_ba_get_states",
+    "spp_synchronize", "spp_set_allreduce", "spp_partition_landmarks", "spp_rcs_block_pattern", "spp_ba_get_partition", "spp_ba_set_graph", "spp_ba_set_states", "spp_ba_get_states",
     "spp_ba_restore_initial", "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_get_blocks", "spp_ba_chi2", "spp_ba_solve_step",
     "spp_ba_optimize", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_get_reduced_system",
     "spp_schur_set_rcs_solver", "spp_schur_set_rcs_ordering", "spp_schur_get_rcs_info", "spp_block_ordering",
@@ -85,6 +85,8 @@ def load_library() -> C.CDLL:
     lib.spp_synchronize.argtypes = [vp]
     lib.spp_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp, C.c_int, C.c_int]
     lib.spp_partition_landmarks.argtypes = [C.c_size_t, C.POINTER(C.c_uint32), C.c_int, u64p]
+    lib.spp_rcs_block_pattern.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), u64p,
+                                          C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.spp_ba_get_partition.argtypes = [vp, u64p, u64p]
     lib.spp_ba_set_graph.argtypes = [vp, C.c_size_t, u8p, dp, dp, C.c_size_t, u64p, u64p, dp, dp]
     lib.spp_ba_set_states.argtypes = [vp, dp, dp]
@@ -143,6 +145,24 @@ def partition_landmarks(track_length, world: int) -> np.ndarray:
     if rc != SPP_OK:
         raise ValueError("spp_partition_landmarks: invalid arguments")
     return bounds.astype(np.int64)
+
+
+def rcs_block_pattern(n_cameras: int, n_points: int, obs_camera, obs_point):
+    """Pure host helper: (rows, cols) of the upper blocks of the reduced camera system of a BA graph."""
+    lib = load_library()
+    oc = np.ascontiguousarray(obs_camera, np.uint32)
+    op = np.ascontiguousarray(obs_point, np.uint32)
+    u32p = C.POINTER(C.c_uint32)
+    n = C.c_uint64(0)
+    rc = lib.spp_rcs_block_pattern(n_cameras, n_points, len(oc), oc.ctypes.data_as(u32p), op.ctypes.data_as(u32p), C.byref(n), None, None)
+    if rc != SPP_OK:
+        raise RuntimeError(f"spp_rcs_block_pattern failed: {rc}")
+    r, c = np.empty(n.value, np.uint32), np.empty(n.value, np.uint32)
+    rc = lib.spp_rcs_block_pattern(n_cameras, n_points, len(oc), oc.ctypes.data_as(u32p), op.ctypes.data_as(u32p), C.byref(n),
+                                   r.ctypes.data_as(u32p), c.ctypes.data_as(u32p))
+    if rc != SPP_OK:
+        raise RuntimeError(f"spp_rcs_block_pattern failed: {rc}")
+    return r, c
 
 
 def block_ordering(col_ptr, row_idx) -> np.ndarray:

@@ -17,6 +17,8 @@ void build_schur_structure(spp_ctx *ctx, size_t C, size_t P, const std::vector<u
 bool schur_structure_device_supported(size_t C);
 void ba_upload_and_analyse_device(spp_ctx *ctx, size_t C, size_t P, size_t O, const uint64_t *p_obs_point,
 	const uint64_t *p_obs_camera, const double *p_z, const double *p_info);
+void ba_upload_and_analyse_device_sliced(spp_ctx *ctx, size_t C, size_t P, size_t O, const uint64_t *p_obs_point,
+	const uint64_t *p_obs_camera, const double *p_z, const double *p_info);
 void ba_fetch_host_maps(spp_ctx *ctx);
 void schur_fetch_host_pattern(spp_ctx *ctx);
 void build_global_rcs_pattern(size_t C, size_t P, const std::vector<uint32_t> &h_cam, const std::vector<uint32_t> &h_pt,
@@ -509,6 +511,13 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 		ba_upload_and_analyse_device(ctx, C, P, O, p_obs_point, p_obs_camera, p_z, p_info);
 		ba.pts.upload(p_points, P * 3, st);
 		ba.pts0.upload(p_points, P * 3, st);
+	} else if(ctx->world > 1 && schur_structure_device_supported(C) && !getenv("SPP_HOST_SYMBOLIC")) {
+		// several ranks: the same analysis on the device, for the whole graph (global block list, track lengths) and
+		// then for this rank's landmark slice
+		ba_upload_and_analyse_device_sliced(ctx, C, P, O, p_obs_point, p_obs_camera, p_z, p_info);
+		const size_t P_local = ba.pt_end - ba.pt_begin;
+		ba.pts.upload(p_points + ba.pt_begin * 3, P_local * 3, st);
+		ba.pts0.upload(p_points + ba.pt_begin * 3, P_local * 3, st);
 	} else {
 		std::vector<uint32_t> h_cam(O), h_pt(O);
 		for(size_t e = 0; e < O; ++ e) {

@@ -246,6 +246,28 @@ void map_blocks_to_global(size_t C, const std::vector<uint32_t> &l_row, const st
 
 } // namespace spp
 
+extern "C" int spp_rcs_block_pattern(size_t n_cameras, size_t n_points, size_t n_observations, const uint32_t *p_obs_camera,
+	const uint32_t *p_obs_point, uint64_t *p_n_blocks, uint32_t *p_block_row, uint32_t *p_block_col)
+{
+	if(!p_n_blocks || (n_observations && (!p_obs_camera || !p_obs_point)))
+		return SPP_ERR_INVALID;
+	try {
+		for(size_t e = 0; e < n_observations; ++ e)
+			if(p_obs_camera[e] >= n_cameras || p_obs_point[e] >= n_points) return SPP_ERR_INVALID;
+		std::vector<uint32_t> h_cam(p_obs_camera, p_obs_camera + n_observations), h_pt(p_obs_point, p_obs_point + n_observations), r, c;
+		spp::build_global_rcs_pattern(n_cameras, n_points, h_cam, h_pt, r, c);
+		if(p_block_row && p_block_col) {
+			if(*p_n_blocks < r.size()) return SPP_ERR_INVALID;
+			std::copy(r.begin(), r.end(), p_block_row);
+			std::copy(c.begin(), c.end(), p_block_col);
+		}
+		*p_n_blocks = r.size();
+	} catch(const std::bad_alloc&) {
+		return SPP_ERR_NOMEM;
+	}
+	return SPP_OK;
+}
+
 extern "C" int spp_partition_landmarks(size_t n_points, const uint32_t *p_track_length, int world, uint64_t *p_bounds)
 {
 	if(world < 1 || !p_bounds || (n_points && !p_track_length))

@@ -14,6 +14,7 @@
 // enumeration kernels are below. Integer work only; nothing here runs per LM iteration.
 
 #include "spp_ctx.h"
+#include <algorithm>
 #include <cub/cub.cuh>
 
 namespace spp {
@@ -375,6 +376,137 @@ void ba_upload_and_analyse_device(spp_ctx *ctx, size_t C, size_t P, size_t O, co
 		LAUNCH_CHECK(ctx);
 		k_sg_gather_rows<4><<<n_blocks(O * 4, T), T, 0, st>>>(O, ba.d_obs_orig.p(), w.info_in.p(), ba.info.p());
 		LAUNCH_CHECK(ctx);
+	}
+	ba.host_maps_valid = false;
+}
+
+// ---- several ranks: this rank keeps a contiguous slice of the landmarks ---------------------------------------------
+
+__global__ void k_sg_slice_flags(size_t O, const uint32_t *__restrict__ opt, uint32_t pt_begin, uint32_t pt_end, uint32_t *__restrict__ flag)
+{
+	size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(e < O) flag[e] = (opt[e] >= pt_begin && opt[e] < pt_end)? 1u : 0u;
+}
+
+// stable compaction of the edges of the slice: kept[pos] = edge, local camera / point index (point relative to the slice)
+__global__ void k_sg_slice_compact(size_t O, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+	const uint32_t *__restrict__ ocam, const uint32_t *__restrict__ opt, uint32_t pt_begin, uint32_t *__restrict__ kept,
+	uint32_t *__restrict__ ocam_l, uint32_t *__restrict__ opt_l)
+{
+	size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(e >= O || !flag[e]) return;
+	const uint32_t k = pos[e];
+	kept[k] = (uint32_t)e;
+	ocam_l[k] = ocam[e];
+	opt_l[k] = opt[e] - pt_begin;
+}
+
+__global__ void k_sg_compose(size_t n, uint32_t *__restrict__ map, const uint32_t *__restrict__ kept)
+{
+	size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(i < n) map[i] = kept[map[i]];
+}
+
+// The multi-rank body of spp_ba_set_graph, on the device: (a) the structure of the WHOLE graph gives the global block
+// list of the reduced camera system (identical on every rank) and the track lengths; (b) the landmark slices are cut
+// (spp_partition_landmarks); (c) the edges of this rank's slice are compacted (edge insertion order kept) and the
+// structure is built again for the slice; (d) every block of the slice is located in the global list.
+void ba_upload_and_analyse_device_sliced(spp_ctx *ctx, size_t C, size_t P, size_t O, const uint64_t *p_obs_point,
+	const uint64_t *p_obs_camera, const double *p_z, const double *p_info)
+{
+	BAProblem &ba = ctx->ba;
+	SchurSystem &s = ctx->sys;
+	SymbolicScratch &w = ctx->sym;
+	cudaStream_t st = ctx->stream;
+	const unsigned T = 256;
+	w.vtype.upload(ba.vtype.data(), ba.n_vertices, st);
+	w.vlocal.upload(ba.vertex_local.data(), ba.n_vertices, st);
+	w.obs_pt_id.upload(p_obs_point, O, st);
+	w.obs_cam_id.upload(p_obs_camera, O, st);
+	w.z_in.upload(p_z, O * 2, st);
+	w.info_in.upload(p_info, O * 4, st);
+	w.ocam.resize(O); w.opt.resize(O);
+	w.err.resize(1);
+	SPP_CUDA(cudaMemsetAsync(w.err.p(), 0, sizeof(int), st));
+	if(O) {
+		k_sg_edge_local<<<n_blocks(O, T), T, 0, st>>>(O, ba.n_vertices, w.obs_pt_id.p(), w.obs_cam_id.p(), w.vtype.p(),
+			w.vlocal.p(), w.ocam.p(), w.opt.p(), w.err.p());
+		LAUNCH_CHECK(ctx);
+		int h_err = 0;
+		SPP_CUDA(cudaMemcpyAsync(&h_err, w.err.p(), sizeof(int), cudaMemcpyDeviceToHost, st));
+		SPP_CUDA(cudaStreamSynchronize(st));
+		if(h_err)
+			throw invalid_error("observation references a vertex of the wrong type or out of range");
+	}
+	// (a) the whole graph
+	build_schur_structure_device(ctx, C, P, O, w.ocam.p(), w.opt.p(), ba.d_obs_orig);
+	s.n_blocks_global = s.n_blocks;
+	s.h_gblk_row.resize(s.n_blocks);
+	s.h_gblk_col.resize(s.n_blocks);
+	s.blk_row.download(s.h_gblk_row.data(), s.n_blocks, st);
+	s.blk_col.download(s.h_gblk_col.data(), s.n_blocks, st);
+	std::vector<uint32_t> pt_ptr(P + 1);
+	s.pt_ptr.download(pt_ptr.data(), P + 1, st);
+	SPP_CUDA(cudaStreamSynchronize(st));
+	s.gblk_row.upload(s.h_gblk_row, st);
+	s.gblk_col.upload(s.h_gblk_col, st);
+	// (b) slices balanced by the Schur-product work
+	std::vector<uint32_t> track_len(P);
+	for(size_t p = 0; p < P; ++ p) track_len[p] = pt_ptr[p + 1] - pt_ptr[p];
+	std::vector<uint64_t> bounds(ctx->world + 1);
+	spp_partition_landmarks(P, P? &track_len[0] : 0, ctx->world, &bounds[0]);
+	ba.pt_begin = bounds[ctx->rank];
+	ba.pt_end = bounds[ctx->rank + 1];
+	const size_t P_local = ba.pt_end - ba.pt_begin;
+	const size_t O_local = pt_ptr[ba.pt_end] - pt_ptr[ba.pt_begin];
+	// (c) this rank's edges
+	SgTemp tmp(w.cub_temp);
+	DBuf<uint32_t> flag, pos, kept, ocam_l, opt_l;
+	flag.resize(O); pos.resize(O); kept.resize(O_local); ocam_l.resize(O_local); opt_l.resize(O_local);
+	if(O) {
+		k_sg_slice_flags<<<n_blocks(O, T), T, 0, st>>>(O, w.opt.p(), (uint32_t)ba.pt_begin, (uint32_t)ba.pt_end, flag.p());
+		LAUNCH_CHECK(ctx);
+		exclusive_scan(ctx, tmp, flag.p(), pos.p(), O);
+		k_sg_slice_compact<<<n_blocks(O, T), T, 0, st>>>(O, flag.p(), pos.p(), w.ocam.p(), w.opt.p(), (uint32_t)ba.pt_begin,
+			kept.p(), ocam_l.p(), opt_l.p());
+		LAUNCH_CHECK(ctx);
+	}
+	build_schur_structure_device(ctx, C, P_local, O_local, ocam_l.p(), opt_l.p(), ba.d_obs_orig);
+	if(O_local) { // track position -> edge of the slice -> original edge
+		k_sg_compose<<<n_blocks(O_local, T), T, 0, st>>>(O_local, ba.d_obs_orig.p(), kept.p());
+		LAUNCH_CHECK(ctx);
+	}
+	ba.z.resize(O_local * 2);
+	ba.info.resize(O_local * 4);
+	if(O_local) {
+		k_sg_gather_rows<2><<<n_blocks(O_local * 2, T), T, 0, st>>>(O_local, ba.d_obs_orig.p(), w.z_in.p(), ba.z.p());
+		LAUNCH_CHECK(ctx);
+		k_sg_gather_rows<4><<<n_blocks(O_local * 4, T), T, 0, st>>>(O_local, ba.d_obs_orig.p(), w.info_in.p(), ba.info.p());
+		LAUNCH_CHECK(ctx);
+	}
+	// (d) position of this rank's blocks in the global list (host: one sort of the global keys, binary searches)
+	s.h_blk_row.resize(s.n_blocks);
+	s.h_blk_col.resize(s.n_blocks);
+	s.blk_row.download(s.h_blk_row.data(), s.n_blocks, st);
+	s.blk_col.download(s.h_blk_col.data(), s.n_blocks, st);
+	SPP_CUDA(cudaStreamSynchronize(st)); // also: flag / pos / kept go out of scope
+	{
+		const size_t ng = s.n_blocks_global;
+		std::vector<std::pair<uint64_t, uint32_t> > keys(ng);
+		for(size_t b = 0; b < ng; ++ b)
+			keys[b] = std::make_pair((uint64_t)s.h_gblk_row[b] * C + s.h_gblk_col[b], (uint32_t)b);
+		std::sort(keys.begin(), keys.end());
+		std::vector<uint32_t> slot(s.n_blocks);
+		for(size_t b = 0; b < s.n_blocks; ++ b) {
+			const uint64_t k = (uint64_t)s.h_blk_row[b] * C + s.h_blk_col[b];
+			std::vector<std::pair<uint64_t, uint32_t> >::const_iterator it =
+				std::lower_bound(keys.begin(), keys.end(), std::make_pair(k, (uint32_t)0));
+			if(it == keys.end() || it->first != k)
+				throw invalid_error("internal error: a block of this rank is missing from the global block list");
+			slot[b] = it->second;
+		}
+		s.blk_slot.upload(slot, st);
+		SPP_CUDA(cudaStreamSynchronize(st));
 	}
 	ba.host_maps_valid = false;
 }

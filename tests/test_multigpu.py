@@ -49,6 +49,33 @@ def test_partition_edge_cases():
     assert np.all(np.diff(b) == 125)
 
 
+def test_global_block_pattern_of_the_reduced_camera_system():
+    """the block list under which the ranks sum their partial systems (pure host helper) against an independent
+    numpy derivation; every landmark slice's blocks are contained in it"""
+    import numpy as np
+    from slam_plus_plus_b200 import capi, graphs
+    for g in (graphs.ba_shape("small"), graphs.ba_shape("mid", interleave_ids=True, shuffle_edges=True)):
+        loc = g.vertex_local_index()
+        oc, op = loc[g.obs_cam], loc[g.obs_pt]
+        r, c = capi.rcs_block_pattern(g.n_cams, g.n_pts, oc, op)
+        C = g.n_cams
+        assert np.array_equal(r[:C], np.arange(C)) and np.array_equal(c[:C], np.arange(C))  # diagonal blocks first
+        assert np.all(r[C:] < c[C:]) and np.all(np.diff(r[C:].astype(np.int64) * C + c[C:]) > 0)  # row-major, unique
+        cp, ri = graphs.rcs_block_pattern(g)
+        ref = {(int(ri[k]), j) for j in range(C) for k in range(int(cp[j]), int(cp[j + 1]))}
+        assert {(int(a), int(b)) for a, b in zip(r, c)} == ref
+        track = np.bincount(op, minlength=g.n_pts)
+        bounds = capi.partition_landmarks(track, 3)
+        union = set()
+        for k in range(3):
+            m = (op >= bounds[k]) & (op < bounds[k + 1])
+            rk, ck = capi.rcs_block_pattern(C, g.n_pts, oc[m], op[m])
+            sk = {(int(a), int(b)) for a, b in zip(rk, ck)}
+            assert sk <= ref
+            union |= sk
+        assert union == ref
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("rcs", ["dense", "sparse"])
 def test_sharded_lm_on_two_gpus_matches_single_gpu(rcs):
