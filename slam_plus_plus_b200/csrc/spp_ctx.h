@@ -96,6 +96,7 @@ struct SymbolicScratch {
 	DBuf<uint64_t> obs_pt_id, obs_cam_id; // staging of the caller's vertex ids
 	DBuf<uint8_t> vtype;
 	DBuf<double> z_in, info_in;         // staging of the caller's measurements (edge insertion order)
+	DBuf<uint32_t> sl_flag, sl_pos, sl_kept, sl_ocam, sl_opt; // several ranks: compaction of this rank's edges
 };
 
 // block-sparse Cholesky (sparse_chol.cu): symbolic structures and the factor

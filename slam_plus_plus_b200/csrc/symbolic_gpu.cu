@@ -461,7 +461,7 @@ void ba_upload_and_analyse_device_sliced(spp_ctx *ctx, size_t C, size_t P, size_
 	const size_t O_local = pt_ptr[ba.pt_end] - pt_ptr[ba.pt_begin];
 	// (c) this rank's edges
 	SgTemp tmp(w.cub_temp);
-	DBuf<uint32_t> flag, pos, kept, ocam_l, opt_l;
+	DBuf<uint32_t> &flag = w.sl_flag, &pos = w.sl_pos, &kept = w.sl_kept, &ocam_l = w.sl_ocam, &opt_l = w.sl_opt;
 	flag.resize(O); pos.resize(O); kept.resize(O_local); ocam_l.resize(O_local); opt_l.resize(O_local);
 	if(O) {
 		k_sg_slice_flags<<<n_blocks(O, T), T, 0, st>>>(O, w.opt.p(), (uint32_t)ba.pt_begin, (uint32_t)ba.pt_end, flag.p());
@@ -489,7 +489,7 @@ void ba_upload_and_analyse_device_sliced(spp_ctx *ctx, size_t C, size_t P, size_
 	s.h_blk_col.resize(s.n_blocks);
 	s.blk_row.download(s.h_blk_row.data(), s.n_blocks, st);
 	s.blk_col.download(s.h_blk_col.data(), s.n_blocks, st);
-	SPP_CUDA(cudaStreamSynchronize(st)); // also: flag / pos / kept go out of scope
+	SPP_CUDA(cudaStreamSynchronize(st));
 	{
 		const size_t ng = s.n_blocks_global;
 		std::vector<std::pair<uint64_t, uint32_t> > keys(ng);
