@@ -1,0 +1,249 @@
+/*
+ * NonlinearSolver_Lambda_LM_B200.h -- reference-side adapter for slot 3: a nonlinear solver type with the
+ * interface of CNonlinearSolver_Lambda_LM (include/slam/NonlinearSolver_Lambda_LM.h:318-1116) for bundle-adjustment
+ * systems, whose Optimize() runs ENTIRELY on the GPU through libspp_b200.so -- linearisation of the CEdgeP2C3D edges,
+ * Levenberg-Marquardt control, landmark Schur complement, Cholesky of the reduced camera system, back-substitution,
+ * update and chi2 (spp_ba_set_graph / spp_ba_optimize / spp_ba_get_states).
+ *
+ * Compiled INSIDE a SLAM++ build. The user keeps the reference's CFlatSystem with CVertexCam / CVertexXYZ vertices and
+ * CEdgeP2C3D edges (include/slam/BA_Types.h:54-110,355-390,403-531) and changes one type:
+ *
+ *     typedef CNonlinearSolver_Lambda_LM_B200<CSystemType, CLinearSolverType> CNonlinearSolverType; // was CNonlinearSolver_Lambda_LM
+ *     CNonlinearSolverType solver(system, TIncrementalSolveSetting(), TMarginalsComputationPolicy(), b_verbose,
+ *         CLinearSolverType(), b_use_schur);
+ *     solver.Optimize(n_max_iteration_num, f_min_dx_norm);
+ *
+ * It is a valid CNonlinearSolverType template-template argument of the application's solver list (ctor signature and the
+ * solver_Has* / solver_Exports* traits of include/slam/NonlinearSolver_Lambda_LM.h:351-365; include/slam_app/Main.h:
+ * 1108-1114,1376-1377). The system is read and written back through public accessors only: vertex pool For_Each with
+ * r_v_State() / v_Intrinsics(), edge pool For_Each with n_Vertex_Id(), v_Measurement(), t_Sigma_Inv()
+ * (include/slam/FlatSystem.h:1355-1366, include/slam/BaseTypes_Binary.h:344-366). Optimize() re-reads the system every
+ * time it is called, so vertices and edges added since the last call are picked up: the marker-driven incremental
+ * bundle adjustment of the application (CParseLoop_ConsistencyMarker, include/slam_app/IncBAParsePrimitives.h:154-168)
+ * works unchanged. The CLinearSolver argument is accepted for interface compatibility and not used: the reduced camera
+ * system is solved by the library (dense or block-sparse, spp_schur_set_rcs_solver).
+ *
+ * Not provided (the traits say so): marginal covariances, Jacobian / Hessian export.
+ */
+#pragma once
+#ifndef __NONLINEAR_SOLVER_LAMBDA_LM_B200_INCLUDED
+#define __NONLINEAR_SOLVER_LAMBDA_LM_B200_INCLUDED
+
+#include <stdexcept>
+#include <new>
+#include <vector>
+#include <string>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "slam/FlatSystem.h"         // reference
+#include "slam/BA_Types.h"           // reference: CVertexCam, CVertexXYZ, CEdgeP2C3D
+#include "slam/IncrementalPolicy.h"  // reference: TIncrementalSolveSetting, TMarginalsComputationPolicy
+#include "spp_b200.h"
+
+template <class CSystem, class CLinearSolver, class CAMatrixBlockSizes = typename CSystem::_TyJacobianMatrixBlockList,
+	class CLambdaMatrixBlockSizes = typename CSystem::_TyHessianMatrixBlockList>
+class CNonlinearSolver_Lambda_LM_B200 {
+public:
+	typedef CSystem _TySystem; /**< @brief system type */
+	typedef CLinearSolver _TyLinearSolver; /**< @brief linear solver type (unused) */
+	typedef typename CSystem::_TyBaseVertex _TyBaseVertex; /**< @brief the data type for storing vertices */
+	typedef typename CSystem::_TyBaseEdge _TyBaseEdge; /**< @brief the data type for storing measurements */
+
+	/** solver interface properties (cf. NonlinearSolver_Lambda_LM.h:351-365) */
+	enum {
+		solver_HasDump = true,
+		solver_HasChi2 = true,
+		solver_HasMarginals = false,
+		solver_HasGaussNewton = false,
+		solver_HasLevenberg = true,
+		solver_HasGradient = false,
+		solver_HasSchur = true,
+		solver_HasDelayedOptimization = false,
+		solver_IsPreferredBatch = true,
+		solver_IsPreferredIncremental = false,
+		solver_ExportsJacobian = false,
+		solver_ExportsHessian = false,
+		solver_ExportsFactor = false
+	};
+
+protected:
+	CSystem &m_r_system; /**< @brief reference to the system */
+	TIncrementalSolveSetting m_t_incremental_config; /**< @brief incremental solving configuration */
+	TMarginalsComputationPolicy m_t_marginals_config; /**< @brief marginal covariance policy (must be "do not calculate") */
+	bool m_b_verbose; /**< @brief verbosity flag */
+	spp_ctx_t m_p_context; /**< @brief device context */
+	size_t m_n_last_optimized_vertex_num; /**< @brief for the vertex-counted nonlinear solve period */
+	size_t m_n_iteration_num; /**< @brief linear solves so far */
+	double m_f_device_ms; /**< @brief device time spent in Optimize() so far */
+
+	std::vector<uint8_t> m_vertex_type;
+	std::vector<double> m_cams, m_points, m_z, m_info, m_cam_states;
+	std::vector<uint64_t> m_obs_point, m_obs_camera;
+
+	/** gathers the vertices: cameras 11 numbers (state 6 + intrinsics 5), points 3 */
+	struct CGatherVertices {
+		CNonlinearSolver_Lambda_LM_B200 &m_r;
+		CGatherVertices(CNonlinearSolver_Lambda_LM_B200 &r) :m_r(r) {}
+		void operator ()(const CVertexCam &r_vertex)
+		{
+			m_r.m_vertex_type.push_back(0);
+			for(int i = 0; i < 6; ++ i) m_r.m_cams.push_back(r_vertex.r_v_State()(i));
+			for(int i = 0; i < 5; ++ i) m_r.m_cams.push_back(r_vertex.v_Intrinsics()(i));
+		}
+		void operator ()(const CVertexXYZ &r_vertex)
+		{
+			m_r.m_vertex_type.push_back(1);
+			for(int i = 0; i < 3; ++ i) m_r.m_points.push_back(r_vertex.r_v_State()(i));
+		}
+	};
+
+	/** gathers the observations in edge insertion order */
+	struct CGatherEdges {
+		CNonlinearSolver_Lambda_LM_B200 &m_r;
+		CGatherEdges(CNonlinearSolver_Lambda_LM_B200 &r) :m_r(r) {}
+		void operator ()(const CEdgeP2C3D &r_edge)
+		{
+			m_r.m_obs_camera.push_back(r_edge.n_Vertex_Id(0)); // vertex 0 is the camera (BA_Types.h:403)
+			m_r.m_obs_point.push_back(r_edge.n_Vertex_Id(1));
+			for(int i = 0; i < 2; ++ i) m_r.m_z.push_back(r_edge.v_Measurement()(i));
+			for(int i = 0; i < 2; ++ i)
+				for(int j = 0; j < 2; ++ j) m_r.m_info.push_back(r_edge.t_Sigma_Inv()(i, j));
+		}
+	};
+
+	/** writes the optimized states back into the system */
+	struct CScatterVertices {
+		const double *m_p_cam, *m_p_point;
+		CScatterVertices(const double *p_cam, const double *p_point) :m_p_cam(p_cam), m_p_point(p_point) {}
+		void operator ()(CVertexCam &r_vertex)
+		{
+			for(int i = 0; i < 6; ++ i) r_vertex.r_v_State()(i) = m_p_cam[i];
+			m_p_cam += 6;
+		}
+		void operator ()(CVertexXYZ &r_vertex)
+		{
+			for(int i = 0; i < 3; ++ i) r_vertex.r_v_State()(i) = m_p_point[i];
+			m_p_point += 3;
+		}
+	};
+
+public:
+	/** same arguments as CNonlinearSolver_Lambda_LM (NonlinearSolver_Lambda_LM.h:470-492) */
+	CNonlinearSolver_Lambda_LM_B200(CSystem &r_system,
+		TIncrementalSolveSetting t_incremental_config = TIncrementalSolveSetting(),
+		TMarginalsComputationPolicy t_marginals_config = TMarginalsComputationPolicy(),
+		bool b_verbose = false, CLinearSolver UNUSED(linear_solver) = CLinearSolver(), bool UNUSED(b_use_schur) = true,
+		int n_device = 0)
+		:m_r_system(r_system), m_t_incremental_config(t_incremental_config), m_t_marginals_config(t_marginals_config),
+		m_b_verbose(b_verbose), m_p_context(0), m_n_last_optimized_vertex_num(0), m_n_iteration_num(0), m_f_device_ms(0)
+	{
+		if(t_marginals_config.b_calculate)
+			throw std::runtime_error("CNonlinearSolver_Lambda_LM_B200: marginal covariances are not provided (solver_HasMarginals = false)");
+		Check(spp_create(n_device, &m_p_context));
+	}
+
+	~CNonlinearSolver_Lambda_LM_B200()
+	{
+		spp_destroy(m_p_context);
+	}
+
+	inline const TIncrementalSolveSetting &t_IncrementalConfig() const
+	{
+		return m_t_incremental_config;
+	}
+
+	inline const TMarginalsComputationPolicy &t_MarginalsPolicy() const
+	{
+		return m_t_marginals_config;
+	}
+
+	/** the device context, e.g. for spp_schur_set_rcs_solver() */
+	inline spp_ctx_t p_Context()
+	{
+		return m_p_context;
+	}
+
+	/** timing statistics (cf. CNonlinearSolver_Lambda_LM::Dump, LM.h:547-...) */
+	void Dump(double f_total_time = -1) const
+	{
+		printf("solver took " PRIsize " iterations\n", m_n_iteration_num); // debug, to be able to say we didn't botch it numerically
+		if(f_total_time > 0)
+			printf("solver spent %f seconds in parallelizable section (updating lambda; disparity %g seconds)\n",
+				m_f_device_ms * 1e-3, f_total_time - m_f_device_ms * 1e-3);
+		printf("out of which:\n\tdevice (libspp_b200: lambda, rhs, schur, linsolve, update, chi2): %f\n", m_f_device_ms * 1e-3);
+	}
+
+	/** f_Chi_Squared_Error_Denorm (NonlinearSolver_Base.h:278-297) of the system as it is now */
+	double f_Chi_Squared_Error_Denorm() // throw(std::bad_alloc, std::runtime_error)
+	{
+		Upload();
+		double f_chi2 = 0;
+		Check(spp_ba_chi2(m_p_context, &f_chi2));
+		return f_chi2;
+	}
+
+	/** incremental optimization function (cf. LM.h:671-760): runs Optimize() when the nonlinear solve period elapses */
+	void Incremental_Step(_TyBaseEdge &UNUSED(r_last_edge)) // throw(std::bad_alloc, std::runtime_error)
+	{
+		const size_t n_vertex_num = m_r_system.r_Vertex_Pool().n_Size();
+		const size_t n_period = m_t_incremental_config.t_nonlinear_freq.n_period;
+		if(n_period && n_vertex_num - m_n_last_optimized_vertex_num >= n_period) {
+			m_n_last_optimized_vertex_num = n_vertex_num;
+			Optimize(m_t_incremental_config.n_max_nonlinear_iteration_num, m_t_incremental_config.f_nonlinear_error_thresh);
+		}
+	}
+
+	/** CNonlinearSolver_Lambda_LM::Optimize (LM.h:796-1116) on the device; the system receives the optimized states */
+	void Optimize(size_t n_max_iteration_num = 5, double f_min_dx_norm = .01) // throw(std::bad_alloc, std::runtime_error)
+	{
+		if(m_r_system.r_Edge_Pool().b_Empty())
+			return; // nothing to optimize
+		Upload();
+		spp_report_t t_report;
+		Check(spp_ba_optimize(m_p_context, n_max_iteration_num, f_min_dx_norm, &t_report));
+		m_n_iteration_num += t_report.n_iterations;
+		m_f_device_ms += t_report.ms_total;
+		if(m_b_verbose) {
+			for(int i = 0; i < t_report.n_iterations && i < SPP_MAX_TRACE; ++ i) {
+				printf("chi2: %f%s, alpha %g, residual norm: %.4f\n", t_report.trace_chi2[i],
+					(t_report.trace_accepted[i])? "" : " (rising: step rejected)", t_report.trace_alpha[i], t_report.trace_dx_norm[i]);
+			}
+		}
+		if(t_report.status == SPP_NOT_POSDEF)
+			fprintf(stderr, "warning: Cholesky failed\n"); // as the reference (the loop stops)
+		m_cam_states.resize((m_cams.size() / 11) * 6);
+		Check(spp_ba_get_states(m_p_context, m_cam_states.empty()? 0 : &m_cam_states[0], m_points.empty()? 0 : &m_points[0]));
+		m_r_system.r_Vertex_Pool().For_Each(CScatterVertices(m_cam_states.empty()? 0 : &m_cam_states[0],
+			m_points.empty()? 0 : &m_points[0]));
+	}
+
+protected:
+	/** flattens the system and hands it to the library */
+	void Upload() // throw(std::bad_alloc, std::runtime_error)
+	{
+		m_vertex_type.clear(); m_cams.clear(); m_points.clear();
+		m_obs_point.clear(); m_obs_camera.clear(); m_z.clear(); m_info.clear();
+		m_r_system.r_Vertex_Pool().For_Each(CGatherVertices(*this));
+		m_r_system.r_Edge_Pool().For_Each(CGatherEdges(*this));
+		Check(spp_ba_set_graph(m_p_context, m_vertex_type.size(), m_vertex_type.empty()? 0 : &m_vertex_type[0],
+			m_cams.empty()? 0 : &m_cams[0], m_points.empty()? 0 : &m_points[0], m_obs_point.size(),
+			m_obs_point.empty()? 0 : &m_obs_point[0], m_obs_camera.empty()? 0 : &m_obs_camera[0],
+			m_z.empty()? 0 : &m_z[0], m_info.empty()? 0 : &m_info[0]));
+	}
+
+	void Check(int n_result) const // throw(std::bad_alloc, std::runtime_error)
+	{
+		if(n_result == SPP_OK)
+			return;
+		if(n_result == SPP_ERR_NOMEM)
+			throw std::bad_alloc();
+		throw std::runtime_error(std::string("libspp_b200: ") + spp_last_error(m_p_context));
+	}
+
+private:
+	CNonlinearSolver_Lambda_LM_B200(const CNonlinearSolver_Lambda_LM_B200 &r_solver); // no copy
+	CNonlinearSolver_Lambda_LM_B200 &operator =(const CNonlinearSolver_Lambda_LM_B200 &r_solver); // no copy
+};
+
+#endif // !__NONLINEAR_SOLVER_LAMBDA_LM_B200_INCLUDED

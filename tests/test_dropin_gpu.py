@@ -98,3 +98,42 @@ def test_reference_gauss_newton_with_b200_block_cholesky(name, tmp_path):
     tol = 1e-9 if name.startswith("se2") else 1e-5
     assert abs(r["chi2"][0] - ref["chi2"][0]) <= tol * ref["chi2"][0]
     assert abs(r["chi2"][0] - d["chi2"][0]) <= tol * d["chi2"][0]
+
+
+# ---- slot 3: CNonlinearSolver_Lambda_LM_B200 in place of the reference's nonlinear solver ----------------------------
+
+BIN_LM = os.path.join(ROOT, "oracle", "_ref", "ref_driver_dropin_lm")
+
+
+@pytest.mark.parametrize("mode,name", [("batch", "ba_tiny_interleaved"), ("batch", "ba_small"), ("incremental", "ba_small"),
+                                       ("incremental", "ba_small_hard")])
+def test_reference_system_with_b200_nonlinear_solver(mode, name, tmp_path):
+    """the UNMODIFIED reference's CFlatSystem / vertices / edges with the solver TYPE swapped for
+    CNonlinearSolver_Lambda_LM_B200 (everything from the linearisation on runs on the GPU), against the reference's own
+    CNonlinearSolver_Lambda_LM on the same machine; "incremental" = Optimize() at a marker every 6 cameras on a growing,
+    append-only system (the application's CParseLoop_ConsistencyMarker behaviour)"""
+    if not os.path.exists(BIN_LM):
+        pytest.skip("oracle/_ref/ref_driver_dropin_lm not built (needs /root/reference at build time)")
+    from slam_plus_plus_b200 import sppio
+    g, d = load_golden(name)
+    gp = str(tmp_path / "g.bin")
+    sppio.write_graph(gp, g)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = {}
+    for impl in ("b200", "ref"):
+        dp = str(tmp_path / (impl + ".dump"))
+        subprocess.run([BIN_LM, impl, mode, gp, dp, "5", "0", "6"], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, env=env)
+        out[impl] = sppio.read_dump(dp)
+    b, r = out["b200"], out["ref"]
+    assert int(b["n_vertices"][0]) == int(r["n_vertices"][0]) and int(b["n_edges"][0]) == int(r["n_edges"][0])
+    tb, tr = b["chi2_trace"], r["chi2_trace"]
+    assert len(tb) == len(tr)
+    if mode == "batch":
+        assert abs(tb[0] - tr[0]) <= 1e-11 * tr[0]  # chi2 of the untouched system: no Jacobians involved
+    # chi2 after every Optimize(): FD-noise floor in between (the two runs linearise with forward differences on
+    # different libm implementations), north-star bound on the final value
+    for a, c in zip(tb[:-1], tr[:-1]):
+        assert abs(a - c) <= 2e-5 * max(c, 1.0)
+    assert abs(tb[-1] - tr[-1]) <= 1e-6 * tr[-1]
+    assert rel_err(b["states"], r["states"]) < 1e-4
