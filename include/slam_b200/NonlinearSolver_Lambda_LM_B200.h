@@ -39,6 +39,7 @@
 #include "slam/FlatSystem.h"         // reference
 #include "slam/BA_Types.h"           // reference: CVertexCam, CVertexXYZ, CEdgeP2C3D
 #include "slam/IncrementalPolicy.h"  // reference: TIncrementalSolveSetting, TMarginalsComputationPolicy
+#include "slam/Timer.h"              // reference: CTimer
 #include "spp_b200.h"
 
 template <class CSystem, class CLinearSolver, class CAMatrixBlockSizes = typename CSystem::_TyJacobianMatrixBlockList,
@@ -75,10 +76,13 @@ protected:
 	spp_ctx_t m_p_context; /**< @brief device context */
 	size_t m_n_last_optimized_vertex_num; /**< @brief for the vertex-counted nonlinear solve period */
 	size_t m_n_iteration_num; /**< @brief linear solves so far */
+	size_t m_n_gathered_edge_num; /**< @brief edges already flattened (edges are immutable once added: only new ones are read) */
 	double m_f_device_ms; /**< @brief device time spent in Optimize() so far */
+	double m_f_upload_time, m_f_optimize_time, m_f_download_time; /**< @brief wall-clock split of Optimize() */
 
-	std::vector<uint8_t> m_vertex_type;
-	std::vector<double> m_cams, m_points, m_z, m_info, m_cam_states;
+	bool m_b_uploaded; /**< @brief the device holds the system described by the arrays below */
+	std::vector<uint8_t> m_vertex_type, m_prev_vertex_type;
+	std::vector<double> m_cams, m_points, m_z, m_info, m_cam_states, m_prev_cams, m_prev_points;
 	std::vector<uint64_t> m_obs_point, m_obs_camera;
 
 	/** gathers the vertices: cameras 11 numbers (state 6 + intrinsics 5), points 3 */
@@ -136,7 +140,9 @@ public:
 		bool b_verbose = false, CLinearSolver UNUSED(linear_solver) = CLinearSolver(), bool UNUSED(b_use_schur) = true,
 		int n_device = 0)
 		:m_r_system(r_system), m_t_incremental_config(t_incremental_config), m_t_marginals_config(t_marginals_config),
-		m_b_verbose(b_verbose), m_p_context(0), m_n_last_optimized_vertex_num(0), m_n_iteration_num(0), m_f_device_ms(0)
+		m_b_verbose(b_verbose), m_p_context(0), m_n_last_optimized_vertex_num(0), m_n_iteration_num(0),
+		m_n_gathered_edge_num(0), m_f_device_ms(0), m_f_upload_time(0), m_f_optimize_time(0), m_f_download_time(0),
+		m_b_uploaded(false)
 	{
 		if(t_marginals_config.b_calculate)
 			throw std::runtime_error("CNonlinearSolver_Lambda_LM_B200: marginal covariances are not provided (solver_HasMarginals = false)");
@@ -172,6 +178,8 @@ public:
 			printf("solver spent %f seconds in parallelizable section (updating lambda; disparity %g seconds)\n",
 				m_f_device_ms * 1e-3, f_total_time - m_f_device_ms * 1e-3);
 		printf("out of which:\n\tdevice (libspp_b200: lambda, rhs, schur, linsolve, update, chi2): %f\n", m_f_device_ms * 1e-3);
+		printf("host side of Optimize(): flatten + upload + structure %f, spp_ba_optimize %f, download + write-back %f\n",
+			m_f_upload_time, m_f_optimize_time, m_f_download_time);
 	}
 
 	/** f_Chi_Squared_Error_Denorm (NonlinearSolver_Base.h:278-297) of the system as it is now */
@@ -199,9 +207,15 @@ public:
 	{
 		if(m_r_system.r_Edge_Pool().b_Empty())
 			return; // nothing to optimize
+		CTimer timer;
+		double f_t0 = timer.f_Time();
 		Upload();
+		double f_t1 = timer.f_Time();
 		spp_report_t t_report;
 		Check(spp_ba_optimize(m_p_context, n_max_iteration_num, f_min_dx_norm, &t_report));
+		double f_t2 = timer.f_Time();
+		m_f_upload_time += f_t1 - f_t0;
+		m_f_optimize_time += f_t2 - f_t1;
 		m_n_iteration_num += t_report.n_iterations;
 		m_f_device_ms += t_report.ms_total;
 		if(m_b_verbose) {
@@ -216,20 +230,46 @@ public:
 		Check(spp_ba_get_states(m_p_context, m_cam_states.empty()? 0 : &m_cam_states[0], m_points.empty()? 0 : &m_points[0]));
 		m_r_system.r_Vertex_Pool().For_Each(CScatterVertices(m_cam_states.empty()? 0 : &m_cam_states[0],
 			m_points.empty()? 0 : &m_points[0]));
+		for(size_t i = 0, n = m_cams.size() / 11; i < n; ++ i) // the cached copy follows: the device and the system agree
+			for(int j = 0; j < 6; ++ j) m_cams[i * 11 + j] = m_cam_states[i * 6 + j];
+		m_f_download_time += timer.f_Time() - f_t2;
 	}
 
 protected:
-	/** flattens the system and hands it to the library */
+	/** flattens the system and hands it to the library; what is already on the device is not sent again */
 	void Upload() // throw(std::bad_alloc, std::runtime_error)
 	{
+		m_prev_vertex_type.swap(m_vertex_type); m_prev_cams.swap(m_cams); m_prev_points.swap(m_points);
 		m_vertex_type.clear(); m_cams.clear(); m_points.clear();
-		m_obs_point.clear(); m_obs_camera.clear(); m_z.clear(); m_info.clear();
-		m_r_system.r_Vertex_Pool().For_Each(CGatherVertices(*this));
-		m_r_system.r_Edge_Pool().For_Each(CGatherEdges(*this));
+		m_r_system.r_Vertex_Pool().For_Each(CGatherVertices(*this)); // the states may have been changed by the caller
+		const size_t n_edge_num = m_r_system.r_Edge_Pool().n_Size();
+		const bool b_same_structure = m_b_uploaded && n_edge_num == m_n_gathered_edge_num && m_vertex_type == m_prev_vertex_type;
+		if(b_same_structure) {
+			if(m_cams == m_prev_cams && m_points == m_prev_points)
+				return; // the device holds exactly this system
+			bool b_same_intrinsics = true;
+			for(size_t i = 0, n = m_cams.size() / 11; i < n && b_same_intrinsics; ++ i)
+				for(int j = 6; j < 11; ++ j) b_same_intrinsics = b_same_intrinsics && m_cams[i * 11 + j] == m_prev_cams[i * 11 + j];
+			if(b_same_intrinsics) { // only the states moved
+				m_cam_states.resize((m_cams.size() / 11) * 6);
+				for(size_t i = 0, n = m_cams.size() / 11; i < n; ++ i)
+					for(int j = 0; j < 6; ++ j) m_cam_states[i * 6 + j] = m_cams[i * 11 + j];
+				Check(spp_ba_set_states(m_p_context, m_cam_states.empty()? 0 : &m_cam_states[0], m_points.empty()? 0 : &m_points[0]));
+				return;
+			}
+		}
+		if(n_edge_num < m_n_gathered_edge_num) { // not an append-only change: start over
+			m_obs_point.clear(); m_obs_camera.clear(); m_z.clear(); m_info.clear();
+			m_n_gathered_edge_num = 0;
+		}
+		if(n_edge_num > m_n_gathered_edge_num)
+			m_r_system.r_Edge_Pool().For_Each(m_n_gathered_edge_num, n_edge_num, CGatherEdges(*this)); // the new edges only
+		m_n_gathered_edge_num = n_edge_num;
 		Check(spp_ba_set_graph(m_p_context, m_vertex_type.size(), m_vertex_type.empty()? 0 : &m_vertex_type[0],
 			m_cams.empty()? 0 : &m_cams[0], m_points.empty()? 0 : &m_points[0], m_obs_point.size(),
 			m_obs_point.empty()? 0 : &m_obs_point[0], m_obs_camera.empty()? 0 : &m_obs_camera[0],
 			m_z.empty()? 0 : &m_z[0], m_info.empty()? 0 : &m_info[0]));
+		m_b_uploaded = true;
 	}
 
 	void Check(int n_result) const // throw(std::bad_alloc, std::runtime_error)

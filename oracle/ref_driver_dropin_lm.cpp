@@ -121,6 +121,8 @@ static int Run(const spp_graph_t &g, bool b_incremental, FILE *p_fw, size_t n_ma
 			}
 		}
 	}
+	if(getenv("SPP_REF_DUMP_TIMING"))
+		solver.Dump(f_opt_time);
 	TStates states;
 	system.r_Vertex_Pool().For_Each(states);
 	uint64_t n_vertices = system.r_Vertex_Pool().n_Size(), n_edges = system.r_Edge_Pool().n_Size();

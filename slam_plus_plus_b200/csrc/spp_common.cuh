@@ -31,7 +31,9 @@ struct invalid_error : std::runtime_error {
 		} \
 	} while(0)
 
-// device buffer owned by a context; grows, never shrinks
+// device buffer owned by a context; grows, never shrinks. The first allocation is exact (batch use: no slack); a
+// buffer that has to grow again grows by at least half (a system that is extended step by step -- incremental bundle
+// adjustment -- does not reallocate at every step)
 template <class T>
 class DBuf {
 	T *m_p;
@@ -44,10 +46,16 @@ public:
 	void resize(size_t n)
 	{
 		if(n > m_cap) {
+			size_t want = (m_cap && n < m_cap + m_cap / 2)? m_cap + m_cap / 2 : n;
 			if(m_p) cudaFree(m_p);
 			m_p = 0; m_cap = 0;
-			SPP_CUDA(cudaMalloc((void**)&m_p, (n ? n : 1) * sizeof(T)));
-			m_cap = n;
+			if(cudaMalloc((void**)&m_p, (want ? want : 1) * sizeof(T)) != cudaSuccess) { // no room for the slack: exact size
+				(void)cudaGetLastError();
+				m_p = 0;
+				want = n;
+				SPP_CUDA(cudaMalloc((void**)&m_p, (want ? want : 1) * sizeof(T)));
+			}
+			m_cap = want;
 		}
 		m_n = n;
 	}
