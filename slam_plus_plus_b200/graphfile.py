@@ -15,8 +15,8 @@ including what the parser does to the numbers before the optimizer sees them:
     Absolute_to_Relative(z, 0) (2DSolverBase.h:373-430) and the information matrix read in the "french" order
     |0 1 5; . 2 4; . . 3| unless its zeros say it is in the usual upper-triangular order (ParsePrimitives.h:171-246);
   * information matrices come as upper triangles, row by row.
-Pinned against the reference's own parser: tests/golden/parse_ref.npz (oracle/ref_driver_parse.cpp),
-tests/test_graphfile_cpu.py. Host-side plumbing only: no numerics of the hot path live here.
+Pinned against the reference's own parser: tests/golden/parse_ref.npz (made by the reference-parser driver of the test
+infrastructure), tests/test_graphfile_cpu.py. Host-side plumbing only: no numerics of the hot path live here.
 """
 from __future__ import annotations
 
