@@ -22,6 +22,7 @@
 //     produces V_p and g_p -- the same summation order as the reference's reduction plan.
 
 #include "spp_ctx.h"
+#include <stdlib.h>
 #include "ba_geometry.cuh"
 
 namespace spp {
@@ -172,8 +173,10 @@ __device__ __forceinline__ double warp_max(double v)
 
 #define CAM_THREADS 256
 
-// one CTA per camera
-__global__ void __launch_bounds__(CAM_THREADS) k_linearise_cams(int jac_mode, const uint32_t *__restrict__ cam_ptr,
+// one CTA per camera. JAC: Jacobian mode as a compile-time constant (the other branch does not cost registers);
+// MINB: CTAs per SM the register allocation aims for
+template <int JAC, int MINB>
+__global__ void __launch_bounds__(CAM_THREADS, MINB) k_linearise_cams(int, const uint32_t *__restrict__ cam_ptr,
 	const uint32_t *__restrict__ cam_obs, const uint32_t *__restrict__ obs_pt, const double *__restrict__ pts,
 	const double *__restrict__ z, const double *__restrict__ info, const double *__restrict__ camRt,
 	const double *__restrict__ camK, double *__restrict__ W, double *__restrict__ U, double *__restrict__ gc,
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(CAM_THREADS) k_linearise_cams(int jac_mode, co
 		const double2 i01 = *reinterpret_cast<const double2*>(info + (size_t)o * 4);
 		const double2 i23 = *reinterpret_cast<const double2*>(info + (size_t)o * 4 + 2);
 		double Jc[12], Jp[6], ru, rv;
-		observation_jacobians(jac_mode, sRt, sK, X, Y, Z, zz.x, zz.y, Jc, Jp, ru, rv, true, true);
+		observation_jacobians(JAC, sRt, sK, X, Y, Z, zz.x, zz.y, Jc, Jp, ru, rv, true, true);
 		// T = Jc^T Sigma^-1 (6x2): T(j,0) = Jc(0,j) s00 + Jc(1,j) s10 ; T(j,1) = Jc(0,j) s01 + Jc(1,j) s11
 		double T0[6], T1[6];
 		#pragma unroll
@@ -464,9 +467,16 @@ void ba_linearise(spp_ctx *ctx, bool b_want_maxdiag)
 		p_max = ba.maxdiag.p();
 	}
 	if(s.C) {
-		k_linearise_cams<<<(unsigned)s.C, CAM_THREADS, 0, ctx->stream>>>(ba.jac_mode, s.cam_ptr.p(), s.cam_obs.p(),
-			s.obs_pt.p(), ba.pts.p(), ba.z.p(), ba.info.p(), ba.camRt.p(), ba.camK.p(), s.W.p(), s.U.p(), s.gc.p(),
-			p_max, ba.uf_is_cam? ba.uf_index : -1);
+		static const int occ = getenv("SPP_CAM_OCC")? atoi(getenv("SPP_CAM_OCC")) : 1;
+#define LAUNCH_CAMS(JAC, MINB) k_linearise_cams<JAC, MINB><<<(unsigned)s.C, CAM_THREADS, 0, ctx->stream>>>(ba.jac_mode, s.cam_ptr.p(), \
+			s.cam_obs.p(), s.obs_pt.p(), ba.pts.p(), ba.z.p(), ba.info.p(), ba.camRt.p(), ba.camK.p(), s.W.p(), s.U.p(), s.gc.p(), \
+			p_max, ba.uf_is_cam? ba.uf_index : -1)
+		if(ba.jac_mode == SPP_JAC_FD_REFERENCE) {
+			if(occ >= 2) LAUNCH_CAMS(SPP_JAC_FD_REFERENCE, 2); else LAUNCH_CAMS(SPP_JAC_FD_REFERENCE, 1);
+		} else {
+			if(occ >= 2) LAUNCH_CAMS(SPP_JAC_ANALYTIC, 2); else LAUNCH_CAMS(SPP_JAC_ANALYTIC, 1);
+		}
+#undef LAUNCH_CAMS
 		LAUNCH_CHECK(ctx);
 	}
 	if(s.P) {

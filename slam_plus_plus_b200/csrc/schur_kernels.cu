@@ -78,14 +78,18 @@ __global__ void __launch_bounds__(LI_WARPS * 32) k_landmark_inverse(size_t P, do
 // S(i,j) = [i == j] (U_i + alpha I) - sum_pairs Y_a W_b^T ; for i == j also b_i = gc_i - sum_a Y_a gp_{p(a)}
 //
 // Lane mapping: a warp is three groups of nine lanes (27 of 32 lanes work). Lane q = r3 + 3 c3 of a group owns the
-// 2 x 2 sub-block {r3, r3 + 3} x {c3, c3 + 3} of the 6 x 6 product: it needs two rows of Y_a and two rows of W_b
-// (12 scalar loads that the nine lanes of the group coalesce into the two 144-byte blocks) and does 12 FMAs per
-// pair; no accumulator ever crosses a lane until the three groups are summed at the end (fixed order, so the
-// result is bit-reproducible). Group g of a warp takes pairs g, g + 3 * n_warps, ... of the list.
+// 2 x 2 sub-block of ADJACENT rows {2 r3, 2 r3 + 1} x columns {2 c3, 2 c3 + 1} of the 6 x 6 product: the two rows of
+// Y_a and the two rows of W_b it needs are one 16-byte load per column of the 6 x 3 blocks (three + three LDG.128 per
+// pair, half the L1 wavefronts of 8-byte loads -- the kernel is bound by L1 wavefronts), 12 FMAs per pair; no
+// accumulator ever crosses a lane until the three groups are summed at the end (fixed order, so the result is
+// bit-reproducible). Group g of a warp takes pairs g, g + 3 * n_warps, ... of the list.
+// (Measured alternatives, Venice shape: one DMMA m8n8k4 per pair with one value per lane -- warp per block 1.15 ms,
+// pair lists cut into 128-pair work items 1.25 ms -- against 0.75 ms for this kernel: a pair is a dependent gather of two
+// 144-byte blocks and the product is bound by the latency / L2 traffic of those gathers, not by the 108 FMAs.)
 #define SB_WARPS 8
 
 struct SchurAcc {
-	double s00, s01, s10, s11, b0, b1;
+	double s00, s01, s10, s11, b0, b1; // (row 2 r3 + i, column 2 c3 + j) -> s_ij; b_i: rhs rows 2 r3 + i
 };
 
 template <bool RHS, int SB_UNROLL>
@@ -93,37 +97,53 @@ __device__ __forceinline__ void schur_accumulate(uint64_t k0, uint64_t end, uint
 	const uint32_t *__restrict__ pair_a, const uint32_t *__restrict__ pair_b, const double *__restrict__ Y,
 	const double *__restrict__ W, const double *__restrict__ gp, const uint32_t *__restrict__ obs_pt, SchurAcc &acc)
 {
+	const double2 zero2 = make_double2(0.0, 0.0);
+	// the observation indices of a trip are fetched one trip ahead, so that the dependent chain of a trip is one
+	// memory round trip (the Y / W blocks) instead of two (index, then block)
+	unsigned oa[SB_UNROLL], ob[SB_UNROLL];
+	bool ok[SB_UNROLL];
+	#pragma unroll
+	for(int u = 0; u < SB_UNROLL; ++ u) {
+		const uint64_t kk = k0 + u * stride;
+		ok[u] = kk < end;
+		oa[u] = ok[u]? pair_a[kk] : 0u;
+		ob[u] = RHS? oa[u] : (ok[u]? pair_b[kk] : 0u);
+	}
 	for(uint64_t k = k0; k < end; k += SB_UNROLL * stride) {
-		double y[SB_UNROLL][6], w[SB_UNROLL][6], g[SB_UNROLL][3];
+		double2 y[SB_UNROLL][3], w[SB_UNROLL][3];
+		double g[SB_UNROLL][3];
 		#pragma unroll
 		for(int u = 0; u < SB_UNROLL; ++ u) {
-			const uint64_t kk = k + u * stride;
-			const bool ok = kk < end;
-			const unsigned oa = ok? pair_a[kk] : 0u, ob = RHS? oa : (ok? pair_b[kk] : 0u);
-			const double *Ya = Y + (size_t)oa * 18 + r3, *Wb = W + (size_t)ob * 18 + c3;
+			const double2 *Ya = reinterpret_cast<const double2*>(Y + (size_t)oa[u] * 18 + 2 * r3);
+			const double2 *Wb = reinterpret_cast<const double2*>(W + (size_t)ob[u] * 18 + 2 * c3);
 			#pragma unroll
-			for(int q = 0; q < 3; ++ q) {
-				y[u][q] = ok? Ya[q * 6] : 0.0;
-				y[u][3 + q] = ok? Ya[q * 6 + 3] : 0.0;
-				w[u][q] = ok? Wb[q * 6] : 0.0;
-				w[u][3 + q] = ok? Wb[q * 6 + 3] : 0.0;
+			for(int q = 0; q < 3; ++ q) { // column q of the 6 x 3 blocks: 6 doubles = 3 double2 further on
+				y[u][q] = ok[u]? Ya[q * 3] : zero2;
+				w[u][q] = ok[u]? Wb[q * 3] : zero2;
 			}
 			if(RHS) {
-				const unsigned p = ok? obs_pt[oa] : 0u;
+				const unsigned p = ok[u]? obs_pt[oa[u]] : 0u;
 				#pragma unroll
 				for(int q = 0; q < 3; ++ q)
-					g[u][q] = ok? gp[(size_t)p * 3 + q] : 0.0;
+					g[u][q] = ok[u]? gp[(size_t)p * 3 + q] : 0.0;
 			}
 		}
 		#pragma unroll
+		for(int u = 0; u < SB_UNROLL; ++ u) { // next trip's indices
+			const uint64_t kk = k + (SB_UNROLL + u) * stride;
+			ok[u] = kk < end;
+			oa[u] = ok[u]? pair_a[kk] : 0u;
+			ob[u] = RHS? oa[u] : (ok[u]? pair_b[kk] : 0u);
+		}
+		#pragma unroll
 		for(int u = 0; u < SB_UNROLL; ++ u) {
-			acc.s00 += y[u][0] * w[u][0] + y[u][1] * w[u][1] + y[u][2] * w[u][2];
-			acc.s10 += y[u][3] * w[u][0] + y[u][4] * w[u][1] + y[u][5] * w[u][2];
-			acc.s01 += y[u][0] * w[u][3] + y[u][1] * w[u][4] + y[u][2] * w[u][5];
-			acc.s11 += y[u][3] * w[u][3] + y[u][4] * w[u][4] + y[u][5] * w[u][5];
+			acc.s00 += y[u][0].x * w[u][0].x + y[u][1].x * w[u][1].x + y[u][2].x * w[u][2].x;
+			acc.s10 += y[u][0].y * w[u][0].x + y[u][1].y * w[u][1].x + y[u][2].y * w[u][2].x;
+			acc.s01 += y[u][0].x * w[u][0].y + y[u][1].x * w[u][1].y + y[u][2].x * w[u][2].y;
+			acc.s11 += y[u][0].y * w[u][0].y + y[u][1].y * w[u][1].y + y[u][2].y * w[u][2].y;
 			if(RHS) {
-				acc.b0 += y[u][0] * g[u][0] + y[u][1] * g[u][1] + y[u][2] * g[u][2];
-				acc.b1 += y[u][3] * g[u][0] + y[u][4] * g[u][1] + y[u][5] * g[u][2];
+				acc.b0 += y[u][0].x * g[u][0] + y[u][1].x * g[u][1] + y[u][2].x * g[u][2];
+				acc.b1 += y[u][0].y * g[u][0] + y[u][1].y * g[u][1] + y[u][2].y * g[u][2];
 			}
 		}
 	}
@@ -153,11 +173,12 @@ __global__ void __launch_bounds__(SB_WARPS * 32, (UNROLL >= 4)? 2 : 4) k_schur_b
 	}
 	if(lane < 9) { // ld == 0: compact block list (block blk at S + 36 blk), else the dense matrix
 		const size_t ldo = ld? ld : 6;
-		double *Sb = ld? S + ((size_t)bj * 6 + c3) * ld + (size_t)bi * 6 + r3 : S + (size_t)(slot? slot[blk] : blk) * 36 + c3 * 6 + r3;
+		double *Sb = ld? S + ((size_t)bj * 6 + 2 * c3) * ld + (size_t)bi * 6 + 2 * r3 :
+			S + (size_t)(slot? slot[blk] : blk) * 36 + 2 * c3 * 6 + 2 * r3;
 		Sb[0] = -v[0];
-		Sb[3] = -v[1];
-		Sb[3 * ldo] = -v[2];
-		Sb[3 * ldo + 3] = -v[3];
+		Sb[1] = -v[1];
+		Sb[ldo] = -v[2];
+		Sb[ldo + 1] = -v[3];
 	}
 }
 
@@ -187,16 +208,16 @@ __global__ void __launch_bounds__(SB_WARPS * 32) k_schur_diag(size_t ld, double 
 			for(int i = 0; i < 6; ++ i)
 				v[i] += part[s][q9][i];
 		}
-		const double *Ub = U + bi * 36 + c3 * 6 + r3; // column-major 6x6
+		const double *Ub = U + bi * 36 + 2 * c3 * 6 + 2 * r3; // column-major 6x6
 		const size_t ldo = ld? ld : 6; // ld == 0: compact block list
-		double *Sb = ld? S + (bi * 6 + c3) * ld + bi * 6 + r3 : S + (size_t)(slot? slot[bi] : bi) * 36 + c3 * 6 + r3;
+		double *Sb = ld? S + (bi * 6 + 2 * c3) * ld + bi * 6 + 2 * r3 : S + (size_t)(slot? slot[bi] : bi) * 36 + 2 * c3 * 6 + 2 * r3;
 		Sb[0] = (Ub[0] + ((r3 == c3)? alpha : 0.0)) - v[0];
-		Sb[3] = Ub[3] - v[1];
-		Sb[3 * ldo] = Ub[18] - v[2];
-		Sb[3 * ldo + 3] = (Ub[21] + ((r3 == c3)? alpha : 0.0)) - v[3];
+		Sb[1] = Ub[1] - v[1];
+		Sb[ldo] = Ub[6] - v[2];
+		Sb[ldo + 1] = (Ub[7] + ((r3 == c3)? alpha : 0.0)) - v[3];
 		if(c3 == 0) {
-			b[bi * 6 + r3] = gc[bi * 6 + r3] - v[4];
-			b[bi * 6 + r3 + 3] = gc[bi * 6 + r3 + 3] - v[5];
+			b[bi * 6 + 2 * r3] = gc[bi * 6 + 2 * r3] - v[4];
+			b[bi * 6 + 2 * r3 + 1] = gc[bi * 6 + 2 * r3 + 1] - v[5];
 		}
 	}
 }
