@@ -413,6 +413,7 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 	if(!attr_done) {
 		SPP_CUDA(cudaFuncSetAttribute(k_snode_update<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snode_update_smem<128, 128>()));
 		SPP_CUDA(cudaFuncSetAttribute(k_snode_update<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snode_update_smem<64, 64>()));
+		SPP_CUDA(cudaFuncSetAttribute(k_snode_update<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snode_update_smem<128, 64>()));
 		attr_done = true;
 	}
 	const Supernodes &sn = sc.sn;
@@ -479,9 +480,14 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 			if(!single_stream)
 				SPP_CUDA(cudaStreamWaitEvent(su, sc.ev_factor[s], 0));
 			const size_t tiles = (size_t)((u.M + 127) / 128) * ((u.N + 127) / 128);
-			if(tiles >= 96) {
+			static const int big_tile = getenv("SPP_SNODE_TILE")? atoi(getenv("SPP_SNODE_TILE")) : 1;
+			if(tiles >= 96 && big_tile == 0) {
 				dim3 grid((u.N + 127) / 128, (u.M + 127) / 128);
 				k_snode_update<128, 128><<<grid, 512, snode_update_smem<128, 128>(), su>>>(Ps, ld, u.col0, (uint32_t)(cols - 1), u.M, u.N,
+					n_kt, Pt, sc.panel_ld[u.t], sc.d_cmap.p() + u.map_off);
+			} else if(tiles >= 48) { // two CTAs per SM
+				dim3 grid((u.N + 63) / 64, (u.M + 127) / 128);
+				k_snode_update<128, 64><<<grid, 256, snode_update_smem<128, 64>(), su>>>(Ps, ld, u.col0, (uint32_t)(cols - 1), u.M, u.N,
 					n_kt, Pt, sc.panel_ld[u.t], sc.d_cmap.p() + u.map_off);
 			} else {
 				dim3 grid((u.N + 63) / 64, (u.M + 63) / 64);
