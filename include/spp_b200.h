@@ -234,7 +234,7 @@ int spp_dense_posdef_solve(spp_ctx_t ctx, size_t n, const double *p_A, double *p
  *   p_order_in[n] or NULL   the fill-reducing block ordering to use (new position -> original block column). The
  *                           reference-side adapter passes the reference's own AMD ordering
  *                           (CMatrixOrdering::p_BlockOrdering, src/slam/OrderingMagic.cpp:701-1033) so that the
- *                           elimination order is the reference's, bit for bit; with NULL a minimum-degree ordering is
+ *                           elimination order is the reference's, bit for bit; with NULL the approximate-minimum-degree ordering of spp_block_ordering is
  *                           computed by the library.
  *   p_order_out[n] or NULL  receives the ordering in use. */
 int spp_chol_symbolic(spp_ctx_t ctx, size_t n_block_cols, size_t block_size, const uint64_t *p_col_ptr,

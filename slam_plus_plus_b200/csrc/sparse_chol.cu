@@ -10,7 +10,7 @@
 //
 // The reference factors column by column on one thread (ereach + dense block kernels). Here the host does the
 // integer work once per structure -- ordering (given by the caller, e.g. the reference's own AMD through the
-// adapter, or a minimum-degree ordering computed here), elimination tree, column structures of the factor, and for
+// adapter, or the approximate minimum degree of block_ordering.cpp), elimination tree, column structures of the factor, and for
 // every block L(i, j) the list of block pairs (L(i, k), L(j, k)) that update it -- and the device runs the numeric
 // phase level by level of the elimination tree: all columns of a level are independent.
 //   k_sparse_chol<B>    per level: (a) diagonal blocks: D = A_jj - sum_k L_jk L_jk^T, Cholesky + inverse of the
@@ -25,7 +25,6 @@
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <numeric>
-#include <set>
 #include <stdlib.h>
 
 namespace cg = cooperative_groups;
@@ -39,59 +38,6 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x);
 #define LAUNCH_CHECK(ctx) do { ++ (ctx)->n_launches; SPP_CUDA(cudaGetLastError()); } while(0)
 #define SC_WARPS 8
 #define SC_ROOT_MAX_SCALARS 6144 // the dense root front is at most this wide
-
-// ---- host: ordering ------------------------------------------------------------------------------------
-
-// Minimum-degree ordering of the block graph (symmetric structure given by its upper part in CSC): explicit
-// elimination graph, exact external degree, ties broken by the smallest index. The reference uses SuiteSparse AMD
-// (approximate degrees, aggressive absorption); fill is comparable, the permutation is not the same one -- callers
-// that need the reference's ordering bit for bit pass it in (the reference-side adapter does).
-static void minimum_degree_ordering(size_t n, const uint64_t *col_ptr, const uint64_t *row_idx, std::vector<uint32_t> &order)
-{
-	std::vector<std::vector<uint32_t> > adj(n);
-	for(size_t c = 0; c < n; ++ c) {
-		for(uint64_t k = col_ptr[c]; k < col_ptr[c + 1]; ++ k) {
-			const size_t r = row_idx[k];
-			if(r != c) {
-				adj[r].push_back((uint32_t)c);
-				adj[c].push_back((uint32_t)r);
-			}
-		}
-	}
-	for(size_t i = 0; i < n; ++ i) {
-		std::sort(adj[i].begin(), adj[i].end());
-		adj[i].erase(std::unique(adj[i].begin(), adj[i].end()), adj[i].end());
-	}
-	std::set<std::pair<uint32_t, uint32_t> > queue; // (degree, vertex)
-	std::vector<uint32_t> degree(n);
-	std::vector<char> eliminated(n, 0);
-	for(size_t i = 0; i < n; ++ i) {
-		degree[i] = (uint32_t)adj[i].size();
-		queue.insert(std::make_pair(degree[i], (uint32_t)i));
-	}
-	order.clear();
-	order.reserve(n);
-	std::vector<uint32_t> merged;
-	while(!queue.empty()) {
-		const uint32_t v = queue.begin()->second;
-		queue.erase(queue.begin());
-		eliminated[v] = 1;
-		order.push_back(v);
-		const std::vector<uint32_t> &nb = adj[v]; // live neighbours (eliminated ones are removed eagerly)
-		for(size_t a = 0; a < nb.size(); ++ a) {
-			const uint32_t u = nb[a];
-			// adj[u] = (adj[u] U nb) \ {u, v}
-			merged.clear();
-			std::set_union(adj[u].begin(), adj[u].end(), nb.begin(), nb.end(), std::back_inserter(merged));
-			merged.erase(std::remove_if(merged.begin(), merged.end(), [u, v](uint32_t x) { return x == u || x == v; }), merged.end());
-			queue.erase(std::make_pair(degree[u], u));
-			adj[u].swap(merged);
-			degree[u] = (uint32_t)adj[u].size();
-			queue.insert(std::make_pair(degree[u], u));
-		}
-		std::vector<uint32_t>().swap(adj[v]);
-	}
-}
 
 // ---- host: symbolic analysis ---------------------------------------------------------------------------
 
@@ -115,8 +61,10 @@ void sparse_chol_symbolic(spp_ctx *ctx, size_t n, size_t B, const uint64_t *col_
 			seen[p_order_in[i]] = 1;
 			sc.h_order[i] = (uint32_t)p_order_in[i];
 		}
-	} else
-		minimum_degree_ordering(n, col_ptr, row_idx, sc.h_order);
+	} else { // the library's own approximate minimum degree + elimination-tree postorder (block_ordering.cpp)
+		amd_block_ordering(n, col_ptr, row_idx, sc.h_order);
+		etree_postorder(n, col_ptr, row_idx, sc.h_order);
+	}
 	std::vector<uint32_t> inv(n);
 	for(size_t i = 0; i < n; ++ i)
 		inv[sc.h_order[i]] = (uint32_t)i;
