@@ -371,6 +371,8 @@ int spp_create(int device, spp_ctx_t *p_ctx)
 	ctx->rank = 0;
 	ctx->world = 1;
 	ctx->stream = 0;
+	ctx->copy_stream = 0;
+	ctx->copy_done = 0;
 	for(int i = 0; i < 16; ++ i) ctx->ev[i] = 0;
 	try {
 		SPP_CUDA(cudaSetDevice(device));
@@ -403,6 +405,10 @@ void spp_destroy(spp_ctx_t ctx)
 	}
 	for(int i = 0; i < 16; ++ i)
 		if(ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+	if(ctx->copy_stream) {
+		cudaStreamDestroy(ctx->copy_stream);
+		cudaEventDestroy(ctx->copy_done);
+	}
 	// side streams and events of the two Cholesky drivers
 	spp::DenseChol &ch = ctx->chol;
 	if(ch.bulk_stream) {

@@ -192,6 +192,8 @@ struct DenseChol {
 struct spp_ctx {
 	int device;
 	cudaStream_t stream;
+	cudaStream_t copy_stream;   // host-to-device copies that overlap the symbolic analysis (created on first use)
+	cudaEvent_t copy_done;
 	std::string last_error;
 	std::string description;
 	uint64_t n_launches;

@@ -339,6 +339,26 @@ void build_schur_structure_device(spp_ctx *ctx, size_t C, size_t P, size_t O, co
 	s.dxc.resize(C * 6); s.dxp.resize(P * 3);
 }
 
+// copies z / info to the staging buffers on the context's copy stream; records ctx->copy_done
+static void upload_measurements_async(spp_ctx *ctx, const double *p_z, const double *p_info, size_t O)
+{
+	SymbolicScratch &w = ctx->sym;
+	if(!ctx->copy_stream) {
+		SPP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+		SPP_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+	}
+	w.z_in.resize(O * 2);     // (re)allocation happens here, on the host thread, before anything is enqueued
+	w.info_in.resize(O * 4);
+	// whatever still reads the staging buffers of the previous graph is ordered on the main stream
+	SPP_CUDA(cudaEventRecord(ctx->copy_done, ctx->stream));
+	SPP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done, 0));
+	if(O) {
+		SPP_CUDA(cudaMemcpyAsync(w.z_in.p(), p_z, O * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_stream));
+		SPP_CUDA(cudaMemcpyAsync(w.info_in.p(), p_info, O * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_stream));
+	}
+	SPP_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+}
+
 // uploads the caller's observation arrays, derives the per-edge local indices, builds the structure and gathers the
 // measurements into track order -- the device-side body of spp_ba_set_graph for a single-GPU context
 void ba_upload_and_analyse_device(spp_ctx *ctx, size_t C, size_t P, size_t O, const uint64_t *p_obs_point,
@@ -352,8 +372,9 @@ void ba_upload_and_analyse_device(spp_ctx *ctx, size_t C, size_t P, size_t O, co
 	w.vlocal.upload(ba.vertex_local.data(), ba.n_vertices, st);
 	w.obs_pt_id.upload(p_obs_point, O, st);
 	w.obs_cam_id.upload(p_obs_camera, O, st);
-	w.z_in.upload(p_z, O * 2, st);
-	w.info_in.upload(p_info, O * 4, st);
+	// the measurements (two thirds of the bytes) are only needed when the structure is known: their copy runs on a
+	// second stream beside the analysis kernels (truly asynchronous when the caller's buffers are pinned)
+	upload_measurements_async(ctx, p_z, p_info, O);
 	w.ocam.resize(O); w.opt.resize(O);
 	w.err.resize(1);
 	SPP_CUDA(cudaMemsetAsync(w.err.p(), 0, sizeof(int), st));
@@ -371,6 +392,7 @@ void ba_upload_and_analyse_device(spp_ctx *ctx, size_t C, size_t P, size_t O, co
 	build_schur_structure_device(ctx, C, P, O, w.ocam.p(), w.opt.p(), ba.d_obs_orig);
 	ba.z.resize(O * 2);
 	ba.info.resize(O * 4);
+	SPP_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0)); // the measurements have arrived
 	if(O) {
 		k_sg_gather_rows<2><<<n_blocks(O * 2, T), T, 0, st>>>(O, ba.d_obs_orig.p(), w.z_in.p(), ba.z.p());
 		LAUNCH_CHECK(ctx);
@@ -423,8 +445,7 @@ void ba_upload_and_analyse_device_sliced(spp_ctx *ctx, size_t C, size_t P, size_
 	w.vlocal.upload(ba.vertex_local.data(), ba.n_vertices, st);
 	w.obs_pt_id.upload(p_obs_point, O, st);
 	w.obs_cam_id.upload(p_obs_camera, O, st);
-	w.z_in.upload(p_z, O * 2, st);
-	w.info_in.upload(p_info, O * 4, st);
+	upload_measurements_async(ctx, p_z, p_info, O); // beside the analysis, as in the single-rank path
 	w.ocam.resize(O); w.opt.resize(O);
 	w.err.resize(1);
 	SPP_CUDA(cudaMemsetAsync(w.err.p(), 0, sizeof(int), st));
@@ -478,6 +499,7 @@ void ba_upload_and_analyse_device_sliced(spp_ctx *ctx, size_t C, size_t P, size_
 	}
 	ba.z.resize(O_local * 2);
 	ba.info.resize(O_local * 4);
+	SPP_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0)); // the measurements have arrived
 	if(O_local) {
 		k_sg_gather_rows<2><<<n_blocks(O_local * 2, T), T, 0, st>>>(O_local, ba.d_obs_orig.p(), w.z_in.p(), ba.z.p());
 		LAUNCH_CHECK(ctx);
