@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(CAM_THREADS, MINB) k_linearise_cams(int, const
 	const uint32_t *__restrict__ cam_obs, const uint32_t *__restrict__ obs_pt, const double *__restrict__ pts,
 	const double *__restrict__ z, const double *__restrict__ info, const double *__restrict__ camRt,
 	const double *__restrict__ camK, double *__restrict__ W, double *__restrict__ U, double *__restrict__ gc,
-	unsigned long long *__restrict__ maxdiag, long uf_cam)
+	unsigned long long *__restrict__ maxdiag, long uf_cam, double *__restrict__ PtRec)
 {
 	__shared__ double sRt[7 * 12];
 	__shared__ double sK[5];
@@ -226,6 +226,27 @@ __global__ void __launch_bounds__(CAM_THREADS, MINB) k_linearise_cams(int, const
 			*reinterpret_cast<double2*>(Wo + cc * 6 + 0) = make_double2(w[0], w[1]);
 			*reinterpret_cast<double2*>(Wo + cc * 6 + 2) = make_double2(w[2], w[3]);
 			*reinterpret_cast<double2*>(Wo + cc * 6 + 4) = make_double2(w[4], w[5]);
+		}
+		// the landmark's share of this observation, V_e = upper(Jp^T Sigma^-1 Jp) and g_e = Jp^T (Sigma^-1 r): the Jacobian
+		// is at hand here, so the landmark kernel only has to add these records up along its track (same expressions and
+		// the same summation order as the landmark kernel that recomputed Jp: bit-identical V, gp)
+		{
+			double A0[3], A1[3];
+			#pragma unroll
+			for(int j = 0; j < 3; ++ j) {
+				A0[j] = Jp[j] * i01.x + Jp[3 + j] * i23.x;
+				A1[j] = Jp[j] * i01.y + Jp[3 + j] * i23.y;
+			}
+			const double e00 = A0[0] * Jp[0] + A1[0] * Jp[3], e01 = A0[0] * Jp[1] + A1[0] * Jp[4], e02 = A0[0] * Jp[2] + A1[0] * Jp[5];
+			const double e11 = A0[1] * Jp[1] + A1[1] * Jp[4], e12 = A0[1] * Jp[2] + A1[1] * Jp[5], e22 = A0[2] * Jp[2] + A1[2] * Jp[5];
+			const double s0 = i01.x * ru + i01.y * rv, s1 = i23.x * ru + i23.y * rv;
+			double *rec = PtRec + (size_t)o * 10;
+			*reinterpret_cast<double2*>(rec + 0) = make_double2(e00, e01);
+			*reinterpret_cast<double2*>(rec + 2) = make_double2(e02, e11);
+			*reinterpret_cast<double2*>(rec + 4) = make_double2(e12, e22);
+			*reinterpret_cast<double2*>(rec + 6) = make_double2(Jp[0] * s0 + Jp[3] * s1, Jp[1] * s0 + Jp[4] * s1);
+			*reinterpret_cast<double2*>(rec + 8) = make_double2(Jp[2] * s0 + Jp[5] * s1, 0.0);
+			dmax = fmax(dmax, fmax(e00, fmax(e11, e22)));
 		}
 		// U_e = upper(T Jc), g = T r
 		int t = 0;
@@ -341,6 +362,31 @@ __global__ void k_linearise_points(int jac_mode, size_t P, const uint32_t *__res
 		if((threadIdx.x & 31) == 0 && dmax > 0)
 			atomicMax(maxdiag, (unsigned long long)__double_as_longlong(dmax));
 	}
+}
+
+// thread per landmark: V_p, g_p = sum of the per-observation records written by k_linearise_cams, along the track in
+// edge insertion order (the reference's summation order, NonlinearSolver_Lambda_Base.h:152-197, 563-607)
+__global__ void k_sum_point_records(size_t P, const uint32_t *__restrict__ pt_ptr, const double *__restrict__ PtRec,
+	double *__restrict__ V, double *__restrict__ gp, long uf_pt)
+{
+	size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(p >= P) return;
+	double v00 = 0, v01 = 0, v02 = 0, v11 = 0, v12 = 0, v22 = 0, g0 = 0, g1 = 0, g2 = 0;
+	const unsigned beg = pt_ptr[p], end = pt_ptr[p + 1];
+	for(unsigned o = beg; o < end; ++ o) {
+		const double2 *rec = reinterpret_cast<const double2*>(PtRec + (size_t)o * 10);
+		const double2 a = rec[0], b = rec[1], c = rec[2], d = rec[3], e = rec[4];
+		v00 += a.x; v01 += a.y; v02 += b.x; v11 += b.y; v12 += c.x; v22 += c.y;
+		g0 += d.x; g1 += d.y; g2 += e.x;
+	}
+	if((long)p == uf_pt) {
+		v00 += 1.0; v11 += 1.0; v22 += 1.0;
+	}
+	double *Vp = V + p * 9;
+	Vp[0] = v00; Vp[1] = v01; Vp[2] = v02;
+	Vp[3] = v01; Vp[4] = v11; Vp[5] = v12;
+	Vp[6] = v02; Vp[7] = v12; Vp[8] = v22;
+	gp[p * 3] = g0; gp[p * 3 + 1] = g1; gp[p * 3 + 2] = g2;
 }
 
 // chi2: thread per observation, block partials, then a fixed-order final pass
@@ -466,11 +512,13 @@ void ba_linearise(spp_ctx *ctx, bool b_want_maxdiag)
 		ba.maxdiag.zero(ctx->stream);
 		p_max = ba.maxdiag.p();
 	}
+	static const bool recompute = getenv("SPP_POINTS_RECOMPUTE") != 0; // the landmark kernel that recomputes Jp (comparison)
+	ba.pt_rec.resize(s.O * 10);
 	if(s.C) {
 		static const int occ = getenv("SPP_CAM_OCC")? atoi(getenv("SPP_CAM_OCC")) : 1;
 #define LAUNCH_CAMS(JAC, MINB) k_linearise_cams<JAC, MINB><<<(unsigned)s.C, CAM_THREADS, 0, ctx->stream>>>(ba.jac_mode, s.cam_ptr.p(), \
 			s.cam_obs.p(), s.obs_pt.p(), ba.pts.p(), ba.z.p(), ba.info.p(), ba.camRt.p(), ba.camK.p(), s.W.p(), s.U.p(), s.gc.p(), \
-			p_max, ba.uf_is_cam? ba.uf_index : -1)
+			p_max, ba.uf_is_cam? ba.uf_index : -1, ba.pt_rec.p())
 		if(ba.jac_mode == SPP_JAC_FD_REFERENCE) {
 			if(occ >= 2) LAUNCH_CAMS(SPP_JAC_FD_REFERENCE, 2); else LAUNCH_CAMS(SPP_JAC_FD_REFERENCE, 1);
 		} else {
@@ -479,7 +527,11 @@ void ba_linearise(spp_ctx *ctx, bool b_want_maxdiag)
 #undef LAUNCH_CAMS
 		LAUNCH_CHECK(ctx);
 	}
-	if(s.P) {
+	if(s.P && !recompute) {
+		k_sum_point_records<<<n_blocks(s.P, 128), 128, 0, ctx->stream>>>(s.P, s.pt_ptr.p(), ba.pt_rec.p(), s.V.p(), s.gp.p(),
+			ba.uf_is_cam? -1 : ba.uf_index);
+		LAUNCH_CHECK(ctx);
+	} else if(s.P) {
 		k_linearise_points<<<n_blocks(s.P, 128), 128, 0, ctx->stream>>>(ba.jac_mode, s.P, s.pt_ptr.p(), s.obs_cam.p(),
 			ba.pts.p(), ba.z.p(), ba.info.p(), ba.camRt.p(), ba.camK.p(), s.V.p(), s.gp.p(), p_max,
 			ba.uf_is_cam? -1 : ba.uf_index);

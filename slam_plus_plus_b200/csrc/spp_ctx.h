@@ -65,6 +65,7 @@ struct BAProblem {
 	DBuf<double> z, info;                         // [2O], [4O] track order
 	DBuf<double> camRt;                           // [C*7*12] base + 6 perturbed [R|t]
 	DBuf<double> camK;                            // [C*5] fx fy cx cy k
+	DBuf<double> pt_rec;                          // [O*10] per observation: upper(Jp^T Sigma^-1 Jp) (6), Jp^T Sigma^-1 r (3), pad
 	DBuf<double> partial;                         // reduction scratch
 	DBuf<unsigned long long> maxdiag;             // [1] bits of the max per-edge Hessian diagonal
 	bool linearised;
