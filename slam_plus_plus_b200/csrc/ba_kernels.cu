@@ -16,10 +16,10 @@
 //     (7 x 12 doubles) -- every observation then costs ten cheap projections instead of ten pose
 //     compositions with sin/cos/atan.
 //   * k_linearise_cams: one CTA per camera, camera [R|t]s staged in shared memory, observations gathered
-//     through the camera's list; writes W, accumulates U_c and g_c in registers and reduces them with a
-//     fixed-shape tree (no atomics, bit-reproducible).
-//   * k_linearise_points: one thread per landmark walks its (contiguous) track in insertion order and
-//     produces V_p and g_p -- the same summation order as the reference's reduction plan.
+//     through the camera's list; writes W and the landmark share (V_e, g_e) of every observation, accumulates U_c
+//     and g_c in registers and reduces them with a fixed-shape tree (no atomics, bit-reproducible).
+//   * k_sum_point_records: one thread per landmark walks its (contiguous) track in insertion order and adds the
+//     records up into V_p and g_p -- the same summation order as the reference's reduction plan.
 
 #include "spp_ctx.h"
 #include <stdlib.h>
@@ -173,10 +173,10 @@ __device__ __forceinline__ double warp_max(double v)
 
 #define CAM_THREADS 256
 
-// one CTA per camera. JAC: Jacobian mode as a compile-time constant (the other branch does not cost registers);
-// MINB: CTAs per SM the register allocation aims for
-template <int JAC, int MINB>
-__global__ void __launch_bounds__(CAM_THREADS, MINB) k_linearise_cams(int, const uint32_t *__restrict__ cam_ptr,
+// one CTA per camera. JAC: Jacobian mode as a compile-time constant (the other branch does not cost registers).
+// (Two CTAs per SM at 128 registers spill and run 6 % slower: the kernel stays at one CTA per SM.)
+template <int JAC>
+__global__ void __launch_bounds__(CAM_THREADS) k_linearise_cams(int, const uint32_t *__restrict__ cam_ptr,
 	const uint32_t *__restrict__ cam_obs, const uint32_t *__restrict__ obs_pt, const double *__restrict__ pts,
 	const double *__restrict__ z, const double *__restrict__ info, const double *__restrict__ camRt,
 	const double *__restrict__ camK, double *__restrict__ W, double *__restrict__ U, double *__restrict__ gc,
@@ -303,65 +303,6 @@ __global__ void __launch_bounds__(CAM_THREADS, MINB) k_linearise_cams(int, const
 		gc[(size_t)c * 6 + threadIdx.x - 36] = sred[0][21 + threadIdx.x - 36];
 	else if(threadIdx.x == 42 && maxdiag)
 		atomicMax(maxdiag, (unsigned long long)__double_as_longlong(sred[0][27]));
-}
-
-// thread per landmark; walks the track in edge insertion order
-__global__ void k_linearise_points(int jac_mode, size_t P, const uint32_t *__restrict__ pt_ptr,
-	const uint32_t *__restrict__ obs_cam, const double *__restrict__ pts, const double *__restrict__ z,
-	const double *__restrict__ info, const double *__restrict__ camRt, const double *__restrict__ camK,
-	double *__restrict__ V, double *__restrict__ gp, unsigned long long *__restrict__ maxdiag, long uf_pt)
-{
-	size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-	double dmax = 0;
-	if(p < P) {
-		const double X = pts[p * 3], Y = pts[p * 3 + 1], Z = pts[p * 3 + 2];
-		double v00 = 0, v01 = 0, v02 = 0, v11 = 0, v12 = 0, v22 = 0, g0 = 0, g1 = 0, g2 = 0;
-		const unsigned beg = pt_ptr[p], end = pt_ptr[p + 1];
-		for(unsigned o = beg; o < end; ++ o) {
-			const unsigned c = obs_cam[o];
-			double Rt[12], K[5];
-			#pragma unroll
-			for(int i = 0; i < 12; ++ i)
-				Rt[i] = camRt[(size_t)c * 84 + i];
-			#pragma unroll
-			for(int i = 0; i < 5; ++ i)
-				K[i] = camK[(size_t)c * 5 + i];
-			const double2 zz = *reinterpret_cast<const double2*>(z + (size_t)o * 2);
-			const double2 i01 = *reinterpret_cast<const double2*>(info + (size_t)o * 4);
-			const double2 i23 = *reinterpret_cast<const double2*>(info + (size_t)o * 4 + 2);
-			double Jp[6], ru, rv;
-			observation_jacobians(jac_mode, Rt, K, X, Y, Z, zz.x, zz.y, 0, Jp, ru, rv, false, true);
-			// A = Jp^T Sigma^-1 (3x2)
-			double A0[3], A1[3];
-			#pragma unroll
-			for(int j = 0; j < 3; ++ j) {
-				A0[j] = Jp[j] * i01.x + Jp[3 + j] * i23.x;
-				A1[j] = Jp[j] * i01.y + Jp[3 + j] * i23.y;
-			}
-			double e00 = A0[0] * Jp[0] + A1[0] * Jp[3], e01 = A0[0] * Jp[1] + A1[0] * Jp[4], e02 = A0[0] * Jp[2] + A1[0] * Jp[5];
-			double e11 = A0[1] * Jp[1] + A1[1] * Jp[4], e12 = A0[1] * Jp[2] + A1[1] * Jp[5], e22 = A0[2] * Jp[2] + A1[2] * Jp[5];
-			v00 += e00; v01 += e01; v02 += e02; v11 += e11; v12 += e12; v22 += e22;
-			dmax = fmax(dmax, fmax(e00, fmax(e11, e22)));
-			// g = Jp^T (Sigma^-1 r)
-			double s0 = i01.x * ru + i01.y * rv, s1 = i23.x * ru + i23.y * rv;
-			g0 += Jp[0] * s0 + Jp[3] * s1;
-			g1 += Jp[1] * s0 + Jp[4] * s1;
-			g2 += Jp[2] * s0 + Jp[5] * s1;
-		}
-		if((long)p == uf_pt) {
-			v00 += 1.0; v11 += 1.0; v22 += 1.0;
-		}
-		double *Vp = V + p * 9;
-		Vp[0] = v00; Vp[1] = v01; Vp[2] = v02;
-		Vp[3] = v01; Vp[4] = v11; Vp[5] = v12;
-		Vp[6] = v02; Vp[7] = v12; Vp[8] = v22;
-		gp[p * 3] = g0; gp[p * 3 + 1] = g1; gp[p * 3 + 2] = g2;
-	}
-	if(maxdiag) {
-		dmax = warp_max(dmax);
-		if((threadIdx.x & 31) == 0 && dmax > 0)
-			atomicMax(maxdiag, (unsigned long long)__double_as_longlong(dmax));
-	}
 }
 
 // thread per landmark: V_p, g_p = sum of the per-observation records written by k_linearise_cams, along the track in
@@ -512,28 +453,20 @@ void ba_linearise(spp_ctx *ctx, bool b_want_maxdiag)
 		ba.maxdiag.zero(ctx->stream);
 		p_max = ba.maxdiag.p();
 	}
-	static const bool recompute = getenv("SPP_POINTS_RECOMPUTE") != 0; // the landmark kernel that recomputes Jp (comparison)
 	ba.pt_rec.resize(s.O * 10);
 	if(s.C) {
-		static const int occ = getenv("SPP_CAM_OCC")? atoi(getenv("SPP_CAM_OCC")) : 1;
-#define LAUNCH_CAMS(JAC, MINB) k_linearise_cams<JAC, MINB><<<(unsigned)s.C, CAM_THREADS, 0, ctx->stream>>>(ba.jac_mode, s.cam_ptr.p(), \
+#define LAUNCH_CAMS(JAC) k_linearise_cams<JAC><<<(unsigned)s.C, CAM_THREADS, 0, ctx->stream>>>(ba.jac_mode, s.cam_ptr.p(), \
 			s.cam_obs.p(), s.obs_pt.p(), ba.pts.p(), ba.z.p(), ba.info.p(), ba.camRt.p(), ba.camK.p(), s.W.p(), s.U.p(), s.gc.p(), \
 			p_max, ba.uf_is_cam? ba.uf_index : -1, ba.pt_rec.p())
-		if(ba.jac_mode == SPP_JAC_FD_REFERENCE) {
-			if(occ >= 2) LAUNCH_CAMS(SPP_JAC_FD_REFERENCE, 2); else LAUNCH_CAMS(SPP_JAC_FD_REFERENCE, 1);
-		} else {
-			if(occ >= 2) LAUNCH_CAMS(SPP_JAC_ANALYTIC, 2); else LAUNCH_CAMS(SPP_JAC_ANALYTIC, 1);
-		}
+		if(ba.jac_mode == SPP_JAC_FD_REFERENCE)
+			LAUNCH_CAMS(SPP_JAC_FD_REFERENCE);
+		else
+			LAUNCH_CAMS(SPP_JAC_ANALYTIC);
 #undef LAUNCH_CAMS
 		LAUNCH_CHECK(ctx);
 	}
-	if(s.P && !recompute) {
+	if(s.P) {
 		k_sum_point_records<<<n_blocks(s.P, 128), 128, 0, ctx->stream>>>(s.P, s.pt_ptr.p(), ba.pt_rec.p(), s.V.p(), s.gp.p(),
-			ba.uf_is_cam? -1 : ba.uf_index);
-		LAUNCH_CHECK(ctx);
-	} else if(s.P) {
-		k_linearise_points<<<n_blocks(s.P, 128), 128, 0, ctx->stream>>>(ba.jac_mode, s.P, s.pt_ptr.p(), s.obs_cam.p(),
-			ba.pts.p(), ba.z.p(), ba.info.p(), ba.camRt.p(), ba.camK.p(), s.V.p(), s.gp.p(), p_max,
 			ba.uf_is_cam? -1 : ba.uf_index);
 		LAUNCH_CHECK(ctx);
 	}
