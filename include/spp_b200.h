@@ -207,6 +207,11 @@ int spp_schur_set_rcs_ordering(spp_ctx_t ctx, size_t n_cameras, const uint64_t *
  * (amalgamation zeros included), flops of one numeric factorisation, bytes of factor storage, supernode updates. */
 int spp_schur_get_rcs_info(spp_ctx_t ctx, uint64_t *p_order, double *p_stats);
 
+/* After a successful solve on the block-sparse path: || S dx_cam - b || / || b || of the reduced camera system, evaluated
+ * on the device from the block list of S (which survives the factorisation) -- the size-independent check of stage 3
+ * at sizes where no dense copy of S can be taken (BAL-13682 shape). The reference has no counterpart. */
+int spp_schur_get_rcs_residual(spp_ctx_t ctx, double *p_relative_residual);
+
 /* Pure host helpers (no context, no GPU). spp_block_ordering: the library's fill-reducing ordering (approximate
  * minimum degree on the block graph of A + A^T, then a postorder of the elimination tree) of an upper block-triangular
  * structure in block CSC (rows ascending, diagonal present) -- what CMatrixOrdering::p_BlockOrdering / amd_l2 does in

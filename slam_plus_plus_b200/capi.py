@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "spp_synchronize", "spp_set_allreduce", "spp_partition_landmarks", "spp_rcs_block_pattern", "spp_ba_get_partition", "spp_ba_set_graph", "spp_ba_set_states", "spp_ba_get_states",
     "spp_ba_restore_initial", "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_get_blocks", "spp_ba_chi2", "spp_ba_solve_step",
     "spp_ba_optimize", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_get_reduced_system",
-    "spp_schur_set_rcs_solver", "spp_schur_set_rcs_ordering", "spp_schur_get_rcs_info", "spp_block_ordering",
+    "spp_schur_set_rcs_solver", "spp_schur_set_rcs_ordering", "spp_schur_get_rcs_info", "spp_schur_get_rcs_residual", "spp_block_ordering",
     "spp_block_symbolic_stats", "spp_dense_posdef_solve",
     "spp_chol_symbolic", "spp_chol_solve", "spp_chol_get_factor",
     "spp_pose_set_graph", "spp_pose_set_ordering", "spp_pose_set_states", "spp_pose_get_states", "spp_pose_restore_initial",
@@ -106,6 +106,7 @@ def load_library() -> C.CDLL:
     lib.spp_schur_set_rcs_solver.argtypes = [vp, C.c_int]
     lib.spp_schur_set_rcs_ordering.argtypes = [vp, C.c_size_t, u64p]
     lib.spp_schur_get_rcs_info.argtypes = [vp, u64p, dp]
+    lib.spp_schur_get_rcs_residual.argtypes = [vp, dp]
     lib.spp_block_ordering.argtypes = [C.c_size_t, u64p, u64p, u64p]
     lib.spp_block_symbolic_stats.argtypes = [C.c_size_t, u64p, u64p, u64p, u64p, u64p, dp]
     lib.spp_chol_symbolic.argtypes = [vp, C.c_size_t, C.c_size_t, u64p, u64p, u64p, u64p]
@@ -391,6 +392,11 @@ class Context:
         self._check(self.lib.spp_schur_get_rcs_info(self.h, _u64p(order), None))
         return dict(order=order, cameras=int(st[0]), rcs_blocks=int(st[1]), supernodes=int(st[2]), factor_blocks_exact=int(st[3]),
                     factor_blocks_stored=int(st[4]), factor_flops=float(st[5]), factor_bytes=float(st[6]), updates=int(st[7]))
+
+    def schur_get_rcs_residual(self) -> float:
+        v = C.c_double()
+        self._check(self.lib.spp_schur_get_rcs_residual(self.h, C.byref(v)))
+        return v.value
 
     def dense_posdef_solve(self, A, b) -> np.ndarray:
         A = np.asfortranarray(A, np.float64)

@@ -84,6 +84,43 @@ struct EventTimer {
 	}
 };
 
+// r += S x for the symmetric matrix given by its upper block list (diagnostics: atomics are fine here)
+__global__ void k_blocks_symv(size_t n_vals, const double *__restrict__ Sblk, const uint32_t *__restrict__ blk_row,
+	const uint32_t *__restrict__ blk_col, const double *__restrict__ x, double *__restrict__ r)
+{
+	const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(e >= n_vals) return;
+	const size_t b = e / 36;
+	const unsigned q = (unsigned)(e - b * 36), c = q / 6, rr = q - c * 6;
+	const size_t i = (size_t)blk_row[b] * 6 + rr, j = (size_t)blk_col[b] * 6 + c;
+	const double v = Sblk[e];
+	if(blk_row[b] != blk_col[b]) {
+		atomicAdd(r + i, v * x[j]);
+		atomicAdd(r + j, v * x[i]);
+	} else if(rr <= c) { // the diagonal blocks hold both triangles: take the upper one
+		atomicAdd(r + i, v * x[j]);
+		if(rr != c) atomicAdd(r + j, v * x[i]);
+	}
+}
+
+__global__ void k_residual_norms(size_t n, const double *__restrict__ r, const double *__restrict__ b, double *__restrict__ out)
+{
+	__shared__ double s0[256], s1[256];
+	double a0 = 0, a1 = 0;
+	for(size_t i = threadIdx.x; i < n; i += 256) {
+		const double d = r[i] - b[i];
+		a0 += d * d;
+		a1 += b[i] * b[i];
+	}
+	s0[threadIdx.x] = a0; s1[threadIdx.x] = a1;
+	__syncthreads();
+	for(int w = 128; w > 0; w >>= 1) {
+		if((int)threadIdx.x < w) { s0[threadIdx.x] += s0[threadIdx.x + w]; s1[threadIdx.x] += s1[threadIdx.x + w]; }
+		__syncthreads();
+	}
+	if(threadIdx.x == 0) { out[0] = s0[0]; out[1] = s1[0]; }
+}
+
 // scatters the compact block list of S into a dense column-major n x n matrix (upper blocks; diagnostics only)
 __global__ void k_blocks_to_dense(size_t n_vals, const double *__restrict__ Sblk, const uint32_t *__restrict__ blk_row,
 	const uint32_t *__restrict__ blk_col, size_t ld, double *__restrict__ S)
@@ -139,14 +176,14 @@ int schur_solve_current(spp_ctx *ctx, double alpha, spp_report_t *rep)
 			SPP_CUDA(cudaGetLastError());
 		}
 	}
-	if(s.keep_reduced) {
+	if(s.keep_reduced && sparse && (s.n_blocks_global || n > 32768))
+		s.S_copy.resize(0); // no dense copy of a block-sparse system this large / on several ranks: the query will say so
+	else if(s.keep_reduced) {
 		s.b_copy.resize(n);
 		if(sparse) {
 			const size_t ld = dense_chol_ld(n);
 			s.S_copy.resize(dense_chol_storage(n));
 			s.S_copy.zero(ctx->stream);
-			if(s.n_blocks_global || n > 32768)
-				throw invalid_error("spp_schur_get_reduced_system: no dense copy of a block-sparse reduced camera system this large / on several ranks");
 			k_blocks_to_dense<<<n_blocks(s.n_blocks * 36, 256), 256, 0, ctx->stream>>>(s.n_blocks * 36, s.Sblk.p(), s.blk_row.p(),
 				s.blk_col.p(), ld, s.S_copy.p());
 			++ ctx->n_launches;
@@ -159,7 +196,12 @@ int schur_solve_current(spp_ctx *ctx, double alpha, spp_report_t *rep)
 	}
 	if(rep) rep->ms_schur += tm.stop_ms();
 	tm.start();
+	if(sparse) { // the block list survives the factorisation: with a copy of b the residual can be checked afterwards
+		s.b_copy.resize(n);
+		SPP_CUDA(cudaMemcpyAsync(s.b_copy.p(), s.b.p(), n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+	}
 	int rc = sparse? snode_factor_solve(ctx, s.Sblk.p(), s.b.p(), s.b.p()) : dense_chol_solve_device(ctx, s.S.p(), n, s.b.p());
+	s.sparse_solved = sparse && rc == SPP_OK;
 	if(rep) rep->ms_factor += tm.stop_ms();
 	if(rc != SPP_OK)
 		return rc;
@@ -869,7 +911,8 @@ int spp_schur_get_reduced_system(spp_ctx_t ctx, uint64_t *p_n, double *p_S, doub
 	if(p_n) *p_n = n;
 	if(p_S || p_rhs) {
 		if(!s.keep_reduced || s.S_copy.size() == 0)
-			throw invalid_error("no reduced system kept: solve first (the context keeps a copy after the first query)");
+			throw invalid_error("no reduced system kept: solve first (the context keeps a copy after the first query; no dense "
+				"copy is taken of a block-sparse system with more than 32768 unknowns or on several ranks)");
 		const size_t ld = dense_chol_ld(n);
 		if(p_S)
 			SPP_CUDA(cudaMemcpy2DAsync(p_S, n * 8, s.S_copy.p(), ld * 8, n * 8, n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -930,6 +973,29 @@ int spp_schur_get_rcs_info(spp_ctx_t ctx, uint64_t *p_order, double *p_stats)
 		p_stats[6] = (double)sc.d_L.size() * 8.0;
 		p_stats[7] = (double)sc.updates.size();
 	}
+	API_END(ctx)
+}
+
+int spp_schur_get_rcs_residual(spp_ctx_t ctx, double *p_relative_residual)
+{
+	API_BEGIN(ctx)
+	SchurSystem &s = ctx->sys;
+	if(!p_relative_residual) throw invalid_error("null argument");
+	if(!s.sparse_solved) throw invalid_error("no successful solve on the block-sparse path to check");
+	const size_t n = s.C * 6, nb = s.n_blocks_global? s.n_blocks_global : s.n_blocks;
+	const uint32_t *rows = s.n_blocks_global? s.gblk_row.p() : s.blk_row.p(), *cols = s.n_blocks_global? s.gblk_col.p() : s.blk_col.p();
+	DBuf<double> r, out;
+	r.resize(n);
+	out.resize(2);
+	r.zero(ctx->stream);
+	k_blocks_symv<<<n_blocks(nb * 36, 256), 256, 0, ctx->stream>>>(nb * 36, s.Sblk.p(), rows, cols, s.dxc.p(), r.p());
+	k_residual_norms<<<1, 256, 0, ctx->stream>>>(n, r.p(), s.b_copy.p(), out.p());
+	ctx->n_launches += 2;
+	SPP_CUDA(cudaGetLastError());
+	double h[2];
+	out.download(h, 2, ctx->stream);
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	*p_relative_residual = (h[1] > 0)? sqrt(h[0] / h[1]) : sqrt(h[0]);
 	API_END(ctx)
 }
 

@@ -42,7 +42,8 @@ struct SchurSystem {
 	DBuf<double> b, b_copy; // [n] reduced right-hand side / camera increment
 	DBuf<double> dxc, dxp; // [6C], [3P] increments
 	bool keep_reduced;
-	SchurSystem() : C(0), P(0), O(0), n_blocks(0), n_pairs(0), n_blocks_global(0), keep_reduced(false) {}
+	bool sparse_solved;  // the last solve went through the block-sparse path and succeeded (Sblk, b_copy, dxc are consistent)
+	SchurSystem() : C(0), P(0), O(0), n_blocks(0), n_pairs(0), n_blocks_global(0), keep_reduced(false), sparse_solved(false) {}
 };
 
 struct BAProblem {
