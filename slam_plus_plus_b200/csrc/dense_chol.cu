@@ -248,10 +248,10 @@ size_t dense_chol_storage(size_t n)
 	return ld * (ld + CH_NB);
 }
 
-static void chol_init_attributes()
+static void chol_init_attributes(int device)
 {
-	static bool done = false;
-	if(done) return;
+	static bool done[64] = {false}; // the attribute belongs to the (kernel, device) pair
+	if(device < 0 || device >= 64 || done[device]) return;
 	SPP_CUDA(cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM_EXCLUSIVE));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 128>()));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
@@ -259,13 +259,13 @@ static void chol_init_attributes()
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_TRSM, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
 	SPP_CUDA(cudaFuncSetAttribute((k_gemm_tn<GEMM_TRSM, 128, 16, 32, 16, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 16, 8>()));
 	SPP_CUDA(cudaFuncSetAttribute((k_gemm_tn<GEMM_SYRK, 32, 32, 16, 16, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<32, 32, 8>()));
-	done = true;
+	done[device] = true;
 }
 
 static void chol_init_streams(spp_ctx *ctx)
 {
 	DenseChol &ch = ctx->chol;
-	chol_init_attributes();
+	chol_init_attributes(ctx->device);
 	if(ch.bulk_stream)
 		return;
 	// the context stream carries the critical chain (created with the highest priority in spp_create); the
@@ -472,6 +472,21 @@ void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols, 
 			fprintf(stderr, "[spp chol profile] n=%zu potrf %.3f ms, trsm %.3f, bulk %.3f, la_diag %.3f, la_row %.3f (serialised)\n",
 				n, t_acc[0], t_acc[1], t_acc[2], t_acc[3], t_acc[4]);
 		}
+	}
+}
+
+// The same for a panel with ONE diagonal block (ld == 128) on a stream of the caller's choice: the diagonal-block
+// kernel and the solve of the block row, no look-ahead needed -- the supernodal factorisation runs its many narrow
+// supernodes side by side with this.
+void dense_chol_factor_single_panel(spp_ctx *ctx, cudaStream_t stream, double *A, size_t n_cols, double *Rinv, int *info)
+{
+	chol_init_streams(ctx);
+	DenseChol &ch = ctx->chol;
+	k_potrf128<<<1, PT, ch.potrf_exclusive? POTRF_SMEM_EXCLUSIVE : POTRF_SMEM, stream>>>(A, CH_NB, 0, Rinv, info, 0);
+	LAUNCH_CHECK(ctx);
+	if(n_cols > CH_NB) {
+		k_gemm_tn<GEMM_TRSM, 128, 64><<<(unsigned)((n_cols - CH_NB) / 64), 256, gemm_smem<128, 64>(), stream>>>(A, CH_NB, 0, 0, CH_NB, Rinv);
+		LAUNCH_CHECK(ctx);
 	}
 }
 

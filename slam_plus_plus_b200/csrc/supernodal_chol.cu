@@ -32,6 +32,7 @@
 namespace spp {
 
 void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols, double *Rinv, int *info);
+void dense_chol_factor_single_panel(spp_ctx *ctx, cudaStream_t stream, double *A, size_t n_cols, double *Rinv, int *info);
 void dense_chol_backsolve_panel(spp_ctx *ctx, cudaStream_t stream, const double *A, size_t ld, const double *Rinv, double *y, int *flags);
 void schur_fetch_host_pattern(spp_ctx *ctx);
 
@@ -41,7 +42,7 @@ void schur_fetch_host_pattern(spp_ctx *ctx);
 #define SN_BK 16
 #define SN_LDS (SN_BK + 4)
 #define SN_STAGES 3
-#define SN_GEMV_COLS 384
+#define SN_GEMV_COLS 64 // columns per CTA of the backward-solve GEMV: a short dependent chain per thread, many CTAs
 
 static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
@@ -367,11 +368,11 @@ __global__ void __launch_bounds__(128) k_snode_gemv(const double *__restrict__ P
 	double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 	const size_t nc = c1 - c0;
 	size_t c = 0;
-	for(; c + 4 <= nc; c += 4) {
-		s0 += p[c * ld] * xs[c];
-		s1 += p[(c + 1) * ld] * xs[c + 1];
-		s2 += p[(c + 2) * ld] * xs[c + 2];
-		s3 += p[(c + 3) * ld] * xs[c + 3];
+	for(; c + 8 <= nc; c += 8) { // eight independent loads in flight
+		const double a0 = p[c * ld], a1 = p[(c + 1) * ld], a2 = p[(c + 2) * ld], a3 = p[(c + 3) * ld];
+		const double a4 = p[(c + 4) * ld], a5 = p[(c + 5) * ld], a6 = p[(c + 6) * ld], a7 = p[(c + 7) * ld];
+		s0 += a0 * xs[c]; s1 += a1 * xs[c + 1]; s2 += a2 * xs[c + 2]; s3 += a3 * xs[c + 3];
+		s0 += a4 * xs[c + 4]; s1 += a5 * xs[c + 5]; s2 += a6 * xs[c + 6]; s3 += a7 * xs[c + 7];
 	}
 	for(; c < nc; ++ c)
 		s0 += p[c * ld] * xs[c];
@@ -409,7 +410,8 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 	SupernodalChol &sc = ctx->snode;
 	if(!sc.valid)
 		throw invalid_error("supernodal Cholesky: no symbolic factorisation");
-	static bool attr_done = false;
+	static bool attr_done_on[64] = {false}; // the attribute belongs to the (kernel, device) pair
+	bool &attr_done = attr_done_on[(ctx->device >= 0 && ctx->device < 64)? ctx->device : 0];
 	if(!attr_done) {
 		SPP_CUDA(cudaFuncSetAttribute(k_snode_update<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snode_update_smem<128, 128>()));
 		SPP_CUDA(cudaFuncSetAttribute(k_snode_update<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snode_update_smem<64, 64>()));
@@ -461,16 +463,35 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 		cudaEventRecord(ctx->ev[4], st);
 	};
 	lap(0);
+	char assembled_seen[SupernodalChol::N_STREAMS] = {0};
+	int side_used[SupernodalChol::N_STREAMS] = {0};
+	if(!single_stream)
+		SPP_CUDA(cudaEventRecord(sc.ev_x[0], st)); // "panels assembled" (the backward solve re-records ev_x later)
 	// factorisation, elimination order (a postorder: every descendant of t precedes t)
 	for(size_t s = 0; s < ns; ++ s) {
 		double *Ps = L + sc.panel_off[s];
 		const size_t ld = sc.panel_ld[s], cols = sc.panel_cols[s];
-		if(pending[s]) // every update into this panel went to one side stream, in elimination order
-			SPP_CUDA(cudaStreamWaitEvent(st, sc.ev_target[s], 0));
-		dense_chol_factor_panel(ctx, Ps, ld, cols, sc.d_Rinv.p() + (size_t)sc.rinv_first[s] * SN_NB * SN_NB, sc.d_info.p());
+		// a supernode with a single diagonal block is factored on the side stream that carries the updates into it (no
+		// event needed: same stream), so the many narrow supernodes of the lower tree levels run side by side; the wide
+		// ones use the look-ahead panel factorisation on the main stream
+		const bool on_side = !single_stream && ld == SN_NB;
+		cudaStream_t sf = on_side? sc.side[s % SupernodalChol::N_STREAMS] : st;
+		if(on_side) {
+			if(!assembled_seen[s % SupernodalChol::N_STREAMS]) { // the panels were assembled on the main stream
+				SPP_CUDA(cudaStreamWaitEvent(sf, sc.ev_x[0], 0));
+				assembled_seen[s % SupernodalChol::N_STREAMS] = 1;
+			}
+			dense_chol_factor_single_panel(ctx, sf, Ps, cols, sc.d_Rinv.p() + (size_t)sc.rinv_first[s] * SN_NB * SN_NB, sc.d_info.p());
+		} else {
+			if(pending[s]) // every update into this panel went to one side stream, in elimination order
+				SPP_CUDA(cudaStreamWaitEvent(st, sc.ev_target[s], 0));
+			dense_chol_factor_panel(ctx, Ps, ld, cols, sc.d_Rinv.p() + (size_t)sc.rinv_first[s] * SN_NB * SN_NB, sc.d_info.p());
+		}
 		if(profile) lap(&t_factor[s]);
-		if(!single_stream && sc.upd_ptr[s + 1] > sc.upd_ptr[s])
-			SPP_CUDA(cudaEventRecord(sc.ev_factor[s], st));
+		if(!single_stream && (sc.upd_ptr[s + 1] > sc.upd_ptr[s] || on_side))
+			SPP_CUDA(cudaEventRecord(sc.ev_factor[s], sf));
+		if(on_side)
+			side_used[s % SupernodalChol::N_STREAMS] = (int)s + 1; // joined before the backward solve
 		const size_t w = 6 * (size_t)(sn.first[s + 1] - sn.first[s]);
 		const uint32_t n_kt = (uint32_t)(round_up(w, SN_BK) / SN_BK);
 		for(uint64_t q = sc.upd_ptr[s]; q < sc.upd_ptr[s + 1]; ++ q) {
@@ -502,8 +523,13 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 		}
 		if(profile) lap(&t_update[s]);
 	}
-	if(!single_stream)
-		SPP_CUDA(cudaEventRecord(sc.ev_factor[ns - 1], st)); // the last supernode (a root) has no updates: its event is free
+	if(!single_stream) {
+		for(int i = 0; i < SupernodalChol::N_STREAMS; ++ i) { // supernodes factored on the side streams (roots among them)
+			if(side_used[i])
+				SPP_CUDA(cudaStreamWaitEvent(st, sc.ev_factor[side_used[i] - 1], 0));
+		}
+		SPP_CUDA(cudaEventRecord(sc.ev_factor[ns - 1], st)); // "factorisation complete"
+	}
 	if(profile) {
 		double tf = 0, tu = 0, ff = 0, fu = 0, tf_small = 0, tu_small = 0;
 		size_t n_small = 0;
