@@ -412,7 +412,9 @@ void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols, 
 			if(!prof)
 				SPP_CUDA(cudaStreamWaitEvent(sC, ch.ev_first[e], 0));
 			tic();
-			syrk(sC, k0, c0, c0 + CH_NB, CH_NB, n_cols - (c0 + CH_NB), 2);
+			// 64 x 64 tiles while they are needed to occupy the SMs (a dense matrix), 128 x 64 for the long block rows of a
+			// supernode panel
+			syrk(sC, k0, c0, c0 + CH_NB, CH_NB, n_cols - (c0 + CH_NB), ((n_cols - (c0 + CH_NB)) / 64 >= 148)? 1 : 2);
 			toc(4);
 			if(!prof)
 				SPP_CUDA(cudaEventRecord(ch.ev_row[e], sC));

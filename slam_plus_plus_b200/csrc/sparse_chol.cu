@@ -288,6 +288,9 @@ void sparse_chol_symbolic(spp_ctx *ctx, size_t n, size_t B, const uint64_t *col_
 	sc.d_y.resize(n * B);
 	sc.d_info.resize(1);
 	SPP_CUDA(cudaStreamSynchronize(st));
+	if(getenv("SPP_SPARSE_VERBOSE"))
+		fprintf(stderr, "[spp sparse chol] n %zu (B = %zu), A blocks %zu, L blocks %zu, levels %u (cooperative 0..%u, single CTA ..%u), "
+			"dense root front %zu columns (%zu blocks)\n", n, B, sc.n_a_blocks, nb, n_levels_all, tail, n_levels, m, sc.n_root_blocks);
 	sc.valid = true;
 }
 
