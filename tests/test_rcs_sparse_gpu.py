@@ -142,3 +142,18 @@ def test_full_size_bal13682_properties(ctx):
     assert np.all(np.isfinite(dx))
     rep = ctx.ba_optimize(3, 0.0)
     assert rep["n_accepted"] >= 1 and rep["chi2_final"] < 0.5 * rep["chi2_initial"]
+
+
+def test_sparse_path_is_bit_reproducible(sparse_ctx):
+    """side streams carry the supernode updates, but all updates into one panel stay on one stream in elimination
+    order: two solves of the same system give the same bits (no floating-point atomics anywhere on the path)"""
+    from slam_plus_plus_b200 import graphs
+    g = graphs.make_ba(600, 40000, 600, mean_extra_track=3.0, max_track=20, max_stride=4, loops=2)
+    sparse_ctx.ba_set_graph(g)
+    sparse_ctx.ba_linearise()
+    a = sparse_ctx.ba_solve_step(3.0)
+    b = sparse_ctx.ba_solve_step(3.0)
+    info = sparse_ctx.schur_get_rcs_info()
+    assert info["supernodes"] > 10 and info["updates"] > 20
+    assert np.array_equal(a, b)
+    assert sparse_ctx.schur_get_rcs_residual() < 1e-13
