@@ -525,6 +525,10 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 	LAUNCH_CHECK(ctx);
 	k_copy_rhs<<<n_blocks(n, 256), 256, 0, st>>>(d_rhs_x, rhs_col, n);
 	LAUNCH_CHECK(ctx);
+	if(ctx->async_mode && ctx->async_info) { // the caller synchronises later and reads the status there
+		SPP_CUDA(cudaMemcpyAsync(ctx->async_info, ch.info.p(), sizeof(int), cudaMemcpyDeviceToHost, st));
+		return SPP_OK;
+	}
 	ctx->h_scalars.resize(16);
 	int *h_info = reinterpret_cast<int*>(ctx->h_scalars.p());
 	SPP_CUDA(cudaMemcpyAsync(h_info, ch.info.p(), sizeof(int), cudaMemcpyDeviceToHost, st));

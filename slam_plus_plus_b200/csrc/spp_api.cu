@@ -143,7 +143,49 @@ static bool rcs_is_sparse(spp_ctx *ctx, size_t C)
 	return C * 6 > 16384;
 }
 
-// Solves the damped Schur system on the current (U, V, W, gc, gp): dxc, dxp. Returns SPP_OK / SPP_NOT_POSDEF.
+static const size_t g_phase_field[PH_COUNT] = {offsetof(spp_report_t, ms_linearise), offsetof(spp_report_t, ms_schur),
+	offsetof(spp_report_t, ms_factor), offsetof(spp_report_t, ms_backsubst), offsetof(spp_report_t, ms_update),
+	offsetof(spp_report_t, ms_chi2)};
+
+static void phase_begin(spp_ctx *ctx, int ph)
+{
+	if(!ctx->phase_ev[ph][0]) {
+		SPP_CUDA(cudaEventCreate(&ctx->phase_ev[ph][0]));
+		SPP_CUDA(cudaEventCreate(&ctx->phase_ev[ph][1]));
+	}
+	SPP_CUDA(cudaEventRecord(ctx->phase_ev[ph][0], ctx->stream));
+}
+
+static void phase_add(spp_ctx *ctx, int ph, spp_report_t *rep)
+{
+	float ms = 0;
+	cudaEventElapsedTime(&ms, ctx->phase_ev[ph][0], ctx->phase_ev[ph][1]);
+	if(rep) *reinterpret_cast<double*>(reinterpret_cast<char*>(rep) + g_phase_field[ph]) += ms;
+}
+
+// synchronous mode: waits for the phase and adds its time to the report; asynchronous mode: only records the event
+static void phase_end(spp_ctx *ctx, int ph, spp_report_t *rep)
+{
+	SPP_CUDA(cudaEventRecord(ctx->phase_ev[ph][1], ctx->stream));
+	if(ctx->async_mode) {
+		ctx->phase_used[ph] = true;
+		return;
+	}
+	SPP_CUDA(cudaEventSynchronize(ctx->phase_ev[ph][1]));
+	phase_add(ctx, ph, rep);
+}
+
+// after the synchronisation of an asynchronous iteration
+static void phase_collect(spp_ctx *ctx, spp_report_t *rep)
+{
+	for(int ph = 0; ph < PH_COUNT; ++ ph) {
+		if(ctx->phase_used[ph]) phase_add(ctx, ph, rep);
+		ctx->phase_used[ph] = false;
+	}
+}
+
+// Solves the damped Schur system on the current (U, V, W, gc, gp): dxc, dxp. Returns SPP_OK / SPP_NOT_POSDEF (in
+// asynchronous mode always SPP_OK: the status arrives in ctx->async_info with the next synchronisation).
 int schur_solve_current(spp_ctx *ctx, double alpha, spp_report_t *rep)
 {
 	SchurSystem &s = ctx->sys;
@@ -160,8 +202,7 @@ int schur_solve_current(spp_ctx *ctx, double alpha, spp_report_t *rep)
 			snode_symbolic(ctx, s.C, s.h_blk_row, s.h_blk_col);
 		}
 	}
-	EventTimer tm(ctx);
-	tm.start();
+	phase_begin(ctx, PH_SCHUR);
 	schur_form_reduced_system(ctx, alpha, (ctx->rank == 0)? alpha : 0.0, compact); // dense: S lives in the padded storage of the dense solver
 	if(ctx->world > 1) { // sum the partial reduced camera systems and right-hand sides over the ranks
 		allreduce_device(ctx, s.Sblk.p(), s.n_blocks_global * 36);
@@ -194,22 +235,22 @@ int schur_solve_current(spp_ctx *ctx, double alpha, spp_report_t *rep)
 		}
 		SPP_CUDA(cudaMemcpyAsync(s.b_copy.p(), s.b.p(), n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
 	}
-	if(rep) rep->ms_schur += tm.stop_ms();
-	tm.start();
+	phase_end(ctx, PH_SCHUR, rep);
+	phase_begin(ctx, PH_FACTOR);
 	if(sparse) { // the block list survives the factorisation: with a copy of b the residual can be checked afterwards
 		s.b_copy.resize(n);
 		SPP_CUDA(cudaMemcpyAsync(s.b_copy.p(), s.b.p(), n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
 	}
 	int rc = sparse? snode_factor_solve(ctx, s.Sblk.p(), s.b.p(), s.b.p()) : dense_chol_solve_device(ctx, s.S.p(), n, s.b.p());
 	s.sparse_solved = sparse && rc == SPP_OK;
-	if(rep) rep->ms_factor += tm.stop_ms();
+	phase_end(ctx, PH_FACTOR, rep);
 	if(rc != SPP_OK)
 		return rc;
-	tm.start();
+	phase_begin(ctx, PH_BACKSUBST);
 	s.dxc.resize(n);
 	SPP_CUDA(cudaMemcpyAsync(s.dxc.p(), s.b.p(), n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
 	schur_backsubstitute(ctx);
-	if(rep) rep->ms_backsubst += tm.stop_ms();
+	phase_end(ctx, PH_BACKSUBST, rep);
 	return SPP_OK;
 }
 
@@ -296,44 +337,70 @@ static int ba_optimize(spp_ctx *ctx, size_t n_max_iteration_num, double f_min_dx
 
 	bool b_system_dirty = false; // lambda matches the current linearisation point
 	int fail = 10;
+	// One host synchronisation per iteration: solve, step norms, update and chi2 are enqueued back to back, then the
+	// factorisation status, the two dot products and chi2 are read together. The reference tests the step norm BEFORE it
+	// applies the update (LM.h:1054) and stops at a failed factorisation (LM.h:972-974): both cases are undone here by
+	// restoring the saved state, which leaves the same system behind.
+	ctx->h_scalars.resize(16);
+	double *h_vals = ctx->h_scalars.p();                    // [0..1] dots, [2] chi2
+	int *h_info = reinterpret_cast<int*>(ctx->h_scalars.p() + 8);
+	struct AsyncGuard { // the stages fall back to synchronous behaviour however this function is left
+		spp_ctx *c;
+		AsyncGuard(spp_ctx *ctx, int *info) : c(ctx) { c->async_mode = true; c->async_info = info; }
+		~AsyncGuard() { c->async_mode = false; c->async_info = 0; for(int i = 0; i < PH_COUNT; ++ i) c->phase_used[i] = false; }
+	} guard(ctx, h_info);
 	for(size_t n_iteration = 0; n_iteration < n_max_iteration_num; ++ n_iteration) {
 		if(n_iteration && b_system_dirty) {
-			tm.start();
+			phase_begin(ctx, PH_LINEARISE);
 			ba_linearise(ctx, false); // LM.h:942-949; a rejected step only re-damps (alpha is applied on the fly)
-			rep->ms_linearise += tm.stop_ms();
+			phase_end(ctx, PH_LINEARISE, rep);
 		}
 		b_system_dirty = false;
 
-		int rc = schur_solve_current(ctx, f_alpha, rep); // LinearSolve, LM.h:1512-1568
+		*h_info = 0;
+		schur_solve_current(ctx, f_alpha, rep); // LinearSolve, LM.h:1512-1568 (status deferred)
 		const int it = rep->n_iterations;
 		++ rep->n_iterations;
 		if(it < SPP_MAX_TRACE)
 			rep->trace_alpha[it] = f_alpha;
-		if(rc != SPP_OK) {
-			rep->status = rc;
-			break; // "in case cholesky failed, quit", LM.h:972-974
-		}
 
-		double dots[2];
 		ba.partial.resize(4 * 1024);
 		ba_step_dots_device(ctx, f_alpha, ba.partial.p() + 2048);
 		allreduce_device(ctx, ba.partial.p() + 2048, 2);
-		read_scalar(ctx, ba.partial.p() + 2048, 2, dots);
+		SPP_CUDA(cudaMemcpyAsync(h_vals, ba.partial.p() + 2048, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+
+		phase_begin(ctx, PH_UPDATE);
+		ba_save_state(ctx);       // LM.h:1062
+		ba_apply_update(ctx);     // PushValuesInGraphSystem, LM.h:1066
+		phase_end(ctx, PH_UPDATE, rep);
+
+		phase_begin(ctx, PH_CHI2);
+		{
+			double *d_chi2 = ba.partial.p() + 2048 + 8; // LM.h:1078
+			ba_chi2_device(ctx, d_chi2);
+			allreduce_device(ctx, d_chi2, 1);
+			SPP_CUDA(cudaMemcpyAsync(h_vals + 2, d_chi2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+		}
+		phase_end(ctx, PH_CHI2, rep);
+
+		SPP_CUDA(cudaStreamSynchronize(ctx->stream)); // the one synchronisation of the iteration
+		phase_collect(ctx, rep);
+		if(*h_info != 0) {
+			ba_load_state(ctx);
+			s.sparse_solved = false;
+			rep->status = SPP_NOT_POSDEF;
+			break; // "in case cholesky failed, quit", LM.h:972-974
+		}
+		const double dots[2] = {h_vals[0], h_vals[1]};
 		const double f_residual_norm = sqrt(dots[0]);
 		rep->last_dx_norm = f_residual_norm;
 		if(it < SPP_MAX_TRACE)
 			rep->trace_dx_norm[it] = f_residual_norm;
-		if(f_residual_norm <= f_min_dx_norm)
+		if(f_residual_norm <= f_min_dx_norm) {
+			ba_load_state(ctx); // the reference leaves before applying this step
 			break; // LM.h:1054
-
-		tm.start();
-		ba_save_state(ctx);       // LM.h:1062
-		ba_apply_update(ctx);     // PushValuesInGraphSystem, LM.h:1066
-		rep->ms_update += tm.stop_ms();
-
-		tm.start();
-		const double f_error = ba_chi2_host(ctx); // LM.h:1078
-		rep->ms_chi2 += tm.stop_ms();
+		}
+		const double f_error = h_vals[2];
 		if(it < SPP_MAX_TRACE)
 			rep->trace_chi2[it] = f_error;
 
@@ -412,6 +479,9 @@ int spp_create(int device, spp_ctx_t *p_ctx)
 	ctx->allreduce_user = 0;
 	ctx->rank = 0;
 	ctx->world = 1;
+	ctx->async_mode = false;
+	ctx->async_info = 0;
+	for(int i = 0; i < PH_COUNT; ++ i) { ctx->phase_ev[i][0] = ctx->phase_ev[i][1] = 0; ctx->phase_used[i] = false; }
 	ctx->stream = 0;
 	ctx->copy_stream = 0;
 	ctx->copy_done = 0;
@@ -447,6 +517,9 @@ void spp_destroy(spp_ctx_t ctx)
 	}
 	for(int i = 0; i < 16; ++ i)
 		if(ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+	for(int i = 0; i < PH_COUNT; ++ i) {
+		if(ctx->phase_ev[i][0]) { cudaEventDestroy(ctx->phase_ev[i][0]); cudaEventDestroy(ctx->phase_ev[i][1]); }
+	}
 	if(ctx->copy_stream) {
 		cudaStreamDestroy(ctx->copy_stream);
 		cudaEventDestroy(ctx->copy_done);

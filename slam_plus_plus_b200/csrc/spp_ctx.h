@@ -191,8 +191,16 @@ struct DenseChol {
 
 } // namespace spp
 
+// phases of one LM iteration; in asynchronous mode (the LM loop) their event pairs are recorded without host
+// synchronisation and read after the one synchronisation of the iteration
+enum { PH_LINEARISE = 0, PH_SCHUR, PH_FACTOR, PH_BACKSUBST, PH_UPDATE, PH_CHI2, PH_COUNT };
+
 struct spp_ctx {
 	int device;
+	bool async_mode;            // no host synchronisation inside the stages (the LM loop synchronises once per iteration)
+	int *async_info;            // pinned slot that receives the factorisation status in asynchronous mode
+	cudaEvent_t phase_ev[PH_COUNT][2];
+	bool phase_used[PH_COUNT];
 	cudaStream_t stream;
 	cudaStream_t copy_stream;   // host-to-device copies that overlap the symbolic analysis (created on first use)
 	cudaEvent_t copy_done;

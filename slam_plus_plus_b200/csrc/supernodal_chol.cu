@@ -597,6 +597,10 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 		lap(&t_back);
 		fprintf(stderr, "[spp snode profile] backward solve %.2f ms\n", t_back);
 	}
+	if(ctx->async_mode && ctx->async_info) { // the caller synchronises later and reads the status there
+		SPP_CUDA(cudaMemcpyAsync(ctx->async_info, sc.d_info.p(), sizeof(int), cudaMemcpyDeviceToHost, st));
+		return SPP_OK;
+	}
 	ctx->h_scalars.resize(16);
 	int *h_info = reinterpret_cast<int*>(ctx->h_scalars.p());
 	SPP_CUDA(cudaMemcpyAsync(h_info, sc.d_info.p(), sizeof(int), cudaMemcpyDeviceToHost, st));
