@@ -1,9 +1,12 @@
 """Graph-file ingest: the reference's text formats -> the SoA arrays the C ABI takes.
 
-Replaces, for the BA and SE(2) formats, the reference's parser front end:
+Replaces, for the BA, SE(2) and SE(3) formats, the reference's parser front end:
     CParserTemplate / CParserBase            include/slam/Parser.h:1137-..., TEdge2D :166-205, TEdgeP2C3D :625-664
     CVertex2DParsePrimitive                  include/slam_app/ParsePrimitives.h:409-460   VERTEX2 / VERTEX_SE2 / VERTEX
     CEdge2DParsePrimitive                    include/slam_app/ParsePrimitives.h:75-258    EDGE2 / EDGE_SE2 / EDGE / ODOMETRY
+    CVertex3DParsePrimitive                  include/slam_app/ParsePrimitives.h:740-787   VERTEX3 / VERTEX_SE3
+    CEdge3DParsePrimitive                    include/slam_app/ParsePrimitives.h:463-538   EDGE3 / EDGE_SE3
+    CEdge3DParsePrimitiveAxisAngle           include/slam_app/ParsePrimitives.h:553-610   EDGE3:AXISANGLE / EDGE_SE3:AXISANGLE
     CVertexXYZParsePrimitive                 include/slam_app/ParsePrimitives.h:809-856   VERTEX_XYZ
     CVertexCam3DParsePrimitive               include/slam_app/ParsePrimitives.h:861-927   VERTEX_CAM
     CEdgeP2C3DParsePrimitive                 include/slam_app/ParsePrimitives.h:1123-1183 EDGE_PROJECT_P2MC / EDGE_P2MC / EDGE_P2C
@@ -14,7 +17,11 @@ including what the parser does to the numbers before the optimizer sees them:
   * 2D edges written with from > to (Manhattan datasets) are inverted: ids swapped, measurement replaced by
     Absolute_to_Relative(z, 0) (2DSolverBase.h:373-430) and the information matrix read in the "french" order
     |0 1 5; . 2 4; . . 3| unless its zeros say it is in the usual upper-triangular order (ParsePrimitives.h:171-246);
-  * information matrices come as upper triangles, row by row.
+  * VERTEX3 / EDGE3 hold rotations as roll, pitch, yaw; the parser builds R = Rz(yaw) Ry(pitch) Rx(roll) and converts it
+    to axis-angle through a quaternion (v_RotMatrix_to_AxisAngle, 3DSolverBase.h:357-366: Eigen's matrix -> quaternion,
+    then Quat_to_AxisAngle); EDGE3 lines with from >= to are reported and DROPPED (ParsePrimitives.h:496-533), while
+    EDGE3:AXISANGLE lines are taken as they are;
+  * information matrices come as upper triangles, row by row (21 values for the 6x6 of TEdge3D, Parser.h:352-371).
 Pinned against the reference's own parser: tests/golden/parse_ref.npz (made by the reference-parser driver of the test
 infrastructure), tests/test_graphfile_cpu.py. Host-side plumbing only: no numerics of the hot path live here.
 """
@@ -24,11 +31,14 @@ import math
 
 import numpy as np
 
-from .sppio import GRAPH_SE2, BAGraph, PoseGraph
+from .sppio import GRAPH_SE2, GRAPH_SE3, BAGraph, PoseGraph
 
 _V2 = ("VERTEX2", "VERTEX_SE2", "VERTEX")
 _E2 = ("EDGE2", "EDGE_SE2", "EDGE", "ODOMETRY")
 _P2C = ("EDGE_PROJECT_P2MC", "EDGE_P2MC", "EDGE_P2C")
+_V3 = ("VERTEX3", "VERTEX_SE3")
+_E3 = ("EDGE3", "EDGE_SE3")
+_E3AA = ("EDGE3:AXISANGLE", "EDGE_SE3:AXISANGLE")
 
 
 def _quat_to_axis_angle(w, x, y, z):
@@ -50,6 +60,55 @@ def _quat_rotate(w, x, y, z, v):
     return (v[0] + w * ux + (y * uz - z * uy), v[1] + w * uy + (z * ux - x * uz), v[2] + w * uz + (x * uy - y * ux))
 
 
+def _rotmat_to_quat(m):
+    """Eigen::Quaternion(Matrix3) (Eigen/src/Geometry/Quaternion.h, quaternionbase_assign_impl<Other, 3, 3>: the
+    trace / largest-diagonal branches of Shoemake's method) -> (w, x, y, z)"""
+    t = m[0][0] + m[1][1] + m[2][2]
+    if t > 0:
+        t = math.sqrt(t + 1.0)
+        w = .5 * t
+        t = .5 / t
+        return w, (m[2][1] - m[1][2]) * t, (m[0][2] - m[2][0]) * t, (m[1][0] - m[0][1]) * t
+    i = 0
+    if m[1][1] > m[0][0]:
+        i = 1
+    if m[2][2] > m[i][i]:
+        i = 2
+    j = (i + 1) % 3
+    k = (j + 1) % 3
+    t = math.sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0)
+    q = [0.0, 0.0, 0.0]
+    q[i] = .5 * t
+    t = .5 / t
+    w = (m[k][j] - m[j][k]) * t
+    q[j] = (m[j][i] + m[i][j]) * t
+    q[k] = (m[k][i] + m[i][k]) * t
+    return w, q[0], q[1], q[2]
+
+
+def _rpy_to_axis_angle(roll, pitch, yaw):
+    """the RPY -> axis-angle conversion of CVertex3DParsePrimitive / CEdge3DParsePrimitive (ParsePrimitives.h:509-521,
+    765-777): R = Rz(yaw) Ry(pitch) Rx(roll), then C3DJacobians::v_RotMatrix_to_AxisAngle"""
+    cx, sx = math.cos(yaw), math.sin(yaw)
+    cy, sy = math.cos(pitch), math.sin(pitch)
+    cz, sz = math.cos(roll), math.sin(roll)
+    q = ((cy * cx, -cz * sx + sz * sy * cx, sz * sx + cz * sy * cx),
+         (cy * sx, cz * cx + sz * sy * sx, -sz * cx + cz * sy * sx),
+         (-sy, sz * cy, cz * cy))
+    return _quat_to_axis_angle(*_rotmat_to_quat(q))
+
+
+def _upper21_to_full(u):
+    """TEdge3D's 6x6 information matrix from its 21 upper-triangular values, row-major (Parser.h:362-369)"""
+    m = [[0.0] * 6 for _ in range(6)]
+    k = 0
+    for i in range(6):
+        for j in range(i, 6):
+            m[i][j] = m[j][i] = u[k]
+            k += 1
+    return tuple(v for row in m for v in row)
+
+
 def _clamp_angle_2pi(a):
     return math.fmod(a, 2 * math.pi) if math.isfinite(a) else 0.0
 
@@ -66,9 +125,10 @@ class ParsedGraph:
     """What the reference's parse loop would receive, in file order."""
 
     def __init__(self):
-        self.vertex2d, self.vertex_xyz, self.vertex_cam = [], [], []  # (id, state...)
-        self.edge2d, self.edge_p2c = [], []                          # (id0, id1, z..., info row-major...)
+        self.vertex2d, self.vertex_xyz, self.vertex_cam, self.vertex3d = [], [], [], []  # (id, state...)
+        self.edge2d, self.edge_p2c, self.edge3d = [], [], []          # (id0, id1, z..., info row-major...)
         self.n_ignored = 0
+        self.n_switched = 0  # EDGE3 lines with from >= to, which the reference's parser reports and drops
 
 
 def parse(path) -> ParsedGraph:
@@ -115,6 +175,23 @@ def parse(path) -> ParsedGraph:
                         z = list(_se2_absolute_to_relative(z, (0.0, 0.0, 0.0)))
                     info = (up[0], up[1], up[2], up[1], up[3], up[4], up[2], up[4], up[5])
                     out.edge2d.append((i0, i1, z[0], z[1], z[2]) + info)
+                elif name in _V3:
+                    v = [float(x) for x in a[1:7]]
+                    if len(v) != 6:
+                        raise ValueError
+                    out.vertex3d.append((int(a[0]), v[0], v[1], v[2]) + tuple(_rpy_to_axis_angle(v[3], v[4], v[5])))
+                elif name in _E3 or name in _E3AA:
+                    i0, i1 = int(a[0]), int(a[1])
+                    z = [float(x) for x in a[2:8]]
+                    m = [float(x) for x in a[8:29]]
+                    if len(m) != 21:
+                        raise ValueError
+                    if name in _E3:
+                        if not i0 < i1:
+                            out.n_switched += 1
+                            continue
+                        z[3:6] = _rpy_to_axis_angle(z[3], z[4], z[5])
+                    out.edge3d.append((i0, i1) + tuple(z) + _upper21_to_full(m))
                 elif name in _P2C:
                     m = [float(x) for x in a[4:7]]
                     if len(m) != 3:
@@ -168,6 +245,43 @@ def load_se2(path) -> PoseGraph:
                      e[:, 5:14].reshape(-1, 3, 3).copy())
 
 
+def _quat_mul(a, b):
+    """Eigen quaternion product, (w, x, y, z)"""
+    return (a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+            a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3], a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1])
+
+
+def _se3_relative_to_absolute(v1, v2):
+    """C3DJacobians::Relative_to_Absolute (value), include/slam/3DSolverBase.h:807-850 (the quaternion branch)"""
+    q1, q2 = _axis_angle_to_quat(v1[3:6]), _axis_angle_to_quat(v2[3:6])
+    t = _quat_rotate(q1[0], q1[1], q1[2], q1[3], v2[0:3])
+    return (v1[0] + t[0], v1[1] + t[1], v1[2] + t[2]) + tuple(_quat_to_axis_angle(*_quat_mul(q1, q2)))
+
+
+def load_se3(path) -> PoseGraph:
+    """A 3D pose graph (VERTEX3 / EDGE3 / EDGE3:AXISANGLE). Poses without a VERTEX line are initialised from the first
+    edge that reaches them (CEdgePose3D constructor, SE3_Types.h: Relative_to_Absolute)."""
+    p = parse(path)
+    e = np.array(p.edge3d, np.float64).reshape(-1, 44)
+    n = int(max([v[0] for v in p.vertex3d] + ([int(e[:, :2].max())] if len(e) else []) + [-1])) + 1
+    poses = np.zeros((n, 6))
+    known = np.zeros(n, bool)
+    for v in p.vertex3d:
+        poses[v[0]] = v[1:]
+        known[v[0]] = True
+    if n and not known[0]:
+        known[0] = True
+    for k in range(len(e)):
+        a, b = int(e[k, 0]), int(e[k, 1])
+        if known[a] and not known[b]:
+            poses[b] = _se3_relative_to_absolute(poses[a], e[k, 2:8])
+            known[b] = True
+    if not known.all():
+        raise ValueError(f"{path}: pose {int(np.flatnonzero(~known)[0])} is neither given nor reachable from an initialised pose")
+    return PoseGraph(GRAPH_SE3, poses, e[:, 0].astype(np.int64), e[:, 1].astype(np.int64), e[:, 2:8].copy(),
+                     e[:, 8:44].reshape(-1, 6, 6).copy())
+
+
 # ---- writers (synthetic graphs -> the reference's text formats) ------------------------------------------------------
 
 def _axis_angle_to_quat(a):
@@ -210,3 +324,25 @@ def write_se2(path, g: PoseGraph, with_vertices: bool = True):
             m = g.info[k]
             f.write("EDGE2 %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n"
                     % (g.e_from[k], g.e_to[k], g.z[k, 0], g.z[k, 1], g.z[k, 2], m[0, 0], m[0, 1], m[0, 2], m[1, 1], m[1, 2], m[2, 2]))
+
+
+def _axis_angle_to_rpy(a):
+    """inverse of _rpy_to_axis_angle away from pitch = +-pi/2: R = Rz(yaw) Ry(pitch) Rx(roll)"""
+    w, x, y, z = _axis_angle_to_quat(a)
+    r00, r10, r20 = 1 - 2 * (y * y + z * z), 2 * (x * y + w * z), 2 * (x * z - w * y)
+    r21, r22 = 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)
+    return math.atan2(r21, r22), math.atan2(-r20, math.hypot(r00, r10)), math.atan2(r10, r00)
+
+
+def write_se3(path, g: PoseGraph, with_vertices: bool = True, axis_angle_edges: bool = True):
+    """VERTEX3 lines carry roll, pitch, yaw (the only 3D vertex format the reference reads); edges are written as
+    EDGE3:AXISANGLE (exact round trip) or, with axis_angle_edges=False, as EDGE3 with roll, pitch, yaw."""
+    iu = [(i, j) for i in range(6) for j in range(i, 6)]
+    with open(path, "w") as f:
+        if with_vertices:
+            for i, v in enumerate(g.poses):
+                f.write(("VERTEX3 %d" + " %.17g" * 6 + "\n") % ((i, v[0], v[1], v[2]) + _axis_angle_to_rpy(v[3:6])))
+        for k in range(len(g.e_from)):
+            z = tuple(g.z[k, :3]) + (tuple(g.z[k, 3:6]) if axis_angle_edges else _axis_angle_to_rpy(g.z[k, 3:6]))
+            f.write((("EDGE3:AXISANGLE" if axis_angle_edges else "EDGE3") + " %d %d" + " %.17g" * 27 + "\n")
+                    % ((g.e_from[k], g.e_to[k]) + z + tuple(g.info[k][i, j] for i, j in iu)))

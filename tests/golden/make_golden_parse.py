@@ -38,8 +38,26 @@ def main():
         f.write("EDGE_SE2 2 3 1.0 0.0 1.57 10 1 2 20 3 30\n")
         f.write("EDGE2 5 3 -0.5 0.25 -3.0 11 0.5 333 22 0.25 0.125\n")
         f.write("EQUIV 1 2\nEDGE2 3 4 0.3 0.2 0.1 1 0 0 1 0 1\n")
+    # SE(3): a small sphere (VERTEX3 with roll-pitch-yaw, EDGE3:AXISANGLE), then a hand-written file with EDGE3 in
+    # roll-pitch-yaw, rotations near pi about each axis (the three non-trace branches of the matrix -> quaternion
+    # conversion), a full information matrix, a switched edge (reported and dropped) and the alternative tokens
+    s3 = graphs.make_sphere(5, 8, seed=5, radius=5.0)
+    graphfile.write_se3(os.path.join(HERE, "parse_se3.txt"), s3)
+    diag = "100 0 0 0 0 0 100 0 0 0 0 100 0 0 0 400 0 0 400 0 400"
+    full = " ".join("%.17g" % v for v in (np.arange(21) * 0.01 + np.array([5 if k in (0, 6, 11, 15, 18, 20) else 0 for k in range(21)])))
+    with open(os.path.join(HERE, "parse_se3_mixed.txt"), "w") as f:
+        f.write("VERTEX_SE3 0 0 0 0 0 0 0\nVERTEX3 1 1.0 0.1 -0.2 0.3 -0.4 0.5\n")
+        f.write("VERTEX3 2 2.0 0.0 0.5 3.1 0.02 -0.01\nVERTEX3 3 2.5 1.0 0.5 0.03 3.12 0.01\n")
+        f.write("VERTEX3 4 3.0 1.5 0.7 -0.02 0.01 -3.13\nVERTEX3 5 3.5 2.5 0.9 2.5 -1.2 -2.8\n")
+        f.write("EDGE3 0 1 1.01 0.09 -0.21 0.31 -0.39 0.49 " + diag + "\n")
+        f.write("EDGE_SE3 1 2 1.0 -0.1 0.7 2.8 0.4 -0.5 " + full + "\n")
+        f.write("EDGE3 3 2 0.5 1.0 0.0 0.1 0.2 0.3 " + diag + "\n")           # switched order: dropped by the parser
+        f.write("EDGE3 2 3 0.5 1.0 0.0 -3.0 3.0 0.1 " + diag + "\n")
+        f.write("EDGE3:AXISANGLE 3 4 0.5 0.5 0.2 0.1 -3.0 0.2 " + full + "\n")
+        f.write("EDGE_SE3:AXISANGLE 5 4 -0.5 -1.0 -0.2 1.5 0.5 -2.5 " + diag + "\n")  # kept as it is
+        f.write("EDGE3 4 5 0.5 1.0 0.2 1e-9 -2e-9 1e-10 " + diag + "\n")     # tiny rotation
     out = {}
-    for name in ("parse_ba", "parse_se2", "parse_se2_mixed"):
+    for name in ("parse_ba", "parse_se2", "parse_se2_mixed", "parse_se3", "parse_se3_mixed"):
         with tempfile.TemporaryDirectory() as td:
             dp = os.path.join(td, "d.dump")
             subprocess.run([REF, os.path.join(HERE, name + ".txt"), dp], check=True)

@@ -65,3 +65,31 @@ def test_truncated_line_is_an_error(tmp_path):
         f.write("VERTEX_XYZ 0 1 2\n")
     with pytest.raises(ValueError):
         graphfile.parse(path)
+
+
+@pytest.mark.parametrize("name", ["parse_se3", "parse_se3_mixed"])
+def test_se3_file_matches_reference_parser(ref, name):
+    p = graphfile.parse(os.path.join(GOLDEN, name + ".txt"))
+    v, r = np.array(p.vertex3d).reshape(-1, 7), ref[name + ".vertex3d"].reshape(-1, 7)
+    assert v.shape == r.shape and np.array_equal(v[:, :4], r[:, :4])
+    # roll-pitch-yaw -> rotation matrix -> quaternion -> axis-angle, all three non-trace branches in the mixed file
+    assert np.max(np.abs(v[:, 4:] - r[:, 4:])) <= 2e-15
+    e, q = np.array(p.edge3d).reshape(-1, 44), ref[name + ".edge3d"].reshape(-1, 44)
+    assert e.shape == q.shape                                      # the switched EDGE3 line is dropped, as the reference does
+    assert np.array_equal(e[:, :5], q[:, :5]) and np.max(np.abs(e[:, 5:8] - q[:, 5:8])) <= 2e-15
+    assert np.array_equal(e[:, 8:], q[:, 8:])                      # 21 upper-triangular values -> symmetric 6x6
+    assert p.n_switched == (1 if name == "parse_se3_mixed" else 0)
+
+
+def test_se3_file_round_trip(tmp_path):
+    g = graphs.make_sphere(5, 8, seed=5, radius=5.0)
+    h = graphfile.load_se3(os.path.join(GOLDEN, "parse_se3.txt"))
+    assert np.array_equal(h.e_from, g.e_from) and np.array_equal(h.e_to, g.e_to)
+    assert np.array_equal(h.z, g.z) and np.array_equal(h.info, g.info)
+    assert np.max(np.abs(h.poses - g.poses)) < 1e-14               # vertices go through roll-pitch-yaw
+    # roll-pitch-yaw edges and no vertex lines: poses are chained from the edges (Relative_to_Absolute)
+    path = str(tmp_path / "rpy.txt")
+    graphfile.write_se3(path, g, with_vertices=False, axis_angle_edges=False)
+    k = graphfile.load_se3(path)
+    assert np.max(np.abs(k.z - g.z)) < 1e-14 and np.allclose(k.poses[0], 0)
+    assert k.poses.shape == g.poses.shape and np.all(np.isfinite(k.poses))
