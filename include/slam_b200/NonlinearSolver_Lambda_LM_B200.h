@@ -23,7 +23,12 @@
  * works unchanged. The CLinearSolver argument is accepted for interface compatibility and not used: the reduced camera
  * system is solved by the library (dense or block-sparse, spp_schur_set_rcs_solver).
  *
- * Not provided (the traits say so): marginal covariances, Jacobian / Hessian export.
+ * Marginal covariances: with TMarginalsComputationPolicy(true, ..., mpart_Diagonal, mpart_Diagonal) every Optimize()
+ * ends as the reference's does (NonlinearSolver_Lambda_LM.h:1118-1350): the block diagonal of lambda^-1 at zero damping,
+ * recovered from the Schur-complemented system on the device (spp_ba_marginals), is what
+ * r_MarginalCovariance().r_SparseMatrix() holds afterwards (vertex id order). Other matrix parts are not provided.
+ *
+ * Not provided (the traits say so): Jacobian / Hessian export.
  */
 #pragma once
 #ifndef __NONLINEAR_SOLVER_LAMBDA_LM_B200_INCLUDED
@@ -40,6 +45,7 @@
 #include "slam/BA_Types.h"           // reference: CVertexCam, CVertexXYZ, CEdgeP2C3D
 #include "slam/IncrementalPolicy.h"  // reference: TIncrementalSolveSetting, TMarginalsComputationPolicy
 #include "slam/Timer.h"              // reference: CTimer
+#include "slam/Marginals.h"          // reference: CMarginalCovariance
 #include "spp_b200.h"
 
 template <class CSystem, class CLinearSolver, class CAMatrixBlockSizes = typename CSystem::_TyJacobianMatrixBlockList,
@@ -55,7 +61,7 @@ public:
 	enum {
 		solver_HasDump = true,
 		solver_HasChi2 = true,
-		solver_HasMarginals = false,
+		solver_HasMarginals = true,
 		solver_HasGaussNewton = false,
 		solver_HasLevenberg = true,
 		solver_HasGradient = false,
@@ -79,6 +85,8 @@ protected:
 	size_t m_n_gathered_edge_num; /**< @brief edges already flattened (edges are immutable once added: only new ones are read) */
 	double m_f_device_ms; /**< @brief device time spent in Optimize() so far */
 	double m_f_upload_time, m_f_optimize_time, m_f_download_time; /**< @brief wall-clock split of Optimize() */
+	double m_f_marginals_time; /**< @brief wall-clock time of the marginals recovery */
+	CMarginalCovariance m_marginals; /**< @brief marginal covariances (block diagonal) */
 
 	bool m_b_uploaded; /**< @brief the device holds the system described by the arrays below */
 	std::vector<uint8_t> m_vertex_type, m_prev_vertex_type;
@@ -142,10 +150,10 @@ public:
 		:m_r_system(r_system), m_t_incremental_config(t_incremental_config), m_t_marginals_config(t_marginals_config),
 		m_b_verbose(b_verbose), m_p_context(0), m_n_last_optimized_vertex_num(0), m_n_iteration_num(0),
 		m_n_gathered_edge_num(0), m_f_device_ms(0), m_f_upload_time(0), m_f_optimize_time(0), m_f_download_time(0),
-		m_b_uploaded(false)
+		m_f_marginals_time(0), m_b_uploaded(false)
 	{
-		if(t_marginals_config.b_calculate)
-			throw std::runtime_error("CNonlinearSolver_Lambda_LM_B200: marginal covariances are not provided (solver_HasMarginals = false)");
+		if(t_marginals_config.b_calculate && t_marginals_config.n_relinearize_policy != mpart_Diagonal)
+			throw std::runtime_error("CNonlinearSolver_Lambda_LM_B200: only the block diagonal of the marginal covariances (mpart_Diagonal) is provided");
 		Check(spp_create(n_device, &m_p_context));
 	}
 
@@ -164,6 +172,17 @@ public:
 		return m_t_marginals_config;
 	}
 
+	/** marginal covariances of the last Optimize() (cf. NonlinearSolver_Base.h:750-763) */
+	inline CMarginalCovariance &r_MarginalCovariance()
+	{
+		return m_marginals;
+	}
+
+	inline const CMarginalCovariance &r_MarginalCovariance() const
+	{
+		return m_marginals;
+	}
+
 	/** the device context, e.g. for spp_schur_set_rcs_solver() */
 	inline spp_ctx_t p_Context()
 	{
@@ -180,6 +199,8 @@ public:
 		printf("out of which:\n\tdevice (libspp_b200: lambda, rhs, schur, linsolve, update, chi2): %f\n", m_f_device_ms * 1e-3);
 		printf("host side of Optimize(): flatten + upload + structure %f, spp_ba_optimize %f, download + write-back %f\n",
 			m_f_upload_time, m_f_optimize_time, m_f_download_time);
+		if(m_t_marginals_config.b_calculate)
+			printf("solver spent %f seconds in marginals (spp_ba_marginals + the block matrix)\n", m_f_marginals_time);
 	}
 
 	/** f_Chi_Squared_Error_Denorm (NonlinearSolver_Base.h:278-297) of the system as it is now */
@@ -233,6 +254,35 @@ public:
 		for(size_t i = 0, n = m_cams.size() / 11; i < n; ++ i) // the cached copy follows: the device and the system agree
 			for(int j = 0; j < 6; ++ j) m_cams[i * 11 + j] = m_cam_states[i * 6 + j];
 		m_f_download_time += timer.f_Time() - f_t2;
+		if(m_t_marginals_config.b_calculate)
+			Calculate_Marginals();
+	}
+
+	/** block diagonal of lambda^-1 at the current states and zero damping -> r_MarginalCovariance()
+	 *	(NonlinearSolver_Lambda_LM.h:1118-1350 with mpart_Diagonal -> BAMarginals.h:579-760) */
+	void Calculate_Marginals() // throw(std::bad_alloc, std::runtime_error)
+	{
+		CTimer timer;
+		const size_t n_cam_num = m_cams.size() / 11, n_point_num = m_points.size() / 3;
+		std::vector<double> cam_cov(n_cam_num * 36), point_cov(n_point_num * 9);
+		Check(spp_ba_marginals(m_p_context, 0.0, cam_cov.empty()? 0 : &cam_cov[0], point_cov.empty()? 0 : &point_cov[0]));
+		CUberBlockMatrix margs;
+		size_t n_cam = 0, n_point = 0;
+		for(size_t i = 0, n = m_vertex_type.size(); i < n; ++ i) {
+			if(m_vertex_type[i] == 0) {
+				Eigen::Map<const Eigen::Matrix<double, 6, 6> > t_block(&cam_cov[n_cam * 36]);
+				++ n_cam;
+				margs.t_GetBlock_Log(i, i, 6, 6, true, false) = t_block;
+			} else {
+				Eigen::Map<const Eigen::Matrix<double, 3, 3> > t_block(&point_cov[n_point * 9]);
+				++ n_point;
+				margs.t_GetBlock_Log(i, i, 3, 3, true, false) = t_block;
+			}
+		}
+		m_marginals.Swap_SparseMatrix(margs);
+		m_marginals.EnableUpdate();
+		m_marginals.Set_Edge_Num(m_r_system.r_Edge_Pool().n_Size());
+		m_f_marginals_time += timer.f_Time();
 	}
 
 protected:

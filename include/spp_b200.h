@@ -161,6 +161,18 @@ int spp_ba_solve_step(spp_ctx_t ctx, double alpha, double *p_dx);
  * (initial damping, rho test, rollback, <= 10 extra iterations on rejected steps). */
 int spp_ba_optimize(spp_ctx_t ctx, size_t n_max_iterations, double f_min_dx_norm, spp_report_t *p_report);
 
+/* Block diagonal of the covariance (lambda + alpha I)^-1 at the current vertex states, recovered from the
+ * Schur-complemented system. Replaces the marginals step at the end of CNonlinearSolver_Lambda_LM::Optimize()
+ * (NonlinearSolver_Lambda_LM.h:1118-1350, policy mpart_Diagonal) -> CSchurComplement_Marginals::Schur_Marginals
+ * (include/slam/BAMarginals.h:579-760); the reference uses alpha = 0.
+ *   p_cam_cov[36 * n_cameras]  6x6 blocks, cameras in vertex id order (symmetric: row- or column-major)
+ *   p_pt_cov[9 * n_points]     3x3 blocks, points in vertex id order
+ * Either output may be null. Needs the dense reduced camera system (6 * n_cameras <= 16384 or
+ * spp_schur_set_rcs_solver(SPP_RCS_DENSE)) and 16 * ld^2 bytes of device memory, ld = 6 * n_cameras rounded up to 128.
+ * Returns SPP_OK / SPP_NOT_POSDEF. Note: a monocular BA system with one fixed camera has an unobservable scale; its
+ * variance (1 / the smallest eigenvalue of lambda, finite-difference noise) dominates every block at alpha = 0. */
+int spp_ba_marginals(spp_ctx_t ctx, double alpha, double *p_cam_cov, double *p_pt_cov);
+
 /* ---- slot 1: linear solver on a lambda given by the caller ------------------------------------------ */
 
 /* Replaces CLinearSolver_Schur::SymbolicDecomposition_Blocky(lambda) (LinearSolver_Schur.h:1566-1606): takes the
@@ -178,6 +190,11 @@ int spp_schur_symbolic(spp_ctx_t ctx, size_t n_block_cols, const uint64_t *p_col
  * p_eta_dx[n_scalars] is the right-hand side on input and the solution on output.
  * Returns SPP_NOT_POSDEF where the reference returns false. */
 int spp_schur_solve(spp_ctx_t ctx, const double *p_values, double *p_eta_dx);
+
+/* Schur_Marginals (include/slam/BAMarginals.h:579-760) on the lambda of the last spp_schur_solve: block diagonal of
+ * (lambda + alpha I)^-1, 6-wide block columns in p_cam_cov[36 * cut], 3-wide ones in p_pt_cov[9 * (n - cut)], each
+ * group in the order of the block columns. Same requirements and return values as spp_ba_marginals. */
+int spp_schur_marginals(spp_ctx_t ctx, double alpha, double *p_cam_cov, double *p_pt_cov);
 
 /* Stage outputs of the last Schur solve, for the parity tests: the reduced camera system as a
  * dense column-major (6C x 6C) matrix (upper triangle valid), its right-hand side, and the pattern of non-zero

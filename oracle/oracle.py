@@ -106,6 +106,37 @@ def ba_optimize(g, max_iter=5, min_dx=0.0, max_trace=64):
                 trace=trace[:min(n, max_trace)], cams=cam_out, pts=pts_out)
 
 
+def ba_dense_lambda(g, U, V, W):
+    """(U, V, W) -> dense lambda with the cameras first, then the points (each group in vertex id order)."""
+    c, p = g.n_cams, g.n_pts
+    loc = g.vertex_local_index()
+    L = np.zeros((6 * c + 3 * p, 6 * c + 3 * p))
+    for i in range(c):
+        L[6 * i:6 * i + 6, 6 * i:6 * i + 6] = U[i].reshape(6, 6)
+    for j in range(p):
+        L[6 * c + 3 * j:6 * c + 3 * j + 3, 6 * c + 3 * j:6 * c + 3 * j + 3] = V[j].reshape(3, 3)
+    for e in range(g.n_obs):
+        i, j = int(loc[g.obs_cam[e]]), int(loc[g.obs_pt[e]])
+        w = W[e].reshape(3, 6).T
+        L[6 * i:6 * i + 6, 6 * c + 3 * j:6 * c + 3 * j + 3] = w
+        L[6 * c + 3 * j:6 * c + 3 * j + 3, 6 * i:6 * i + 6] = w.T
+    return L
+
+
+def ba_marginals(g, alpha=0.0):
+    """Block diagonal of (lambda + alpha I)^-1 at the states of g, the quantity the reference recovers from the
+    Schur-complemented system (CSchurComplement_Marginals::Schur_Marginals, include/slam/BAMarginals.h:579-760, called
+    from NonlinearSolver_Lambda_LM.h:1118-1350 with alpha = 0), here by a plain dense inverse (small cases only).
+    Returns cam_cov (C, 6, 6), pt_cov (P, 3, 3) and the dense lambda."""
+    U, V, W, _, _, _ = ba_linearise(g)
+    L = ba_dense_lambda(g, U, V, W)
+    S = np.linalg.inv(L + alpha * np.eye(L.shape[0]))
+    c, p = g.n_cams, g.n_pts
+    cc = np.stack([S[6 * i:6 * i + 6, 6 * i:6 * i + 6] for i in range(c)])
+    pc = np.stack([S[6 * c + 3 * j:6 * c + 3 * j + 3, 6 * c + 3 * j:6 * c + 3 * j + 3] for j in range(p)])
+    return cc, pc, L
+
+
 def lambda_blocks_to_reference_layout(g, U, V, W):
     """(U, V, W) -> the reference's block layout of lambda (upper block-triangular, vertex id order, column-major
     blocks): col_dims, col_ptr, row_idx, vals -- what CUberBlockMatrix accessors enumerate."""

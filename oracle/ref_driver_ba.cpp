@@ -213,7 +213,7 @@ static void Build_System(CSystemType &r_system, const spp_graph_t &g)
 int main(int n_arg_num, const char **p_arg_list)
 {
 	if(n_arg_num < 4) {
-		fprintf(stderr, "usage: %s <time|dump> <graph.bin> <out.dump> [max_iter=5] [min_dx=0]\n", p_arg_list[0]);
+		fprintf(stderr, "usage: %s <time|dump|steps|margs> <graph.bin> <out.dump> [max_iter=5] [min_dx=0]\n", p_arg_list[0]);
 		return -1;
 	}
 	const bool b_dump = !strcmp(p_arg_list[1], "dump");
@@ -257,6 +257,34 @@ int main(int n_arg_num, const char **p_arg_list)
 		g_dump = p_keep;
 		f_chi2 = solver.f_Chi_Squared_Error_Denorm();
 		spp_dump_f64(g_dump, "step_seconds", step_seconds.size(), &step_seconds[0]);
+	} else if(!strcmp(p_arg_list[1], "margs")) {
+		// Optimize(max_iter), then the block diagonal of the covariance the reference recovers from the
+		// Schur-complemented system (NonlinearSolver_Lambda_LM.h:1118-1350 -> BAMarginals.h:579, mpart_Diagonal)
+		typedef CNonlinearSolver_Lambda_LM<CSystemType, CRefLinearSolver> CSolver;
+		CSolver solver(system, TIncrementalSolveSetting(), TMarginalsComputationPolicy(true, frequency::Never(),
+			mpart_Diagonal, mpart_Diagonal), getenv("SPP_REF_VERBOSE") != 0, CRefLinearSolver(), true);
+		FILE *p_keep = g_dump;
+		g_dump = 0;
+		double f_start = timer.f_Time();
+		solver.Optimize(n_max_iter, f_min_dx);
+		f_opt_time = timer.f_Time() - f_start;
+		g_dump = p_keep;
+		f_chi2 = solver.f_Chi_Squared_Error_Denorm();
+		if(getenv("SPP_REF_VERBOSE"))
+			solver.Dump(f_opt_time); // time spent in the marginals among the rest
+		Dump_States<CSolver>(system, "states");
+		const CUberBlockMatrix &r_m = solver.r_MarginalCovariance().r_SparseMatrix();
+		std::vector<double> cov6, cov3;
+		for(size_t i = 0, n = r_m.n_BlockColumn_Num(); i < n; ++ i) {
+			CUberBlockMatrix::_TyConstMatrixXdRef t_b = r_m.t_GetBlock_Log(i, i);
+			std::vector<double> &r_dst = (t_b.cols() == 6)? cov6 : cov3;
+			for(int r = 0; r < t_b.rows(); ++ r)
+				for(int c = 0; c < t_b.cols(); ++ c)
+					r_dst.push_back(t_b(r, c));
+		}
+		double f_zero = 0;
+		spp_dump_f64(g_dump, "cam_cov", cov6.size(), cov6.empty()? &f_zero : &cov6[0]); // vertex id order, row-major
+		spp_dump_f64(g_dump, "pt_cov", cov3.size(), cov3.empty()? &f_zero : &cov3[0]);
 	} else if(!b_dump) {
 		typedef CNonlinearSolver_Lambda_LM<CSystemType, CRefLinearSolver> CSolver;
 		CSolver solver(system, TIncrementalSolveSetting(), TMarginalsComputationPolicy(),

@@ -48,8 +48,9 @@ template <class CSolver>
 static int Run(const spp_graph_t &g, bool b_incremental, FILE *p_fw, size_t n_max_iter, double f_min_dx, size_t n_batch)
 {
 	CSystemType system;
-	CSolver solver(system, TIncrementalSolveSetting(), TMarginalsComputationPolicy(), getenv("SPP_REF_VERBOSE") != 0,
-		CLinearSolverType(), true);
+	const bool b_marginals = getenv("SPP_DROPIN_MARGS") != 0; // every Optimize() ends with the block diagonal of the covariance
+	CSolver solver(system, TIncrementalSolveSetting(), (b_marginals)? TMarginalsComputationPolicy(true, frequency::Never(),
+		mpart_Diagonal, mpart_Diagonal) : TMarginalsComputationPolicy(), getenv("SPP_REF_VERBOSE") != 0, CLinearSolverType(), true);
 	std::vector<double> chi2_trace;
 	CTimer timer;
 	double f_opt_time = 0;
@@ -123,14 +124,27 @@ static int Run(const spp_graph_t &g, bool b_incremental, FILE *p_fw, size_t n_ma
 	}
 	if(getenv("SPP_REF_DUMP_TIMING"))
 		solver.Dump(f_opt_time);
-	TStates states;
-	system.r_Vertex_Pool().For_Each(states);
+	TStates states = system.r_Vertex_Pool().For_Each(TStates()); // the functor travels by value
 	uint64_t n_vertices = system.r_Vertex_Pool().n_Size(), n_edges = system.r_Edge_Pool().n_Size();
 	spp_dump_f64(p_fw, "chi2_trace", chi2_trace.size(), &chi2_trace[0]);
 	spp_dump_f64(p_fw, "states", states.v.size(), &states.v[0]);
 	spp_dump_f64(p_fw, "optimize_time", 1, &f_opt_time);
 	spp_dump_u64(p_fw, "n_vertices", 1, &n_vertices);
 	spp_dump_u64(p_fw, "n_edges", 1, &n_edges);
+	if(b_marginals) { // diagonal blocks in vertex id order, row-major
+		const CUberBlockMatrix &r_m = solver.r_MarginalCovariance().r_SparseMatrix();
+		std::vector<double> cov6, cov3;
+		for(size_t i = 0, n = r_m.n_BlockColumn_Num(); i < n; ++ i) {
+			CUberBlockMatrix::_TyConstMatrixXdRef t_b = r_m.t_GetBlock_Log(i, i);
+			std::vector<double> &r_dst = (t_b.cols() == 6)? cov6 : cov3;
+			for(int r = 0; r < t_b.rows(); ++ r)
+				for(int c = 0; c < t_b.cols(); ++ c)
+					r_dst.push_back(t_b(r, c));
+		}
+		double f_zero = 0;
+		spp_dump_f64(p_fw, "cam_cov", cov6.size(), cov6.empty()? &f_zero : &cov6[0]);
+		spp_dump_f64(p_fw, "pt_cov", cov3.size(), cov3.empty()? &f_zero : &cov3[0]);
+	}
 	printf("ref_driver_dropin_lm: %zu vertices, %zu edges, %zu optimisations, %.6f s in Optimize(), final chi2 %.17g\n",
 		size_t(n_vertices), size_t(n_edges), chi2_trace.size() - (b_incremental? 0 : 1), f_opt_time, chi2_trace.back());
 	return 0;

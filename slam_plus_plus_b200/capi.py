@@ -25,7 +25,8 @@ EXPORTED_SYMBOLS = [
     "spp_create", "spp_destroy", "spp_last_error", "spp_describe", "spp_kernel_launches", "spp_stream",
     "spp_synchronize", "spp_set_allreduce", "spp_partition_landmarks", "spp_rcs_block_pattern", "spp_ba_get_partition", "spp_ba_set_graph", "spp_ba_set_states", "spp_ba_get_states",
     "spp_ba_restore_initial", "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_get_blocks", "spp_ba_chi2", "spp_ba_solve_step",
-    "spp_ba_optimize", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_get_reduced_system",
+    "spp_ba_optimize", "spp_ba_marginals", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_marginals",
+    "spp_schur_get_reduced_system",
     "spp_schur_set_rcs_solver", "spp_schur_set_rcs_ordering", "spp_schur_get_rcs_info", "spp_schur_get_rcs_residual", "spp_block_ordering",
     "spp_block_symbolic_stats", "spp_dense_posdef_solve",
     "spp_chol_symbolic", "spp_chol_solve", "spp_chol_get_factor",
@@ -101,6 +102,8 @@ def load_library() -> C.CDLL:
     lib.spp_ba_optimize.argtypes = [vp, C.c_size_t, C.c_double, C.POINTER(Report)]
     lib.spp_schur_symbolic.argtypes = [vp, C.c_size_t, u64p, u64p, u64p, u64p, u64p]
     lib.spp_schur_solve.argtypes = [vp, dp, dp]
+    lib.spp_ba_marginals.argtypes = [vp, C.c_double, dp, dp]
+    lib.spp_schur_marginals.argtypes = [vp, C.c_double, dp, dp]
     lib.spp_schur_get_reduced_system.argtypes = [vp, u64p, dp, dp, u8p]
     lib.spp_dense_posdef_solve.argtypes = [vp, C.c_size_t, dp, dp]
     lib.spp_schur_set_rcs_solver.argtypes = [vp, C.c_int]
@@ -342,6 +345,13 @@ class Context:
         self._check(self.lib.spp_ba_optimize(self.h, max_iterations, min_dx_norm, C.byref(rep)))
         return rep.as_dict()
 
+    def ba_marginals(self, alpha: float = 0.0):
+        """Block diagonal of (lambda + alpha I)^-1 at the current states: (C, 6, 6), (P, 3, 3)."""
+        c, p, _, _ = self._ba_dims
+        cc, pc = np.empty((c, 6, 6)), np.empty((p, 3, 3))
+        self._check(self.lib.spp_ba_marginals(self.h, alpha, _dp(cc), _dp(pc)))
+        return cc, pc
+
     # ---- slot 1: Schur linear solver on a caller-supplied lambda ---------------------------------
     def schur_symbolic(self, col_dims, col_ptr, row_idx):
         cd = np.ascontiguousarray(col_dims, np.uint64)
@@ -352,7 +362,15 @@ class Context:
         self._check(self.lib.spp_schur_symbolic(self.h, cd.shape[0], _u64p(cd), _u64p(cp), _u64p(ri), _u64p(order),
                                                 C.byref(cut)))
         self._schur_n = int(cd.astype(np.int64).sum())
+        self._schur_cut = (int(cut.value), int(cd.shape[0]) - int(cut.value))
         return order.astype(np.int64), int(cut.value)
+
+    def schur_marginals(self, alpha: float = 0.0):
+        """Block diagonal of (lambda + alpha I)^-1 for the lambda of the last schur_solve: (cut, 6, 6), (n - cut, 3, 3)."""
+        c, p = self._schur_cut
+        cc, pc = np.empty((c, 6, 6)), np.empty((p, 3, 3))
+        self._check(self.lib.spp_schur_marginals(self.h, alpha, _dp(cc), _dp(pc)))
+        return cc, pc
 
     def schur_solve(self, values, eta) -> np.ndarray:
         v = np.ascontiguousarray(values, np.float64)

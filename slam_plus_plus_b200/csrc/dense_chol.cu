@@ -41,11 +41,13 @@ static const size_t POTRF_SMEM_EXCLUSIVE = 227 * 1024; // the opt-in maximum per
 
 // ---- FP64 tensor-core GEMM: C (op)= A^T B with K = 128, operands K-contiguous ---------------------------
 
-enum { GEMM_SYRK = 0, GEMM_TRSM = 1 };
+enum { GEMM_SYRK = 0, GEMM_TRSM = 1, GEMM_GRAM = 2 };
 
 // SYRK: C(i0.., j0..) -= P(:, i0..)^T P(:, j0..), P = rows k0..k0+127 of A; tiles with i0 > j0 are skipped.
 //       grid.x = column tile (from column cbase), grid.y = row tile (from row rbase).
 // TRSM: P(:, j0..) <- Rinv^T P(:, j0..) in place; BM must be 128 (a CTA owns whole columns of the panel).
+// GRAM: SYRK with the operand rows taken from another matrix Z of the same leading dimension (passed in the Rinv
+//       slot): C(i0.., j0..) -= Z(k0.., i0..)^T Z(k0.., j0..) -- the inverse of a factored matrix as Z^T Z, Z = R^-T.
 // WM x WN is the warp tile (multiples of 8): 32 x 32 for the bulk updates, smaller for the few tiles on the critical
 // chain, where more warps with shorter DMMA chains finish sooner.
 template <int MODE, int BM, int BN, int WM = 32, int WN = 32, int STAGES = CH_STAGES>
@@ -53,8 +55,9 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) k_gemm_tn(double *
 	size_t rbase, size_t cbase, const double *__restrict__ Rinv)
 {
 	constexpr int WARPS_N = BN / WN, NT = (BM / WM) * (BN / WN) * 32, MA = WM / 8, NB = WN / 8;
+	constexpr bool SYRK_LIKE = MODE != GEMM_TRSM;
 	size_t i0, j0;
-	if(MODE == GEMM_SYRK) {
+	if(SYRK_LIKE) {
 		i0 = rbase + blockIdx.y * (size_t)BM;
 		j0 = cbase + blockIdx.x * (size_t)BN;
 		if(i0 > j0 + (BN - 1))
@@ -73,8 +76,9 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) k_gemm_tn(double *
 	// operand pointers: element (k, m) at base[m * stride + k]
 	const double *pa; size_t sa;
 	if(MODE == GEMM_SYRK) { pa = A + i0 * ld + k0; sa = ld; }
+	else if(MODE == GEMM_GRAM) { pa = Rinv + i0 * ld + k0; sa = ld; }
 	else { pa = Rinv; sa = CH_NB; }
-	const double *pb = A + j0 * ld + k0;
+	const double *pb = ((MODE == GEMM_GRAM)? Rinv : A) + j0 * ld + k0;
 
 	auto stage_load = [&](int st, int kc) {
 		// BM (BN) rows x 8 chunks of 16 bytes
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) k_gemm_tn(double *
 	for(int a = 0; a < MA; ++ a) {
 		#pragma unroll
 		for(int b = 0; b < NB; ++ b) {
-			if(MODE == GEMM_SYRK) {
+			if(SYRK_LIKE) {
 				const size_t c = j0 + wj + b * 8 + 2 * t, r = i0 + wi + a * 8 + g;
 				acc[a][b][0] = A[c * ld + r];
 				acc[a][b][1] = A[(c + 1) * ld + r];
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) k_gemm_tn(double *
 			double fa[MA], fb[NB];
 			#pragma unroll
 			for(int a = 0; a < MA; ++ a)
-				fa[a] = (MODE == GEMM_SYRK)? -As[st][wi + a * 8 + g][k4 + t] : As[st][wi + a * 8 + g][k4 + t];
+				fa[a] = SYRK_LIKE? -As[st][wi + a * 8 + g][k4 + t] : As[st][wi + a * 8 + g][k4 + t];
 			#pragma unroll
 			for(int b = 0; b < NB; ++ b)
 				fb[b] = Bs[st][wj + b * 8 + g][k4 + t];
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) k_gemm_tn(double *
 		#pragma unroll
 		for(int b = 0; b < NB; ++ b) {
 			const size_t c = j0 + wj + b * 8 + 2 * t;
-			if(MODE == GEMM_SYRK) {
+			if(SYRK_LIKE) {
 				const size_t r = i0 + wi + a * 8 + g;
 				A[c * ld + r] = acc[a][b][0];
 				A[(c + 1) * ld + r] = acc[a][b][1];
@@ -257,6 +261,8 @@ static void chol_init_attributes(int device)
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64, 64>()));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_TRSM, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
+	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_GRAM, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
+	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_GRAM, 64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64, 64>()));
 	SPP_CUDA(cudaFuncSetAttribute((k_gemm_tn<GEMM_TRSM, 128, 16, 32, 16, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 16, 8>()));
 	SPP_CUDA(cudaFuncSetAttribute((k_gemm_tn<GEMM_SYRK, 32, 32, 16, 16, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<32, 32, 8>()));
 	done[device] = true;
@@ -528,6 +534,59 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 	if(ctx->async_mode && ctx->async_info) { // the caller synchronises later and reads the status there
 		SPP_CUDA(cudaMemcpyAsync(ctx->async_info, ch.info.p(), sizeof(int), cudaMemcpyDeviceToHost, st));
 		return SPP_OK;
+	}
+	ctx->h_scalars.resize(16);
+	int *h_info = reinterpret_cast<int*>(ctx->h_scalars.p());
+	SPP_CUDA(cudaMemcpyAsync(h_info, ch.info.p(), sizeof(int), cudaMemcpyDeviceToHost, st));
+	SPP_CUDA(cudaStreamSynchronize(st));
+	return (*h_info == 0)? SPP_OK : SPP_NOT_POSDEF;
+}
+
+__global__ void k_set_identity(double *__restrict__ Z, size_t ld)
+{
+	size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(i < ld) Z[i * ld + i] = 1.0;
+}
+
+// Inverse of a dense SPD matrix through its Cholesky factor (marginal covariances of the reduced camera system:
+// the reference recovers them from the factor of the Schur complement, include/slam/BAMarginals.h:579-760).
+// A: device, column-major, ld = dense_chol_ld(n) rows and 2 * ld columns; on entry the upper triangle of the n x n
+// matrix sits in the first ld columns (everything else there zero), the second ld columns are scratch. The panel
+// factorisation of [A | I] leaves [R | Z], Z = R^-T (lower triangular); then the first ld columns are overwritten with
+// MINUS the inverse, -Z^T Z, upper tiles (every 128 x 128 diagonal tile in full), 41 rank-128 DMMA updates that stop at
+// the last non-zero block row of Z. Returns SPP_OK / SPP_NOT_POSDEF. Synchronises the stream.
+int dense_chol_inverse_device(spp_ctx *ctx, double *A, size_t n)
+{
+	DenseChol &ch = ctx->chol;
+	const size_t ld = dense_chol_ld(n), n_blk = ld / CH_NB;
+	cudaStream_t st = ctx->stream;
+	chol_init_streams(ctx);
+	ch.info.resize(1 + n_blk);
+	SPP_CUDA(cudaMemsetAsync(ch.info.p(), 0, (1 + n_blk) * sizeof(int), st));
+	if(ch.work.size() != n_blk * CH_NB * CH_NB) {
+		ch.work.resize(n_blk * CH_NB * CH_NB);
+		ch.work.zero(st);
+	}
+	if(ld > n) {
+		k_pad_identity<<<n_blocks(ld - n, 64), 64, 0, st>>>(A, ld, n, ld);
+		LAUNCH_CHECK(ctx);
+	}
+	double *Z = A + ld * ld;
+	SPP_CUDA(cudaMemsetAsync(Z, 0, ld * ld * sizeof(double), st));
+	k_set_identity<<<n_blocks(ld, 256), 256, 0, st>>>(Z, ld);
+	LAUNCH_CHECK(ctx);
+	dense_chol_factor_panel(ctx, A, ld, 2 * ld, ch.work.p(), ch.info.p());
+	SPP_CUDA(cudaMemsetAsync(A, 0, ld * ld * sizeof(double), st));
+	for(size_t kb = 0; kb < n_blk; ++ kb) { // block row kb of Z is non-zero in its first kb + 1 column blocks
+		const size_t m = (kb + 1) * CH_NB;
+		if((m / 128) * (m / 64) >= 148) {
+			dim3 grid((unsigned)(m / 64), (unsigned)(m / 128));
+			k_gemm_tn<GEMM_GRAM, 128, 64><<<grid, 256, gemm_smem<128, 64>(), st>>>(A, ld, kb * CH_NB, 0, 0, Z);
+		} else {
+			dim3 grid((unsigned)(m / 64), (unsigned)(m / 64));
+			k_gemm_tn<GEMM_GRAM, 64, 64><<<grid, 128, gemm_smem<64, 64>(), st>>>(A, ld, kb * CH_NB, 0, 0, Z);
+		}
+		LAUNCH_CHECK(ctx);
 	}
 	ctx->h_scalars.resize(16);
 	int *h_info = reinterpret_cast<int*>(ctx->h_scalars.p());

@@ -1,0 +1,133 @@
+// marginals.cu -- block diagonal of the covariance (Lambda + alpha I)^-1 recovered from the Schur-complemented system
+// (SURVEY 8(f) rank 4).
+//
+// Reference replaced: CSchurComplement_Marginals::Schur_Marginals, include/slam/BAMarginals.h:579-760, as it is
+// called at the end of CNonlinearSolver_Lambda_LM::Optimize() (NonlinearSolver_Lambda_LM.h:1118-1350, marginals policy
+// mpart_Diagonal): with Lambda = [A U; U^T D], S = A - U D^-1 U^T = R^T R,
+//     camera blocks    Sigma_cc = (S^-1)_cc                                              (BAMarginals.h:735-742)
+//     landmark blocks  Sigma_pp = D_p^-1 + (R^-T U D^-1)_p^T (R^-T U D^-1)_p             (BAMarginals.h:671-699)
+//                               = D_p^-1 + sum_{a,b in track(p)} Y_a^T (S^-1)_{c(a) c(b)} Y_b,   Y_o = W_o D_p^-1.
+// The reference solves with R^T one camera at a time and keeps the sparse result; here S is dense (the dense-RCS
+// path, 6C <= 16384), so S^-1 is formed once on the FP64 tensor pipe (dense_chol_inverse_device: panel factorisation of
+// [S | I], then Z^T Z) and every landmark gathers the k x k camera blocks of its track from it.
+
+#include "spp_ctx.h"
+
+namespace spp {
+
+size_t dense_chol_ld(size_t n);
+void schur_form_reduced_system(spp_ctx *ctx, double alpha, double alpha_diag, bool sparse_rcs);
+int dense_chol_inverse_device(spp_ctx *ctx, double *A, size_t n);
+
+#define LAUNCH_CHECK(ctx) do { ++ (ctx)->n_launches; SPP_CUDA(cudaGetLastError()); } while(0)
+
+// element (r, c) of the symmetric matrix whose upper tiles hold MINUS the inverse
+__device__ __forceinline__ double minus_inv_at(const double *__restrict__ Ni, size_t ld, unsigned r, unsigned c)
+{
+	return (r <= c)? Ni[(size_t)c * ld + r] : Ni[(size_t)r * ld + c];
+}
+
+// thread per element: cov[c * 36 + i * 6 + j] = (S^-1)(6c + i, 6c + j)
+__global__ void k_camera_marginals(size_t C, const double *__restrict__ Ni, size_t ld, double *__restrict__ cov)
+{
+	size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(i >= C * 36) return;
+	const unsigned c = (unsigned)(i / 36), e = (unsigned)(i % 36);
+	cov[i] = -minus_inv_at(Ni, ld, c * 6 + e / 6, c * 6 + e % 6);
+}
+
+// warp per landmark: the k^2 (a, b) pairs of its track are dealt to the lanes, every lane adds Y_a^T (S^-1)_ab Y_b to
+// its own 3 x 3 accumulator, a fixed-shape shuffle tree sums the lanes (no atomics: reproducible), lane 0 adds D^-1
+#define PM_WARPS 4
+__global__ void __launch_bounds__(PM_WARPS * 32) k_point_marginals(size_t P, const uint32_t *__restrict__ pt_ptr,
+	const uint32_t *__restrict__ obs_cam, const double *__restrict__ Y, const double *__restrict__ Cinv,
+	const double *__restrict__ Ni, size_t ld, double *__restrict__ cov)
+{
+	const size_t p = blockIdx.x * (size_t)PM_WARPS + (threadIdx.x >> 5);
+	if(p >= P) return;
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned beg = pt_ptr[p], k = pt_ptr[p + 1] - beg;
+	double acc[9];
+	#pragma unroll
+	for(int i = 0; i < 9; ++ i) acc[i] = 0;
+	const unsigned long long n_pairs = (unsigned long long)k * k;
+	for(unsigned long long q = lane; q < n_pairs; q += 32) {
+		const unsigned a = (unsigned)(q / k), b = (unsigned)(q % k);
+		const unsigned ca = obs_cam[beg + a], cb = obs_cam[beg + b];
+		const double *Ya = Y + (size_t)(beg + a) * 18, *Yb = Y + (size_t)(beg + b) * 18; // column-major 6 x 3
+		double yb[18];
+		#pragma unroll
+		for(int i = 0; i < 18; i += 2) {
+			double2 t = *reinterpret_cast<const double2*>(Yb + i);
+			yb[i] = t.x; yb[i + 1] = t.y;
+		}
+		double t[18]; // t = (-S^-1)_ab Y_b, 6 x 3 column-major
+		#pragma unroll
+		for(int i = 0; i < 18; ++ i) t[i] = 0;
+		#pragma unroll
+		for(int j = 0; j < 6; ++ j) {
+			#pragma unroll
+			for(int i = 0; i < 6; ++ i) {
+				const double m = minus_inv_at(Ni, ld, ca * 6 + i, cb * 6 + j);
+				t[i] += m * yb[j];
+				t[6 + i] += m * yb[6 + j];
+				t[12 + i] += m * yb[12 + j];
+			}
+		}
+		#pragma unroll
+		for(int r = 0; r < 3; ++ r) {
+			double ya[6];
+			#pragma unroll
+			for(int i = 0; i < 6; i += 2) {
+				double2 v = *reinterpret_cast<const double2*>(Ya + r * 6 + i);
+				ya[i] = v.x; ya[i + 1] = v.y;
+			}
+			#pragma unroll
+			for(int c = 0; c < 3; ++ c) {
+				double s = 0;
+				#pragma unroll
+				for(int i = 0; i < 6; ++ i)
+					s += ya[i] * t[c * 6 + i];
+				acc[r * 3 + c] -= s; // the matrix holds minus the inverse
+			}
+		}
+	}
+	#pragma unroll
+	for(int i = 0; i < 9; ++ i) {
+		#pragma unroll
+		for(int off = 16; off; off >>= 1)
+			acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+	}
+	if(lane == 0) {
+		const double *Ci = Cinv + p * 9;
+		#pragma unroll
+		for(int i = 0; i < 9; ++ i)
+			cov[p * 9 + i] = Ci[i] + acc[i]; // symmetric: row- and column-major agree up to rounding
+	}
+}
+
+// Marginals of the system currently held as (U, V, W): d_cam_cov [36 C], d_pt_cov [9 P] on the device (either may be
+// null). Returns SPP_OK / SPP_NOT_POSDEF.
+int schur_marginals_current(spp_ctx *ctx, double alpha, double *d_cam_cov, double *d_pt_cov)
+{
+	SchurSystem &s = ctx->sys;
+	const size_t n = s.C * 6, ld = dense_chol_ld(n);
+	schur_form_reduced_system(ctx, alpha, alpha, false); // Cinv, Y and the dense S at this damping
+	s.Sinv.resize(2 * ld * ld);
+	SPP_CUDA(cudaMemcpyAsync(s.Sinv.p(), s.S.p(), ld * ld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+	int rc = dense_chol_inverse_device(ctx, s.Sinv.p(), n);
+	if(rc != SPP_OK)
+		return rc;
+	if(d_cam_cov && s.C) {
+		k_camera_marginals<<<n_blocks(s.C * 36, 256), 256, 0, ctx->stream>>>(s.C, s.Sinv.p(), ld, d_cam_cov);
+		LAUNCH_CHECK(ctx);
+	}
+	if(d_pt_cov && s.P) {
+		k_point_marginals<<<n_blocks(s.P, PM_WARPS), PM_WARPS * 32, 0, ctx->stream>>>(s.P, s.pt_ptr.p(), s.obs_cam.p(),
+			s.Y.p(), s.Cinv.p(), s.Sinv.p(), ld, d_pt_cov);
+		LAUNCH_CHECK(ctx);
+	}
+	return SPP_OK;
+}
+
+} // namespace spp

@@ -70,6 +70,7 @@ void slot_symbolic(spp_ctx *ctx, size_t n, const uint64_t *col_dims, const uint6
 {
 	SchurSlot &sl = ctx->slot;
 	sl.valid = false;
+	sl.filled = false;
 	ctx->ba.valid = false; // the Schur system buffers are shared
 	std::vector<uint32_t> local(n);
 	std::vector<uint64_t> cam_cols, pt_cols;
@@ -164,6 +165,7 @@ int slot_solve(spp_ctx *ctx, const double *p_values, double *p_eta_dx)
 		sl.v_src.p(), sl.w_src.p(), sl.w_transposed.p(), sl.cam_eta_off.p(), sl.pt_eta_off.p(), s.U.p(), s.V.p(),
 		s.W.p(), s.gc.p(), s.gp.p());
 	LAUNCH_CHECK(ctx);
+	sl.filled = true;
 	int rc = schur_solve_current(ctx, 0.0, 0);
 	if(rc != SPP_OK)
 		return rc;

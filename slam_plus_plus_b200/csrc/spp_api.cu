@@ -36,6 +36,7 @@ void schur_backsubstitute(spp_ctx *ctx);
 size_t dense_chol_ld(size_t n);
 size_t dense_chol_storage(size_t n);
 int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x);
+int schur_marginals_current(spp_ctx *ctx, double alpha, double *d_cam_cov, double *d_pt_cov);
 void slot_symbolic(spp_ctx *ctx, size_t n, const uint64_t *col_dims, const uint64_t *col_ptr, const uint64_t *row_idx,
 	uint64_t *p_order, uint64_t *p_cut);
 int slot_solve(spp_ctx *ctx, const double *p_values, double *p_eta_dx);
@@ -592,6 +593,7 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 	BAProblem &ba = ctx->ba;
 	ba.valid = false;
 	ctx->slot.valid = false;
+	ctx->slot.filled = false;
 	ctx->snode.valid = false;
 	ctx->sys.n_blocks_global = 0;
 	if(!p_vertex_type || (n_observations && (!p_obs_point || !p_obs_camera || !p_z || !p_info)))
@@ -942,6 +944,47 @@ int spp_ba_solve_step(spp_ctx_t ctx, double alpha, double *p_dx)
 	rc = schur_solve_current(ctx, alpha, 0);
 	if(rc == SPP_OK && p_dx)
 		ba_download_dx(ctx, p_dx);
+	if(rc != SPP_OK) return rc;
+	API_END(ctx)
+}
+
+// marginals of the system held as (U, V, W) to host arrays (local camera / point order)
+static int marginals_to_host(spp_ctx *ctx, double alpha, double *p_cam_cov, double *p_pt_cov)
+{
+	SchurSystem &s = ctx->sys;
+	if(ctx->world > 1) throw invalid_error("marginals are not available on a landmark-partitioned (multi-GPU) context");
+	if(!s.C) throw invalid_error("no cameras");
+	if(rcs_is_sparse(ctx, s.C))
+		throw invalid_error("marginals need the dense reduced camera system (6 C <= 16384, or spp_schur_set_rcs_solver(SPP_RCS_DENSE))");
+	DBuf<double> d_cam, d_pt;
+	if(p_cam_cov) d_cam.resize(s.C * 36);
+	if(p_pt_cov) d_pt.resize(s.P * 9);
+	int rc = schur_marginals_current(ctx, alpha, p_cam_cov? d_cam.p() : 0, p_pt_cov? d_pt.p() : 0);
+	if(rc != SPP_OK)
+		return rc;
+	if(p_cam_cov) d_cam.download(p_cam_cov, s.C * 36, ctx->stream);
+	if(p_pt_cov) d_pt.download(p_pt_cov, s.P * 9, ctx->stream);
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	return SPP_OK;
+}
+
+int spp_ba_marginals(spp_ctx_t ctx, double alpha, double *p_cam_cov, double *p_pt_cov)
+{
+	int rc = SPP_OK;
+	API_BEGIN(ctx)
+	if(!ctx->ba.valid) throw invalid_error("no BA graph");
+	if(!ctx->ba.linearised) ba_linearise(ctx, true);
+	rc = marginals_to_host(ctx, alpha, p_cam_cov, p_pt_cov);
+	if(rc != SPP_OK) return rc;
+	API_END(ctx)
+}
+
+int spp_schur_marginals(spp_ctx_t ctx, double alpha, double *p_cam_cov, double *p_pt_cov)
+{
+	int rc = SPP_OK;
+	API_BEGIN(ctx)
+	if(!ctx->slot.valid || !ctx->slot.filled) throw invalid_error("no system: spp_schur_symbolic and spp_schur_solve first");
+	rc = marginals_to_host(ctx, alpha, p_cam_cov, p_pt_cov);
 	if(rc != SPP_OK) return rc;
 	API_END(ctx)
 }

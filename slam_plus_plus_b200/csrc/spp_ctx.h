@@ -39,6 +39,7 @@ struct SchurSystem {
 	DBuf<double> S;    // [n*n] dense column-major reduced camera system, n = 6C (upper triangle valid)
 	DBuf<double> Sblk; // [n_blocks*36] the same as a compact block list (sparse reduced camera system), order of blk_row/col
 	DBuf<double> S_copy; // optional copy kept for spp_schur_get_reduced_system
+	DBuf<double> Sinv; // [ld * 2 ld] marginals: [S | I] -> [-S^-1 | R^-T] (marginals.cu)
 	DBuf<double> b, b_copy; // [n] reduced right-hand side / camera increment
 	DBuf<double> dxc, dxp; // [6C], [3P] increments
 	bool keep_reduced;
@@ -77,6 +78,7 @@ struct BAProblem {
 // slot-1 state: map from the caller's lambda values to the SchurSystem arrays
 struct SchurSlot {
 	bool valid;
+	bool filled;                          // (U, V, W) hold the values of the last spp_schur_solve
 	size_t n_bcols, n_scalars, n_values;
 	std::vector<uint64_t> col_base;       // scalar offset of each block column
 	std::vector<uint64_t> order;          // new position -> original block column
@@ -85,7 +87,7 @@ struct SchurSlot {
 	DBuf<uint64_t> u_src, v_src, w_src;   // value offsets of the U / V / W blocks
 	DBuf<uint8_t> w_transposed;           // W block stored 3x6 in lambda (point id < camera id)
 	DBuf<uint64_t> cam_eta_off, pt_eta_off; // scalar offsets in eta
-	SchurSlot() : valid(false), n_bcols(0), n_scalars(0), n_values(0), cut(0) {}
+	SchurSlot() : valid(false), filled(false), n_bcols(0), n_scalars(0), n_values(0), cut(0) {}
 };
 
 // scratch of the device-side symbolic analysis (symbolic_gpu.cu); grows only

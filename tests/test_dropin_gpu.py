@@ -136,4 +136,45 @@ def test_reference_system_with_b200_nonlinear_solver(mode, name, tmp_path):
     for a, c in zip(tb[:-1], tr[:-1]):
         assert abs(a - c) <= 2e-5 * max(c, 1.0)
     assert abs(tb[-1] - tr[-1]) <= 1e-6 * tr[-1]
+    assert len(b["states"]) == len(r["states"]) > 6
     assert rel_err(b["states"], r["states"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["ba_tiny", "ba_small"])
+def test_b200_nonlinear_solver_marginals(name, tmp_path):
+    """the marginals policy of the reference's solver interface (TMarginalsComputationPolicy, mpart_Diagonal) on the
+    swapped-in solver type: r_MarginalCovariance().r_SparseMatrix() after Optimize() against the reference's own, up to
+    the variance of the unobservable scale (tests/test_marginals_cpu.py explains the one-scalar fit)"""
+    if not os.path.exists(BIN_LM):
+        pytest.skip("oracle/_ref/ref_driver_dropin_lm not built (needs /root/reference at build time)")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    from conftest import gauge_fit_residual, weakest_modes
+    from slam_plus_plus_b200 import sppio
+    g, d = load_golden(name)
+    assert g.vtype[0] == 0  # the unary factor sits on a camera: one gauge mode
+    gp = str(tmp_path / "g.bin")
+    sppio.write_graph(gp, g)
+    env = dict(os.environ, OMP_NUM_THREADS="1", SPP_DROPIN_MARGS="1")
+    out = {}
+    for impl in ("b200", "ref"):
+        dp = str(tmp_path / (impl + ".dump"))
+        subprocess.run([BIN_LM, impl, "batch", gp, dp, "5", "0", "6"], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, env=env)
+        out[impl] = sppio.read_dump(dp)
+    b, r = out["b200"], out["ref"]
+    assert len(b["states"]) == len(r["states"]) == 6 * g.n_cams + 3 * g.n_pts
+    assert rel_err(b["states"], r["states"]) < 1e-4
+    cb, pb = b["cam_cov"].reshape(-1, 6, 6), b["pt_cov"].reshape(-1, 3, 3)
+    cr, pr = r["cam_cov"].reshape(-1, 6, 6), r["pt_cov"].reshape(-1, 3, 3)
+    assert cb.shape == cr.shape == (g.n_cams, 6, 6) and pb.shape == pr.shape == (g.n_pts, 3, 3)
+    loc, off = g.vertex_local_index(), 0
+    for v in range(g.n_vertices):  # the graph at the final states, for the gauge mode of its lambda
+        k = 6 if g.vtype[v] == 0 else 3
+        (g.cams if k == 6 else g.pts)[loc[v], :k] = b["states"][off:off + k]
+        off += k
+    _, _, L = oracle.ba_marginals(g)
+    rc, rp, _ = gauge_fit_residual(g.n_cams, cb, pb, cr, pr, weakest_modes(L, 1))
+    print(f"{name}: marginals after the gauge fit: cameras {rc:.3g}, points {rp:.3g}")
+    assert rc < 1e-3 and rp < 1e-2
