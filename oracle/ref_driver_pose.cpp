@@ -221,6 +221,28 @@ static int Run(const spp_graph_t &g, const char *p_s_mode, size_t n_arg4, double
 		f_opt_time = timer.f_Time() - f_begin;
 		f_chi2 = solver.f_Chi_Squared_Error_Denorm();
 		spp_dump_f64(g_dump, "step_seconds", step_seconds.size(), &step_seconds[0]);
+	} else if(!strcmp(p_s_mode, "margs")) {
+		// Optimize(max_iter), then the block diagonal of the covariance (NonlinearSolver_Lambda.h:669-767 ->
+		// CMarginals::Calculate_DenseMarginals_Recurrent_FBS, marginals policy mpart_Diagonal)
+		typedef CNonlinearSolver_Lambda<CSystemType, CRefLinearSolver> CSolver;
+		CSolver solver(system, TIncrementalSolveSetting(), TMarginalsComputationPolicy(true, frequency::Never(),
+			mpart_Diagonal, mpart_Diagonal), false, CRefLinearSolver(), false);
+		double f_start = timer.f_Time();
+		solver.Optimize(n_arg4, f_arg5);
+		f_opt_time = timer.f_Time() - f_start;
+		f_chi2 = solver.f_Chi_Squared_Error_Denorm();
+		if(getenv("SPP_REF_VERBOSE"))
+			solver.Dump(f_opt_time);
+		Dump_States(system, "states");
+		const CUberBlockMatrix &r_m = solver.r_MarginalCovariance().r_SparseMatrix();
+		std::vector<double> cov;
+		for(size_t i = 0, n = r_m.n_BlockColumn_Num(); i < n; ++ i) {
+			CUberBlockMatrix::_TyConstMatrixXdRef t_b = r_m.t_GetBlock_Log(i, i);
+			for(int r = 0; r < t_b.rows(); ++ r)
+				for(int c = 0; c < t_b.cols(); ++ c)
+					cov.push_back(t_b(r, c));
+		}
+		spp_dump_f64(g_dump, "cov", cov.size(), &cov[0]); // vertex id order, row-major blocks
 	} else if(strcmp(p_s_mode, "dump")) {
 		typedef CNonlinearSolver_Lambda<CSystemType, CRefLinearSolver> CSolver;
 		CSolver solver(system, TIncrementalSolveSetting(), TMarginalsComputationPolicy(), false, CRefLinearSolver(), false);
@@ -254,7 +276,7 @@ static int Run(const spp_graph_t &g, const char *p_s_mode, size_t n_arg4, double
 int main(int n_arg_num, const char **p_arg_list)
 {
 	if(n_arg_num < 4) {
-		fprintf(stderr, "usage: %s <time|dump|steps> <graph.bin> <out.dump> [max_iter=5 | warmup] [min_dx=0 | steps]\n", p_arg_list[0]);
+		fprintf(stderr, "usage: %s <time|dump|steps|margs> <graph.bin> <out.dump> [max_iter=5 | warmup] [min_dx=0 | steps]\n", p_arg_list[0]);
 		return -1;
 	}
 	const size_t n_arg4 = (n_arg_num > 4)? atol(p_arg_list[4]) : 5;

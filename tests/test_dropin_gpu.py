@@ -177,4 +177,4 @@ def test_b200_nonlinear_solver_marginals(name, tmp_path):
     _, _, L = oracle.ba_marginals(g)
     rc, rp, _ = gauge_fit_residual(g.n_cams, cb, pb, cr, pr, weakest_modes(L, 1))
     print(f"{name}: marginals after the gauge fit: cameras {rc:.3g}, points {rp:.3g}")
-    assert rc < 1e-3 and rp < 1e-2
+    assert rc < 1e-4 and rp < 1e-3  # measured 8e-6 / 1.3e-5
