@@ -305,6 +305,11 @@ int spp_pose_get_lambda(spp_ctx_t ctx, uint64_t *p_n_block_cols, uint64_t *p_n_b
 int spp_pose_chi2(spp_ctx_t ctx, double *p_chi2);
 /* one Gauss-Newton increment on the current linearisation: lambda dx = eta; does not move the vertices */
 int spp_pose_solve_step(spp_ctx_t ctx, double *p_dx);
+/* Block diagonal of lambda^-1 at the current states: replaces the marginals step at the end of
+ * CNonlinearSolver_Lambda::Optimize() (NonlinearSolver_Lambda.h:669-767 -> CMarginals::
+ * Calculate_DenseMarginals_Recurrent_FBS, policy mpart_Diagonal). p_cov[n_poses * dim * dim], poses in id order. Through a
+ * dense inverse on the FP64 tensor pipe: at most 16384 unknowns. Returns SPP_OK / SPP_NOT_POSDEF. */
+int spp_pose_marginals(spp_ctx_t ctx, double *p_cov);
 /* Replaces CNonlinearSolver_Lambda::Optimize(max_iter, min_dx_norm) (include/slam/NonlinearSolver_Lambda.h:476-667) */
 int spp_pose_optimize(spp_ctx_t ctx, size_t n_max_iterations, double f_min_dx_norm, spp_report_t *p_report);
 

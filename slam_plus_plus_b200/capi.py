@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "spp_chol_symbolic", "spp_chol_solve", "spp_chol_get_factor",
     "spp_pose_set_graph", "spp_pose_set_ordering", "spp_pose_set_states", "spp_pose_get_states", "spp_pose_restore_initial",
     "spp_pose_linearise", "spp_pose_get_lambda", "spp_pose_chi2", "spp_pose_solve_step", "spp_pose_optimize",
+    "spp_pose_marginals",
 ]
 
 
@@ -124,6 +125,7 @@ def load_library() -> C.CDLL:
     lib.spp_pose_get_lambda.argtypes = [vp, u64p, u64p, u64p, u64p, dp, dp]
     lib.spp_pose_chi2.argtypes = [vp, dp]
     lib.spp_pose_solve_step.argtypes = [vp, dp]
+    lib.spp_pose_marginals.argtypes = [vp, dp]
     lib.spp_pose_optimize.argtypes = [vp, C.c_size_t, C.c_double, C.POINTER(Report)]
     _lib = lib
     return lib
@@ -499,6 +501,13 @@ class Context:
         dx = np.empty(n * d)
         self._check(self.lib.spp_pose_solve_step(self.h, _dp(dx)))
         return dx
+
+    def pose_marginals(self) -> np.ndarray:
+        """Block diagonal of lambda^-1 at the current states: (N, dim, dim)."""
+        n, d = self._pose_dims
+        cov = np.empty((n, d, d))
+        self._check(self.lib.spp_pose_marginals(self.h, _dp(cov)))
+        return cov
 
     def pose_optimize(self, max_iterations: int = 5, min_dx_norm: float = 0.01) -> dict:
         rep = Report()

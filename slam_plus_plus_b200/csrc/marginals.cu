@@ -12,6 +12,7 @@
 // [S | I], then Z^T Z) and every landmark gathers the k x k camera blocks of its track from it.
 
 #include "spp_ctx.h"
+#include <vector>
 
 namespace spp {
 
@@ -127,6 +128,60 @@ int schur_marginals_current(spp_ctx *ctx, double alpha, double *d_cam_cov, doubl
 			s.Y.p(), s.Cinv.p(), s.Sinv.p(), ld, d_pt_cov);
 		LAUNCH_CHECK(ctx);
 	}
+	return SPP_OK;
+}
+
+// ---- pose graphs -------------------------------------------------------------------------------------------------
+// Reference replaced: the marginals step of CNonlinearSolver_Lambda::Optimize() (NonlinearSolver_Lambda.h:669-767 ->
+// CMarginals::Calculate_DenseMarginals_Recurrent_FBS on the Cholesky factor of lambda, policy mpart_Diagonal). The pose
+// systems of the configurations in scope have at most a few thousand block columns: lambda is scattered into the
+// dense solver's storage and inverted there.
+
+__global__ void k_pose_blocks_to_dense(size_t n_vals, int dim, const double *__restrict__ vals,
+	const uint32_t *__restrict__ blk_row, const uint32_t *__restrict__ blk_col, size_t ld, double *__restrict__ A)
+{
+	size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(i >= n_vals) return;
+	const size_t b = i / (dim * dim);
+	const unsigned e = (unsigned)(i - b * (dim * dim)), r = blk_row[b] * dim + e % dim, c = blk_col[b] * dim + e / dim; // column-major blocks
+	if(r <= c)
+		A[(size_t)c * ld + r] = vals[i];
+}
+
+__global__ void k_pose_marginals(size_t N, int dim, const double *__restrict__ Ni, size_t ld, double *__restrict__ cov)
+{
+	size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if(i >= N * dim * dim) return;
+	const unsigned v = (unsigned)(i / (dim * dim)), e = (unsigned)(i % (dim * dim));
+	cov[i] = -minus_inv_at(Ni, ld, v * dim + e / dim, v * dim + e % dim);
+}
+
+// d_cov [N dim^2] on the device; lambda must be current (pose_linearise). Returns SPP_OK / SPP_NOT_POSDEF.
+int pose_marginals(spp_ctx *ctx, double *d_cov)
+{
+	PoseProblem &pp = ctx->pose;
+	const size_t n = pp.N * pp.dim, ld = dense_chol_ld(n);
+	std::vector<uint32_t> h_row(pp.n_blocks), h_col(pp.n_blocks);
+	for(size_t c = 0; c < pp.N; ++ c) {
+		for(uint64_t k = pp.h_col_ptr[c]; k < pp.h_col_ptr[c + 1]; ++ k) {
+			h_row[k] = (uint32_t)pp.h_row_idx[k];
+			h_col[k] = (uint32_t)c;
+		}
+	}
+	DBuf<uint32_t> d_row, d_col;
+	d_row.upload(h_row, ctx->stream);
+	d_col.upload(h_col, ctx->stream);
+	DBuf<double> &A = ctx->sys.Sinv;
+	A.resize(2 * ld * ld);
+	SPP_CUDA(cudaMemsetAsync(A.p(), 0, ld * ld * sizeof(double), ctx->stream));
+	const size_t n_vals = pp.n_blocks * pp.dim * pp.dim;
+	k_pose_blocks_to_dense<<<n_blocks(n_vals, 256), 256, 0, ctx->stream>>>(n_vals, pp.dim, pp.vals.p(), d_row.p(), d_col.p(), ld, A.p());
+	LAUNCH_CHECK(ctx);
+	int rc = dense_chol_inverse_device(ctx, A.p(), n); // synchronises: the index arrays may go
+	if(rc != SPP_OK)
+		return rc;
+	k_pose_marginals<<<n_blocks(pp.N * pp.dim * pp.dim, 256), 256, 0, ctx->stream>>>(pp.N, pp.dim, A.p(), ld, d_cov);
+	LAUNCH_CHECK(ctx);
 	return SPP_OK;
 }
 

@@ -37,6 +37,7 @@ size_t dense_chol_ld(size_t n);
 size_t dense_chol_storage(size_t n);
 int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x);
 int schur_marginals_current(spp_ctx *ctx, double alpha, double *d_cam_cov, double *d_pt_cov);
+int pose_marginals(spp_ctx *ctx, double *d_cov);
 void slot_symbolic(spp_ctx *ctx, size_t n, const uint64_t *col_dims, const uint64_t *col_ptr, const uint64_t *row_idx,
 	uint64_t *p_order, uint64_t *p_cut);
 int slot_solve(spp_ctx *ctx, const double *p_values, double *p_eta_dx);
@@ -1321,6 +1322,24 @@ int spp_pose_solve_step(spp_ctx_t ctx, double *p_dx)
 		SPP_CUDA(cudaStreamSynchronize(ctx->stream));
 	}
 	if(rc != SPP_OK) return rc;
+	API_END(ctx)
+}
+
+int spp_pose_marginals(spp_ctx_t ctx, double *p_cov)
+{
+	int rc = SPP_OK;
+	API_BEGIN(ctx)
+	PoseProblem &pp = ctx->pose;
+	if(!pp.valid) throw invalid_error("no pose graph");
+	if(!p_cov) throw invalid_error("null argument");
+	if(pp.N * pp.dim > 16384) throw invalid_error("pose marginals go through a dense inverse: at most 16384 unknowns");
+	if(!pp.linearised) pose_linearise(ctx);
+	DBuf<double> d_cov;
+	d_cov.resize(pp.N * pp.dim * pp.dim);
+	rc = pose_marginals(ctx, d_cov.p());
+	if(rc != SPP_OK) return rc;
+	d_cov.download(p_cov, pp.N * pp.dim * pp.dim, ctx->stream);
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
 	API_END(ctx)
 }
 

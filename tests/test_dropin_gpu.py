@@ -161,7 +161,7 @@ def test_b200_nonlinear_solver_marginals(name, tmp_path):
     for impl in ("b200", "ref"):
         dp = str(tmp_path / (impl + ".dump"))
         subprocess.run([BIN_LM, impl, "batch", gp, dp, "5", "0", "6"], check=True, stdout=subprocess.DEVNULL,
-                       stderr=subprocess.DEVNULL, env=env)
+                       stderr=subprocess.DEVNULL, env=env, cwd=str(tmp_path))  # the reference writes marginals.txt
         out[impl] = sppio.read_dump(dp)
     b, r = out["b200"], out["ref"]
     assert len(b["states"]) == len(r["states"]) == 6 * g.n_cams + 3 * g.n_pts

@@ -45,3 +45,19 @@ def test_oracle_marginals_damped_schur_identity():
     full = Dinv + Dinv @ U.T @ Sinv @ U @ Dinv
     assert rel_err(np.stack([Sinv[6 * i:6 * i + 6, 6 * i:6 * i + 6] for i in range(g.n_cams)]), cc) < 1e-10
     assert rel_err(np.stack([full[3 * j:3 * j + 3, 3 * j:3 * j + 3] for j in range(g.n_pts)]), pc) < 1e-10
+
+
+@pytest.mark.parametrize("name,tol", [("margs_se2", 1e-9), ("margs_se3", 1e-3)])
+def test_oracle_pose_marginals_vs_reference(name, tol):
+    """pose graphs: the unary factor on pose 0 fixes the whole gauge, so the block diagonal of a dense inverse of the
+    restated lambda meets the reference's recursive formula directly -- SE(2) (analytic Jacobians) to rounding times the
+    condition number (measured 4e-11), SE(3) (forward differences, cond 1e11) at the FD noise floor"""
+    import oracle
+    from test_pose_cpu import load_pose_golden
+    g, d = load_pose_golden(name)
+    L, _ = oracle.pose_linearise_dense(g, d["states"])
+    S = np.linalg.inv(L)
+    n, dim = d["states"].shape
+    cov = np.stack([S[dim * i:dim * i + dim, dim * i:dim * i + dim] for i in range(n)])
+    from test_pose_cpu import dx_tolerance
+    assert rel_err(cov, d["cov"]) < max(tol, dx_tolerance(L))  # O(cond * eps) between two stable inversions

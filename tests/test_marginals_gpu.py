@@ -102,3 +102,60 @@ def test_marginals_mid_size_and_errors(ctx):
             ctx.ba_marginals(alpha)
     finally:
         ctx.schur_set_rcs_solver(capi.RCS_AUTO)
+
+
+@pytest.mark.parametrize("name,tol", [("margs_se2", 1e-9), ("margs_se3", 1e-3)])
+def test_pose_marginals_vs_reference(ctx, name, tol):
+    """pose graphs (gauge fixed by the unary factor on pose 0): spp_pose_marginals at the reference's final states
+    against the reference's own marginals -- SE(2) to 1e-9, SE(3) at the FD noise floor times cond(lambda) ~ 1e11 --
+    and against a float64 dense inverse of the device's lambda"""
+    from test_pose_cpu import load_pose_golden, pose_lambda_to_dense
+    g, d = load_pose_golden(name)
+    ctx.pose_set_graph(g)
+    ctx.pose_set_states(d["states"])
+    cov = ctx.pose_marginals()
+    assert cov.shape == d["cov"].shape
+    cp, ri, vals, _ = ctx.pose_get_lambda()
+    dim = cov.shape[1]
+    A = pose_lambda_to_dense(cp, ri, vals, dim)
+    assert rel_err(cov, d["cov"]) < max(tol, 1e-2 * np.linalg.cond(A) * np.finfo(float).eps)
+    Ai = np.linalg.inv(A)
+    ref = np.stack([Ai[dim * i:dim * i + dim, dim * i:dim * i + dim] for i in range(cov.shape[0])])
+    assert rel_err(cov, ref) < max(1e-9, 1e-2 * np.linalg.cond(A) * np.finfo(float).eps)
+    assert np.array_equal(cov, ctx.pose_marginals())  # bit-reproducible
+
+
+def test_pose_marginals_manhattan_size(ctx):
+    """Manhattan-3500 shape (10 500 unknowns, 83 panels): consistency of the dense inverse with a solve of the same
+    system -- Sigma_ii is the i-th diagonal block of lambda^-1, so lambda-solves against unit vectors must reproduce it"""
+    from slam_plus_plus_b200 import graphs
+    from test_pose_cpu import pose_lambda_to_dense
+    import scipy.sparse
+    import scipy.sparse.linalg
+    g = graphs.make_manhattan()
+    ctx.pose_set_graph(g)
+    ctx.pose_optimize(5, 0.0)
+    ctx.pose_linearise()
+    cov = ctx.pose_marginals()
+    n = g.poses.shape[0]
+    assert cov.shape == (n, 3, 3) and np.all(np.einsum("kii->ki", cov) > 0)
+    cp, ri, vals, _ = ctx.pose_get_lambda()
+    # sparse lambda (upper blocks -> symmetric) and a handful of columns of its inverse
+    rows, cols, v = [], [], []
+    for c in range(n):
+        for k in range(int(cp[c]), int(cp[c + 1])):
+            r = int(ri[k])
+            blk = vals[9 * k:9 * k + 9].reshape(3, 3).T
+            for i in range(3):
+                for j in range(3):
+                    if r < c or i <= j:
+                        rows.append(3 * r + i); cols.append(3 * c + j); v.append(blk[i, j])
+                        if 3 * r + i != 3 * c + j:
+                            rows.append(3 * c + j); cols.append(3 * r + i); v.append(blk[i, j])
+    A = scipy.sparse.csc_matrix((v, (rows, cols)), shape=(3 * n, 3 * n))
+    lu = scipy.sparse.linalg.splu(A)
+    for p in (0, 1, n // 3, n // 2, n - 1):
+        E = np.zeros((3 * n, 3))
+        E[3 * p:3 * p + 3] = np.eye(3)
+        X = lu.solve(E)
+        assert rel_err(cov[p], X[3 * p:3 * p + 3]) < 1e-8

@@ -31,3 +31,17 @@ for alpha in (0.0, 1.0):
                               asym=float(np.abs(cc - cc.transpose(0, 2, 1)).max() / np.abs(cc).max()))), flush=True)
     cc2, pc2 = ctx.ba_marginals(alpha)
     print("bitwise reproducible:", bool(np.array_equal(cc, cc2) and np.array_equal(pc, pc2)), flush=True)
+
+# pose graphs: block diagonal of lambda^-1 through the dense inverse (spp_pose_marginals)
+for name, gp in (("manhattan3500", graphs.make_manhattan()),
+                 ("sphere2500", graphs.make_sphere(n_rings=50, n_per_ring=50, seed=2500, sigma_t=0.004, sigma_r=0.0004, radius=5.0))):
+    ctx.pose_set_graph(gp)
+    ctx.pose_optimize(5, 0.0)
+    ctx.pose_linearise()
+    for r in range(3):
+        l0 = ctx.kernel_launches
+        t = time.time()
+        cov = ctx.pose_marginals()
+        wall = time.time() - t
+        print(json.dumps(dict(graph=name, run=r, wall_ms=round(wall * 1e3, 2), launches=ctx.kernel_launches - l0,
+                              var_max=float(np.einsum("kii->ki", cov).max()), var_min=float(np.einsum("kii->ki", cov).min()))), flush=True)
