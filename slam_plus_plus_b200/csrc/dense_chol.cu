@@ -299,7 +299,9 @@ static void chol_init_streams(spp_ctx *ctx)
 // (supernodal_chol.cu) is the case "ld = its own columns, n_cols - ld = its row structure + right-hand side".
 // Rinv receives the inverses of the ld / 128 diagonal blocks of R11; *info the first non-positive pivot (1-based).
 // Asynchronous: everything is ordered on (or joined back into) the context's stream.
-void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols, double *Rinv, int *info)
+// identity_tail: the columns right of R11 start as the identity (the inverse, dense_chol_inverse_device): block row b of
+// them is zero right of column block b until panel b has been applied, so panel b only touches the first b + 1 of them.
+void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols_all, double *Rinv, int *info, bool identity_tail)
 {
 	DenseChol &ch = ctx->chol;
 	chol_init_streams(ctx);
@@ -357,6 +359,7 @@ void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols, 
 		bool bulk_in_flight = false, row_in_flight = false;
 		for(size_t b = 0; b < n_blk; ++ b) {
 			const size_t k0 = b * CH_NB, c0 = k0 + CH_NB;
+			const size_t n_cols = identity_tail? ld + (b + 1) * CH_NB : n_cols_all;
 			const int e = int(b & 1);
 			double *Rinv_b = Rinv + b * (size_t)(CH_NB * CH_NB);
 			stamp();
@@ -526,7 +529,7 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 	double *rhs_col = A + ld * ld; // first column of the rhs block
 	k_copy_rhs<<<n_blocks(n, 256), 256, 0, st>>>(rhs_col, d_rhs_x, n);
 	LAUNCH_CHECK(ctx);
-	dense_chol_factor_panel(ctx, A, ld, ld + CH_NB, ch.work.p(), ch.info.p());
+	dense_chol_factor_panel(ctx, A, ld, ld + CH_NB, ch.work.p(), ch.info.p(), false);
 	k_backsolve<<<(unsigned)n_blk, 256, 0, st>>>(A, ld, n_blk, ch.work.p(), rhs_col, ch.info.p() + 1);
 	LAUNCH_CHECK(ctx);
 	k_copy_rhs<<<n_blocks(n, 256), 256, 0, st>>>(d_rhs_x, rhs_col, n);
@@ -575,7 +578,7 @@ int dense_chol_inverse_device(spp_ctx *ctx, double *A, size_t n)
 	SPP_CUDA(cudaMemsetAsync(Z, 0, ld * ld * sizeof(double), st));
 	k_set_identity<<<n_blocks(ld, 256), 256, 0, st>>>(Z, ld);
 	LAUNCH_CHECK(ctx);
-	dense_chol_factor_panel(ctx, A, ld, 2 * ld, ch.work.p(), ch.info.p());
+	dense_chol_factor_panel(ctx, A, ld, 2 * ld, ch.work.p(), ch.info.p(), true);
 	SPP_CUDA(cudaMemsetAsync(A, 0, ld * ld * sizeof(double), st));
 	for(size_t kb = 0; kb < n_blk; ++ kb) { // block row kb of Z is non-zero in its first kb + 1 column blocks
 		const size_t m = (kb + 1) * CH_NB;

@@ -158,4 +158,6 @@ def test_pose_marginals_manhattan_size(ctx):
         E = np.zeros((3 * n, 3))
         E[3 * p:3 * p + 3] = np.eye(3)
         X = lu.solve(E)
-        assert rel_err(cov[p], X[3 * p:3 * p + 3]) < 1e-8
+        # two stable inversions agree to O(cond * eps): cond(lambda) ~ 2e10 on this graph (identity prior on pose 0
+        # against edge information of 400 .. 2500, see test_pose_cpu.dx_tolerance) -- measured 1.4e-6
+        assert rel_err(cov[p], X[3 * p:3 * p + 3]) < 1e-5
