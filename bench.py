@@ -284,7 +284,7 @@ def gpu_arm(args):
                      "traffic_source": "profiles/r1g_chol_traffic.csv" if (not sparse_rcs and args.shape == "venice871") else None,
                      "flops_per_launch": chol_flops,
                      "peak_source": "FP64: cuBLAS DGEMM 4096^3 via torch.matmul measured in this run (no FP64 entry in MEASURED_PEAKS.json)",
-                     "hbm_stage": {"kernel": "linearise (k_linearise_cams + k_linearise_points)",
+                     "hbm_stage": {"kernel": "linearise (k_cam_prepare + k_linearise_cams + k_sum_point_records)",
                                    "achieved_gbs": bytes_lin / (phase["linearise"] / max(n_iters, 1) * 1e-3) / 1e9,
                                    "peak_gbs": hbm_peak, "peak_source": hbm_src}},
     }
