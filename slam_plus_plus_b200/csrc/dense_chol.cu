@@ -50,7 +50,8 @@ enum { GEMM_SYRK = 0, GEMM_TRSM = 1, GEMM_GRAM = 2 };
 //       slot): C(i0.., j0..) -= Z(k0.., i0..)^T Z(k0.., j0..) -- the inverse of a factored matrix as Z^T Z, Z = R^-T.
 // WM x WN is the warp tile (multiples of 8): 32 x 32 for the bulk updates, smaller for the few tiles on the critical
 // chain, where more warps with shorter DMMA chains finish sooner.
-template <int MODE, int BM, int BN, int WM = 32, int WN = 32, int STAGES = CH_STAGES>
+// KN: number of operand rows = K of the product (128: one panel; 256: two consecutive panels applied in one pass).
+template <int MODE, int BM, int BN, int WM = 32, int WN = 32, int STAGES = CH_STAGES, int KN = CH_NB>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) k_gemm_tn(double *__restrict__ A, size_t ld, size_t k0,
 	size_t rbase, size_t cbase, const double *__restrict__ Rinv)
 {
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) k_gemm_tn(double *
 
 	double acc[MA][NB][2];
 
-	constexpr int KT = CH_NB / CH_BK;
+	constexpr int KT = KN / CH_BK;
 	#pragma unroll
 	for(int s = 0; s < STAGES - 1; ++ s) {
 		stage_load(s, s);
@@ -265,6 +266,10 @@ static void chol_init_attributes(int device)
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_GRAM, 64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64, 64>()));
 	SPP_CUDA(cudaFuncSetAttribute((k_gemm_tn<GEMM_TRSM, 128, 16, 32, 16, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 16, 8>()));
 	SPP_CUDA(cudaFuncSetAttribute((k_gemm_tn<GEMM_SYRK, 32, 32, 16, 16, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<32, 32, 8>()));
+	SPP_CUDA(cudaFuncSetAttribute((k_gemm_tn<GEMM_SYRK, 128, 128, 32, 32, CH_STAGES, 256>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 128>()));
+	SPP_CUDA(cudaFuncSetAttribute((k_gemm_tn<GEMM_SYRK, 128, 64, 32, 32, CH_STAGES, 256>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
+	SPP_CUDA(cudaFuncSetAttribute((k_gemm_tn<GEMM_SYRK, 64, 64, 32, 32, CH_STAGES, 256>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64, 64>()));
+	SPP_CUDA(cudaFuncSetAttribute((k_gemm_tn<GEMM_SYRK, 32, 32, 16, 16, 8, 256>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<32, 32, 8>()));
 	done[device] = true;
 }
 
@@ -343,20 +348,39 @@ void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols_a
 			}
 		};
 		// C(rows r0.., cols c0..) -= P^T P on the upper tiles of a (n_r x n_c) region, tile shape by size
-		auto syrk = [&](cudaStream_t s, size_t k0, size_t r0, size_t c0, size_t n_r, size_t n_c, int tile) {
+		// two_panels: P = the 256 rows from k0 on (the deferred update of the previous panel rides along)
+		auto syrk = [&](cudaStream_t s, size_t k0, size_t r0, size_t c0, size_t n_r, size_t n_c, int tile, bool two_panels) {
 			if(tile == 0) {
 				dim3 grid((unsigned)(n_c / 128), (unsigned)(n_r / 128));
-				k_gemm_tn<GEMM_SYRK, 128, 128><<<grid, 512, gemm_smem<128, 128>(), s>>>(A, ld, k0, r0, c0, 0);
+				if(two_panels)
+					k_gemm_tn<GEMM_SYRK, 128, 128, 32, 32, CH_STAGES, 256><<<grid, 512, gemm_smem<128, 128>(), s>>>(A, ld, k0, r0, c0, 0);
+				else
+					k_gemm_tn<GEMM_SYRK, 128, 128><<<grid, 512, gemm_smem<128, 128>(), s>>>(A, ld, k0, r0, c0, 0);
 			} else if(tile == 1) {
 				dim3 grid((unsigned)(n_c / 64), (unsigned)(n_r / 128));
-				k_gemm_tn<GEMM_SYRK, 128, 64><<<grid, 256, gemm_smem<128, 64>(), s>>>(A, ld, k0, r0, c0, 0);
+				if(two_panels)
+					k_gemm_tn<GEMM_SYRK, 128, 64, 32, 32, CH_STAGES, 256><<<grid, 256, gemm_smem<128, 64>(), s>>>(A, ld, k0, r0, c0, 0);
+				else
+					k_gemm_tn<GEMM_SYRK, 128, 64><<<grid, 256, gemm_smem<128, 64>(), s>>>(A, ld, k0, r0, c0, 0);
 			} else {
 				dim3 grid((unsigned)(n_c / 64), (unsigned)(n_r / 64));
-				k_gemm_tn<GEMM_SYRK, 64, 64><<<grid, 128, gemm_smem<64, 64>(), s>>>(A, ld, k0, r0, c0, 0);
+				if(two_panels)
+					k_gemm_tn<GEMM_SYRK, 64, 64, 32, 32, CH_STAGES, 256><<<grid, 128, gemm_smem<64, 64>(), s>>>(A, ld, k0, r0, c0, 0);
+				else
+					k_gemm_tn<GEMM_SYRK, 64, 64><<<grid, 128, gemm_smem<64, 64>(), s>>>(A, ld, k0, r0, c0, 0);
 			}
 			LAUNCH_CHECK(ctx);
 		};
+		// Bulk updates in pairs (SPP_CHOL_PAIRS=1, off by default): the bulk update of an even panel is deferred and applied
+		// together with the next panel's as one rank-256 pass (half the launches, half the read-modify-write traffic of the
+		// trailing matrix, twice the K per tile); the look-ahead of the odd panel then carries both panels into the next
+		// tile row. Bit-identical results, but MEASURED SLOWER on the Venice system (5226^2: 3.55 ms against 3.39 ms per
+		// factorisation): the deferred update starts one panel later, so less of it hides behind the critical chain, and
+		// the rank-256 look-ahead of the diagonal tile sits on that chain.
+		static const bool pair_updates = getenv("SPP_CHOL_PAIRS") != 0;
+		bool pending = false; // panel b - 1 has not been applied below tile row b yet
 		bool bulk_in_flight = false, row_in_flight = false;
+		int bulk_slot = 0; // the event the last bulk update was recorded in
 		for(size_t b = 0; b < n_blk; ++ b) {
 			const size_t k0 = b * CH_NB, c0 = k0 + CH_NB;
 			const size_t n_cols = identity_tail? ld + (b + 1) * CH_NB : n_cols_all;
@@ -406,14 +430,18 @@ void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols_a
 				SPP_CUDA(cudaEventRecord(ch.ev_panel[e], sC)); // panel b is final (together with ev_first)
 				// the look-ahead updates write tile row b + 1, which the bulk update of step b - 1 also wrote
 				if(bulk_in_flight) {
-					SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_bulk[e ^ 1], 0));
-					SPP_CUDA(cudaStreamWaitEvent(sC, ch.ev_bulk[e ^ 1], 0));
+					SPP_CUDA(cudaStreamWaitEvent(sA, ch.ev_bulk[bulk_slot], 0));
+					SPP_CUDA(cudaStreamWaitEvent(sC, ch.ev_bulk[bulk_slot], 0));
 					bulk_in_flight = false;
 				}
 			}
 			// look-ahead, critical part: the next diagonal tile (32 x 32 tiles of four 16 x 16 warps: short chains)
+			const size_t ku = pending? k0 - CH_NB : k0; // first row of the panels this step applies
 			tic();
-			k_gemm_tn<GEMM_SYRK, 32, 32, 16, 16, 8><<<dim3(CH_NB / 32, CH_NB / 32), 128, gemm_smem<32, 32, 8>(), sA>>>(A, ld, k0, c0, c0, 0);
+			if(pending)
+				k_gemm_tn<GEMM_SYRK, 32, 32, 16, 16, 8, 256><<<dim3(CH_NB / 32, CH_NB / 32), 128, gemm_smem<32, 32, 8>(), sA>>>(A, ld, ku, c0, c0, 0);
+			else
+				k_gemm_tn<GEMM_SYRK, 32, 32, 16, 16, 8><<<dim3(CH_NB / 32, CH_NB / 32), 128, gemm_smem<32, 32, 8>(), sA>>>(A, ld, k0, c0, c0, 0);
 			LAUNCH_CHECK(ctx);
 			toc(3);
 			stamp();
@@ -423,13 +451,15 @@ void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols_a
 			tic();
 			// 64 x 64 tiles while they are needed to occupy the SMs (a dense matrix), 128 x 64 for the long block rows of a
 			// supernode panel
-			syrk(sC, k0, c0, c0 + CH_NB, CH_NB, n_cols - (c0 + CH_NB), ((n_cols - (c0 + CH_NB)) / 64 >= 148)? 1 : 2);
+			syrk(sC, ku, c0, c0 + CH_NB, CH_NB, n_cols - (c0 + CH_NB), ((n_cols - (c0 + CH_NB)) / 64 >= 148)? 1 : 2, pending);
 			toc(4);
 			if(!prof)
 				SPP_CUDA(cudaEventRecord(ch.ev_row[e], sC));
 			row_in_flight = true;
 			const size_t r1 = c0 + CH_NB; // first row below the next panel's tile row
-			if(r1 < ld) {
+			if(r1 < ld && pair_updates && !pending && r1 + CH_NB < ld)
+				pending = true; // an even panel with at least two tile rows below the next one: its bulk update waits for the next panel
+			else if(r1 < ld) {
 				if(!prof) {
 					SPP_CUDA(cudaStreamWaitEvent(sB, ch.ev_panel[e], 0));
 					SPP_CUDA(cudaStreamWaitEvent(sB, ch.ev_first[e], 0));
@@ -440,12 +470,15 @@ void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols_a
 				int tile = (n_tiles >= 74)? 1 : 2;
 				if(ch.force_tile >= 0) tile = ch.force_tile;
 				tic();
-				syrk(sB, k0, r1, r1, ld - r1, n_cols - r1, tile);
+				syrk(sB, ku, r1, r1, ld - r1, n_cols - r1, tile, pending);
 				toc(2);
 				if(!prof)
 					SPP_CUDA(cudaEventRecord(ch.ev_bulk[e], sB));
 				bulk_in_flight = true;
-			}
+				bulk_slot = e;
+				pending = false;
+			} else
+				pending = false;
 		}
 		if(timeline && !prof && !tl.empty()) {
 			cudaEventSynchronize(tl.back());
