@@ -377,7 +377,8 @@ void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols_a
 		// tile row. Bit-identical results, but MEASURED SLOWER on the Venice system (5226^2: 3.55 ms against 3.39 ms per
 		// factorisation): the deferred update starts one panel later, so less of it hides behind the critical chain, and
 		// the rank-256 look-ahead of the diagonal tile sits on that chain.
-		static const bool pair_updates = getenv("SPP_CHOL_PAIRS") != 0;
+		static const int pair_min_rows = getenv("SPP_CHOL_PAIRS")? atoi(getenv("SPP_CHOL_PAIRS")) : 0; // pair while at least this many tile rows are left
+		const bool pair_updates = pair_min_rows > 0;
 		bool pending = false; // panel b - 1 has not been applied below tile row b yet
 		bool bulk_in_flight = false, row_in_flight = false;
 		int bulk_slot = 0; // the event the last bulk update was recorded in
@@ -457,7 +458,7 @@ void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols_a
 				SPP_CUDA(cudaEventRecord(ch.ev_row[e], sC));
 			row_in_flight = true;
 			const size_t r1 = c0 + CH_NB; // first row below the next panel's tile row
-			if(r1 < ld && pair_updates && !pending && r1 + CH_NB < ld)
+			if(r1 < ld && pair_updates && !pending && r1 + CH_NB < ld && (ld - r1) / CH_NB >= (size_t)pair_min_rows)
 				pending = true; // an even panel with at least two tile rows below the next one: its bulk update waits for the next panel
 			else if(r1 < ld) {
 				if(!prof) {
