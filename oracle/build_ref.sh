@@ -11,7 +11,7 @@
 # (mixing -march settings breaks Eigen's alignment ABI), /usr/bin/g++ (the image's $CC gcc
 # has no libgomp spec).
 #
-# usage: oracle/build_ref.sh [driver ...]      (default drivers: ba dropin pose order dropin_pose parse dropin_lm)
+# usage: oracle/build_ref.sh [driver ...]      (default drivers: ba dropin pose order dropin_pose parse dropin_lm dropin_gn)
 set -u
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${SPP_REFERENCE:-/root/reference}"
@@ -34,7 +34,7 @@ if [ ! -d "$REF/include/slam" ]; then
 fi
 mkdir -p "$OBJ"
 DRIVERS=("$@")
-[ ${#DRIVERS[@]} -eq 0 ] && DRIVERS=(ba dropin pose order dropin_pose parse dropin_lm)
+[ ${#DRIVERS[@]} -eq 0 ] && DRIVERS=(ba dropin pose order dropin_pose parse dropin_lm dropin_gn)
 
 compile_one() { # src obj compiler extra
 	local src="$1" obj="$2" comp="$3"; shift 3
@@ -69,7 +69,7 @@ LIBOBJ=$(ls "$OBJ"/slam_*.o "$OBJ"/csparse_*.o "$OBJ"/amd_*.o "$OBJ"/camd_*.o)
 rc=0
 for d in "${DRIVERS[@]}"; do
 	EXTRA=""
-	if [ "$d" = "dropin" ] || [ "$d" = "dropin_pose" ] || [ "$d" = "dropin_lm" ]; then # links the product library; found at run time relative to the binary
+	if [ "$d" = "dropin" ] || [ "$d" = "dropin_pose" ] || [ "$d" = "dropin_lm" ] || [ "$d" = "dropin_gn" ]; then # links the product library; found at run time relative to the binary
 		EXTRA="-L$HERE/../slam_plus_plus_b200 -lspp_b200 -Wl,-rpath,\$ORIGIN/../../slam_plus_plus_b200"
 	fi
 	$CXX -fopenmp -o "$OUT/ref_driver_$d" "$OBJ/ref_driver_$d.o" $LIBOBJ -lrt $EXTRA || rc=1

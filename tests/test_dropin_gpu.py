@@ -178,3 +178,60 @@ def test_b200_nonlinear_solver_marginals(name, tmp_path):
     rc, rp, _ = gauge_fit_residual(g.n_cams, cb, pb, cr, pr, weakest_modes(L, 1))
     print(f"{name}: marginals after the gauge fit: cameras {rc:.3g}, points {rp:.3g}")
     assert rc < 1e-4 and rp < 1e-3  # measured 8e-6 / 1.3e-5
+
+
+# ---- slot 3 for pose graphs: CNonlinearSolver_Lambda_B200 in place of the reference's Gauss-Newton solver ------------
+
+BIN_GN = os.path.join(ROOT, "oracle", "_ref", "ref_driver_dropin_gn")
+
+
+@pytest.mark.parametrize("kind,mode", [("se2", "batch"), ("se2", "incremental"), ("se3", "batch"), ("se3", "incremental")])
+def test_reference_pose_system_with_b200_nonlinear_solver(kind, mode, tmp_path):
+    """the UNMODIFIED reference's CFlatSystem of CVertexPose2D/3D + CEdgePose2D/3D with the solver TYPE swapped for
+    CNonlinearSolver_Lambda_B200, against the reference's own CNonlinearSolver_Lambda on the same machine. "incremental"
+    = slam_app's feeding order: edges sorted by their later pose, new poses initialised by the edge constructors on the
+    host, Incremental_Step() after every edge with a nonlinear solve every 10 new vertices once a loop has closed. The
+    marginals policy (mpart_Diagonal) is on: r_MarginalCovariance() is compared as well."""
+    if not os.path.exists(BIN_GN):
+        pytest.skip("oracle/_ref/ref_driver_dropin_gn not built (needs /root/reference at build time)")
+    from slam_plus_plus_b200 import graphs, sppio
+    # SE(3): the graph of the golden se3_tiny (tests/golden/make_golden.py) -- the reference's robust SE(3) Gauss-Newton
+    # does not settle (w^2 / w gradient weights, BaseTypes_Binary.h:820-843): on a sphere with small noise its chi2 after
+    # 5 / 10 / 20 / 40 iterations is 352.4 / 347.5 / 346.6 / 349.1, so only graphs on which it converges can be compared
+    g = (graphs.make_manhattan(300, 150, seed=21) if kind == "se2" else
+         graphs.make_sphere(n_rings=5, n_per_ring=8, seed=3, sigma_t=0.03, sigma_r=0.005, radius=5.0))
+    gp = str(tmp_path / "g.bin")
+    sppio.write_graph(gp, g)
+    env = dict(os.environ, OMP_NUM_THREADS="1", SPP_DROPIN_MARGS="1")
+    out = {}
+    for impl in ("b200", "ref"):
+        dp = str(tmp_path / (impl + ".dump"))
+        subprocess.run([BIN_GN, impl, mode, gp, dp, "5", "0", "10"], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, env=env, cwd=str(tmp_path))
+        out[impl] = sppio.read_dump(dp)
+    b, r = out["b200"], out["ref"]
+    n, dim = g.poses.shape
+    assert int(b["n_vertices"][0]) == int(r["n_vertices"][0]) == n and int(b["n_edges"][0]) == int(r["n_edges"][0])
+    assert len(b["states"]) == len(r["states"]) == n * dim
+    # SE(2): analytic Jacobians, the two runs differ by rounding times the conditioning of the solves; SE(3): forward
+    # differences (delta = 1e-9) on two libm implementations -- the FD noise floor of the other SE(3) tests
+    tol_chi2, tol_state, tol_cov = (1e-9, 1e-7, 1e-6) if kind == "se2" else (1e-5, 1e-4, 1e-3)
+    print(f"{kind} {mode}: chi2 {b['chi2_trace']} vs {r['chi2_trace']}, states {rel_err(b['states'], r['states']):.3g}, "
+          f"cov {rel_err(b['cov'], r['cov']):.3g}")
+    for a, c in zip(b["chi2_trace"], r["chi2_trace"]):
+        assert abs(a - c) <= tol_chi2 * max(c, 1.0)
+    if kind == "se2":
+        assert rel_err(b["states"], r["states"]) < tol_state
+    else:
+        # SE(3): the identity prior on pose 0 against edge information of 1e3 .. 4e4 leaves a rigid motion of the whole
+        # graph almost free (cond 1e10), and an axis-angle vector near pi has two representations: compare what the
+        # edges see, the relative poses of consecutive vertices
+        def relative_poses(st):
+            st = st.reshape(n, 6)
+            R = graphs._axis_angle_to_rotmat(st[:, 3:])
+            return (np.einsum("nji,njk->nik", R[:-1], R[1:]), np.einsum("nji,nj->ni", R[:-1], st[1:, :3] - st[:-1, :3]))
+        (Rb, tb), (Rr, tr) = relative_poses(b["states"]), relative_poses(r["states"])
+        assert np.abs(Rb - Rr).max() < 1e-5 and np.abs(tb - tr).max() < 1e-4  # measured 1e-7 / 1.1e-5 (FD noise floor)
+        print(f"   relative poses: rotation {np.abs(Rb - Rr).max():.3g}, translation {np.abs(tb - tr).max():.3g}")
+    assert b["cov"].shape == r["cov"].shape == (n * dim * dim,)
+    assert rel_err(b["cov"], r["cov"]) < tol_cov
