@@ -131,19 +131,44 @@ class ParsedGraph:
         self.n_switched = 0  # EDGE3 lines with from >= to, which the reference's parser reports and drops
 
 
+def _bulk_numbers(path, lines, line_nos, n_col):
+    """the records of one type that need no per-record arithmetic (landmarks, projections: all but a few thousand lines of
+    a BA file), converted in one pass; numbers beyond the first n_col of a line are ignored, as sscanf does"""
+    if not lines:
+        return np.zeros((0, n_col))
+    a = np.array(" ".join(lines).split(), np.float64)
+    if a.size == len(lines) * n_col:
+        return a.reshape(-1, n_col)
+    rows = np.empty((len(lines), n_col))  # ragged: the slow way, which also finds the truncated line
+    for k, line in enumerate(lines):
+        tok = line.split()
+        if len(tok) < n_col:
+            raise ValueError(f"{path}: line {line_nos[k] + 1}: line is truncated")
+        rows[k] = [float(x) for x in tok[:n_col]]
+    return rows
+
+
 def parse(path) -> ParsedGraph:
     out = ParsedGraph()
+    xyz_lines, xyz_nos, p2c_lines, p2c_nos = [], [], [], []
     with open(path) as f:
         for line_no, line in enumerate(f):
-            tok = line.split()
-            if not tok or tok[0].startswith("#") or tok[0].startswith("%"):
+            head = line.split(None, 1)
+            if not head or head[0].startswith("#") or head[0].startswith("%"):
                 continue
-            name, a = tok[0].upper(), tok[1:]
+            name = head[0].upper()
+            if name == "VERTEX_XYZ":       # bulk records: converted after the loop
+                xyz_lines.append(head[1] if len(head) > 1 else "")
+                xyz_nos.append(line_no)
+                continue
+            if name in _P2C:
+                p2c_lines.append(head[1] if len(head) > 1 else "")
+                p2c_nos.append(line_no)
+                continue
+            a = head[1].split() if len(head) > 1 else []
             try:
                 if name in _V2:
                     out.vertex2d.append((int(a[0]), float(a[1]), float(a[2]), float(a[3])))
-                elif name == "VERTEX_XYZ":
-                    out.vertex_xyz.append((int(a[0]), float(a[1]), float(a[2]), float(a[3])))
                 elif name == "VERTEX_CAM":
                     v = [float(x) for x in a[1:13]]
                     if len(v) != 12:
@@ -192,15 +217,18 @@ def parse(path) -> ParsedGraph:
                             continue
                         z[3:6] = _rpy_to_axis_angle(z[3], z[4], z[5])
                     out.edge3d.append((i0, i1) + tuple(z) + _upper21_to_full(m))
-                elif name in _P2C:
-                    m = [float(x) for x in a[4:7]]
-                    if len(m) != 3:
-                        raise ValueError
-                    out.edge_p2c.append((int(a[0]), int(a[1]), float(a[2]), float(a[3]), m[0], m[1], m[1], m[2]))
                 else:
                     out.n_ignored += 1  # CONSISTENCY_MARKER and the primitives of other problem types
             except (ValueError, IndexError):
                 raise ValueError(f"{path}: line {line_no + 1}: line is truncated") from None
+    try:
+        out.vertex_xyz = _bulk_numbers(path, xyz_lines, xyz_nos, 4)              # (id, x, y, z)
+        e = _bulk_numbers(path, p2c_lines, p2c_nos, 7)                           # ids, z, upper triangle of the 2x2 information
+    except ValueError as err:
+        if "truncated" in str(err):
+            raise
+        raise ValueError(f"{path}: a landmark or projection line does not parse as numbers") from None
+    out.edge_p2c = e[:, [0, 1, 2, 3, 4, 5, 5, 6]]
     return out
 
 
@@ -208,13 +236,16 @@ def load_ba(path) -> BAGraph:
     """A BA file (VERTEX_CAM / VERTEX_XYZ / EDGE_PROJECT_P2MC) as the arrays spp_ba_set_graph takes. Vertex ids must be
     0 .. n-1 (any interleaving of cameras and points); edges keep their file order (= edge insertion order)."""
     p = parse(path)
-    ids = sorted([(v[0], 0, k) for k, v in enumerate(p.vertex_cam)] + [(v[0], 1, k) for k, v in enumerate(p.vertex_xyz)])
-    if [i for i, _, _ in ids] != list(range(len(ids))):
+    cam = np.array(p.vertex_cam, np.float64).reshape(-1, 12)
+    xyz = np.asarray(p.vertex_xyz, np.float64).reshape(-1, 4)
+    ids = np.concatenate([cam[:, 0], xyz[:, 0]]).astype(np.int64)
+    order = np.argsort(ids, kind="stable")
+    if not np.array_equal(ids[order], np.arange(len(ids))):
         raise ValueError(f"{path}: vertex ids must be 0 .. n-1 without gaps or repeats")
-    vtype = np.array([t for _, t, _ in ids], np.int64)
-    cams = np.array([p.vertex_cam[k][1:] for _, t, k in ids if t == 0], np.float64).reshape(-1, 11)
-    pts = np.array([p.vertex_xyz[k][1:] for _, t, k in ids if t == 1], np.float64).reshape(-1, 3)
-    e = np.array(p.edge_p2c, np.float64).reshape(-1, 8)
+    vtype = (order >= len(cam)).astype(np.int64)          # per vertex id: 0 camera, 1 point
+    cams = cam[np.argsort(cam[:, 0], kind="stable"), 1:].copy()
+    pts = xyz[np.argsort(xyz[:, 0], kind="stable"), 1:].copy()
+    e = np.asarray(p.edge_p2c, np.float64).reshape(-1, 8)
     return BAGraph(vtype, cams, pts, e[:, 0].astype(np.int64), e[:, 1].astype(np.int64), e[:, 2:4].copy(),
                    e[:, 4:8].reshape(-1, 2, 2).copy())
 

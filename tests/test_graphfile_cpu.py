@@ -93,3 +93,26 @@ def test_se3_file_round_trip(tmp_path):
     k = graphfile.load_se3(path)
     assert np.max(np.abs(k.z - g.z)) < 1e-14 and np.allclose(k.poses[0], 0)
     assert k.poses.shape == g.poses.shape and np.all(np.isfinite(k.poses))
+
+
+def test_ba_bulk_records_ragged_and_bad(tmp_path):
+    """landmark / projection lines go through a one-pass conversion: trailing extra numbers are ignored (sscanf reads what
+    it needs), a short line is reported with its line number, a non-number is an error"""
+    path = str(tmp_path / "g.txt")
+    with open(path, "w") as f:
+        f.write("VERTEX_CAM 0 0 0 0 0 0 0 1 500 500 320 240 0\n")
+        f.write("VERTEX_XYZ 1 0.5 0.25 4.0 99\n")                       # an extra number
+        f.write("VERTEX_XYZ 2 -0.5 0.25 5.0\n")
+        f.write("EDGE_PROJECT_P2MC 1 0 380.0 270.0 1 0 1\nEDGE_P2C 2 0 270.0 265.0 2 0.5 3 7 7\n")
+    g = graphfile.load_ba(path)
+    assert np.array_equal(g.vtype, [0, 1, 1]) and np.array_equal(g.pts, [[0.5, 0.25, 4.0], [-0.5, 0.25, 5.0]])
+    assert np.array_equal(g.obs_pt, [1, 2]) and np.array_equal(g.obs_cam, [0, 0])
+    assert np.array_equal(g.info[1], [[2, 0.5], [0.5, 3]]) and np.array_equal(g.z, [[380.0, 270.0], [270.0, 265.0]])
+    with open(path, "a") as f:
+        f.write("EDGE_PROJECT_P2MC 2 0 1.0 2.0 1 0\n")                  # line 6 is short
+    with pytest.raises(ValueError, match="line 6"):
+        graphfile.parse(path)
+    with open(path, "w") as f:
+        f.write("VERTEX_XYZ 1 0.5 abc 4.0\n")
+    with pytest.raises(ValueError):
+        graphfile.parse(path)
