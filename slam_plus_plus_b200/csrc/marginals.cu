@@ -40,7 +40,9 @@ __global__ void k_camera_marginals(size_t C, const double *__restrict__ Ni, size
 // warp per landmark: the k^2 (a, b) pairs of its track are dealt to the lanes, every lane adds Y_a^T (S^-1)_ab Y_b to
 // its own 3 x 3 accumulator, a fixed-shape shuffle tree sums the lanes (no atomics: reproducible), lane 0 adds D^-1
 // (Measured alternative: only the k (k + 1) / 2 pairs a <= b with X + X^T for a < b, triangular index decoded per pair --
-// correct, but the whole call went from 13.9 ms to 40 - 70 ms on the Venice shape; not investigated further.)
+// correct, but the whole call went from 13.9 ms to 40 - 70 ms on the Venice shape; the same happened with 16-byte loads of
+// the stored block columns (LDG.128 in the SASS, 22 - 67 ms). Both runs were erratic from call to call, which the kernel
+// alone does not explain; not resolved within the round's GPU budget -- the next step is a per-kernel ncu timing of both.)
 #define PM_WARPS 4
 __global__ void __launch_bounds__(PM_WARPS * 32) k_point_marginals(size_t P, const uint32_t *__restrict__ pt_ptr,
 	const uint32_t *__restrict__ obs_cam, const double *__restrict__ Y, const double *__restrict__ Cinv,
