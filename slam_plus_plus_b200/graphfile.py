@@ -313,6 +313,32 @@ def load_se3(path) -> PoseGraph:
                      e[:, 8:44].reshape(-1, 6, 6).copy())
 
 
+def peek(path, max_lines: int = 1000) -> str:
+    """What kind of graph a file holds -- "ba", "se2" or "se3" -- from the tokens of its first lines: the decision the
+    reference's TDatasetPeeker takes before slam_app picks a system type (include/slam_app/Main.h:780-860: it parses the
+    first 1000 lines and records which kinds of vertices and edges occur)."""
+    seen = set()
+    with open(path) as f:
+        for k, line in enumerate(f):
+            if k >= max_lines:
+                break
+            head = line.split(None, 1)
+            if head and not head[0].startswith(("#", "%")):
+                seen.add(head[0].upper())
+    if seen & (set(_P2C) | {"VERTEX_CAM", "VERTEX_XYZ"}):
+        return "ba"
+    if seen & (set(_V3) | set(_E3) | set(_E3AA)):
+        return "se3"
+    if seen & (set(_V2) | set(_E2)):
+        return "se2"
+    raise ValueError(f"{path}: no vertex or edge token of a supported graph type in the first {max_lines} lines")
+
+
+def load(path):
+    """load_ba / load_se2 / load_se3, chosen by peek()"""
+    return {"ba": load_ba, "se2": load_se2, "se3": load_se3}[peek(path)](path)
+
+
 # ---- writers (synthetic graphs -> the reference's text formats) ------------------------------------------------------
 
 def _axis_angle_to_quat(a):

@@ -116,3 +116,18 @@ def test_ba_bulk_records_ragged_and_bad(tmp_path):
         f.write("VERTEX_XYZ 1 0.5 abc 4.0\n")
     with pytest.raises(ValueError):
         graphfile.parse(path)
+
+
+def test_peek_and_load_pick_the_graph_type(tmp_path):
+    from slam_plus_plus_b200 import sppio
+    kinds = {"parse_ba": "ba", "parse_se2": "se2", "parse_se2_mixed": "se2", "parse_se3": "se3", "parse_se3_mixed": "se3"}
+    for name, kind in kinds.items():
+        assert graphfile.peek(os.path.join(GOLDEN, name + ".txt")) == kind
+    assert isinstance(graphfile.load(os.path.join(GOLDEN, "parse_ba.txt")), sppio.BAGraph)
+    g3 = graphfile.load(os.path.join(GOLDEN, "parse_se3.txt"))
+    assert g3.kind == sppio.GRAPH_SE3 and g3.poses.shape[1] == 6
+    path = str(tmp_path / "x.txt")
+    with open(path, "w") as f:
+        f.write("# nothing here\nEQUIV 1 2\n")
+    with pytest.raises(ValueError):
+        graphfile.peek(path)
