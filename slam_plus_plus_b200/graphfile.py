@@ -315,7 +315,7 @@ def load_se3(path) -> PoseGraph:
 
 def peek(path, max_lines: int = 1000) -> str:
     """What kind of graph a file holds -- "ba", "se2" or "se3" -- from the tokens of its first lines: the decision the
-    reference's TDatasetPeeker takes before slam_app picks a system type (include/slam_app/Main.h:780-860: it parses the
+    reference's TDatasetPeeker takes before slam_app picks a system type (include/slam_app/Main.h:830-900: it parses the
     first 1000 lines and records which kinds of vertices and edges occur)."""
     seen = set()
     with open(path) as f:
