@@ -957,7 +957,7 @@ static int marginals_to_host(spp_ctx *ctx, double alpha, double *p_cam_cov, doub
 	if(!s.C) throw invalid_error("no cameras");
 	if(rcs_is_sparse(ctx, s.C))
 		throw invalid_error("marginals need the dense reduced camera system (6 C <= 16384, or spp_schur_set_rcs_solver(SPP_RCS_DENSE))");
-	DBuf<double> d_cam, d_pt;
+	DBuf<double> &d_cam = s.cov_cam, &d_pt = s.cov_pt;
 	if(p_cam_cov) d_cam.resize(s.C * 36);
 	if(p_pt_cov) d_pt.resize(s.P * 9);
 	int rc = schur_marginals_current(ctx, alpha, p_cam_cov? d_cam.p() : 0, p_pt_cov? d_pt.p() : 0);
@@ -1334,7 +1334,7 @@ int spp_pose_marginals(spp_ctx_t ctx, double *p_cov)
 	if(!p_cov) throw invalid_error("null argument");
 	if(pp.N * pp.dim > 16384) throw invalid_error("pose marginals go through a dense inverse: at most 16384 unknowns");
 	if(!pp.linearised) pose_linearise(ctx);
-	DBuf<double> d_cov;
+	DBuf<double> &d_cov = ctx->sys.cov_cam;
 	d_cov.resize(pp.N * pp.dim * pp.dim);
 	rc = pose_marginals(ctx, d_cov.p());
 	if(rc != SPP_OK) return rc;
