@@ -131,3 +131,41 @@ def test_peek_and_load_pick_the_graph_type(tmp_path):
         f.write("# nothing here\nEQUIV 1 2\n")
     with pytest.raises(ValueError):
         graphfile.peek(path)
+
+
+def test_round_trips_on_random_graphs(tmp_path):
+    """write -> parse round trips on seeded random graphs of the three kinds: ids, measurements and information matrices
+    exact (17 significant digits), states that go through a quaternion or roll-pitch-yaw to rounding"""
+    from slam_plus_plus_b200 import sppio
+    rng = np.random.default_rng(1234)
+    for trial in range(6):
+        # SE(2): random information matrices (symmetric), descending loop closures written as they are in memory
+        g2 = graphs.make_manhattan(int(rng.integers(5, 60)), int(rng.integers(0, 20)), seed=int(rng.integers(1 << 30)))
+        a = rng.normal(size=(len(g2.e_from), 3, 3))
+        g2.info = a @ a.transpose(0, 2, 1) + 3 * np.eye(3)
+        asc = g2.e_from < g2.e_to                                   # descending edges are inverted by the parser (tested above)
+        g2 = sppio.PoseGraph(g2.kind, g2.poses, g2.e_from[asc], g2.e_to[asc], g2.z[asc], g2.info[asc])
+        p2 = str(tmp_path / f"a{trial}.txt")
+        graphfile.write_se2(p2, g2)
+        h2 = graphfile.load(p2)
+        assert np.array_equal(h2.poses, g2.poses) and np.array_equal(h2.e_from, g2.e_from) and np.array_equal(h2.e_to, g2.e_to)
+        assert np.array_equal(h2.z, g2.z) and np.array_equal(h2.info, g2.info)
+        # SE(3)
+        g3 = graphs.make_sphere(int(rng.integers(2, 6)), int(rng.integers(3, 9)), seed=int(rng.integers(1 << 30)), radius=5.0)
+        b = rng.normal(size=(len(g3.e_from), 6, 6))
+        g3.info = b @ b.transpose(0, 2, 1) + 6 * np.eye(6)
+        p3 = str(tmp_path / f"b{trial}.txt")
+        graphfile.write_se3(p3, g3)
+        h3 = graphfile.load(p3)
+        assert np.array_equal(h3.e_from, g3.e_from) and np.array_equal(h3.z, g3.z) and np.array_equal(h3.info, g3.info)
+        R, Rh = graphs._axis_angle_to_rotmat(g3.poses[:, 3:]), graphs._axis_angle_to_rotmat(h3.poses[:, 3:])
+        assert np.array_equal(h3.poses[:, :3], g3.poses[:, :3]) and np.abs(R - Rh).max() < 1e-14   # same rotations
+        # BA
+        gb = graphs.make_ba(int(rng.integers(3, 9)), int(rng.integers(10, 80)), int(rng.integers(1 << 30)),
+                            interleave_ids=bool(trial & 1), shuffle_edges=bool(trial & 2), distortion=float(rng.normal(0, .05)))
+        pb = str(tmp_path / f"c{trial}.txt")
+        graphfile.write_ba(pb, gb)
+        hb = graphfile.load(pb)
+        assert np.array_equal(hb.vtype, gb.vtype) and np.array_equal(hb.obs_pt, gb.obs_pt) and np.array_equal(hb.obs_cam, gb.obs_cam)
+        assert np.array_equal(hb.pts, gb.pts) and np.array_equal(hb.z, gb.z) and np.array_equal(hb.info, gb.info)
+        assert rel_err(hb.cams, gb.cams) < 1e-13
