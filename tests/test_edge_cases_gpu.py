@@ -127,3 +127,30 @@ def test_call_order_errors(ctx):
             c.schur_get_rcs_info()
     finally:
         c.close()
+
+
+def test_ba_set_states_moves_the_linearisation_point(ctx):
+    """spp_ba_set_states (what the slot-3 adapter calls when only the states of an uploaded system changed): chi2,
+    lambda and the marginals afterwards are those of a graph uploaded at the new states, bit for bit; get_states
+    returns what was set; restore_initial goes back to the states of spp_ba_set_graph"""
+    from conftest import load_golden, load_margs_golden
+    g0, d = load_golden("margs_small")            # the graph at its initial states
+    g1, _ = load_margs_golden("margs_small")      # the same graph at the reference's final states
+    ctx.ba_set_graph(g1)
+    chi2_1 = ctx.ba_chi2()
+    ctx.ba_linearise()
+    vals_1 = ctx.ba_get_lambda()[3]
+    ctx.ba_set_graph(g0)
+    chi2_0 = ctx.ba_chi2()
+    assert abs(chi2_1 - d["chi2"][0]) <= 1e-11 * d["chi2"][0] and chi2_0 > chi2_1
+    ctx.ba_set_states(g1.cams[:, :6], g1.pts)
+    assert ctx.ba_chi2() == chi2_1
+    ctx.ba_linearise()
+    assert np.array_equal(ctx.ba_get_lambda()[3], vals_1)
+    cams, pts = ctx.ba_get_states()
+    assert np.array_equal(cams, g1.cams[:, :6]) and np.array_equal(pts, g1.pts)
+    ctx.ba_set_states(None, g0.pts)               # either array may be left alone
+    cams, pts = ctx.ba_get_states()
+    assert np.array_equal(cams, g1.cams[:, :6]) and np.array_equal(pts, g0.pts)
+    ctx.ba_restore_initial()
+    assert ctx.ba_chi2() == chi2_0
