@@ -37,16 +37,14 @@
 #include "slam/IncrementalPolicy.h"  // reference: TIncrementalSolveSetting, TMarginalsComputationPolicy
 #include "slam/Timer.h"              // reference: CTimer
 #include "slam/Marginals.h"          // reference: CMarginalCovariance
+#include "slam/NonlinearSolver_Base.h" // reference: nonlinear_detail::CNonlinearSolver_Base (incremental policy, loop-closure detection)
 #include "spp_b200.h"
-
-#ifndef __SLAM_COUNT_ITERATIONS_AS_VERTICES
-#error "CNonlinearSolver_Lambda_B200 counts the incremental solve periods in vertices (the reference's default)"
-#endif
 
 template <class CSystem, class CLinearSolver, class CAMatrixBlockSizes = typename CSystem::_TyJacobianMatrixBlockList,
 	class CLambdaMatrixBlockSizes = typename CSystem::_TyHessianMatrixBlockList>
-class CNonlinearSolver_Lambda_B200 {
+class CNonlinearSolver_Lambda_B200 : public nonlinear_detail::CNonlinearSolver_Base<CSystem, CLinearSolver, CAMatrixBlockSizes, false, true> {
 public:
+	typedef nonlinear_detail::CNonlinearSolver_Base<CSystem, CLinearSolver, CAMatrixBlockSizes, false, true> _TyBase; /**< @brief the reference's solver base: configuration, marginals cache, t_Incremental_Step() */
 	typedef CSystem _TySystem; /**< @brief system type */
 	typedef CLinearSolver _TyLinearSolver; /**< @brief linear solver type (unused) */
 	typedef typename CSystem::_TyBaseVertex _TyBaseVertex; /**< @brief the data type for storing vertices */
@@ -70,19 +68,16 @@ public:
 	};
 
 protected:
-	CSystem &m_r_system; /**< @brief reference to the system */
-	TIncrementalSolveSetting m_t_incremental_config; /**< @brief incremental solving configuration */
-	TMarginalsComputationPolicy m_t_marginals_config; /**< @brief marginal covariance policy */
-	bool m_b_verbose; /**< @brief verbosity flag */
+	using _TyBase::m_r_system; // the system, the incremental / marginals configuration, the verbosity flag and the marginals
+	using _TyBase::m_t_incremental_config; // cache live in the reference's base class
+	using _TyBase::m_t_marginals_config;
+	using _TyBase::m_b_verbose;
+	using _TyBase::m_marginals;
 	spp_ctx_t m_p_context; /**< @brief device context */
-	size_t m_n_last_optimized_vertex_num; /**< @brief for the vertex-counted solve periods */
-	size_t m_n_prev_vertex_num; /**< @brief vertices before the last edge (loop-closure detection) */
-	bool m_b_had_loop_closure; /**< @brief a loop was closed since the last solve */
 	size_t m_n_iteration_num; /**< @brief linear solves so far */
 	size_t m_n_optimize_num; /**< @brief calls of Optimize() that reached the device */
 	size_t m_n_gathered_edge_num; /**< @brief edges already flattened (edges are immutable once added) */
 	double m_f_device_ms, m_f_upload_time, m_f_optimize_time, m_f_download_time, m_f_marginals_time;
-	CMarginalCovariance m_marginals; /**< @brief marginal covariances (block diagonal) */
 
 	int m_n_dim; /**< @brief 3 (SE(2)) or 6 (SE(3)); 0 until the first vertex is seen */
 	bool m_b_uploaded; /**< @brief the device holds the graph described by the arrays below */
@@ -139,11 +134,10 @@ public:
 	CNonlinearSolver_Lambda_B200(CSystem &r_system,
 		TIncrementalSolveSetting t_incremental_config = TIncrementalSolveSetting(),
 		TMarginalsComputationPolicy t_marginals_config = TMarginalsComputationPolicy(),
-		bool b_verbose = false, CLinearSolver UNUSED(linear_solver) = CLinearSolver(), bool UNUSED(b_use_schur) = false,
+		bool b_verbose = false, CLinearSolver linear_solver = CLinearSolver(), bool UNUSED(b_use_schur) = false,
 		int n_device = 0)
-		:m_r_system(r_system), m_t_incremental_config(t_incremental_config), m_t_marginals_config(t_marginals_config),
-		m_b_verbose(b_verbose), m_p_context(0), m_n_last_optimized_vertex_num(0), m_n_prev_vertex_num(0),
-		m_b_had_loop_closure(false), m_n_iteration_num(0), m_n_optimize_num(0), m_n_gathered_edge_num(0), m_f_device_ms(0),
+		:_TyBase(r_system, t_incremental_config, t_marginals_config, b_verbose, linear_solver, false),
+		m_p_context(0), m_n_iteration_num(0), m_n_optimize_num(0), m_n_gathered_edge_num(0), m_f_device_ms(0),
 		m_f_upload_time(0), m_f_optimize_time(0), m_f_download_time(0), m_f_marginals_time(0), m_n_dim(0),
 		m_b_uploaded(false), m_n_uploaded_vertex_num(0), m_n_uploaded_edge_num(0)
 	{
@@ -157,25 +151,7 @@ public:
 		spp_destroy(m_p_context);
 	}
 
-	inline const TIncrementalSolveSetting &t_IncrementalConfig() const
-	{
-		return m_t_incremental_config;
-	}
-
-	inline const TMarginalsComputationPolicy &t_MarginalsPolicy() const
-	{
-		return m_t_marginals_config;
-	}
-
-	inline CMarginalCovariance &r_MarginalCovariance()
-	{
-		return m_marginals;
-	}
-
-	inline const CMarginalCovariance &r_MarginalCovariance() const
-	{
-		return m_marginals;
-	}
+	// t_IncrementalConfig(), t_MarginalsPolicy(), r_MarginalCovariance(): inherited (NonlinearSolver_Base.h:466-473,740-763)
 
 	/** the device context, e.g. for spp_pose_set_ordering() */
 	inline spp_ctx_t p_Context()
@@ -214,47 +190,17 @@ public:
 		return f_chi2;
 	}
 
-	/** incremental optimization function: CNonlinearSolver_Lambda::Incremental_Step (NonlinearSolver_Lambda.h:334-441) over
-	 *	CNonlinearSolver_Base::t_Incremental_Step (NonlinearSolver_Base.h:557-622) */
-	void Incremental_Step(_TyBaseEdge &UNUSED(r_last_edge)) // throw(std::bad_alloc, std::runtime_error)
+	/** incremental optimization function: CNonlinearSolver_Lambda::Incremental_Step (NonlinearSolver_Lambda.h:334-441) on top
+	 *	of the reference's own period counting and loop-closure detection (the inherited t_Incremental_Step,
+	 *	NonlinearSolver_Base.h:557-622) */
+	void Incremental_Step(_TyBaseEdge &r_last_edge) // throw(std::bad_alloc, std::runtime_error)
 	{
-		const size_t n_vertex_num = m_r_system.r_Vertex_Pool().n_Size();
-		if(!m_b_had_loop_closure) { // b_Detect_LoopClosures, NonlinearSolver_Base.h:502-543
-			typename CSystem::_TyEdgeMultiPool::_TyConstBaseRef r_edge =
-				m_r_system.r_Edge_Pool()[m_r_system.r_Edge_Pool().n_Size() - 1];
-			const size_t n = r_edge.n_Vertex_Num();
-			if(n > 1) {
-				size_t n_first_vertex = r_edge.n_Vertex_Id(0);
-				for(size_t i = 1; i < n; ++ i)
-					n_first_vertex = std::min(n_first_vertex, size_t(r_edge.n_Vertex_Id(i)));
-				m_b_had_loop_closure = n_first_vertex + n < n_vertex_num;
-			} else if(n == 1)
-				m_b_had_loop_closure = r_edge.n_Vertex_Id(0) + 1 < m_n_prev_vertex_num;
-		}
-		m_n_prev_vertex_num = n_vertex_num;
-		const size_t n_new_vertex_num = n_vertex_num - m_n_last_optimized_vertex_num;
-		bool b_new_vert = false;
-		int n_opt_type = 0;
-		if(m_t_incremental_config.t_nonlinear_freq.n_period && n_new_vertex_num >= m_t_incremental_config.t_nonlinear_freq.n_period) {
-			m_n_last_optimized_vertex_num = n_vertex_num;
-			if(m_b_had_loop_closure) {
-				n_opt_type = 2;
-				m_b_had_loop_closure = false;
-			}
-			b_new_vert = true;
-		} else if(m_t_incremental_config.t_linear_freq.n_period && n_new_vertex_num >= m_t_incremental_config.t_linear_freq.n_period) {
-			m_n_last_optimized_vertex_num = n_vertex_num;
-			if(m_b_had_loop_closure) {
-				n_opt_type = 1;
-				m_b_had_loop_closure = false;
-			}
-			b_new_vert = true;
-		}
-		if(n_opt_type == 2)
+		std::pair<bool, int> t_optimize = this->t_Incremental_Step(r_last_edge);
+		if(t_optimize.second == 2)
 			Optimize(m_t_incremental_config.n_max_nonlinear_iteration_num, m_t_incremental_config.f_nonlinear_error_thresh);
-		else if(n_opt_type == 1)
+		else if(t_optimize.second == 1)
 			Optimize(1, 0);
-		if(b_new_vert && !n_opt_type && m_t_marginals_config.b_calculate)
+		if(t_optimize.first && !t_optimize.second && m_t_marginals_config.b_calculate)
 			Optimize(0, 0); // the marginals follow the system (NonlinearSolver_Lambda.h:436-437)
 	}
 

@@ -46,12 +46,14 @@
 #include "slam/IncrementalPolicy.h"  // reference: TIncrementalSolveSetting, TMarginalsComputationPolicy
 #include "slam/Timer.h"              // reference: CTimer
 #include "slam/Marginals.h"          // reference: CMarginalCovariance
+#include "slam/NonlinearSolver_Base.h" // reference: nonlinear_detail::CNonlinearSolver_Base (incremental policy, loop-closure detection)
 #include "spp_b200.h"
 
 template <class CSystem, class CLinearSolver, class CAMatrixBlockSizes = typename CSystem::_TyJacobianMatrixBlockList,
 	class CLambdaMatrixBlockSizes = typename CSystem::_TyHessianMatrixBlockList>
-class CNonlinearSolver_Lambda_LM_B200 {
+class CNonlinearSolver_Lambda_LM_B200 : public nonlinear_detail::CNonlinearSolver_Base<CSystem, CLinearSolver, CAMatrixBlockSizes, false, true> {
 public:
+	typedef nonlinear_detail::CNonlinearSolver_Base<CSystem, CLinearSolver, CAMatrixBlockSizes, false, true> _TyBase; /**< @brief the reference's solver base: configuration, marginals cache, t_Incremental_Step() */
 	typedef CSystem _TySystem; /**< @brief system type */
 	typedef CLinearSolver _TyLinearSolver; /**< @brief linear solver type (unused) */
 	typedef typename CSystem::_TyBaseVertex _TyBaseVertex; /**< @brief the data type for storing vertices */
@@ -75,18 +77,18 @@ public:
 	};
 
 protected:
-	CSystem &m_r_system; /**< @brief reference to the system */
-	TIncrementalSolveSetting m_t_incremental_config; /**< @brief incremental solving configuration */
-	TMarginalsComputationPolicy m_t_marginals_config; /**< @brief marginal covariance policy (must be "do not calculate") */
-	bool m_b_verbose; /**< @brief verbosity flag */
+	using _TyBase::m_r_system; // the system, the incremental / marginals configuration, the verbosity flag and the marginals
+	using _TyBase::m_t_incremental_config; // cache live in the reference's base class
+	using _TyBase::m_t_marginals_config;
+	using _TyBase::m_b_verbose;
+	using _TyBase::m_marginals;
 	spp_ctx_t m_p_context; /**< @brief device context */
-	size_t m_n_last_optimized_vertex_num; /**< @brief for the vertex-counted nonlinear solve period */
 	size_t m_n_iteration_num; /**< @brief linear solves so far */
 	size_t m_n_gathered_edge_num; /**< @brief edges already flattened (edges are immutable once added: only new ones are read) */
 	double m_f_device_ms; /**< @brief device time spent in Optimize() so far */
 	double m_f_upload_time, m_f_optimize_time, m_f_download_time; /**< @brief wall-clock split of Optimize() */
 	double m_f_marginals_time; /**< @brief wall-clock time of the marginals recovery */
-	CMarginalCovariance m_marginals; /**< @brief marginal covariances (block diagonal) */
+	size_t m_n_optimize_num; /**< @brief Optimize() calls that ran the solver (incremental drop-in test: same count as the reference) */
 
 	bool m_b_uploaded; /**< @brief the device holds the system described by the arrays below */
 	std::vector<uint8_t> m_vertex_type, m_prev_vertex_type;
@@ -145,12 +147,12 @@ public:
 	CNonlinearSolver_Lambda_LM_B200(CSystem &r_system,
 		TIncrementalSolveSetting t_incremental_config = TIncrementalSolveSetting(),
 		TMarginalsComputationPolicy t_marginals_config = TMarginalsComputationPolicy(),
-		bool b_verbose = false, CLinearSolver UNUSED(linear_solver) = CLinearSolver(), bool UNUSED(b_use_schur) = true,
+		bool b_verbose = false, CLinearSolver linear_solver = CLinearSolver(), bool UNUSED(b_use_schur) = true,
 		int n_device = 0)
-		:m_r_system(r_system), m_t_incremental_config(t_incremental_config), m_t_marginals_config(t_marginals_config),
-		m_b_verbose(b_verbose), m_p_context(0), m_n_last_optimized_vertex_num(0), m_n_iteration_num(0),
+		:_TyBase(r_system, t_incremental_config, t_marginals_config, b_verbose, linear_solver, false),
+		m_p_context(0), m_n_iteration_num(0),
 		m_n_gathered_edge_num(0), m_f_device_ms(0), m_f_upload_time(0), m_f_optimize_time(0), m_f_download_time(0),
-		m_f_marginals_time(0), m_b_uploaded(false)
+		m_f_marginals_time(0), m_n_optimize_num(0), m_b_uploaded(false)
 	{
 		if(t_marginals_config.b_calculate && t_marginals_config.n_relinearize_policy != mpart_Diagonal)
 			throw std::runtime_error("CNonlinearSolver_Lambda_LM_B200: only the block diagonal of the marginal covariances (mpart_Diagonal) is provided");
@@ -162,25 +164,12 @@ public:
 		spp_destroy(m_p_context);
 	}
 
-	inline const TIncrementalSolveSetting &t_IncrementalConfig() const
-	{
-		return m_t_incremental_config;
-	}
+	// t_IncrementalConfig(), t_MarginalsPolicy(), r_MarginalCovariance(): inherited (NonlinearSolver_Base.h:466-473,740-763)
 
-	inline const TMarginalsComputationPolicy &t_MarginalsPolicy() const
+	/** number of Optimize() calls that ran the LM loop so far */
+	inline size_t n_Optimize_Num() const
 	{
-		return m_t_marginals_config;
-	}
-
-	/** marginal covariances of the last Optimize() (cf. NonlinearSolver_Base.h:750-763) */
-	inline CMarginalCovariance &r_MarginalCovariance()
-	{
-		return m_marginals;
-	}
-
-	inline const CMarginalCovariance &r_MarginalCovariance() const
-	{
-		return m_marginals;
+		return m_n_optimize_num;
 	}
 
 	/** the device context, e.g. for spp_schur_set_rcs_solver() */
@@ -212,15 +201,20 @@ public:
 		return f_chi2;
 	}
 
-	/** incremental optimization function (cf. LM.h:671-760): runs Optimize() when the nonlinear solve period elapses */
-	void Incremental_Step(_TyBaseEdge &UNUSED(r_last_edge)) // throw(std::bad_alloc, std::runtime_error)
+	/** incremental optimization function: CNonlinearSolver_Lambda_LM::Incremental_Step (LM.h:671-760) on top of the
+	 *	reference's own period counting and loop-closure detection (the inherited t_Incremental_Step,
+	 *	NonlinearSolver_Base.h:557-622): a nonlinear solve when the nonlinear period elapsed after a loop closure, a
+	 *	single step (Optimize(1, 0)) for the linear period, marginals only (Optimize(0, 0)) when vertices were added
+	 *	without a solve and the marginals policy is on */
+	void Incremental_Step(_TyBaseEdge &r_last_edge) // throw(std::bad_alloc, std::runtime_error)
 	{
-		const size_t n_vertex_num = m_r_system.r_Vertex_Pool().n_Size();
-		const size_t n_period = m_t_incremental_config.t_nonlinear_freq.n_period;
-		if(n_period && n_vertex_num - m_n_last_optimized_vertex_num >= n_period) {
-			m_n_last_optimized_vertex_num = n_vertex_num;
+		std::pair<bool, int> t_optimize = this->t_Incremental_Step(r_last_edge);
+		if(t_optimize.second == 2)
 			Optimize(m_t_incremental_config.n_max_nonlinear_iteration_num, m_t_incremental_config.f_nonlinear_error_thresh);
-		}
+		else if(t_optimize.second == 1)
+			Optimize(1, 0);
+		if(t_optimize.first && !t_optimize.second && m_t_marginals_config.b_calculate)
+			Optimize(0, 0);
 	}
 
 	/** CNonlinearSolver_Lambda_LM::Optimize (LM.h:796-1116) on the device; the system receives the optimized states */
@@ -232,8 +226,15 @@ public:
 		double f_t0 = timer.f_Time();
 		Upload();
 		double f_t1 = timer.f_Time();
+		if(!n_max_iteration_num) { // Optimize(0, 0): the marginals follow the system, no solve (LM.h:752-754)
+			m_f_upload_time += f_t1 - f_t0;
+			if(m_t_marginals_config.b_calculate)
+				Calculate_Marginals();
+			return;
+		}
 		spp_report_t t_report;
 		Check(spp_ba_optimize(m_p_context, n_max_iteration_num, f_min_dx_norm, &t_report));
+		++ m_n_optimize_num;
 		double f_t2 = timer.f_Time();
 		m_f_upload_time += f_t1 - f_t0;
 		m_f_optimize_time += f_t2 - f_t1;

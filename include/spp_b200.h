@@ -115,7 +115,11 @@ int spp_ba_get_partition(spp_ctx_t ctx, uint64_t *p_begin, uint64_t *p_end);
  *   p_obs_point / p_obs_camera vertex ids of each observation, in edge insertion order       (CEdgeP2C3D, BA_Types.h:403)
  *   p_z[2 * O], p_info[4 * O]  measurement and 2x2 information matrix per observation
  * The first vertex (id 0) receives the reference's automatic unary factor (identity information,
- * FlatSystem.h:337,432-473; Lambda_Base.h:1903-1923). */
+ * FlatSystem.h:337,432-473; Lambda_Base.h:1903-1923).
+ * Restriction: a landmark observed twice by the SAME camera (a duplicate edge) is refused with SPP_ERR_INVALID; the
+ * reference accepts such graphs and sums the two contributions (Lambda_Base.h:682-738). Pose graphs (spp_pose_set_graph)
+ * do accept duplicate edges.
+ * Host pointers are borrowed for the duration of the call, on every exit path. */
 int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_type,
 	const double *p_cam_params, const double *p_points, size_t n_observations,
 	const uint64_t *p_obs_point, const uint64_t *p_obs_camera, const double *p_z, const double *p_info);

@@ -10,8 +10,12 @@
  *                include/slam_app/IncBAParsePrimitives.h:154-168): cameras arrive in id order, a landmark and its
  *                observations are added once two of its cameras are present, Optimize() is called every <batch> cameras
  *                on the SAME system and solver objects (append-only, as the application does)
+ *   periodic     no markers: the solver is built with TIncrementalSolveSetting(solve::nonlinear, frequency::Every(batch),
+ *                max_iter, min_dx) and decides inside Incremental_Step() when to solve (NonlinearSolver_Base.h:557-622);
+ *                the dump lists the edges after which the states changed ("solve_edges"), so the two solver types can be
+ *                compared solve by solve
  *
- * usage: ref_driver_dropin_lm <b200|ref> <batch|incremental> <graph.bin> <out.dump> [max_iter=5] [min_dx=0] [batch=10]
+ * usage: ref_driver_dropin_lm <b200|ref> <batch|incremental|periodic> <graph.bin> <out.dump> [max_iter=5] [min_dx=0] [batch=10]
  */
 
 #include <string.h>
@@ -45,11 +49,14 @@ struct TStates {
 };
 
 template <class CSolver>
-static int Run(const spp_graph_t &g, bool b_incremental, FILE *p_fw, size_t n_max_iter, double f_min_dx, size_t n_batch)
+static int Run(const spp_graph_t &g, bool b_incremental, bool b_periodic, FILE *p_fw, size_t n_max_iter, double f_min_dx, size_t n_batch)
 {
 	CSystemType system;
 	const bool b_marginals = getenv("SPP_DROPIN_MARGS") != 0; // every Optimize() ends with the block diagonal of the covariance
-	CSolver solver(system, TIncrementalSolveSetting(), (b_marginals)? TMarginalsComputationPolicy(true, frequency::Never(),
+	std::vector<uint64_t> solve_edges; // periodic mode: edges after which Incremental_Step() changed the states
+	std::vector<double> last_states;
+	CSolver solver(system, (b_periodic)? TIncrementalSolveSetting(solve::nonlinear, frequency::Every(n_batch), n_max_iter, f_min_dx) :
+		TIncrementalSolveSetting(), (b_marginals)? TMarginalsComputationPolicy(true, frequency::Never(),
 		mpart_Diagonal, mpart_Diagonal) : TMarginalsComputationPolicy(), getenv("SPP_REF_VERBOSE") != 0, CLinearSolverType(), true);
 	std::vector<double> chi2_trace;
 	CTimer timer;
@@ -93,6 +100,7 @@ static int Run(const spp_graph_t &g, bool b_incremental, FILE *p_fw, size_t n_ma
 			for(int j = 0; j < 11; ++ j) v_cam(j) = p[j];
 			new_id[i] = n_next_id;
 			system.r_Get_Vertex<CVertexCam>(n_next_id ++, v_cam);
+			CEdgeP2C3D *p_last_edge = 0;
 			for(size_t k = 0; k < cam_edges[i].size(); ++ k) {
 				const uint64_t e = cam_edges[i][k], pt = g.e0[e];
 				waiting[pt].push_back(e);
@@ -110,11 +118,28 @@ static int Run(const spp_graph_t &g, bool b_incremental, FILE *p_fw, size_t n_ma
 					t_info << g.info[4 * ee], g.info[4 * ee + 1], g.info[4 * ee + 2], g.info[4 * ee + 3];
 					CEdgeP2C3D &r_edge = system.r_Add_Edge(CEdgeP2C3D(new_id[pt], new_id[g.e1[ee]], // (point, camera)
 						Eigen::Vector2d(g.z[2 * ee], g.z[2 * ee + 1]), t_info, system));
-					solver.Incremental_Step(r_edge);
+					if(!b_periodic)
+						solver.Incremental_Step(r_edge);
+					p_last_edge = &r_edge;
 				}
 				waiting[pt].clear();
 			}
-			if((c + 1) % n_batch == 0 || c + 1 == cams.size()) { // CONSISTENCY_MARKER
+			if(b_periodic) {
+				// one Incremental_Step() per camera, after all of its edges (a solve in the middle of a camera's edges would meet
+				// landmarks with a single observation: the reference itself does not survive that)
+				if(p_last_edge) {
+					solver.Incremental_Step(*p_last_edge);
+					TStates now = system.r_Vertex_Pool().For_Each(TStates());
+					bool b_moved = false;
+					for(size_t q = 0; q < last_states.size() && !b_moved; ++ q) // vertices are appended: compare the common prefix
+						b_moved = now.v[q] != last_states[q];
+					if(b_moved)
+						solve_edges.push_back(system.r_Edge_Pool().n_Size() - 1);
+					last_states.swap(now.v);
+				}
+				if(c + 1 == cams.size())
+					chi2_trace.push_back(solver.f_Chi_Squared_Error_Denorm());
+			} else if((c + 1) % n_batch == 0 || c + 1 == cams.size()) { // CONSISTENCY_MARKER
 				double f_start = timer.f_Time();
 				solver.Optimize(n_max_iter, f_min_dx);
 				f_opt_time += timer.f_Time() - f_start;
@@ -131,6 +156,10 @@ static int Run(const spp_graph_t &g, bool b_incremental, FILE *p_fw, size_t n_ma
 	spp_dump_f64(p_fw, "optimize_time", 1, &f_opt_time);
 	spp_dump_u64(p_fw, "n_vertices", 1, &n_vertices);
 	spp_dump_u64(p_fw, "n_edges", 1, &n_edges);
+	if(b_periodic) {
+		uint64_t n_zero = 0;
+		spp_dump_u64(p_fw, "solve_edges", solve_edges.size(), solve_edges.empty()? &n_zero : &solve_edges[0]);
+	}
 	if(b_marginals) { // diagonal blocks in vertex id order, row-major
 		const CUberBlockMatrix &r_m = solver.r_MarginalCovariance().r_SparseMatrix();
 		std::vector<double> cov6, cov3;
@@ -156,7 +185,8 @@ int main(int n_arg_num, const char **p_arg_list)
 		fprintf(stderr, "usage: %s <b200|ref> <batch|incremental> <graph.bin> <out.dump> [max_iter=5] [min_dx=0] [batch=10]\n", p_arg_list[0]);
 		return -1;
 	}
-	const bool b_b200 = !strcmp(p_arg_list[1], "b200"), b_incremental = !strcmp(p_arg_list[2], "incremental");
+	const bool b_b200 = !strcmp(p_arg_list[1], "b200"), b_periodic = !strcmp(p_arg_list[2], "periodic");
+	const bool b_incremental = b_periodic || !strcmp(p_arg_list[2], "incremental");
 	const size_t n_max_iter = (n_arg_num > 5)? atol(p_arg_list[5]) : 5;
 	const double f_min_dx = (n_arg_num > 6)? atof(p_arg_list[6]) : 0.0;
 	const size_t n_batch = (n_arg_num > 7)? atol(p_arg_list[7]) : 10;
@@ -171,9 +201,9 @@ int main(int n_arg_num, const char **p_arg_list)
 	int n_result;
 	try {
 		if(b_b200)
-			n_result = Run<CNonlinearSolver_Lambda_LM_B200<CSystemType, CLinearSolverType> >(g, b_incremental, p_fw, n_max_iter, f_min_dx, n_batch);
+			n_result = Run<CNonlinearSolver_Lambda_LM_B200<CSystemType, CLinearSolverType> >(g, b_incremental, b_periodic, p_fw, n_max_iter, f_min_dx, n_batch);
 		else
-			n_result = Run<CNonlinearSolver_Lambda_LM<CSystemType, CLinearSolverType> >(g, b_incremental, p_fw, n_max_iter, f_min_dx, n_batch);
+			n_result = Run<CNonlinearSolver_Lambda_LM<CSystemType, CLinearSolverType> >(g, b_incremental, b_periodic, p_fw, n_max_iter, f_min_dx, n_batch);
 	} catch(std::exception &r_exc) {
 		fprintf(stderr, "error: %s\n", r_exc.what());
 		n_result = -1;

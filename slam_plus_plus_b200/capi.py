@@ -279,6 +279,18 @@ class Context:
         oc = np.ascontiguousarray(g.obs_cam, np.uint64)
         z = np.ascontiguousarray(g.z, np.float64)
         info = np.ascontiguousarray(g.info, np.float64)
+        # the library reads raw pointers: a mismatched graph must raise here, not read out of bounds there
+        n_c, n_p, n_o = int(np.count_nonzero(vtype == 0)), int(np.count_nonzero(vtype == 1)), int(op.shape[0])
+        if vtype.ndim != 1 or n_c + n_p != vtype.shape[0]:
+            raise ValueError("vtype must be a vector of 0 (camera) / 1 (point)")
+        if cams.shape != (n_c, 11):
+            raise ValueError(f"cams must be ({n_c}, 11): state 6 + intrinsics 5 per type-0 vertex, got {cams.shape}")
+        if pts.shape != (n_p, 3):
+            raise ValueError(f"pts must be ({n_p}, 3), got {pts.shape}")
+        if op.ndim != 1 or oc.shape != (n_o,):
+            raise ValueError("obs_pt and obs_cam must be vectors of the same length")
+        if z.shape != (n_o, 2) or info.shape != (n_o, 2, 2):
+            raise ValueError(f"z must be ({n_o}, 2) and info ({n_o}, 2, 2), got {z.shape} and {info.shape}")
         self._ba_dims = (int(cams.shape[0]), int(pts.shape[0]), int(op.shape[0]), int(vtype.shape[0]))
         self._check(self.lib.spp_ba_set_graph(self.h, vtype.shape[0], _u8p(vtype), _dp(cams), _dp(pts), op.shape[0],
                                               _u64p(op), _u64p(oc), _dp(z), _dp(info)))
@@ -459,6 +471,11 @@ class Context:
         et = np.ascontiguousarray(g.e_to, np.uint64)
         z = np.ascontiguousarray(g.z, np.float64)
         info = np.ascontiguousarray(g.info, np.float64)
+        if poses.ndim != 2 or poses.shape[1] not in (3, 6):
+            raise ValueError(f"poses must be (N, 3) or (N, 6), got {poses.shape}")
+        n_e, dim = int(ef.shape[0]), int(poses.shape[1])
+        if ef.ndim != 1 or et.shape != (n_e,) or z.shape != (n_e, dim) or info.shape != (n_e, dim, dim):
+            raise ValueError(f"e_from / e_to must be vectors of one length E, z (E, {dim}), info (E, {dim}, {dim})")
         self._pose_dims = (int(poses.shape[0]), int(poses.shape[1]))
         self._check(self.lib.spp_pose_set_graph(self.h, poses.shape[1], poses.shape[0], _dp(poses), ef.shape[0], _u64p(ef),
                                                 _u64p(et), _dp(z), _dp(info)))

@@ -579,6 +579,14 @@ int spp_set_allreduce(spp_ctx_t ctx, spp_allreduce_fn fn, void *p_user, int rank
 {
 	if(!ctx || world < 1 || rank < 0 || rank >= world)
 		return SPP_ERR_INVALID;
+	if(rank != ctx->rank || world != ctx->world) {
+		// the landmark partition and the global block list of a resident graph belong to the old (rank, world): a graph
+		// must be set again before anything is solved
+		ctx->ba.valid = false;
+		ctx->snode.valid = false;
+		ctx->slot.valid = false;
+		ctx->sys.n_blocks_global = 0;
+	}
 	ctx->allreduce = fn;
 	ctx->allreduce_user = p_user;
 	ctx->rank = rank;
@@ -591,6 +599,12 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 	const uint64_t *p_obs_point, const uint64_t *p_obs_camera, const double *p_z, const double *p_info)
 {
 	API_BEGIN(ctx)
+	// host pointers are borrowed for the duration of the call: whichever way it is left (an invalid_error thrown by the
+	// analysis included), no copy from the caller's buffers may still be in flight on the side stream
+	struct CopyGuard {
+		spp_ctx *c;
+		~CopyGuard() { if(c->copy_stream) cudaStreamSynchronize(c->copy_stream); }
+	} copy_guard = {ctx};
 	BAProblem &ba = ctx->ba;
 	ba.valid = false;
 	ctx->slot.valid = false;

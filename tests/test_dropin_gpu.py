@@ -140,6 +140,32 @@ def test_reference_system_with_b200_nonlinear_solver(mode, name, tmp_path):
     assert rel_err(b["states"], r["states"]) < 1e-4
 
 
+@pytest.mark.parametrize("name,period", [("ba_small", 6), ("ba_small_hard", 4)])
+def test_b200_nonlinear_solver_incremental_policy(name, period, tmp_path):
+    """no markers: both solver types are built with TIncrementalSolveSetting(solve::nonlinear, frequency::Every(period))
+    and decide inside Incremental_Step() when to solve -- the adapter inherits the reference's own t_Incremental_Step
+    (NonlinearSolver_Base.h:557-622: vertex-counted periods, a solve only after a loop closure). The solves must happen
+    after the same edges, and the final chi2 must agree to the north-star bound."""
+    if not os.path.exists(BIN_LM):
+        pytest.skip("oracle/_ref/ref_driver_dropin_lm not built (needs /root/reference at build time)")
+    from slam_plus_plus_b200 import sppio
+    g, d = load_golden(name)
+    gp = str(tmp_path / "g.bin")
+    sppio.write_graph(gp, g)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = {}
+    for impl in ("b200", "ref"):
+        dp = str(tmp_path / (impl + ".dump"))
+        subprocess.run([BIN_LM, impl, "periodic", gp, dp, "5", "0", str(period)], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, env=env)
+        out[impl] = sppio.read_dump(dp)
+    b, r = out["b200"], out["ref"]
+    assert len(r["solve_edges"]) >= 3
+    assert list(b["solve_edges"]) == list(r["solve_edges"])  # the same solves, after the same edges
+    assert abs(b["chi2_trace"][-1] - r["chi2_trace"][-1]) <= 1e-6 * r["chi2_trace"][-1]
+    assert rel_err(b["states"], r["states"]) < 1e-4
+
+
 @pytest.mark.parametrize("name", ["ba_tiny", "ba_small"])
 def test_b200_nonlinear_solver_marginals(name, tmp_path):
     """the marginals policy of the reference's solver interface (TMarginalsComputationPolicy, mpart_Diagonal) on the
