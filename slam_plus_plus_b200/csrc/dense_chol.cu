@@ -25,6 +25,7 @@
 #include "spp_ctx.h"
 #include <cuda_pipeline_primitives.h>
 #include <stdlib.h>
+#include <algorithm>
 
 namespace spp {
 
@@ -36,6 +37,7 @@ namespace spp {
 #define CH_STAGES 3
 
 #include "potrf128.cuh"
+#include "chol_dataflow.cuh"
 
 static const size_t POTRF_SMEM_EXCLUSIVE = 227 * 1024; // the opt-in maximum per CTA: nothing else fits on the SM
 
@@ -520,6 +522,96 @@ void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols_a
 	}
 }
 
+// ---- persistent dataflow factorisation (chol_dataflow.cuh): host side -----------------------------------
+
+typedef CUresult (*spp_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+	const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// TMA descriptor of a column-major FP64 matrix (n_rows contiguous, n_cols columns ld apart), boxes of box_rows x box_cols,
+// 128-byte swizzle (box_rows = 16 doubles = one 128-byte line per column of the box)
+static void make_tensor_map(CUtensorMap *map, const void *base, size_t n_rows, size_t n_cols, size_t ld, unsigned box_rows, unsigned box_cols)
+{
+	static spp_encode_tiled_fn encode = 0;
+	if(!encode) {
+		void *fn = 0;
+		cudaDriverEntryPointQueryResult q;
+		SPP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+		if(q != cudaDriverEntryPointSuccess || !fn)
+			throw cuda_error("cuTensorMapEncodeTiled is not available from this driver");
+		encode = (spp_encode_tiled_fn)fn;
+	}
+	const cuuint64_t dims[2] = {(cuuint64_t)n_rows, (cuuint64_t)n_cols}, strides[1] = {(cuuint64_t)(ld * sizeof(double))};
+	const cuuint32_t box[2] = {box_rows, box_cols}, elem[2] = {1, 1};
+	CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if(r != CUDA_SUCCESS) {
+		char b[128];
+		snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+		throw cuda_error(b);
+	}
+}
+
+bool dense_chol_dataflow_enabled()
+{
+	const char *e = getenv("SPP_CHOL_DATAFLOW"); // read at every call: tools / tests switch between the two paths in one process
+	return !e || atoi(e) != 0;
+}
+
+// Factorisation of the leading ld x ld upper triangle of A (column-major, ld a multiple of 128) and forward solve of the
+// n_cols - ld columns right of it (a multiple of 64), as dense_chol_factor_panel() without the identity tail, by the
+// persistent dataflow kernel. Rinv / info as there; info = -1 reports the kernel's watchdog. Asynchronous on the
+// context's stream.
+void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_cols, double *Rinv, int *info)
+{
+	DenseChol &ch = ctx->chol;
+	const size_t NB = ld / CH_NB, NJH = n_cols / 64;
+	if(ld % CH_NB || n_cols % 64 || n_cols < ld || NB >= 0x8000 || NJH >= 0x10000)
+		throw invalid_error("dense_chol_factor_dataflow: bad panel shape");
+	cudaStream_t st = ctx->stream;
+	if(!ch.n_sms) {
+		SPP_CUDA(cudaDeviceGetAttribute(&ch.n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+		SPP_CUDA(cudaFuncSetAttribute(k_chol_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)df::SMEM_BYTES));
+	}
+	if(ch.df_nb != NB || ch.df_njh != NJH) { // worker tasks in row-major order: the two diagonal halves, the two halves next to them, the rest
+		std::vector<uint32_t> tasks;
+		for(size_t i = 0; i < NB; ++ i)
+			for(size_t jh = 2 * i; jh < NJH; ++ jh)
+				tasks.push_back((uint32_t)((i << 16) | jh));
+		ch.df_tasks.upload(tasks, st);
+		SPP_CUDA(cudaStreamSynchronize(st)); // the host vector goes out of scope
+		ch.df_nb = NB; ch.df_njh = NJH; ch.df_n_tasks = tasks.size();
+	}
+	if(ch.df_A != A || ch.df_ld != ld || ch.df_cols != n_cols || ch.df_Rinv != Rinv) {
+		make_tensor_map(&ch.df_maps[0], A, ld, n_cols, ld, 16, 128);
+		make_tensor_map(&ch.df_maps[1], A, ld, n_cols, ld, 16, 64);
+		make_tensor_map(&ch.df_maps[2], A, ld, n_cols, ld, 16, 16);
+		make_tensor_map(&ch.df_maps[3], Rinv, CH_NB, NB * CH_NB, CH_NB, 16, 128);
+		ch.df_A = A; ch.df_ld = ld; ch.df_cols = n_cols; ch.df_Rinv = Rinv;
+	}
+	const size_t n_flags = 4 + 3 * NB + 2 * NB * NJH;
+	ch.df_flags.resize(n_flags);
+	SPP_CUDA(cudaMemsetAsync(ch.df_flags.p(), 0, n_flags * sizeof(int), st));
+	df::Args args;
+	args.A = A; args.Rinv = Rinv; args.info = info; args.flags = ch.df_flags.p(); args.tasks = ch.df_tasks.p();
+	args.ld = ld; args.NB = (int)NB; args.NJH = (int)NJH; args.n_tasks = (int)ch.df_n_tasks;
+	const size_t n_ctas = std::min((size_t)ch.n_sms, 1 + df::G + ch.df_n_tasks);
+	static const bool timing = getenv("SPP_CHOL_TIMING") != 0;
+	if(timing)
+		SPP_CUDA(cudaEventRecord(ctx->ev[4], st));
+	k_chol_dataflow<<<(unsigned)n_ctas, df::THREADS, df::SMEM_BYTES, st>>>(ch.df_maps[0], ch.df_maps[1], ch.df_maps[2], ch.df_maps[3], args);
+	LAUNCH_CHECK(ctx);
+	if(timing) {
+		SPP_CUDA(cudaEventRecord(ctx->ev[5], st));
+		SPP_CUDA(cudaEventSynchronize(ctx->ev[5]));
+		float ms;
+		cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+		int h[3];
+		cudaMemcpy(h, ch.df_flags.p(), sizeof(h), cudaMemcpyDeviceToHost);
+		fprintf(stderr, "[spp chol dataflow] ld %zu, %zu tile columns: %.3f ms = %.2f TFLOP/s (tasks taken %d, roles %d, watchdog %d)\n", ld, NJH,
+			ms, (double)ld * ld * ld / 3 / ms * 1e-9, h[0], h[1], h[2]);
+	}
+}
+
 // The same for a panel with ONE diagonal block (ld == 128) on a stream of the caller's choice: the diagonal-block
 // kernel and the solve of the block row, no look-ahead needed -- the supernodal factorisation runs its many narrow
 // supernodes side by side with this.
@@ -563,9 +655,26 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 	double *rhs_col = A + ld * ld; // first column of the rhs block
 	k_copy_rhs<<<n_blocks(n, 256), 256, 0, st>>>(rhs_col, d_rhs_x, n);
 	LAUNCH_CHECK(ctx);
-	dense_chol_factor_panel(ctx, A, ld, ld + CH_NB, ch.work.p(), ch.info.p(), false);
+	static const bool timing = getenv("SPP_CHOL_TIMING") != 0;
+	if(timing)
+		SPP_CUDA(cudaEventRecord(ctx->ev[6], st));
+	if(dense_chol_dataflow_enabled()) // only the first 64 columns of the right-hand-side block are looked at
+		dense_chol_factor_dataflow(ctx, A, ld, ld + 64, ch.work.p(), ch.info.p());
+	else
+		dense_chol_factor_panel(ctx, A, ld, ld + CH_NB, ch.work.p(), ch.info.p(), false);
+	if(timing)
+		SPP_CUDA(cudaEventRecord(ctx->ev[7], st));
 	k_backsolve<<<(unsigned)n_blk, 256, 0, st>>>(A, ld, n_blk, ch.work.p(), rhs_col, ch.info.p() + 1);
 	LAUNCH_CHECK(ctx);
+	if(timing) {
+		SPP_CUDA(cudaEventRecord(ctx->ev[8], st));
+		SPP_CUDA(cudaEventSynchronize(ctx->ev[8]));
+		float ms_f, ms_b;
+		cudaEventElapsedTime(&ms_f, ctx->ev[6], ctx->ev[7]);
+		cudaEventElapsedTime(&ms_b, ctx->ev[7], ctx->ev[8]);
+		fprintf(stderr, "[spp chol timing] n %zu: factor %.3f ms (%.2f TFLOP/s), backward solve %.3f ms\n", n, ms_f,
+			(double)n * n * n / 3 / ms_f * 1e-9, ms_b);
+	}
 	k_copy_rhs<<<n_blocks(n, 256), 256, 0, st>>>(d_rhs_x, rhs_col, n);
 	LAUNCH_CHECK(ctx);
 	if(ctx->async_mode && ctx->async_info) { // the caller synchronises later and reads the status there
@@ -576,6 +685,8 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 	int *h_info = reinterpret_cast<int*>(ctx->h_scalars.p());
 	SPP_CUDA(cudaMemcpyAsync(h_info, ch.info.p(), sizeof(int), cudaMemcpyDeviceToHost, st));
 	SPP_CUDA(cudaStreamSynchronize(st));
+	if(*h_info < 0)
+		throw cuda_error("dense Cholesky: the dataflow kernel's watchdog fired (a tile flag never arrived)");
 	return (*h_info == 0)? SPP_OK : SPP_NOT_POSDEF;
 }
 

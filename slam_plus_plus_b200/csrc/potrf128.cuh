@@ -21,6 +21,9 @@
 #define P3_LD 132
 #define PT 256              // threads of k_potrf128
 #define PW (PT / 32)
+// barrier of the PT threads that factor the block: the persistent dataflow kernel (chol_dataflow.cuh) runs this body in
+// a CTA that has one more (producer) warp, which does not take part
+#define POTRF_SYNC() asm volatile("bar.sync 0, 256;" ::: "memory")
 
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
 {
@@ -73,7 +76,7 @@ __device__ __forceinline__ void inv_level(double *__restrict__ sm, int warp, int
 			for(int q = 0; q < NH; ++ q)
 				dmma_m8n8k4(c0[1][q], c1[1][q], pA[k * P3_LD + q * 8], bhi);
 		}
-		__syncthreads();
+		POTRF_SYNC();
 		#pragma unroll
 		for(int u = (TH >= 2)? 0 : 1; u < 2; ++ u) {
 			#pragma unroll
@@ -83,7 +86,7 @@ __device__ __forceinline__ void inv_level(double *__restrict__ sm, int warp, int
 				pc[P3_LD] = c1[u][q];
 			}
 		}
-		__syncthreads();
+		POTRF_SYNC();
 	}
 	{
 		#pragma unroll
@@ -112,7 +115,7 @@ __device__ __forceinline__ void inv_level(double *__restrict__ sm, int warp, int
 				dmma_m8n8k4(c0[1][q], c1[1][q], ahi, bv);
 			}
 		}
-		__syncthreads();
+		POTRF_SYNC();
 		#pragma unroll
 		for(int u = (TH >= 2)? 0 : 1; u < 2; ++ u) {
 			#pragma unroll
@@ -122,7 +125,7 @@ __device__ __forceinline__ void inv_level(double *__restrict__ sm, int warp, int
 				pc[P3_LD] = -c1[u][q];
 			}
 		}
-		__syncthreads();
+		POTRF_SYNC();
 	}
 }
 
@@ -234,8 +237,13 @@ __device__ __forceinline__ void lazy_update(double *__restrict__ sm, int k0, int
 	}
 }
 
-__global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size_t ld, size_t k0,
-	double *__restrict__ Rinv_out, int *__restrict__ info, long long *__restrict__ dbg)
+// The body: factors the 128 x 128 block at Akk (leading dimension ld) in place (upper triangle), writes the inverse of
+// the factor to Rinv_out; a non-positive pivot is reported as *info = n_info_value (first report wins). All PT threads of
+// the CTA take part; the whole dynamic shared memory of the CTA is the work tile. Ends with global stores: the caller
+// fences / synchronises before anyone else may read them. Shared between the one-block kernel below and the persistent
+// chain kernel of the dataflow factorisation (chol_dataflow.cu).
+__device__ __forceinline__ void potrf128_block(double *__restrict__ Akk, size_t ld,
+	double *__restrict__ Rinv_out, int *__restrict__ info, int n_info_value, long long *__restrict__ dbg)
 {
 #define DBG_MARK(i) do { if(dbg && threadIdx.x == 0) dbg[i] = clock64(); } while(0)
 #ifdef POTRF_TRACE // per-warp time stamps for tools/micro/potrf_bench.cu: dbg[16 + warp * 64 + i]
@@ -248,7 +256,6 @@ __global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size
 	double *rdv = sm + P3_LD * CH_NB;        // 128 reciprocal pivots
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int g = lane >> 2, t = lane & 3;
-	double *Akk = A + k0 * ld + k0;
 	DBG_MARK(0);
 	// the upper 8 x 8 tiles, whole tile columns with 16-byte async copies
 	for(int idx = tid; idx < CH_NB * (CH_NB / 2); idx += PT) {
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size
 	}
 	__pipeline_commit();
 	__pipeline_wait_prior(0);
-	__syncthreads();
+	POTRF_SYNC();
 	DBG_MARK(1);
 
 	bool bad = false;
@@ -340,7 +347,7 @@ __global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size
 			lazy_update(sm, o - 8, s + 1, warp - 4, g, t);
 			if(s == 2 || s == 4) TR(s * 8 + 3);
 		}
-		__syncthreads();
+		POTRF_SYNC();
 		if(s == 2 || s == 4) TR(s * 8 + 4);
 		if(s == 0) DBG_MARK(2);
 		if(s == 1) DBG_MARK(3);
@@ -352,10 +359,10 @@ __global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size
 		for(int j = 0; j < 8; j += 2)
 			*reinterpret_cast<double2*>(rdv + 120 + j) = make_double2(rd[j], rd[j + 1]);
 	}
-	__syncthreads();
+	POTRF_SYNC();
 	DBG_MARK(5);
 	if(bad && tid == 0 && *info == 0)
-		*info = int(k0) + 1;
+		*info = n_info_value;
 	// R to global
 	#pragma unroll 8
 	for(int idx = tid; idx < CH_NB * CH_NB; idx += PT) {
@@ -394,13 +401,13 @@ __global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size
 			}
 		}
 		TR(40);
-		__syncthreads(); // every R leaf has been read and stored to global
+		POTRF_SYNC(); // every R leaf has been read and stored to global
 		TR(41);
 		if(!(lane & 15))
 			store_leaf<true>(&TC(o, o), x);
 		TR(47);
 	}
-	__syncthreads();
+	POTRF_SYNC();
 	TR(42);
 	inv_level<8>(sm, warp, g, t);
 	TR(43);
@@ -422,6 +429,12 @@ __global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size
 #undef TC
 #undef DBG_MARK
 #undef TR
+}
+
+__global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size_t ld, size_t k0,
+	double *__restrict__ Rinv_out, int *__restrict__ info, long long *__restrict__ dbg)
+{
+	potrf128_block(A + k0 * ld + k0, ld, Rinv_out, info, int(k0) + 1, dbg);
 }
 
 static const size_t POTRF_SMEM = (size_t)(P3_LD * CH_NB + CH_NB) * sizeof(double);

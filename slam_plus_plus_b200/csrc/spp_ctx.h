@@ -3,6 +3,7 @@
 
 #include "spp_common.cuh"
 #include "block_ordering.h"
+#include <cuda.h> // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace spp {
 
@@ -189,7 +190,16 @@ struct DenseChol {
 	bool profile;             // SPP_CHOL_PROFILE: serialised per-kernel timing to stderr
 	bool potrf_exclusive;     // the diagonal-block kernel takes a whole SM (default; SPP_CHOL_SHARED_SM turns it off)
 	int force_tile;           // SPP_CHOL_TILE: force the bulk tile shape (0: 128x128, 1: 128x64, 2: 64x64)
-	DenseChol() : bulk_stream(0), row_stream(0), profile(false), potrf_exclusive(true), force_tile(-1) {}
+	// persistent dataflow factorisation (chol_dataflow.cuh)
+	DBuf<int> df_flags;       // task / role counters, watchdog, tile flags (zeroed before every launch)
+	DBuf<uint32_t> df_tasks;  // worker task list of the (df_nb, df_njh) shape
+	size_t df_nb, df_njh, df_n_tasks;
+	CUtensorMap df_maps[4];   // TMA descriptors of (df_A, df_ld, df_cols) and df_Rinv
+	const void *df_A, *df_Rinv;
+	size_t df_ld, df_cols;
+	int n_sms;
+	DenseChol() : bulk_stream(0), row_stream(0), profile(false), potrf_exclusive(true), force_tile(-1), df_nb(0), df_njh(0),
+		df_n_tasks(0), df_A(0), df_Rinv(0), df_ld(0), df_cols(0), n_sms(0) {}
 };
 
 } // namespace spp
