@@ -25,8 +25,9 @@
 // mma.sync.m8n8k4.f64 (tcgen05 has no FP64 kind). Within a 16-long K chunk a thread feeds the k values
 // 8 (t >> 1) + 2 s + (t & 1), s = 0..3: with the TMA swizzle every fragment load is bank-conflict free.
 // Every tile is summed in a fixed order (k ascending): bit-reproducible whatever the schedule.
-// Inter-CTA hand-off: plain stores, __threadfence, CTA barrier, st.release / red.release of a flag; the reader spins
-// with ld.acquire and issues fence.proxy.async before its TMA loads. A watchdog turns a wait that never ends (a bug, not
+// Inter-CTA hand-off: plain stores, CTA barrier, then one thread's st.release / red.release of a flag (cumulative over
+// the barrier, as in a cooperative-groups grid barrier); the reader spins with ld.acquire and issues fence.proxy.async
+// before its TMA loads. A watchdog turns a wait that never ends (a bug, not
 // a data condition) into an error instead of a hung device.
 #pragma once
 #include <cuda.h>
@@ -53,7 +54,15 @@ struct Args {
 	const uint32_t *tasks;   // worker tasks: (i << 16) | half-tile column
 	unsigned long long ld;
 	int NB, NJH, n_tasks;
+	unsigned long long *dbg; // SPP_CHOL_TIMING: time stamps (ns) of the chain, wait cycles of the workers; null otherwise
 };
+
+__device__ __forceinline__ unsigned long long gtime()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
@@ -190,13 +199,16 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 					wait_ge(dcnt + i, G, f_abort, 1000 + i);
 				POTRF_SYNC();
 			}
+			if(p.dbg && tid == 0)
+				p.dbg[i] = gtime();
 			potrf128_block(p.A + ((size_t)i * CH_NB) * ld + (size_t)i * CH_NB, ld, p.Rinv + (size_t)i * (CH_NB * CH_NB), p.info,
 				i * CH_NB + 1, 0);
-			__threadfence();
 			POTRF_SYNC();
 			if(tid == 0) {
 				fence_proxy_async();
 				st_release(f2 + i, 1);
+				if(p.dbg)
+					p.dbg[NB + i] = gtime();
 			}
 		}
 		if(tid == 0 && ld_relaxed(f_abort))
@@ -278,11 +290,12 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 						out1[(size_t)(8 * b) * ld + 8 * a] = acc[a][b][0];
 						out1[(size_t)(8 * b + 1) * ld + 8 * a] = acc[a][b][1];
 					}
-				__threadfence();
 				bar_consumers();
 				if(tid == 0) {
 					fence_proxy_async();
 					red_release_add(h1cnt + i, 1);
+					if(p.dbg && h == 0)
+						p.dbg[2 * NB + i] = gtime();
 				}
 			}
 			{ // H2: D(i+1)(:, slice) = T(i+1, i+1)(:, slice) - R(i, i+1)^T R(i, i+1)(:, slice), rows above the diagonal: warps <= h
@@ -314,10 +327,12 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 							out2[(size_t)(8 * b + 1) * ld + 8 * a] = c_in[a][b][1] + acc[a][b][1];
 						}
 				}
-				__threadfence();
 				bar_consumers();
-				if(tid == 0)
+				if(tid == 0) {
 					red_release_add(dcnt + i + 1, 1);
+					if(p.dbg && h == 0)
+						p.dbg[3 * NB + i] = gtime();
+				}
 			}
 		}
 		return;
@@ -327,6 +342,7 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 	if(warp == 8) {
 		if(lane != 0)
 			return;
+		long long t_flags = 0, t_trsm = 0; // cycles spent waiting for operand flags / for the diagonal block
 		for(uint32_t tn = 0;; ++ tn) {
 			const uint32_t e = tn & 1;
 			if(tn >= 2)
@@ -335,12 +351,18 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 			const uint32_t code = (tk < p.n_tasks)? p.tasks[tk] : 0xffffffffu;
 			s_task[e] = code;
 			mbar_arrive(bar_tfull + 8 * e);
-			if(code == 0xffffffffu)
+			if(code == 0xffffffffu) {
+				if(p.dbg) {
+					unsigned long long *d = p.dbg + 4 * NB + 8 * blockIdx.x;
+					d[0] = (unsigned long long)t_flags; d[1] = (unsigned long long)t_trsm; d[2] = tn; d[3] = gtime();
+				}
 				return;
+			}
 			const int i = int(code >> 16), jh = int(code & 0xffff), j = jh >> 1;
 			const bool partial = j == i || (j == i + 1 && j < NB);
 			const int kmax = (j == i)? ((i > 0)? i - 1 : 0) : i;
 			for(int k = 0; k < kmax; ++ k) {
+				const long long c0 = clock64();
 				// operands of slab k: R(k, i) (both halves) and R(k, half jh); a tile next to the diagonal comes from the helpers
 				if(i == k + 1)
 					wait_ge(h1cnt + k, G, f_abort, 6000 + k);
@@ -354,6 +376,7 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 					else
 						wait_ge(rdy + (size_t)k * NJH + jh, 1, f_abort, 9000 + k);
 				}
+				t_flags += clock64() - c0;
 				fence_proxy_async();
 				for(int c = 0; c < 8; ++ c, ++ cnt) {
 					const uint32_t st = cnt % STAGES, use = cnt / STAGES;
@@ -366,7 +389,9 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 				}
 			}
 			if(!partial) {
+				const long long c0 = clock64();
 				wait_ge(f2 + i, 1, f_abort, 10000 + i);
+				t_trsm += clock64() - c0;
 				fence_proxy_async();
 				for(int c = 0; c < 8; ++ c, ++ cnt) {
 					const uint32_t st = cnt % STAGES, use = cnt / STAGES;
@@ -381,6 +406,7 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 
 	const int wi = (warp >> 1) * 32, wj = (warp & 1) * 32; // 4 x 2 warps of 32 x 32 over the 128 x 64 tile
 	const uint32_t a_off = (uint32_t)((wi + g) * 128 + (t & 1) * 8), b_off = (uint32_t)((wj + g) * 128 + (t & 1) * 8);
+	long long t_pipe = 0, t_start = clock64(); // cycles this warp waited for operand chunks
 	for(uint32_t tn = 0;; ++ tn) {
 		const uint32_t e = tn & 1;
 		mbar_wait(bar_tfull + 8 * e, (tn >> 1) & 1, f_abort);
@@ -388,8 +414,13 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 		__syncwarp();
 		if(lane == 0)
 			mbar_arrive(bar_tempty + 8 * e);
-		if(code == 0xffffffffu || ld_relaxed(f_abort))
+		if(code == 0xffffffffu) {
+			if(p.dbg && tid == 0) {
+				unsigned long long *d = p.dbg + 4 * NB + 8 * blockIdx.x;
+				d[4] = (unsigned long long)t_pipe; d[5] = (unsigned long long)(clock64() - t_start);
+			}
 			return;
+		}
 		const int i = int(code >> 16), jh = int(code & 0xffff), j = jh >> 1;
 		const bool partial = j == i || (j == i + 1 && j < NB);
 		const int kmax = (j == i)? ((i > 0)? i - 1 : 0) : i;
@@ -405,7 +436,9 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 			}
 		for(int c = 0; c < 8 * kmax; ++ c, ++ cnt) {
 			const uint32_t st = cnt % STAGES, use = cnt / STAGES;
+			const long long c0 = clock64();
 			mbar_wait(bar_full + 8 * st, use & 1, f_abort);
+			t_pipe += clock64() - c0;
 			mma_chunk<4, 4, true>(acc, base + st * STAGE_BYTES + a_off, base + st * STAGE_BYTES + A_BYTES + b_off, g, t);
 			__syncwarp();
 			if(lane == 0)
@@ -420,7 +453,6 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 						out[(size_t)(8 * b) * ld + 8 * a] = acc[a][b][0];
 						out[(size_t)(8 * b + 1) * ld + 8 * a] = acc[a][b][1];
 					}
-				__threadfence();
 			}
 			bar_consumers();
 			if(tid == 0) {
@@ -451,7 +483,9 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 				acc[a][b][0] = acc[a][b][1] = 0;
 		for(int c = 0; c < 8; ++ c, ++ cnt) { // R(i, half) = Rinv(i)^T T; Rinv(k, m) = 0 for k > m
 			const uint32_t st = cnt % STAGES, use = cnt / STAGES;
+			const long long c0 = clock64();
 			mbar_wait(bar_full + 8 * st, use & 1, f_abort);
+			t_pipe += clock64() - c0;
 			if(16 * c <= wi + 31)
 				mma_chunk<4, 4, false>(acc, base + st * STAGE_BYTES + a_off, base + STAGING_OFF + c * 8192 + b_off, g, t);
 			__syncwarp();
@@ -465,7 +499,6 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 				out[(size_t)(8 * b) * ld + 8 * a] = acc[a][b][0];
 				out[(size_t)(8 * b + 1) * ld + 8 * a] = acc[a][b][1];
 			}
-		__threadfence();
 		bar_consumers();
 		if(tid == 0) {
 			fence_proxy_async();

@@ -166,16 +166,27 @@ constexpr size_t gemm_smem() { return (size_t)STAGES * (BM + BN) * CH_LDS * size
 
 // ---- backward solve R x = y ---------------------------------------------------------------------------
 
-// One CTA per block row (blockIdx 0 = last block row), 256 threads: thread (r, h) owns row r, column half h.
+// One CTA per block row (blockIdx 0 = last block row), 256 threads: thread (r, h) owns row r, column half h. The chain
+// x_j -> block row j - 1 -> x_{j-1} is all latency: the CTA's own inverse diagonal block waits in shared memory, the
+// matrix entries of the next step are fetched before the flag is polled, and one thread publishes (release) after
+// the CTA barrier.
 __global__ void __launch_bounds__(256) k_backsolve(const double *__restrict__ A, size_t ld, size_t n_blk,
-	const double *__restrict__ Rinv, double *__restrict__ y /* in: y, out: x */, volatile int *flags)
+	const double *__restrict__ Rinv, double *y /* in: y, out: x */, int *flags)
 {
-	__shared__ double xs[CH_NB];
+	extern __shared__ __align__(16) double ri_s[]; // Rinv_ii, column-major 128 x 128
+	__shared__ double xs[2][CH_NB];
 	__shared__ double part[2][CH_NB];
 	const size_t bi = n_blk - 1 - blockIdx.x;
 	const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
+	{
+		const double *Ri = Rinv + bi * (size_t)(CH_NB * CH_NB);
+		for(int idx = threadIdx.x; idx < CH_NB * CH_NB / 2; idx += 256)
+			__pipeline_memcpy_async(ri_s + 2 * idx, Ri + 2 * idx, 16);
+		__pipeline_commit();
+	}
 	double acc = (h == 0)? y[bi * CH_NB + r] : 0.0;
-	for(size_t bj = n_blk - 1; bj > bi; -- bj) {
+	int p = 0;
+	for(size_t bj = n_blk - 1; bj > bi; -- bj, p ^= 1) {
 		// the 64 matrix entries of this thread do not depend on x_j: fetch them before waiting
 		const double *row = A + (bj * CH_NB + h * 64) * ld + bi * CH_NB + r;
 		double m[64];
@@ -183,49 +194,49 @@ __global__ void __launch_bounds__(256) k_backsolve(const double *__restrict__ A,
 		for(int c = 0; c < 64; ++ c)
 			m[c] = __ldg(row + (size_t)c * ld);
 		if(threadIdx.x == 0) {
-			while(flags[bj] == 0)
+			while(df::ld_acquire(flags + bj) == 0)
 				;
-			__threadfence();
 		}
 		__syncthreads();
 		if(threadIdx.x < CH_NB)
-			xs[threadIdx.x] = ((volatile double*)y)[bj * CH_NB + threadIdx.x];
+			xs[p][threadIdx.x] = __ldcg(y + bj * CH_NB + threadIdx.x);
 		__syncthreads();
 		double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 		#pragma unroll
 		for(int c = 0; c < 64; c += 4) {
-			s0 += m[c] * xs[h * 64 + c];
-			s1 += m[c + 1] * xs[h * 64 + c + 1];
-			s2 += m[c + 2] * xs[h * 64 + c + 2];
-			s3 += m[c + 3] * xs[h * 64 + c + 3];
+			s0 += m[c] * xs[p][h * 64 + c];
+			s1 += m[c + 1] * xs[p][h * 64 + c + 1];
+			s2 += m[c + 2] * xs[p][h * 64 + c + 2];
+			s3 += m[c + 3] * xs[p][h * 64 + c + 3];
 		}
 		acc -= (s0 + s1) + (s2 + s3);
-		__syncthreads();
 	}
+	__pipeline_wait_prior(0);
 	part[h][r] = acc;
 	__syncthreads();
 	if(threadIdx.x < CH_NB)
-		xs[threadIdx.x] = part[0][threadIdx.x] + part[1][threadIdx.x];
+		xs[p][threadIdx.x] = part[0][threadIdx.x] + part[1][threadIdx.x];
 	__syncthreads();
-	// x_i = Rinv_ii (upper triangular) * acc
-	const double *Ri = Rinv + bi * (size_t)(CH_NB * CH_NB);
-	double s0 = 0, s1 = 0;
-	#pragma unroll 8
-	for(int c = h * 64; c < h * 64 + 64; c += 2) {
-		s0 += Ri[(size_t)c * CH_NB + r] * xs[c];
-		s1 += Ri[(size_t)(c + 1) * CH_NB + r] * xs[c + 1];
+	// x_i = Rinv_ii (upper triangular, zeros stored below the diagonal) * acc
+	double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+	#pragma unroll 4
+	for(int c = h * 64; c < h * 64 + 64; c += 4) {
+		s0 += ri_s[c * CH_NB + r] * xs[p][c];
+		s1 += ri_s[(c + 1) * CH_NB + r] * xs[p][c + 1];
+		s2 += ri_s[(c + 2) * CH_NB + r] * xs[p][c + 2];
+		s3 += ri_s[(c + 3) * CH_NB + r] * xs[p][c + 3];
 	}
 	__syncthreads();
-	part[h][r] = s0 + s1;
+	part[h][r] = (s0 + s1) + (s2 + s3);
 	__syncthreads();
-	if(threadIdx.x < CH_NB) {
+	if(threadIdx.x < CH_NB)
 		y[bi * CH_NB + threadIdx.x] = part[0][threadIdx.x] + part[1][threadIdx.x];
-		__threadfence();
-	}
 	__syncthreads();
 	if(threadIdx.x == 0)
-		flags[bi] = 1;
+		df::st_release(flags + bi, 1);
 }
+
+static const size_t BACKSOLVE_SMEM = (size_t)CH_NB * CH_NB * sizeof(double);
 
 __global__ void k_pad_identity(double *__restrict__ A, size_t ld, size_t n, size_t n_pad)
 {
@@ -260,6 +271,7 @@ static void chol_init_attributes(int device)
 	static bool done[64] = {false}; // the attribute belongs to the (kernel, device) pair
 	if(device < 0 || device >= 64 || done[device]) return;
 	SPP_CUDA(cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM_EXCLUSIVE));
+	SPP_CUDA(cudaFuncSetAttribute(k_backsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACKSOLVE_SMEM));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 128>()));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128, 64>()));
 	SPP_CUDA(cudaFuncSetAttribute(k_gemm_tn<GEMM_SYRK, 64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64, 64>()));
@@ -572,11 +584,29 @@ void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_col
 		SPP_CUDA(cudaDeviceGetAttribute(&ch.n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
 		SPP_CUDA(cudaFuncSetAttribute(k_chol_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)df::SMEM_BYTES));
 	}
-	if(ch.df_nb != NB || ch.df_njh != NJH) { // worker tasks in row-major order: the two diagonal halves, the two halves next to them, the rest
+	if(ch.df_nb != NB || ch.df_njh != NJH) {
+		// Worker tasks sorted by the key  i + (j - i) / beta  (row i, tile column j): row-major order with the tiles far from the
+		// diagonal pushed back behind the near-diagonal tiles of the following rows, which the critical chain needs first. Any
+		// beta > 1 keeps the order topological (a tile's operands (k, i), (k, j), k < i, have smaller keys). The partial sums
+		// of the four half tiles on the chain itself (the diagonal tile and the tile right of it) are queued `lead` rows early:
+		// a worker that takes them follows the factorisation slab by slab and is one slab away from done when the chain gets
+		// there (their operands come later in the queue: fine as long as there are more workers than 4 (lead + 1) open chain
+		// tasks; a starved launch ends in the watchdog, not in a hang).
+		static const int lead = getenv("SPP_CHOL_DF_LEAD")? atoi(getenv("SPP_CHOL_DF_LEAD")) : 1;
+		static const double beta = getenv("SPP_CHOL_DF_BETA")? atof(getenv("SPP_CHOL_DF_BETA")) : 0;
+		std::vector<std::pair<double, uint32_t> > keyed;
+		for(size_t i = 0; i < NB; ++ i) {
+			for(size_t jh = 2 * i; jh < NJH; ++ jh) {
+				const size_t j = jh / 2;
+				const bool chain = j == i || (j == i + 1 && j < NB);
+				const double key = chain? (double)i - lead - 0.5 : (beta > 1)? i + (double)(j - i) / beta : (double)i;
+				keyed.push_back(std::make_pair(key, (uint32_t)((i << 16) | jh)));
+			}
+		}
+		std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<double, uint32_t> &a, const std::pair<double, uint32_t> &b) { return a.first < b.first; });
 		std::vector<uint32_t> tasks;
-		for(size_t i = 0; i < NB; ++ i)
-			for(size_t jh = 2 * i; jh < NJH; ++ jh)
-				tasks.push_back((uint32_t)((i << 16) | jh));
+		for(size_t q = 0; q < keyed.size(); ++ q)
+			tasks.push_back(keyed[q].second);
 		ch.df_tasks.upload(tasks, st);
 		SPP_CUDA(cudaStreamSynchronize(st)); // the host vector goes out of scope
 		ch.df_nb = NB; ch.df_njh = NJH; ch.df_n_tasks = tasks.size();
@@ -596,8 +626,14 @@ void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_col
 	args.ld = ld; args.NB = (int)NB; args.NJH = (int)NJH; args.n_tasks = (int)ch.df_n_tasks;
 	const size_t n_ctas = std::min((size_t)ch.n_sms, 1 + df::G + ch.df_n_tasks);
 	static const bool timing = getenv("SPP_CHOL_TIMING") != 0;
-	if(timing)
+	DBuf<unsigned long long> dbg;
+	args.dbg = 0;
+	if(timing) {
+		dbg.resize(4 * NB + 8 * n_ctas);
+		dbg.zero(st);
+		args.dbg = dbg.p();
 		SPP_CUDA(cudaEventRecord(ctx->ev[4], st));
+	}
 	k_chol_dataflow<<<(unsigned)n_ctas, df::THREADS, df::SMEM_BYTES, st>>>(ch.df_maps[0], ch.df_maps[1], ch.df_maps[2], ch.df_maps[3], args);
 	LAUNCH_CHECK(ctx);
 	if(timing) {
@@ -609,6 +645,34 @@ void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_col
 		cudaMemcpy(h, ch.df_flags.p(), sizeof(h), cudaMemcpyDeviceToHost);
 		fprintf(stderr, "[spp chol dataflow] ld %zu, %zu tile columns: %.3f ms = %.2f TFLOP/s (tasks taken %d, roles %d, watchdog %d)\n", ld, NJH,
 			ms, (double)ld * ld * ld / 3 / ms * 1e-9, h[0], h[1], h[2]);
+		std::vector<unsigned long long> d(dbg.size());
+		cudaMemcpy(d.data(), dbg.p(), d.size() * 8, cudaMemcpyDeviceToHost);
+		// the chain: for panel i, wait for the diagonal tile after H2(i-1), potrf + inverse, H1(i), H2(i)
+		double s_wait = 0, s_potrf = 0, s_h1 = 0, s_h2 = 0;
+		for(size_t i = 0; i < NB; ++ i) {
+			const double t_wait = i? (double)(long long)(d[i] - d[3 * NB + i - 1]) * 1e-3 : 0, t_potrf = (double)(long long)(d[NB + i] - d[i]) * 1e-3;
+			const double t_h1 = (i + 1 < NB)? (double)(long long)(d[2 * NB + i] - d[NB + i]) * 1e-3 : 0;
+			const double t_h2 = (i + 1 < NB)? (double)(long long)(d[3 * NB + i] - d[2 * NB + i]) * 1e-3 : 0;
+			s_wait += t_wait; s_potrf += t_potrf; s_h1 += t_h1; s_h2 += t_h2;
+			if(i < 3 || i % 8 == 0 || i + 2 >= NB)
+				fprintf(stderr, "[spp chol dataflow] panel %zu at %.1f us: flag->potrf %.1f, potrf %.1f, H1 %.1f, H2 %.1f\n", i,
+					(double)(long long)(d[i] - d[0]) * 1e-3, t_wait, t_potrf, t_h1, t_h2);
+		}
+		fprintf(stderr, "[spp chol dataflow] chain %.1f us: flag->potrf %.1f, potrf %.1f, H1 (incl. waiting for partial sums) %.1f, H2 %.1f\n",
+			(double)(long long)(d[2 * NB - 1] - d[0]) * 1e-3, s_wait, s_potrf, s_h1, s_h2);
+		double w_flags = 0, w_trsm = 0, w_pipe = 0, w_total = 0, t_end_min = 1e30, t_end_max = 0; size_t n_w = 0;
+		for(size_t c = 0; c < n_ctas; ++ c) {
+			const unsigned long long *w = &d[4 * NB + 8 * c];
+			if(!w[3]) continue; // not a worker
+			++ n_w;
+			w_flags += (double)w[0]; w_trsm += (double)w[1]; w_pipe += (double)w[4]; w_total += (double)w[5];
+			const double te = (double)(long long)(w[3] - d[0]) * 1e-3;
+			t_end_min = std::min(t_end_min, te); t_end_max = std::max(t_end_max, te);
+		}
+		if(n_w)
+			fprintf(stderr, "[spp chol dataflow] %zu workers: producer waits %.1f %% of the run for operand flags, %.1f %% for the diagonal block; "
+				"consumer warp 0 waits %.1f %% for chunks; last task taken at %.1f .. %.1f us\n", n_w, 100 * w_flags / w_total, 100 * w_trsm / w_total,
+				100 * w_pipe / w_total, t_end_min, t_end_max);
 	}
 }
 
@@ -631,7 +695,8 @@ void dense_chol_factor_single_panel(spp_ctx *ctx, cudaStream_t stream, double *A
 // panel's first ld columns; flags: ld / 128 ints, zero on entry.
 void dense_chol_backsolve_panel(spp_ctx *ctx, cudaStream_t stream, const double *A, size_t ld, const double *Rinv, double *y, int *flags)
 {
-	k_backsolve<<<(unsigned)(ld / CH_NB), 256, 0, stream>>>(A, ld, ld / CH_NB, Rinv, y, flags);
+	chol_init_streams(ctx);
+	k_backsolve<<<(unsigned)(ld / CH_NB), 256, BACKSOLVE_SMEM, stream>>>(A, ld, ld / CH_NB, Rinv, y, flags);
 	LAUNCH_CHECK(ctx);
 }
 
@@ -642,6 +707,7 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 	DenseChol &ch = ctx->chol;
 	const size_t ld = dense_chol_ld(n), n_blk = ld / CH_NB;
 	cudaStream_t st = ctx->stream;
+	chol_init_streams(ctx);
 	ch.info.resize(1 + n_blk);
 	SPP_CUDA(cudaMemsetAsync(ch.info.p(), 0, (1 + n_blk) * sizeof(int), st));
 	if(ch.work.size() != n_blk * CH_NB * CH_NB) { // k_potrf128 writes the upper triangles only
@@ -664,7 +730,7 @@ int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x)
 		dense_chol_factor_panel(ctx, A, ld, ld + CH_NB, ch.work.p(), ch.info.p(), false);
 	if(timing)
 		SPP_CUDA(cudaEventRecord(ctx->ev[7], st));
-	k_backsolve<<<(unsigned)n_blk, 256, 0, st>>>(A, ld, n_blk, ch.work.p(), rhs_col, ch.info.p() + 1);
+	k_backsolve<<<(unsigned)n_blk, 256, BACKSOLVE_SMEM, st>>>(A, ld, n_blk, ch.work.p(), rhs_col, ch.info.p() + 1);
 	LAUNCH_CHECK(ctx);
 	if(timing) {
 		SPP_CUDA(cudaEventRecord(ctx->ev[8], st));

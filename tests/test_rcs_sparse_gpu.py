@@ -81,7 +81,10 @@ def test_sparse_vs_dense_step_and_lm(sparse_ctx, shape, kw):
     rep_d = ctx.ba_optimize(4, 0.0)
     assert rel_err(dx_s, dx_d) < 1e-10
     assert rep_s["trace_accepted"] == rep_d["trace_accepted"]
-    assert abs(rep_s["chi2_final"] - rep_d["chi2_final"]) <= 1e-9 * rep_d["chi2_final"]
+    # two factorisations with different summation orders: the 1e-13 difference of the increments goes through forward-
+    # difference Jacobians (delta = 1e-9) at every relinearisation, so the chi2 of later iterations agrees to ~1e-8, not to
+    # rounding (the reference differs from itself by 1.2e-6 between two builds); north_star asks for 1e-6
+    assert abs(rep_s["chi2_final"] - rep_d["chi2_final"]) <= 1e-7 * rep_d["chi2_final"]
     if shape == "seq":
         assert info["supernodes"] > 3 and info["updates"] > 3
         assert info["factor_blocks_stored"] < 0.8 * (400 * 401 // 2)  # it really is sparse
