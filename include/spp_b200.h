@@ -85,6 +85,17 @@ int spp_synchronize(spp_ctx_t ctx);
 typedef int (*spp_allreduce_fn)(void *p_user, void *p_device_doubles, size_t n_doubles);
 int spp_set_allreduce(spp_ctx_t ctx, spp_allreduce_fn fn, void *p_user, int rank, int world);
 
+/* The library's own NCCL path (what a C++ host uses; the hook above remains for host-side tests over gloo). One process
+ * per GPU: rank 0 calls spp_nccl_get_unique_id() and hands the SPP_NCCL_UNIQUE_ID_BYTES bytes to every rank by any means
+ * (a file, MPI, torch.distributed); every rank then calls spp_set_nccl() -- collectively, it runs ncclCommInitRank. From
+ * then on the partial reduced camera systems and the scalar partial sums are summed with ncclAllReduce(double, sum) on
+ * the context's stream, inside the library, without host synchronisation. libnccl.so.2 is opened at run time (dlopen):
+ * a process that already holds an NCCL, e.g. torch's, gets that one. world == 1 drops the communicator.
+ * rank / world select the landmark slice as for spp_set_allreduce(); call before spp_ba_set_graph(). */
+#define SPP_NCCL_UNIQUE_ID_BYTES 128
+int spp_nccl_get_unique_id(void *p_unique_id);
+int spp_set_nccl(spp_ctx_t ctx, const void *p_unique_id, int rank, int world);
+
 /* Pure host helper (no context, no GPU): the landmark slices used by the multi-GPU path. p_track_length[p] = number
  * of observations of landmark p; p_bounds[world + 1] receives the slice boundaries (rank r owns landmarks
  * p_bounds[r] .. p_bounds[r + 1]), contiguous and balanced by the Schur-product work k (k + 1) / 2 + k. */

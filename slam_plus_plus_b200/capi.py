@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "spp_ba_optimize", "spp_ba_marginals", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_marginals",
     "spp_schur_get_reduced_system",
     "spp_schur_set_rcs_solver", "spp_schur_set_rcs_ordering", "spp_schur_get_rcs_info", "spp_schur_get_rcs_residual", "spp_block_ordering",
-    "spp_block_symbolic_stats", "spp_dense_posdef_solve",
+    "spp_block_symbolic_stats", "spp_dense_posdef_solve", "spp_nccl_get_unique_id", "spp_set_nccl",
     "spp_chol_symbolic", "spp_chol_solve", "spp_chol_get_factor",
     "spp_pose_set_graph", "spp_pose_set_ordering", "spp_pose_set_states", "spp_pose_get_states", "spp_pose_restore_initial",
     "spp_pose_linearise", "spp_pose_get_lambda", "spp_pose_chi2", "spp_pose_solve_step", "spp_pose_optimize",
@@ -107,6 +107,8 @@ def load_library() -> C.CDLL:
     lib.spp_schur_marginals.argtypes = [vp, C.c_double, dp, dp]
     lib.spp_schur_get_reduced_system.argtypes = [vp, u64p, dp, dp, u8p]
     lib.spp_dense_posdef_solve.argtypes = [vp, C.c_size_t, dp, dp]
+    lib.spp_nccl_get_unique_id.argtypes = [C.c_void_p]
+    lib.spp_set_nccl.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
     lib.spp_schur_set_rcs_solver.argtypes = [vp, C.c_int]
     lib.spp_schur_set_rcs_ordering.argtypes = [vp, C.c_size_t, u64p]
     lib.spp_schur_get_rcs_info.argtypes = [vp, u64p, dp]
@@ -208,6 +210,19 @@ class NotPositiveDefinite(ArithmeticError):
     """The factorisation met a non-positive pivot (the reference's solvers return false)."""
 
 
+NCCL_UNIQUE_ID_BYTES = 128
+
+
+def nccl_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls this and sends the bytes to the other ranks)."""
+    lib = load_library()
+    buf = C.create_string_buffer(NCCL_UNIQUE_ID_BYTES)
+    rc = lib.spp_nccl_get_unique_id(buf)
+    if rc != SPP_OK:
+        raise SppError(rc, lib.spp_last_error(None).decode())
+    return buf.raw
+
+
 class Context:
     """One solver context on one GPU (``optimizer_t`` of the reference's C API)."""
 
@@ -269,6 +284,12 @@ class Context:
                     return 1
             self._cb = ALLREDUCE_FN(tramp)
         self._check(self.lib.spp_set_allreduce(self.h, self._cb, None, rank, world))
+
+    def set_nccl(self, unique_id: bytes, rank: int, world: int):
+        """The library's own NCCL communicator (ncclCommInitRank inside the library: collective over the ranks); see
+        nccl_unique_id(). The all-reduces of the path then run inside the library on the context's stream."""
+        buf = C.create_string_buffer(bytes(unique_id), NCCL_UNIQUE_ID_BYTES) if world > 1 else None
+        self._check(self.lib.spp_set_nccl(self.h, buf, rank, world))
 
     # ---- bundle adjustment ----------------------------------------------------------------------
     def ba_set_graph(self, g):

@@ -3,6 +3,8 @@
 // (include/slam/NonlinearSolver_Lambda_LM.h:796-1116) with the system resident on the device.
 
 #include "spp_ctx.h"
+#include <nccl.h>  // types only: the library is opened with dlopen (see nccl_api())
+#include <dlfcn.h>
 #include <string.h>
 #include <math.h>
 #include <algorithm>
@@ -58,15 +60,57 @@ struct comm_error : std::runtime_error {
 	explicit comm_error(const std::string &t) : std::runtime_error(t) {}
 };
 
-// sums n doubles at d_ptr over the ranks through the hook installed by spp_set_allreduce (no-op on one rank).
-// The hook orders itself on the context's stream (slam_plus_plus_b200/parallel.py runs the collective with the
-// context stream as torch's current stream).
+// ---- NCCL, bound at run time ----------------------------------------------------------------------------
+// The library calls NCCL itself (ncclAllReduce on the context's stream: no host round trip, no Python in the data
+// plane). libnccl.so.2 is opened with dlopen when spp_set_nccl / spp_nccl_get_unique_id is first called: a process that
+// already holds an NCCL (torch's bundled one) gets that very library, a plain C++ host the system's. Single-GPU users
+// never load it.
+struct NcclApi {
+	void *handle;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+	ncclResult_t (*CommAbort)(ncclComm_t); // teardown without a rendezvous: the peers may already be gone
+	const char *(*GetErrorString)(ncclResult_t);
+	NcclApi() : handle(0), GetUniqueId(0), CommInitRank(0), AllReduce(0), CommAbort(0), GetErrorString(0) {}
+};
+
+static NcclApi &nccl_api()
+{
+	static NcclApi api;
+	if(!api.handle) {
+		void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if(!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+		if(!h)
+			throw comm_error(std::string("cannot load libnccl.so.2: ") + dlerror());
+		api.GetUniqueId = (ncclResult_t (*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+		api.CommInitRank = (ncclResult_t (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+		api.AllReduce = (ncclResult_t (*)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+		api.CommAbort = (ncclResult_t (*)(ncclComm_t))dlsym(h, "ncclCommAbort");
+		api.GetErrorString = (const char *(*)(ncclResult_t))dlsym(h, "ncclGetErrorString");
+		if(!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommAbort || !api.GetErrorString)
+			throw comm_error("libnccl.so.2 lacks one of ncclGetUniqueId / ncclCommInitRank / ncclAllReduce / ncclCommAbort");
+		api.handle = h;
+	}
+	return api;
+}
+
+#define SPP_NCCL(call) do { ncclResult_t r_ = (call); if(r_ != ncclSuccess) \
+	throw comm_error(std::string(#call ": ") + nccl_api().GetErrorString(r_)); } while(0)
+
+// sums n doubles at d_ptr over the ranks (no-op on one rank): ncclAllReduce on the context's stream when the context owns
+// a communicator (spp_set_nccl), else through the hook installed by spp_set_allreduce (host-side tests over gloo; the
+// hook orders itself on the context's stream).
 void allreduce_device(spp_ctx *ctx, double *d_ptr, size_t n)
 {
 	if(ctx->world <= 1 || !n)
 		return;
+	if(ctx->nccl_comm) {
+		SPP_NCCL(nccl_api().AllReduce(d_ptr, d_ptr, n, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+		return;
+	}
 	if(!ctx->allreduce)
-		throw invalid_error("world > 1 but no all-reduce hook installed (spp_set_allreduce)");
+		throw invalid_error("world > 1 but neither a communicator (spp_set_nccl) nor an all-reduce hook (spp_set_allreduce)");
 	if(ctx->allreduce(ctx->allreduce_user, d_ptr, n) != 0)
 		throw comm_error("the all-reduce hook failed");
 }
@@ -479,6 +523,7 @@ int spp_create(int device, spp_ctx_t *p_ctx)
 	ctx->n_launches = 0;
 	ctx->allreduce = 0;
 	ctx->allreduce_user = 0;
+	ctx->nccl_comm = 0;
 	ctx->rank = 0;
 	ctx->world = 1;
 	ctx->async_mode = false;
@@ -513,10 +558,16 @@ void spp_destroy(spp_ctx_t ctx)
 	if(!ctx)
 		return;
 	cudaSetDevice(ctx->device);
-	if(ctx->stream) {
+	if(ctx->stream)
 		cudaStreamSynchronize(ctx->stream);
-		cudaStreamDestroy(ctx->stream);
+	if(ctx->nccl_comm) {
+		// the stream is idle: ncclCommAbort frees the communicator without waiting for the other ranks (ncclCommDestroy
+		// finalises collectively and hangs when a peer has already left)
+		try { spp::nccl_api().CommAbort((ncclComm_t)ctx->nccl_comm); } catch(...) { }
+		ctx->nccl_comm = 0;
 	}
+	if(ctx->stream)
+		cudaStreamDestroy(ctx->stream);
 	for(int i = 0; i < 16; ++ i)
 		if(ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
 	for(int i = 0; i < PH_COUNT; ++ i) {
@@ -592,6 +643,49 @@ int spp_set_allreduce(spp_ctx_t ctx, spp_allreduce_fn fn, void *p_user, int rank
 	ctx->rank = rank;
 	ctx->world = world;
 	return SPP_OK;
+}
+
+int spp_nccl_get_unique_id(void *p_id)
+{
+	if(!p_id)
+		return SPP_ERR_INVALID;
+	try {
+		static_assert(sizeof(ncclUniqueId) == SPP_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+		ncclUniqueId id;
+		SPP_NCCL(nccl_api().GetUniqueId(&id));
+		memcpy(p_id, &id, sizeof(id));
+	} catch(const std::exception &e) {
+		g_create_error = e.what();
+		return SPP_ERR_COMM;
+	}
+	return SPP_OK;
+}
+
+int spp_set_nccl(spp_ctx_t ctx, const void *p_id, int rank, int world)
+{
+	API_BEGIN(ctx)
+	if(world < 1 || rank < 0 || rank >= world || (world > 1 && !p_id)) throw invalid_error("bad rank / world / id");
+	if(ctx->nccl_comm) {
+		SPP_CUDA(cudaStreamSynchronize(ctx->stream)); // nothing of ours is in flight: ncclCommAbort only frees
+		nccl_api().CommAbort((ncclComm_t)ctx->nccl_comm);
+		ctx->nccl_comm = 0;
+	}
+	if(rank != ctx->rank || world != ctx->world) { // as spp_set_allreduce: the resident graph belongs to the old (rank, world)
+		ctx->ba.valid = false;
+		ctx->snode.valid = false;
+		ctx->slot.valid = false;
+		ctx->sys.n_blocks_global = 0;
+	}
+	ctx->rank = rank;
+	ctx->world = world;
+	if(world > 1) {
+		ncclUniqueId id;
+		memcpy(&id, p_id, sizeof(id));
+		ncclComm_t comm;
+		SPP_NCCL(nccl_api().CommInitRank(&comm, world, id, rank));
+		ctx->nccl_comm = comm;
+	}
+	API_END(ctx)
 }
 
 int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_type,

@@ -222,6 +222,7 @@ struct spp_ctx {
 	uint64_t n_launches;
 	spp_allreduce_fn allreduce;
 	void *allreduce_user;
+	void *nccl_comm;            // ncclComm_t created by spp_set_nccl (the library's own NCCL path); 0: the hook is used
 	int rank, world;
 	spp::SchurSystem sys;
 	spp::BAProblem ba;

@@ -63,6 +63,17 @@ def attach_torch_allreduce(ctx, rank: int, world: int, group=None):
     ctx.set_allreduce(make_torch_allreduce(ctx.stream, dev, group), rank, world)
 
 
+def attach_nccl(ctx, rank: int, world: int, group=None):
+    """The library's own NCCL path (spp_set_nccl): rank 0 creates the unique id, torch.distributed only carries those
+    128 bytes to the other ranks (any transport would do); from then on every collective of the path is an
+    ncclAllReduce issued by libspp_b200.so itself on the context's stream. Call BEFORE ba_set_graph."""
+    import torch.distributed as dist
+    from . import capi
+    box = [capi.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    ctx.set_nccl(box[0], rank, world)
+
+
 def gather_points(ctx, pts_full: np.ndarray, group=None) -> np.ndarray:
     """All ranks receive the full landmark array: every rank owns the slice returned by ctx.ba_get_partition()."""
     import torch

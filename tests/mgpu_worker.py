@@ -76,7 +76,10 @@ def run_gpu(rank, world):
     shape = os.environ.get("SPP_TEST_SHAPE", "mid")
     g = graphs.ba_shape(shape)
     ctx = capi.Context(local)
-    parallel.attach_torch_allreduce(ctx, rank, world)
+    if os.environ.get("SPP_TEST_COMM", "nccl") == "hook":  # the callback path (torch.distributed issues the collective)
+        parallel.attach_torch_allreduce(ctx, rank, world)
+    else:  # the library's own communicator: ncclAllReduce inside libspp_b200.so
+        parallel.attach_nccl(ctx, rank, world)
     if os.environ.get("SPP_TEST_RCS") == "sparse":  # block-sparse reduced camera system: the global block list is summed
         ctx.schur_set_rcs_solver(capi.RCS_SPARSE)
     ctx.ba_set_graph(g)
