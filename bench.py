@@ -35,6 +35,28 @@ UNIT = "LM iterations/s"
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_driver_ba")
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """stdout carries exactly ONE JSON line: anything a native library prints to file descriptor 1 (NCCL's version banner
+    from ncclCommInitRank, for one) is sent to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -130,8 +152,10 @@ def reference_arm(args):
     from slam_plus_plus_b200 import graphs
     g = graphs.ba_shape(args.shape)
     path = write_graph_file(g)
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the reference gets all the host cores whatever N is
+    n_threads = (os.cpu_count() or 1) if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None
     try:
-        secs, threads, d = run_reference_steps(path, args.warmup, args.steps)
+        secs, threads, d = run_reference_steps(path, args.warmup, args.steps, threads=n_threads)
     finally:
         os.unlink(path)
     timed = secs[args.warmup:]
@@ -150,7 +174,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def check_chi2(args, rep):
@@ -209,7 +233,7 @@ def gpu_arm(args):
                 bal.pop(k, None)
             line["bal13682"] = bal
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -475,7 +499,7 @@ def pose_arm(args):
         line["cpu_baseline"] = {"value": 1e3 * float(d["optimize_time"][0]), "unit": line["unit"], "cores": int(d["omp_threads"][0]),
                                 "kind": "reference", "sample": "unmodified reference (oracle/_ref/ref_driver_pose), the same graph, one Optimize(%d, 0): %s"
                                                                % (args.lm_iters, out.strip())}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -491,6 +515,7 @@ def main():
     ap.add_argument("--write-chi2-trace", default="", metavar="PATH", help="single-GPU run: record the final chi2 of each shape in this "
                     "JSON file (committed as profiles/chi2_trace.json, which every later run is checked against)")
     args = ap.parse_args()
+    guard_stdout()
     if args.shape in POSE_SHAPES and args.impl == "b200":
         pose_arm(args)
     elif args.impl == "reference":
