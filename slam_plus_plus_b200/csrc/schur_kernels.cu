@@ -16,6 +16,7 @@
 
 #include "spp_ctx.h"
 #include <stdlib.h>
+#include <algorithm>
 
 namespace spp {
 
@@ -149,18 +150,32 @@ __device__ __forceinline__ void schur_accumulate(uint64_t k0, uint64_t end, uint
 	}
 }
 
-// off-diagonal blocks (list entries first_blk ..): one warp per block
+// off-diagonal blocks (list entries first_blk ..): one warp per block. The pair lists differ a lot in length (1 .. several
+// hundred pairs), so with a fixed block -> warp assignment a CTA lives as long as its longest list while its other
+// warps idle (33 % of the warp slots active, profiles/r1k_full.csv); with `queue` the warps of a persistent grid take
+// block after block from a counter instead (with four pairs in flight per lane group: stage 1.26 -> 1.19 ms; the kernel
+// is bound by the L2 sector traffic of its gathers, 2 x 144 bytes per pair, not by the imbalance). (Measured and rejected: the three lane groups sharing ONE pair, each taking
+// one column of Y_a / W_b -- the minimum of L1 wavefronts per pair, but three times the index loads and loop trips per
+// pair: 1.49 ms against 1.32 ms for the stage.)
 template <int UNROLL>
 __global__ void __launch_bounds__(SB_WARPS * 32, (UNROLL >= 4)? 2 : 4) k_schur_blocks(size_t first_blk, size_t n_blocks_total, size_t ld,
 	const uint32_t *__restrict__ blk_row, const uint32_t *__restrict__ blk_col, const uint64_t *__restrict__ blk_ptr,
 	const uint32_t *__restrict__ pair_a, const uint32_t *__restrict__ pair_b, const double *__restrict__ Y,
-	const double *__restrict__ W, double *__restrict__ S, const uint32_t *__restrict__ slot)
+	const double *__restrict__ W, double *__restrict__ S, const uint32_t *__restrict__ slot, unsigned *__restrict__ queue)
 {
 	const int lane = threadIdx.x & 31;
-	const size_t blk = first_blk + blockIdx.x * (size_t)SB_WARPS + (threadIdx.x >> 5);
+	const int grp = lane / 9, q9 = lane - grp * 9, r3 = q9 % 3, c3 = q9 / 3;
+	for(;;) {
+	size_t blk;
+	if(queue) {
+		unsigned idx = 0;
+		if(lane == 0)
+			idx = atomicAdd(queue, 1u);
+		blk = first_blk + __shfl_sync(0xffffffffu, idx, 0);
+	} else
+		blk = first_blk + blockIdx.x * (size_t)SB_WARPS + (threadIdx.x >> 5);
 	if(blk >= n_blocks_total) return;
 	const unsigned bi = blk_row[blk], bj = blk_col[blk];
-	const int grp = lane / 9, q9 = lane - grp * 9, r3 = q9 % 3, c3 = q9 / 3;
 	SchurAcc acc = {0, 0, 0, 0, 0, 0};
 	if(grp < 3)
 		schur_accumulate<false, UNROLL>(blk_ptr[blk] + grp, blk_ptr[blk + 1], 3, r3, c3, pair_a, pair_b, Y, W, 0, 0, acc);
@@ -179,6 +194,8 @@ __global__ void __launch_bounds__(SB_WARPS * 32, (UNROLL >= 4)? 2 : 4) k_schur_b
 		Sb[1] = -v[1];
 		Sb[ldo] = -v[2];
 		Sb[ldo + 1] = -v[3];
+	}
+	if(!queue) return;
 	}
 }
 
@@ -297,13 +314,25 @@ void schur_form_reduced_system(spp_ctx *ctx, double alpha, double alpha_diag, bo
 		LAUNCH_CHECK(ctx);
 	}
 	if(s.n_blocks > s.C) {
-		static const int unroll = getenv("SPP_SCHUR_UNROLL")? atoi(getenv("SPP_SCHUR_UNROLL")) : 2;
+		static const int unroll = getenv("SPP_SCHUR_UNROLL")? atoi(getenv("SPP_SCHUR_UNROLL")) : 4;
+		static const int use_queue = getenv("SPP_SCHUR_QUEUE")? atoi(getenv("SPP_SCHUR_QUEUE")) : 1;
+		unsigned *queue = 0;
+		unsigned grid = n_blocks(s.n_blocks - s.C, SB_WARPS);
+		if(use_queue) {
+			static int n_sms = 0;
+			if(!n_sms)
+				SPP_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+			s.schur_queue.resize(1);
+			queue = s.schur_queue.p();
+			SPP_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned), ctx->stream));
+			grid = std::min(grid, (unsigned)n_sms * ((unroll >= 4)? 2u : 4u));
+		}
 		if(unroll >= 4)
-			k_schur_blocks<4><<<n_blocks(s.n_blocks - s.C, SB_WARPS), SB_WARPS * 32, 0, ctx->stream>>>(s.C, s.n_blocks, ld,
-				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), S_out, slot);
+			k_schur_blocks<4><<<grid, SB_WARPS * 32, 0, ctx->stream>>>(s.C, s.n_blocks, ld,
+				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), S_out, slot, queue);
 		else
-			k_schur_blocks<2><<<n_blocks(s.n_blocks - s.C, SB_WARPS), SB_WARPS * 32, 0, ctx->stream>>>(s.C, s.n_blocks, ld,
-				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), S_out, slot);
+			k_schur_blocks<2><<<grid, SB_WARPS * 32, 0, ctx->stream>>>(s.C, s.n_blocks, ld,
+				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), S_out, slot, queue);
 		LAUNCH_CHECK(ctx);
 	}
 }
