@@ -172,119 +172,138 @@ __device__ __forceinline__ double warp_max(double v)
 }
 
 #define CAM_THREADS 256
+#define CAM_MIN_CTAS 2   // 128 registers: two CTAs per SM (the per-thread accumulators of U_c, g_c are gone, see below)
+#define GR_LD 68         // row length of the Gram operands in shared memory (64 + 4: fragment loads at most 2-way conflicted)
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+		: "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+static const size_t CAM_SMEM = (size_t)(CAM_THREADS / 32) * 2 * 8 * GR_LD * sizeof(double);
 
 // one CTA per camera. JAC: Jacobian mode as a compile-time constant (the other branch does not cost registers).
-// (Measured alternatives: two CTAs per SM at 128 registers spill and run 6 % slower; a variant with ten lanes per
-// observation -- one projection per lane, the Hessian algebra spread over the lanes through shared memory, 64 registers,
-// four CTAs per SM -- gives bit-identical projections but runs 0.97 ms against 0.81 ms: the kernel stays as it is.)
+// U_c = sum_e T_e Jc_e and g_c = sum_e T_e r_e (T_e = Jc_e^T Sigma_e^-1, 6 x 2) are ONE small GEMM per warp: the 32
+// observations of a warp trip put T (6 x 64: two columns per observation) and [Jc | r] (64 x 7) into shared memory and
+// sixteen mma.sync.m8n8k4.f64 add [U | g] (6 x 7 of the 8 x 8 tile) to two accumulator registers per lane -- instead of
+// 27 accumulators (54 registers) per thread and 27 FMAs per observation. With that the kernel fits 128 registers and
+// two CTAs share an SM (it was latency bound at 254 registers, 8 warps per SM, 12 % of the warp slots active:
+// profiles/r1k_full.csv). The expressions of the products are the reference's (U_e = T Jc, g = T r,
+// BaseTypes_Binary.h:813-843); the summation order is fixed (k ascending inside the warp, then the warps in order), so
+// the result is bit-reproducible.
+// (Measured alternatives of round 1: ten lanes per observation -- one projection per lane, the Hessian algebra spread
+// over the lanes through shared memory -- 0.97 ms against 0.81 ms.)
 template <int JAC>
-__global__ void __launch_bounds__(CAM_THREADS) k_linearise_cams(int, const uint32_t *__restrict__ cam_ptr,
+__global__ void __launch_bounds__(CAM_THREADS, CAM_MIN_CTAS) k_linearise_cams(int, const uint32_t *__restrict__ cam_ptr,
 	const uint32_t *__restrict__ cam_obs, const uint32_t *__restrict__ obs_pt, const double *__restrict__ pts,
 	const double *__restrict__ z, const double *__restrict__ info, const double *__restrict__ camRt,
 	const double *__restrict__ camK, double *__restrict__ W, double *__restrict__ U, double *__restrict__ gc,
 	unsigned long long *__restrict__ maxdiag, long uf_cam, double *__restrict__ PtRec)
 {
+	extern __shared__ __align__(16) double gram[]; // per warp: T [8][GR_LD], then [Jc | r] [8][GR_LD]
 	__shared__ double sRt[7 * 12];
 	__shared__ double sK[5];
-	__shared__ double sred[CAM_THREADS / 32][28];
+	__shared__ double sred[CAM_THREADS / 32][65];
 	const unsigned c = blockIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int g = lane >> 2, t = lane & 3;
+	double *sT = gram + (size_t)warp * (2 * 8 * GR_LD), *sJ = sT + 8 * GR_LD;
 	for(int i = threadIdx.x; i < 7 * 12; i += CAM_THREADS)
 		sRt[i] = camRt[(size_t)c * 84 + i];
 	if(threadIdx.x < 5)
 		sK[threadIdx.x] = camK[(size_t)c * 5 + threadIdx.x];
+	for(int i = lane; i < 2 * 8 * GR_LD; i += 32) // rows 6, 7 of T and row 7 of [Jc | r] stay zero
+		sT[i] = 0;
 	__syncthreads();
 
-	double accU[21], accg[6], dmax = 0;
-	#pragma unroll
-	for(int i = 0; i < 21; ++ i) accU[i] = 0;
-	#pragma unroll
-	for(int i = 0; i < 6; ++ i) accg[i] = 0;
-
+	double acc0 = 0, acc1 = 0, dmax = 0; // [U | g](g, 2 t), (g, 2 t + 1)
 	const unsigned beg = cam_ptr[c], end = cam_ptr[c + 1];
-	for(unsigned idx = beg + threadIdx.x; idx < end; idx += CAM_THREADS) {
-		const unsigned o = cam_obs[idx];
-		const unsigned p = obs_pt[o];
-		const double X = pts[(size_t)p * 3], Y = pts[(size_t)p * 3 + 1], Z = pts[(size_t)p * 3 + 2];
-		const double2 zz = *reinterpret_cast<const double2*>(z + (size_t)o * 2);
-		const double2 i01 = *reinterpret_cast<const double2*>(info + (size_t)o * 4);
-		const double2 i23 = *reinterpret_cast<const double2*>(info + (size_t)o * 4 + 2);
-		double Jc[12], Jp[6], ru, rv;
-		observation_jacobians(JAC, sRt, sK, X, Y, Z, zz.x, zz.y, Jc, Jp, ru, rv, true, true);
-		// T = Jc^T Sigma^-1 (6x2): T(j,0) = Jc(0,j) s00 + Jc(1,j) s10 ; T(j,1) = Jc(0,j) s01 + Jc(1,j) s11
-		double T0[6], T1[6];
-		#pragma unroll
-		for(int j = 0; j < 6; ++ j) {
-			T0[j] = Jc[j] * i01.x + Jc[6 + j] * i23.x;
-			T1[j] = Jc[j] * i01.y + Jc[6 + j] * i23.y;
-		}
-		// W = T Jp (6x3), column-major
-		double *Wo = W + (size_t)o * 18;
-		#pragma unroll
-		for(int cc = 0; cc < 3; ++ cc) {
-			double w[6];
+	for(unsigned base = beg; base < end; base += CAM_THREADS) {
+		const unsigned idx = base + threadIdx.x;
+		double2 *pT = reinterpret_cast<double2*>(sT + 2 * lane), *pJ = reinterpret_cast<double2*>(sJ + 2 * lane);
+		if(idx < end) {
+			const unsigned o = cam_obs[idx];
+			const unsigned p = obs_pt[o];
+			const double X = pts[(size_t)p * 3], Y = pts[(size_t)p * 3 + 1], Z = pts[(size_t)p * 3 + 2];
+			const double2 zz = *reinterpret_cast<const double2*>(z + (size_t)o * 2);
+			const double2 i01 = *reinterpret_cast<const double2*>(info + (size_t)o * 4);
+			const double2 i23 = *reinterpret_cast<const double2*>(info + (size_t)o * 4 + 2);
+			double Jc[12], Jp[6], ru, rv;
+			observation_jacobians(JAC, sRt, sK, X, Y, Z, zz.x, zz.y, Jc, Jp, ru, rv, true, true);
+			// T = Jc^T Sigma^-1 (6x2): T(j,0) = Jc(0,j) s00 + Jc(1,j) s10 ; T(j,1) = Jc(0,j) s01 + Jc(1,j) s11
+			double T0[6], T1[6];
 			#pragma unroll
-			for(int j = 0; j < 6; ++ j)
-				w[j] = T0[j] * Jp[cc] + T1[j] * Jp[3 + cc];
-			*reinterpret_cast<double2*>(Wo + cc * 6 + 0) = make_double2(w[0], w[1]);
-			*reinterpret_cast<double2*>(Wo + cc * 6 + 2) = make_double2(w[2], w[3]);
-			*reinterpret_cast<double2*>(Wo + cc * 6 + 4) = make_double2(w[4], w[5]);
-		}
-		// the landmark's share of this observation, V_e = upper(Jp^T Sigma^-1 Jp) and g_e = Jp^T (Sigma^-1 r): the Jacobian
-		// is at hand here, so the landmark kernel only has to add these records up along its track (same expressions and
-		// the same summation order as the landmark kernel that recomputed Jp: bit-identical V, gp)
-		{
-			double A0[3], A1[3];
-			#pragma unroll
-			for(int j = 0; j < 3; ++ j) {
-				A0[j] = Jp[j] * i01.x + Jp[3 + j] * i23.x;
-				A1[j] = Jp[j] * i01.y + Jp[3 + j] * i23.y;
+			for(int j = 0; j < 6; ++ j) {
+				T0[j] = Jc[j] * i01.x + Jc[6 + j] * i23.x;
+				T1[j] = Jc[j] * i01.y + Jc[6 + j] * i23.y;
 			}
-			const double e00 = A0[0] * Jp[0] + A1[0] * Jp[3], e01 = A0[0] * Jp[1] + A1[0] * Jp[4], e02 = A0[0] * Jp[2] + A1[0] * Jp[5];
-			const double e11 = A0[1] * Jp[1] + A1[1] * Jp[4], e12 = A0[1] * Jp[2] + A1[1] * Jp[5], e22 = A0[2] * Jp[2] + A1[2] * Jp[5];
-			const double s0 = i01.x * ru + i01.y * rv, s1 = i23.x * ru + i23.y * rv;
-			double *rec = PtRec + (size_t)o * 10;
-			*reinterpret_cast<double2*>(rec + 0) = make_double2(e00, e01);
-			*reinterpret_cast<double2*>(rec + 2) = make_double2(e02, e11);
-			*reinterpret_cast<double2*>(rec + 4) = make_double2(e12, e22);
-			*reinterpret_cast<double2*>(rec + 6) = make_double2(Jp[0] * s0 + Jp[3] * s1, Jp[1] * s0 + Jp[4] * s1);
-			*reinterpret_cast<double2*>(rec + 8) = make_double2(Jp[2] * s0 + Jp[5] * s1, 0.0);
-			dmax = fmax(dmax, fmax(e00, fmax(e11, e22)));
-		}
-		// U_e = upper(T Jc), g = T r
-		int t = 0;
-		#pragma unroll
-		for(int cc = 0; cc < 6; ++ cc) {
+			// the Gram operands of this observation: columns 2 lane, 2 lane + 1
 			#pragma unroll
-			for(int rr = 0; rr <= cc; ++ rr, ++ t) {
-				double e = T0[rr] * Jc[cc] + T1[rr] * Jc[6 + cc];
-				accU[t] += e;
-				if(rr == cc)
-					dmax = fmax(dmax, e);
+			for(int j = 0; j < 6; ++ j) {
+				pT[j * (GR_LD / 2)] = make_double2(T0[j], T1[j]);
+				pJ[j * (GR_LD / 2)] = make_double2(Jc[j], Jc[6 + j]);
+				dmax = fmax(dmax, T0[j] * Jc[j] + T1[j] * Jc[6 + j]); // the diagonal of U_e (initial damping, LM.h:162-166)
 			}
+			pJ[6 * (GR_LD / 2)] = make_double2(ru, rv);
+			// W = T Jp (6x3), column-major
+			double *Wo = W + (size_t)o * 18;
+			#pragma unroll
+			for(int cc = 0; cc < 3; ++ cc) {
+				double w[6];
+				#pragma unroll
+				for(int j = 0; j < 6; ++ j)
+					w[j] = T0[j] * Jp[cc] + T1[j] * Jp[3 + cc];
+				*reinterpret_cast<double2*>(Wo + cc * 6 + 0) = make_double2(w[0], w[1]);
+				*reinterpret_cast<double2*>(Wo + cc * 6 + 2) = make_double2(w[2], w[3]);
+				*reinterpret_cast<double2*>(Wo + cc * 6 + 4) = make_double2(w[4], w[5]);
+			}
+			// the landmark's share of this observation, V_e = upper(Jp^T Sigma^-1 Jp) and g_e = Jp^T (Sigma^-1 r): the Jacobian
+			// is at hand here, so the landmark kernel only has to add these records up along its track (same expressions and
+			// the same summation order as the landmark kernel that recomputed Jp: bit-identical V, gp)
+			{
+				double A0[3], A1[3];
+				#pragma unroll
+				for(int j = 0; j < 3; ++ j) {
+					A0[j] = Jp[j] * i01.x + Jp[3 + j] * i23.x;
+					A1[j] = Jp[j] * i01.y + Jp[3 + j] * i23.y;
+				}
+				const double e00 = A0[0] * Jp[0] + A1[0] * Jp[3], e01 = A0[0] * Jp[1] + A1[0] * Jp[4], e02 = A0[0] * Jp[2] + A1[0] * Jp[5];
+				const double e11 = A0[1] * Jp[1] + A1[1] * Jp[4], e12 = A0[1] * Jp[2] + A1[1] * Jp[5], e22 = A0[2] * Jp[2] + A1[2] * Jp[5];
+				const double s0 = i01.x * ru + i01.y * rv, s1 = i23.x * ru + i23.y * rv;
+				double *rec = PtRec + (size_t)o * 10;
+				*reinterpret_cast<double2*>(rec + 0) = make_double2(e00, e01);
+				*reinterpret_cast<double2*>(rec + 2) = make_double2(e02, e11);
+				*reinterpret_cast<double2*>(rec + 4) = make_double2(e12, e22);
+				*reinterpret_cast<double2*>(rec + 6) = make_double2(Jp[0] * s0 + Jp[3] * s1, Jp[1] * s0 + Jp[4] * s1);
+				*reinterpret_cast<double2*>(rec + 8) = make_double2(Jp[2] * s0 + Jp[5] * s1, 0.0);
+				dmax = fmax(dmax, fmax(e00, fmax(e11, e22)));
+			}
+		} else {
+			#pragma unroll
+			for(int j = 0; j < 6; ++ j) {
+				pT[j * (GR_LD / 2)] = make_double2(0.0, 0.0);
+				pJ[j * (GR_LD / 2)] = make_double2(0.0, 0.0);
+			}
+			pJ[6 * (GR_LD / 2)] = make_double2(0.0, 0.0);
 		}
-		#pragma unroll
-		for(int j = 0; j < 6; ++ j)
-			accg[j] += T0[j] * ru + T1[j] * rv;
+		__syncwarp();
+		// [U | g] += T [Jc | r]: A(m, k) = T(m, k), B(k, n) = [Jc | r](k, n), k = 0 .. 63
+		#pragma unroll 4
+		for(int k4 = 0; k4 < 64; k4 += 4)
+			dmma884(acc0, acc1, sT[g * GR_LD + k4 + t], sJ[g * GR_LD + k4 + t]);
+		__syncwarp();
 	}
 
-	// fixed-shape reduction: warp tree, then the 8 warp partials in order
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	#pragma unroll
-	for(int i = 0; i < 21; ++ i) {
-		double v = warp_sum(accU[i]);
-		if(lane == 0) sred[warp][i] = v;
-	}
-	#pragma unroll
-	for(int i = 0; i < 6; ++ i) {
-		double v = warp_sum(accg[i]);
-		if(lane == 0) sred[warp][21 + i] = v;
-	}
+	// fixed-shape reduction: the 8 warp tiles in order
+	sred[warp][g * 8 + 2 * t] = acc0;
+	sred[warp][g * 8 + 2 * t + 1] = acc1;
 	dmax = warp_max(dmax);
-	if(lane == 0) sred[warp][27] = dmax;
+	if(lane == 0) sred[warp][64] = dmax;
 	__syncthreads();
-	if(threadIdx.x < 28) {
+	if(threadIdx.x < 65) {
 		double v = sred[0][threadIdx.x];
-		if(threadIdx.x < 27) {
+		if(threadIdx.x < 64) {
 			for(int w = 1; w < CAM_THREADS / 32; ++ w)
 				v += sred[w][threadIdx.x];
 		} else {
@@ -297,14 +316,14 @@ __global__ void __launch_bounds__(CAM_THREADS) k_linearise_cams(int, const uint3
 	if(threadIdx.x < 36) {
 		int cc = threadIdx.x / 6, rr = threadIdx.x % 6;
 		int a = (rr <= cc)? rr : cc, b = (rr <= cc)? cc : rr; // selfadjointView<Upper>
-		double v = sred[0][b * (b + 1) / 2 + a];
+		double v = sred[0][a * 8 + b];
 		if(rr == cc && (long)c == uf_cam)
 			v += 1.0; // unary factor on vertex 0 (FlatSystem.h:432-473)
 		U[(size_t)c * 36 + threadIdx.x] = v;
 	} else if(threadIdx.x < 42)
-		gc[(size_t)c * 6 + threadIdx.x - 36] = sred[0][21 + threadIdx.x - 36];
+		gc[(size_t)c * 6 + threadIdx.x - 36] = sred[0][(threadIdx.x - 36) * 8 + 6];
 	else if(threadIdx.x == 42 && maxdiag)
-		atomicMax(maxdiag, (unsigned long long)__double_as_longlong(sred[0][27]));
+		atomicMax(maxdiag, (unsigned long long)__double_as_longlong(sred[0][64]));
 }
 
 // thread per landmark: V_p, g_p = sum of the per-observation records written by k_linearise_cams, along the track in
@@ -457,7 +476,13 @@ void ba_linearise(spp_ctx *ctx, bool b_want_maxdiag)
 	}
 	ba.pt_rec.resize(s.O * 10);
 	if(s.C) {
-#define LAUNCH_CAMS(JAC) k_linearise_cams<JAC><<<(unsigned)s.C, CAM_THREADS, 0, ctx->stream>>>(ba.jac_mode, s.cam_ptr.p(), \
+		static bool attr_done[64] = {false};
+		if(ctx->device >= 0 && ctx->device < 64 && !attr_done[ctx->device]) {
+			SPP_CUDA(cudaFuncSetAttribute(k_linearise_cams<SPP_JAC_FD_REFERENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAM_SMEM));
+			SPP_CUDA(cudaFuncSetAttribute(k_linearise_cams<SPP_JAC_ANALYTIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAM_SMEM));
+			attr_done[ctx->device] = true;
+		}
+#define LAUNCH_CAMS(JAC) k_linearise_cams<JAC><<<(unsigned)s.C, CAM_THREADS, CAM_SMEM, ctx->stream>>>(ba.jac_mode, s.cam_ptr.p(), \
 			s.cam_obs.p(), s.obs_pt.p(), ba.pts.p(), ba.z.p(), ba.info.p(), ba.camRt.p(), ba.camK.p(), s.W.p(), s.U.p(), s.gc.p(), \
 			p_max, ba.uf_is_cam? ba.uf_index : -1, ba.pt_rec.p())
 		if(ba.jac_mode == SPP_JAC_FD_REFERENCE)
