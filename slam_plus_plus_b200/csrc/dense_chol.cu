@@ -616,9 +616,10 @@ void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_col
 		make_tensor_map(&ch.df_maps[1], A, ld, n_cols, ld, 16, 64);
 		make_tensor_map(&ch.df_maps[2], A, ld, n_cols, ld, 16, 16);
 		make_tensor_map(&ch.df_maps[3], Rinv, CH_NB, NB * CH_NB, CH_NB, 16, 128);
+		make_tensor_map(&ch.df_maps[4], Rinv, CH_NB, NB * CH_NB, CH_NB, 16, 16);
 		ch.df_A = A; ch.df_ld = ld; ch.df_cols = n_cols; ch.df_Rinv = Rinv;
 	}
-	const size_t n_flags = 4 + 3 * NB + 2 * NB * NJH;
+	const size_t n_flags = 4 + 4 * NB + 2 * NB * NJH;
 	ch.df_flags.resize(n_flags);
 	SPP_CUDA(cudaMemsetAsync(ch.df_flags.p(), 0, n_flags * sizeof(int), st));
 	df::Args args;
@@ -629,12 +630,12 @@ void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_col
 	DBuf<unsigned long long> dbg;
 	args.dbg = 0;
 	if(timing) {
-		dbg.resize(4 * NB + 8 * n_ctas);
+		dbg.resize(5 * NB + 8 * n_ctas);
 		dbg.zero(st);
 		args.dbg = dbg.p();
 		SPP_CUDA(cudaEventRecord(ctx->ev[4], st));
 	}
-	k_chol_dataflow<<<(unsigned)n_ctas, df::THREADS, df::SMEM_BYTES, st>>>(ch.df_maps[0], ch.df_maps[1], ch.df_maps[2], ch.df_maps[3], args);
+	k_chol_dataflow<<<(unsigned)n_ctas, df::THREADS, df::SMEM_BYTES, st>>>(ch.df_maps[0], ch.df_maps[1], ch.df_maps[2], ch.df_maps[3], ch.df_maps[4], args);
 	LAUNCH_CHECK(ctx);
 	if(timing) {
 		SPP_CUDA(cudaEventRecord(ctx->ev[5], st));
@@ -658,11 +659,11 @@ void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_col
 				fprintf(stderr, "[spp chol dataflow] panel %zu at %.1f us: flag->potrf %.1f, potrf %.1f, H1 %.1f, H2 %.1f\n", i,
 					(double)(long long)(d[i] - d[0]) * 1e-3, t_wait, t_potrf, t_h1, t_h2);
 		}
-		fprintf(stderr, "[spp chol dataflow] chain %.1f us: flag->potrf %.1f, potrf %.1f, H1 (incl. waiting for partial sums) %.1f, H2 %.1f\n",
-			(double)(long long)(d[2 * NB - 1] - d[0]) * 1e-3, s_wait, s_potrf, s_h1, s_h2);
+		fprintf(stderr, "[spp chol dataflow] chain %.1f us: flag->potrf %.1f, potrf until the helpers can start %.1f, H1 (incl. waiting for partial sums) %.1f, H2 %.1f\n",
+			(double)(long long)(d[5 * NB - 1] - d[0]) * 1e-3, s_wait, s_potrf, s_h1, s_h2);
 		double w_flags = 0, w_trsm = 0, w_pipe = 0, w_total = 0, t_end_min = 1e30, t_end_max = 0; size_t n_w = 0;
 		for(size_t c = 0; c < n_ctas; ++ c) {
-			const unsigned long long *w = &d[4 * NB + 8 * c];
+			const unsigned long long *w = &d[5 * NB + 8 * c];
 			if(!w[3]) continue; // not a worker
 			++ n_w;
 			w_flags += (double)w[0]; w_trsm += (double)w[1]; w_pipe += (double)w[4]; w_total += (double)w[5];

@@ -242,8 +242,15 @@ __device__ __forceinline__ void lazy_update(double *__restrict__ sm, int k0, int
 // the CTA take part; the whole dynamic shared memory of the CTA is the work tile. Ends with global stores: the caller
 // fences / synchronises before anyone else may read them. Shared between the one-block kernel below and the persistent
 // chain kernel of the dataflow factorisation (chol_dataflow.cu).
+// after_x16: called by all PT threads once the inverses of the eight 16 x 16 diagonal blocks of the factor are in
+// Rinv_out (together with the factor itself in Akk): the dataflow kernel's helpers solve the tile next to the diagonal by
+// blocked substitution with these, so the rest of the inversion (three of four doubling levels, most of its time) is
+// off the critical chain.
+struct PotrfNoHook { __device__ __forceinline__ void operator ()() const {} };
+
+template <class Hook>
 __device__ __forceinline__ void potrf128_block(double *__restrict__ Akk, size_t ld,
-	double *__restrict__ Rinv_out, int *__restrict__ info, int n_info_value, long long *__restrict__ dbg)
+	double *__restrict__ Rinv_out, int *__restrict__ info, int n_info_value, long long *__restrict__ dbg, Hook after_x16)
 {
 #define DBG_MARK(i) do { if(dbg && threadIdx.x == 0) dbg[i] = clock64(); } while(0)
 #ifdef POTRF_TRACE // per-warp time stamps for tools/micro/potrf_bench.cu: dbg[16 + warp * 64 + i]
@@ -257,11 +264,13 @@ __device__ __forceinline__ void potrf128_block(double *__restrict__ Akk, size_t 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int g = lane >> 2, t = lane & 3;
 	DBG_MARK(0);
-	// the upper 8 x 8 tiles, whole tile columns with 16-byte async copies
-	for(int idx = tid; idx < CH_NB * (CH_NB / 2); idx += PT) {
-		const int c = idx >> 6, r2 = (idx & 63) * 2;
-		if(r2 < ((c >> 3) + 1) * 8)
-			__pipeline_memcpy_async(&TC(r2, c), Akk + (size_t)c * ld + r2, 16);
+	// the upper 8 x 8 tiles, whole tile columns with 16-byte async copies; column c is paired with column 127 - c, which
+	// makes 68 copies per pair (no idle trips over the lower triangle: the load is on the critical chain of the
+	// factorisation)
+	for(int idx = tid; idx < (CH_NB / 2) * 68; idx += PT) {
+		const int c0 = idx / 68, q = idx - c0 * 68, n1 = ((c0 >> 3) + 1) * 4;
+		const int c = (q < n1)? c0 : CH_NB - 1 - c0, r2 = 2 * ((q < n1)? q : q - n1);
+		__pipeline_memcpy_async(&TC(r2, c), Akk + (size_t)c * ld + r2, 16);
 	}
 	__pipeline_commit();
 	__pipeline_wait_prior(0);
@@ -363,12 +372,12 @@ __device__ __forceinline__ void potrf128_block(double *__restrict__ Akk, size_t 
 	DBG_MARK(5);
 	if(bad && tid == 0 && *info == 0)
 		*info = n_info_value;
-	// R to global
+	// R to global: column c (c + 1 entries) paired with column 127 - c, 129 entries per pair
 	#pragma unroll 8
-	for(int idx = tid; idx < CH_NB * CH_NB; idx += PT) {
-		const int c = idx >> 7, r = idx & 127;
-		if(r <= c)
-			Akk[(size_t)c * ld + r] = TC(r, c);
+	for(int idx = tid; idx < (CH_NB / 2) * 129; idx += PT) {
+		const int c0 = idx / 129, q = idx - c0 * 129;
+		const int c = (q <= c0)? c0 : CH_NB - 1 - c0, r = (q <= c0)? q : q - c0 - 1;
+		Akk[(size_t)c * ld + r] = TC(r, c);
 	}
 	DBG_MARK(6);
 
@@ -411,6 +420,14 @@ __device__ __forceinline__ void potrf128_block(double *__restrict__ Akk, size_t 
 	TR(42);
 	inv_level<8>(sm, warp, g, t);
 	TR(43);
+	// the 16 x 16 diagonal blocks of the inverse (upper parts; the buffer is zero below the diagonal)
+	#pragma unroll 4
+	for(int idx = tid; idx < 8 * 16 * 16; idx += PT) {
+		const int b = idx >> 8, c = (idx >> 4) & 15, r = idx & 15;
+		if(r <= c)
+			Rinv_out[(size_t)(16 * b + c) * CH_NB + 16 * b + r] = TC(16 * b + r, 16 * b + c);
+	}
+	after_x16();
 	inv_level<16>(sm, warp, g, t);
 	TR(44);
 	inv_level<32>(sm, warp, g, t);
@@ -434,7 +451,7 @@ __device__ __forceinline__ void potrf128_block(double *__restrict__ Akk, size_t 
 __global__ void __launch_bounds__(PT, 1) k_potrf128(double *__restrict__ A, size_t ld, size_t k0,
 	double *__restrict__ Rinv_out, int *__restrict__ info, long long *__restrict__ dbg)
 {
-	potrf128_block(A + k0 * ld + k0, ld, Rinv_out, info, int(k0) + 1, dbg);
+	potrf128_block(A + k0 * ld + k0, ld, Rinv_out, info, int(k0) + 1, dbg, PotrfNoHook());
 }
 
 static const size_t POTRF_SMEM = (size_t)(P3_LD * CH_NB + CH_NB) * sizeof(double);

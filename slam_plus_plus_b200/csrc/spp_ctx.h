@@ -195,7 +195,7 @@ struct DenseChol {
 	DBuf<int> df_flags;       // task / role counters, watchdog, tile flags (zeroed before every launch)
 	DBuf<uint32_t> df_tasks;  // worker task list of the (df_nb, df_njh) shape
 	size_t df_nb, df_njh, df_n_tasks;
-	CUtensorMap df_maps[4];   // TMA descriptors of (df_A, df_ld, df_cols) and df_Rinv
+	CUtensorMap df_maps[5];   // TMA descriptors of (df_A, df_ld, df_cols) and df_Rinv
 	const void *df_A, *df_Rinv;
 	size_t df_ld, df_cols;
 	int n_sms;
