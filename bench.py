@@ -332,15 +332,25 @@ def measure_ba(args, torch, dist, dev, rank, world, local):
         dist.barrier()
     if rank != 0:
         return None
-    # ---- roofline of the dominant kernel group: the dense Cholesky of the reduced camera system
+    # ---- roofline of the dominant kernel: the Cholesky factorisation of the reduced camera system.
+    # dense (Venice): ONE kernel, k_chol_dataflow -- achieved = n^3 / 3 flops / its own launch duration (CUDA events around the
+    # launch on the context's stream, recorded inside the LM loop of the timed region: report field ms_factor_kernel);
+    # block-sparse (BAL): the kernel group of the supernodal factorisation, flops of the numeric phase as executed.
     n = 6 * g.n_cams
     chol_flops = rcs_info["factor_flops"] if sparse_rcs else n ** 3 / 3.0
-    chol_ms = phase["factor"] / max(n_iters, 1)
+    phase_ms = phase["factor"] / max(n_iters, 1)
+    chol_ms = phase_ms if sparse_rcs else phase["factor_kernel"] / max(n_iters, 1)
     fp64_peak = measure_fp64_peak(torch, dev)
     achieved = chol_flops / (chol_ms * 1e-3) / 1e12
     hbm_peak, hbm_src = load_peaks()
     O, P, Cn = g.n_obs, g.n_pts, g.n_cams
     bytes_lin = 200 * O + 120 * P + 424 * Cn
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "chol_traffic.json")  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+    if os.path.exists(tpath) and not sparse_rcs:
+        td = json.load(open(tpath)).get(args.shape)
+        if td:
+            traffic, traffic_src = td["dram_bytes_per_launch"], td["source"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -359,12 +369,11 @@ def measure_ba(args, torch, dist, dev, rank, world, local):
         "phase_ms_per_lm_iteration": {k: v / max(n_iters, 1) for k, v in phase.items()},
         "roofline": {"bound": "tensor", "kernel": ("supernodal block Cholesky of the %d^2 reduced camera system, %d supernodes (k_snode_update + k_gemm_tn DMMA, k_potrf128)"
                                                    % (n, rcs_info["supernodes"])) if sparse_rcs else
-                     "dense Cholesky %d^2 (k_potrf128 + k_gemm_tn<TRSM> + k_gemm_tn<SYRK> DMMA)" % n,
+                     "k_chol_dataflow: dense FP64 Cholesky %d^2 as one persistent dataflow kernel (TMA-fed mma.sync.m8n8k4.f64 tile tasks, chain / helper / worker CTAs)" % n,
                      "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                     # DRAM bytes of one factorisation + solves of the Venice-shape system, summed over its kernels from the
-                     # ncu pass recorded in profiles/r1g_chol_traffic.csv (dram__bytes_read.sum + dram__bytes_write.sum)
-                     "traffic": 2396.9e6 if (not sparse_rcs and args.shape == "venice871") else None,
-                     "traffic_source": "profiles/r1g_chol_traffic.csv" if (not sparse_rcs and args.shape == "venice871") else None,
+                     "kernel_ms": chol_ms, "traffic": traffic, "traffic_source": traffic_src,
+                     "factor_phase": {"ms": phase_ms, "tflops": chol_flops / (phase_ms * 1e-3) / 1e12, "frac": chol_flops / (phase_ms * 1e-3) / 1e12 / fp64_peak,
+                                      "note": "the whole factor phase of an LM iteration: flag reset, padding, right-hand side copies, the factorisation kernel, the backward solve"},
                      "flops_per_launch": chol_flops,
                      "peak_source": "FP64: cuBLAS DGEMM 4096^3 via torch.matmul measured in this run (no FP64 entry in MEASURED_PEAKS.json)",
                      "hbm_stage": {"kernel": "linearise (k_cam_prepare + k_linearise_cams + k_sum_point_records)",

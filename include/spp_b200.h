@@ -59,6 +59,9 @@ typedef struct {
 	/* device time of the phases, milliseconds, summed over the call (CUDA events); phase names follow the
 	 * reference's Dump() (LM.h:547-..): lambda, rhs/schur, linsolve, update, chi2 */
 	double ms_linearise, ms_schur, ms_factor, ms_backsubst, ms_update, ms_chi2, ms_total;
+	/* part of ms_factor: the launches of the dense factorisation kernel alone (k_chol_dataflow; 0 when the reduced system
+	 * is factored block-sparse) -- the launch duration the roofline of that kernel is computed from */
+	double ms_factor_kernel;
 } spp_report_t;
 
 /* ---- context ---------------------------------------------------------------------------------------- */

@@ -45,6 +45,7 @@ class Report(C.Structure):
         ("trace_dx_norm", C.c_double * MAX_TRACE), ("trace_accepted", C.c_uint8 * MAX_TRACE),
         ("ms_linearise", C.c_double), ("ms_schur", C.c_double), ("ms_factor", C.c_double),
         ("ms_backsubst", C.c_double), ("ms_update", C.c_double), ("ms_chi2", C.c_double), ("ms_total", C.c_double),
+        ("ms_factor_kernel", C.c_double),
     ]
 
     def as_dict(self) -> dict:
@@ -56,7 +57,8 @@ class Report(C.Structure):
             trace_alpha=list(self.trace_alpha[:n]), trace_chi2=list(self.trace_chi2[:n]),
             trace_dx_norm=list(self.trace_dx_norm[:n]), trace_accepted=[int(x) for x in self.trace_accepted[:n]],
             ms=dict(linearise=self.ms_linearise, schur=self.ms_schur, factor=self.ms_factor,
-                    backsubst=self.ms_backsubst, update=self.ms_update, chi2=self.ms_chi2, total=self.ms_total))
+                    backsubst=self.ms_backsubst, update=self.ms_update, chi2=self.ms_chi2, total=self.ms_total,
+                    factor_kernel=self.ms_factor_kernel))
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)

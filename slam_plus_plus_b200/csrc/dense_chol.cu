@@ -635,8 +635,19 @@ void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_col
 		args.dbg = dbg.p();
 		SPP_CUDA(cudaEventRecord(ctx->ev[4], st));
 	}
+	if(ctx->async_mode) { // the LM loop reads this pair after its one synchronisation (ms_factor_kernel)
+		if(!ctx->phase_ev[PH_CHOL_KERNEL][0]) {
+			SPP_CUDA(cudaEventCreate(&ctx->phase_ev[PH_CHOL_KERNEL][0]));
+			SPP_CUDA(cudaEventCreate(&ctx->phase_ev[PH_CHOL_KERNEL][1]));
+		}
+		SPP_CUDA(cudaEventRecord(ctx->phase_ev[PH_CHOL_KERNEL][0], st));
+	}
 	k_chol_dataflow<<<(unsigned)n_ctas, df::THREADS, df::SMEM_BYTES, st>>>(ch.df_maps[0], ch.df_maps[1], ch.df_maps[2], ch.df_maps[3], ch.df_maps[4], args);
 	LAUNCH_CHECK(ctx);
+	if(ctx->async_mode) {
+		SPP_CUDA(cudaEventRecord(ctx->phase_ev[PH_CHOL_KERNEL][1], st));
+		ctx->phase_used[PH_CHOL_KERNEL] = true;
+	}
 	if(timing) {
 		SPP_CUDA(cudaEventRecord(ctx->ev[5], st));
 		SPP_CUDA(cudaEventSynchronize(ctx->ev[5]));

@@ -191,7 +191,7 @@ static bool rcs_is_sparse(spp_ctx *ctx, size_t C)
 
 static const size_t g_phase_field[PH_COUNT] = {offsetof(spp_report_t, ms_linearise), offsetof(spp_report_t, ms_schur),
 	offsetof(spp_report_t, ms_factor), offsetof(spp_report_t, ms_backsubst), offsetof(spp_report_t, ms_update),
-	offsetof(spp_report_t, ms_chi2)};
+	offsetof(spp_report_t, ms_chi2), offsetof(spp_report_t, ms_factor_kernel)};
 
 static void phase_begin(spp_ctx *ctx, int ph)
 {

@@ -207,7 +207,7 @@ struct DenseChol {
 
 // phases of one LM iteration; in asynchronous mode (the LM loop) their event pairs are recorded without host
 // synchronisation and read after the one synchronisation of the iteration
-enum { PH_LINEARISE = 0, PH_SCHUR, PH_FACTOR, PH_BACKSUBST, PH_UPDATE, PH_CHI2, PH_COUNT };
+enum { PH_LINEARISE = 0, PH_SCHUR, PH_FACTOR, PH_BACKSUBST, PH_UPDATE, PH_CHI2, PH_CHOL_KERNEL /* inside PH_FACTOR */, PH_COUNT };
 
 struct spp_ctx {
 	int device;

@@ -18,6 +18,9 @@ COLS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
         ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64_pipe_pct"),
         ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_cycles_pct"),
+        ("sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active", "dmma_pipe_pct"),
+        ("sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active", "dmma_inst_pct"),
+        ("sm__cycles_active.avg", "sm_cycles_active"), ("sm__cycles_elapsed.avg", "sm_cycles_elapsed"),
         ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"), ("launch__block_size", "block")]
 
 
