@@ -150,6 +150,120 @@ __device__ __forceinline__ void schur_accumulate(uint64_t k0, uint64_t end, uint
 	}
 }
 
+// Second lane mapping (MAP_K): lane q = r3 + 3 k of a group owns the rows {2 r3, 2 r3 + 1} of the product and ONE value k of
+// the summation index (a column of Y_a / W_b): per pair it loads its own 16-byte chunk of Y_a -- the nine lanes of a group
+// cover the 144-byte block exactly once -- and the 48 bytes of column k of W_b, i.e. four 16-byte loads instead of six and
+// ~10 instead of ~16 L1 wavefronts per pair (the kernel is L1-throughput bound: 74 %, profiles/r2q_full.csv); twelve
+// accumulators per lane, the three k-partials of a row pair are added at the very end (k ascending: fixed order).
+struct SchurAccK {
+	double s[2][6], b[2]; // (row 2 r3 + i, column c) partial over this lane's k; rhs rows
+};
+
+template <bool RHS, int SB_UNROLL>
+__device__ __forceinline__ void schur_accumulate_k(uint64_t k0, uint64_t end, uint64_t stride, int r3, int kk,
+	const uint32_t *__restrict__ pair_a, const uint32_t *__restrict__ pair_b, const double *__restrict__ Y,
+	const double *__restrict__ W, const double *__restrict__ gp, const uint32_t *__restrict__ obs_pt, SchurAccK &acc)
+{
+	const double2 zero2 = make_double2(0.0, 0.0);
+	unsigned oa[SB_UNROLL], ob[SB_UNROLL];
+	bool ok[SB_UNROLL];
+	#pragma unroll
+	for(int u = 0; u < SB_UNROLL; ++ u) {
+		const uint64_t q = k0 + u * stride;
+		ok[u] = q < end;
+		oa[u] = ok[u]? pair_a[q] : 0u;
+		ob[u] = RHS? oa[u] : (ok[u]? pair_b[q] : 0u);
+	}
+	for(uint64_t k = k0; k < end; k += SB_UNROLL * stride) {
+		double2 y[SB_UNROLL], w[SB_UNROLL][3];
+		double g[SB_UNROLL];
+		#pragma unroll
+		for(int u = 0; u < SB_UNROLL; ++ u) {
+			const double2 *Wb = reinterpret_cast<const double2*>(W + (size_t)ob[u] * 18 + 6 * kk);
+			y[u] = ok[u]? *reinterpret_cast<const double2*>(Y + (size_t)oa[u] * 18 + 6 * kk + 2 * r3) : zero2;
+			#pragma unroll
+			for(int q = 0; q < 3; ++ q)
+				w[u][q] = ok[u]? Wb[q] : zero2;
+			if(RHS)
+				g[u] = ok[u]? gp[(size_t)obs_pt[oa[u]] * 3 + kk] : 0.0;
+		}
+		#pragma unroll
+		for(int u = 0; u < SB_UNROLL; ++ u) { // next trip's indices
+			const uint64_t q = k + (SB_UNROLL + u) * stride;
+			ok[u] = q < end;
+			oa[u] = ok[u]? pair_a[q] : 0u;
+			ob[u] = RHS? oa[u] : (ok[u]? pair_b[q] : 0u);
+		}
+		#pragma unroll
+		for(int u = 0; u < SB_UNROLL; ++ u) {
+			#pragma unroll
+			for(int q = 0; q < 3; ++ q) {
+				acc.s[0][2 * q] += y[u].x * w[u][q].x;
+				acc.s[0][2 * q + 1] += y[u].x * w[u][q].y;
+				acc.s[1][2 * q] += y[u].y * w[u][q].x;
+				acc.s[1][2 * q + 1] += y[u].y * w[u][q].y;
+			}
+			if(RHS) {
+				acc.b[0] += y[u].x * g[u];
+				acc.b[1] += y[u].y * g[u];
+			}
+		}
+	}
+}
+
+// sums v over the three k-lanes of a row pair (lanes r3, r3 + 3, r3 + 6 of the group; k ascending), result valid in the k = 0 lane
+__device__ __forceinline__ double sum_over_k(double v, int lane)
+{
+	const double v1 = __shfl_sync(0xffffffffu, v, (lane + 3) & 31), v2 = __shfl_sync(0xffffffffu, v, (lane + 6) & 31);
+	return (v + v1) + v2;
+}
+
+// off-diagonal blocks, MAP_K lane mapping
+template <int UNROLL>
+__global__ void __launch_bounds__(SB_WARPS * 32, 2) k_schur_blocks_k(size_t first_blk, size_t n_blocks_total, size_t ld,
+	const uint32_t *__restrict__ blk_row, const uint32_t *__restrict__ blk_col, const uint64_t *__restrict__ blk_ptr,
+	const uint32_t *__restrict__ pair_a, const uint32_t *__restrict__ pair_b, const double *__restrict__ Y,
+	const double *__restrict__ W, double *__restrict__ S, const uint32_t *__restrict__ slot, unsigned *__restrict__ queue)
+{
+	const int lane = threadIdx.x & 31;
+	const int grp = lane / 9, q9 = lane - grp * 9, r3 = q9 % 3, kk = q9 / 3;
+	for(;;) {
+		unsigned idx = 0;
+		if(lane == 0)
+			idx = atomicAdd(queue, 1u);
+		const size_t blk = first_blk + __shfl_sync(0xffffffffu, idx, 0);
+		if(blk >= n_blocks_total) return;
+		const unsigned bi = blk_row[blk], bj = blk_col[blk];
+		SchurAccK acc;
+		#pragma unroll
+		for(int i = 0; i < 2; ++ i) {
+			#pragma unroll
+			for(int c = 0; c < 6; ++ c) acc.s[i][c] = 0;
+			acc.b[i] = 0;
+		}
+		if(grp < 3)
+			schur_accumulate_k<false, UNROLL>(blk_ptr[blk] + grp, blk_ptr[blk + 1], 3, r3, kk, pair_a, pair_b, Y, W, 0, 0, acc);
+		#pragma unroll
+		for(int i = 0; i < 2; ++ i) {
+			#pragma unroll
+			for(int c = 0; c < 6; ++ c) {
+				double v = sum_over_k(acc.s[i][c], lane);
+				const double v1 = __shfl_sync(0xffffffffu, v, (lane + 9) & 31), v2 = __shfl_sync(0xffffffffu, v, (lane + 18) & 31);
+				acc.s[i][c] = (v + v1) + v2; // the three pair groups, fixed order
+			}
+		}
+		if(lane < 3) { // k = 0 lanes of group 0: rows 2 r3, 2 r3 + 1
+			const size_t ldo = ld? ld : 6;
+			double *Sb = ld? S + ((size_t)bj * 6) * ld + (size_t)bi * 6 + 2 * r3 : S + (size_t)(slot? slot[blk] : blk) * 36 + 2 * r3;
+			#pragma unroll
+			for(int c = 0; c < 6; ++ c) {
+				Sb[c * ldo] = -acc.s[0][c];
+				Sb[c * ldo + 1] = -acc.s[1][c];
+			}
+		}
+	}
+}
+
 // off-diagonal blocks (list entries first_blk ..): one warp per block. The pair lists differ a lot in length (1 .. several
 // hundred pairs), so with a fixed block -> warp assignment a CTA lives as long as its longest list while its other
 // warps idle (33 % of the warp slots active, profiles/r1k_full.csv); with `queue` the warps of a persistent grid take
@@ -239,6 +353,59 @@ __global__ void __launch_bounds__(SB_WARPS * 32) k_schur_diag(size_t ld, double 
 	}
 }
 
+// diagonal blocks, MAP_K lane mapping (see k_schur_blocks_k)
+__global__ void __launch_bounds__(SB_WARPS * 32, 2) k_schur_diag_k(size_t ld, double alpha, const uint64_t *__restrict__ blk_ptr,
+	const uint32_t *__restrict__ pair_a, const double *__restrict__ Y, const double *__restrict__ W,
+	const double *__restrict__ U, const double *__restrict__ gc, const double *__restrict__ gp,
+	const uint32_t *__restrict__ obs_pt, double *__restrict__ S, double *__restrict__ b, const uint32_t *__restrict__ slot)
+{
+	__shared__ double part[3 * SB_WARPS][3][14]; // per lane group: rows 2 r3, 2 r3 + 1 x 6 columns, then the two rhs rows
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const size_t bi = blockIdx.x;
+	const int grp = lane / 9, q9 = lane - grp * 9, r3 = q9 % 3, kk = q9 / 3;
+	SchurAccK acc;
+	#pragma unroll
+	for(int i = 0; i < 2; ++ i) {
+		#pragma unroll
+		for(int c = 0; c < 6; ++ c) acc.s[i][c] = 0;
+		acc.b[i] = 0;
+	}
+	if(grp < 3)
+		schur_accumulate_k<true, 4>(blk_ptr[bi] + warp * 3 + grp, blk_ptr[bi + 1], 3 * SB_WARPS, r3, kk, pair_a, pair_a, Y, W, gp, obs_pt, acc);
+	#pragma unroll
+	for(int i = 0; i < 2; ++ i) {
+		#pragma unroll
+		for(int c = 0; c < 6; ++ c)
+			acc.s[i][c] = sum_over_k(acc.s[i][c], lane);
+		acc.b[i] = sum_over_k(acc.b[i], lane);
+	}
+	if(grp < 3 && kk == 0) {
+		double *pp = part[warp * 3 + grp][r3];
+		#pragma unroll
+		for(int c = 0; c < 6; ++ c) {
+			pp[2 * c] = acc.s[0][c];
+			pp[2 * c + 1] = acc.s[1][c];
+		}
+		pp[12] = acc.b[0];
+		pp[13] = acc.b[1];
+	}
+	__syncthreads();
+	if(threadIdx.x < 42) { // 36 entries of the block (column-major: row pair r3, element e = 2 c + i), then the 6 rhs rows
+		const int t = threadIdx.x;
+		const int row = (t < 36)? t % 6 : t - 36, col = (t < 36)? t / 6 : 6;
+		const int pr = row >> 1, e = (t < 36)? 2 * col + (row & 1) : 12 + (row & 1);
+		double v = 0;
+		for(int sgrp = 0; sgrp < 3 * SB_WARPS; ++ sgrp)
+			v += part[sgrp][pr][e];
+		if(t < 36) {
+			const double u = U[bi * 36 + col * 6 + row] + ((row == col)? alpha : 0.0);
+			double *Sb = ld? S + (bi * 6 + col) * ld + bi * 6 + row : S + (size_t)(slot? slot[bi] : bi) * 36 + col * 6 + row;
+			*Sb = u - v;
+		} else
+			b[bi * 6 + row] = gc[bi * 6 + row] - v;
+	}
+}
+
 // thread per landmark: dl = Cinv (gp - sum_o W_o^T dxc_{c(o)})
 __global__ void k_backsubstitute(size_t P, const uint32_t *__restrict__ pt_ptr, const uint32_t *__restrict__ obs_cam,
 	const double *__restrict__ W, const double *__restrict__ Cinv, const double *__restrict__ gp,
@@ -308,9 +475,14 @@ void schur_form_reduced_system(spp_ctx *ctx, double alpha, double alpha_diag, bo
 	}
 	if(!sparse_rcs)
 		s.S.zero(ctx->stream);
+	static const int map_k = getenv("SPP_SCHUR_MAPK")? atoi(getenv("SPP_SCHUR_MAPK")) : 4;
 	if(s.C) { // list entries 0 .. C-1 are the diagonal blocks
-		k_schur_diag<<<(unsigned)s.C, SB_WARPS * 32, 0, ctx->stream>>>(ld, alpha_diag, s.blk_ptr.p(), s.pair_a.p(), s.Y.p(),
-			s.W.p(), s.U.p(), s.gc.p(), s.gp.p(), s.obs_pt.p(), S_out, s.b.p(), slot);
+		if(map_k)
+			k_schur_diag_k<<<(unsigned)s.C, SB_WARPS * 32, 0, ctx->stream>>>(ld, alpha_diag, s.blk_ptr.p(), s.pair_a.p(), s.Y.p(),
+				s.W.p(), s.U.p(), s.gc.p(), s.gp.p(), s.obs_pt.p(), S_out, s.b.p(), slot);
+		else
+			k_schur_diag<<<(unsigned)s.C, SB_WARPS * 32, 0, ctx->stream>>>(ld, alpha_diag, s.blk_ptr.p(), s.pair_a.p(), s.Y.p(),
+				s.W.p(), s.U.p(), s.gc.p(), s.gp.p(), s.obs_pt.p(), S_out, s.b.p(), slot);
 		LAUNCH_CHECK(ctx);
 	}
 	if(s.n_blocks > s.C) {
@@ -327,7 +499,14 @@ void schur_form_reduced_system(spp_ctx *ctx, double alpha, double alpha_diag, bo
 			SPP_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned), ctx->stream));
 			grid = std::min(grid, (unsigned)n_sms * ((unroll >= 4)? 2u : 4u));
 		}
-		if(unroll >= 4)
+		if(map_k && use_queue) {
+			if(map_k >= 4)
+				k_schur_blocks_k<4><<<grid, SB_WARPS * 32, 0, ctx->stream>>>(s.C, s.n_blocks, ld,
+					s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), S_out, slot, queue);
+			else
+				k_schur_blocks_k<2><<<grid, SB_WARPS * 32, 0, ctx->stream>>>(s.C, s.n_blocks, ld,
+					s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), S_out, slot, queue);
+		} else if(unroll >= 4)
 			k_schur_blocks<4><<<grid, SB_WARPS * 32, 0, ctx->stream>>>(s.C, s.n_blocks, ld,
 				s.blk_row.p(), s.blk_col.p(), s.blk_ptr.p(), s.pair_a.p(), s.pair_b.p(), s.Y.p(), s.W.p(), S_out, slot, queue);
 		else
