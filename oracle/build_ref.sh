@@ -15,7 +15,7 @@
 set -u
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${SPP_REFERENCE:-/root/reference}"
-OUT="$HERE/_ref"
+OUT="${SPP_REF_OUT:-$HERE/_ref}"
 OBJ="$OUT/obj"
 CXX=/usr/bin/g++
 CC=/usr/bin/gcc

@@ -85,6 +85,9 @@ static int Run_Solver(const spp_graph_t &g, bool b_incremental, FILE *p_fw, size
 			double f_start = timer.f_Time();
 			solver.Incremental_Step(r_edge);
 			f_opt_time += timer.f_Time() - f_start;
+			if(getenv("SPP_TRACE_STEPS") && k < (uint64_t)atol(getenv("SPP_TRACE_STEPS"))) // debugging aid: the state after every edge
+				printf("step %zu: edge %zu -> %zu, %zu vertices, chi2 %.12g\n", size_t(k), size_t(g.e0[e]), size_t(g.e1[e]),
+					system.r_Vertex_Pool().n_Size(), solver.f_Chi_Squared_Error_Denorm());
 		}
 	}
 	if(!b_incremental)

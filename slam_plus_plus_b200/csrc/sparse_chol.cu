@@ -326,9 +326,12 @@ struct SparseCholArgs {
 
 // one warp: T(r, c) = A-part - sum over the update pairs of La(r, :) . Lb(c, :); lane e = r + B c (lanes >= B*B idle;
 // B = 6 uses lanes 0..17 with two elements each: e and e + 18)
+// b_given: the update pairs are pa / pb [pbeg, pend) instead of the block's own list. (A flag, not "pa != 0": a root front
+// that covers the whole matrix has an EMPTY pair list, a null pointer, and must not fall back to the block's own list,
+// whose L blocks are never formed for root columns.)
 template <int B>
 __device__ __forceinline__ void block_update(const SparseCholArgs &a, uint32_t blk, int lane, double (&t)[2],
-	const uint32_t *pa = 0, const uint32_t *pb = 0, uint64_t pbeg = 0, uint64_t pend = 0)
+	const uint32_t *pa = 0, const uint32_t *pb = 0, uint64_t pbeg = 0, uint64_t pend = 0, bool b_given = false)
 {
 	constexpr int BB = B * B, NE = (BB > 32)? 2 : 1, STEP = (BB > 32)? BB / 2 : 0;
 	const int64_t s = a.src[blk];
@@ -342,8 +345,8 @@ __device__ __forceinline__ void block_update(const SparseCholArgs &a, uint32_t b
 			t[u] = (s > 0)? Ab[e] : Ab[c + B * r]; // transposed source
 		}
 	}
-	const uint32_t *ua = pa? pa : a.ua, *ub = pa? pb : a.ub;
-	const uint64_t beg = pa? pbeg : a.uptr[blk], end = pa? pend : a.uptr[blk + 1];
+	const uint32_t *ua = b_given? pa : a.ua, *ub = b_given? pb : a.ub;
+	const uint64_t beg = b_given? pbeg : a.uptr[blk], end = b_given? pend : a.uptr[blk + 1];
 	for(uint64_t q = beg; q < end; ++ q) {
 		const double *La = a.L + (size_t)ua[q] * BB, *Lb = a.L + (size_t)ub[q] * BB;
 		#pragma unroll
@@ -558,7 +561,7 @@ __global__ void __launch_bounds__(SC_WARPS * 32) k_root_assemble(SparseCholArgs 
 	const uint32_t blk = ra.blk[q];
 	const size_t i = ra.ridx[a.lrow[blk]], j = ra.ridx[a.lcolof[blk]];
 	double t[2];
-	block_update<B>(a, blk, lane, t, ra.ua, ra.ub, ra.uptr[q], ra.uptr[q + 1]);
+	block_update<B>(a, blk, lane, t, ra.ua, ra.ub, ra.uptr[q], ra.uptr[q + 1], true);
 	#pragma unroll
 	for(int u = 0; u < NE; ++ u) {
 		const int e = lane + u * STEP;

@@ -201,3 +201,24 @@ def test_se3_gauss_newton_vs_reference(ctx, name):
         rep = ctx.pose_optimize(n_it, 0.0)
         assert rep["n_iterations"] == int(d["n_solves"][0])
         assert abs(rep["chi2_final"] - d["chi2"][0]) <= 1e-5 * d["chi2"][0]
+
+
+def test_growing_graph_on_one_context_equals_fresh_contexts():
+    """what the slot-3 pose adapter does in an incremental run: the same context receives a longer and longer graph.
+    Small graphs whose whole matrix is one dense root front used to fail or not depending on what the factor buffer held
+    (the root assembly fell back to the update list of the level-scheduled factorisation when its own list was empty)."""
+    from slam_plus_plus_b200 import capi, graphs
+    from slam_plus_plus_b200.sppio import PoseGraph
+    g = graphs.make_manhattan(400, 150, seed=5)
+    ctx = capi.Context(0)
+    for n in (40, 90, 150, 220, 400):
+        m = np.maximum(g.e_from, g.e_to) < n
+        sub = PoseGraph(g.kind, g.poses[:n].copy(), g.e_from[m], g.e_to[m], g.z[m], g.info[m])
+        reps = []
+        for c in (ctx, capi.Context(0)):
+            c.pose_set_graph(sub)
+            reps.append(c.pose_optimize(5, 0.01))
+        a, b = reps
+        assert a["status"] == b["status"] == 0
+        assert a["n_iterations"] == b["n_iterations"] and a["trace_dx_norm"] == b["trace_dx_norm"]
+        assert a["chi2_final"] == b["chi2_final"] < a["chi2_initial"]
