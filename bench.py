@@ -421,7 +421,7 @@ def measure_ba(args, torch, dist, dev, rank, world, local):
 
 POSE_SHAPES = {
     # BASELINE.json configs[0] and configs[2] shapes (replicas only: pose graphs do not shard)
-    "manhattan3500": ("make_manhattan", {}),
+    "manhattan3500": ("make_manhattan", dict(fill_loops=True)),
     "sphere2500": ("make_sphere", dict(n_rings=50, n_per_ring=50, seed=2500, sigma_t=0.004, sigma_r=0.0004, radius=5.0)),
 }
 

@@ -273,7 +273,7 @@ def test_incremental_manhattan3500_matches_reference_solve_for_solve(tmp_path):
     if not os.path.exists(BIN_GN):
         pytest.skip("oracle/_ref/ref_driver_dropin_gn not built (needs /root/reference at build time)")
     from slam_plus_plus_b200 import graphs, sppio
-    g = graphs.make_manhattan()
+    g = graphs.make_manhattan(fill_loops=True)
     gp = str(tmp_path / "g.bin")
     sppio.write_graph(gp, g)
     norms, chi2 = {}, {}

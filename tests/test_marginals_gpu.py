@@ -132,7 +132,7 @@ def test_pose_marginals_manhattan_size(ctx):
     from test_pose_cpu import pose_lambda_to_dense
     import scipy.sparse
     import scipy.sparse.linalg
-    g = graphs.make_manhattan()
+    g = graphs.make_manhattan(fill_loops=True)
     ctx.pose_set_graph(g)
     ctx.pose_optimize(5, 0.0)
     ctx.pose_linearise()

@@ -100,7 +100,7 @@ def test_manhattan_full_size_vs_reference_and_oracle(ctx, tmp_path):
     """BASELINE.json configs[0] shape (3500 poses): against the reference run on this machine when oracle/_ref is
     present, and through size-independent properties (normal-equation residual, chi2 decrease)."""
     from slam_plus_plus_b200 import graphs, sppio
-    g = graphs.make_manhattan()
+    g = graphs.make_manhattan(fill_loops=True)
     ctx.pose_set_graph(g)
     ctx.pose_linearise()
     cp, ri, vals, eta = ctx.pose_get_lambda()

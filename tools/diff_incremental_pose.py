@@ -16,7 +16,7 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "ref_driver_dropin_gn")
 name = sys.argv[1] if len(sys.argv) > 1 else "sphere2500"
 min_dx = sys.argv[2] if len(sys.argv) > 2 else "0.01"
 period = sys.argv[3] if len(sys.argv) > 3 else "10"
-g = graphs.make_manhattan() if name.startswith("manhattan") else graphs.make_sphere(
+g = graphs.make_manhattan(fill_loops=True) if name.startswith("manhattan") else graphs.make_sphere(
     n_rings=50, n_per_ring=50, seed=2500, sigma_t=0.004, sigma_r=0.0004, radius=5.0)
 norms = {}
 with tempfile.TemporaryDirectory() as td:

@@ -16,7 +16,7 @@ def prefix(g, n):
     return PoseGraph(g.kind, g.poses[:n].copy(), g.e_from[m], g.e_to[m], g.z[m], g.info[m])
 
 
-g = graphs.make_manhattan()
+g = graphs.make_manhattan(fill_loops=True)
 sizes = [int(a) for a in sys.argv[1:]] or [50, 150, 220, 280]
 ctx = capi.Context(0)
 for n in sizes:

@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 from slam_plus_plus_b200 import graphs, sppio  # noqa: E402
 
 BIN = os.path.join(ROOT, "oracle", "_ref", "ref_driver_dropin_gn")
-GRAPHS = (("manhattan3500", graphs.make_manhattan()),
+GRAPHS = (("manhattan3500", graphs.make_manhattan(fill_loops=True)),
           ("sphere2500", graphs.make_sphere(n_rings=50, n_per_ring=50, seed=2500, sigma_t=0.004, sigma_r=0.0004, radius=5.0)))
 with tempfile.TemporaryDirectory() as td:
     for name, g in GRAPHS:

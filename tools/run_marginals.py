@@ -33,7 +33,7 @@ for alpha in (0.0, 1.0):
     print("bitwise reproducible:", bool(np.array_equal(cc, cc2) and np.array_equal(pc, pc2)), flush=True)
 
 # pose graphs: block diagonal of lambda^-1 through the dense inverse (spp_pose_marginals)
-for name, gp in (("manhattan3500", graphs.make_manhattan()),
+for name, gp in (("manhattan3500", graphs.make_manhattan(fill_loops=True)),
                  ("sphere2500", graphs.make_sphere(n_rings=50, n_per_ring=50, seed=2500, sigma_t=0.004, sigma_r=0.0004, radius=5.0))):
     ctx.pose_set_graph(gp)
     ctx.pose_optimize(5, 0.0)

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from slam_plus_plus_b200 import capi, graphs, sppio  # noqa: E402
 
-g = graphs.make_manhattan()
+g = graphs.make_manhattan(fill_loops=True)
 ctx = capi.Context(0)
 t = time.time()
 ctx.pose_set_graph(g)

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from slam_plus_plus_b200 import graphs, sppio  # noqa: E402
 
-g = graphs.make_manhattan() if (len(sys.argv) < 3 or sys.argv[2].startswith("manhattan")) else graphs.make_sphere(
+g = graphs.make_manhattan(fill_loops=True) if (len(sys.argv) < 3 or sys.argv[2].startswith("manhattan")) else graphs.make_sphere(
     n_rings=50, n_per_ring=50, seed=2500, sigma_t=0.004, sigma_r=0.0004, radius=5.0)
 td = tempfile.mkdtemp()
 sppio.write_graph(f"{td}/g.bin", g)
