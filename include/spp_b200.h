@@ -264,6 +264,14 @@ int spp_block_symbolic_stats(size_t n_block_cols, const uint64_t *p_col_ptr, con
  * Upper> of a dense column-major n x n matrix of which only the upper triangle is read, then two triangular
  * solves; p_rhs_x is the right-hand side on input, the solution on output. Host pointers. */
 int spp_dense_posdef_solve(spp_ctx_t ctx, size_t n, const double *p_A, double *p_rhs_x);
+/* The dense front primitive underneath both Cholesky paths (the dense reduced camera system is one front with its
+ * right-hand side, a supernode of the block-sparse factorisation a front with its row structure): p_panel is column-major
+ * with n_rows rows (a multiple of 128) and n_cols >= n_rows columns (a multiple of 128); on return its leading n_rows x
+ * n_rows upper triangle holds R11 (R11^T R11 = A11; the strictly lower triangle is unspecified) and the remaining columns
+ * R11^-T A12. Returns SPP_NOT_POSDEF at a non-positive pivot. Exposed for tests and for callers that bring their own
+ * frontal scheme; the reference has no counterpart (its dense step is Eigen's LLT, src/slam/LinearSolver_Schur.cpp:
+ * 2314-2333, its sparse one the block-column CholeskyOf_FBS, include/slam/BlockMatrixFBS.inl:2341-2513). */
+int spp_dense_panel_factor(spp_ctx_t ctx, size_t n_rows, size_t n_cols, double *p_panel);
 
 /* ---- block-sparse FP64 Cholesky (pose graphs; sparse reduced camera systems) ------------------------------ */
 

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "spp_ba_optimize", "spp_ba_marginals", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_marginals",
     "spp_schur_get_reduced_system",
     "spp_schur_set_rcs_solver", "spp_schur_set_rcs_ordering", "spp_schur_get_rcs_info", "spp_schur_get_rcs_residual", "spp_block_ordering",
-    "spp_block_symbolic_stats", "spp_dense_posdef_solve", "spp_nccl_get_unique_id", "spp_set_nccl",
+    "spp_block_symbolic_stats", "spp_dense_posdef_solve", "spp_dense_panel_factor", "spp_nccl_get_unique_id", "spp_set_nccl",
     "spp_chol_symbolic", "spp_chol_solve", "spp_chol_get_factor",
     "spp_pose_set_graph", "spp_pose_set_ordering", "spp_pose_set_states", "spp_pose_get_states", "spp_pose_restore_initial",
     "spp_pose_linearise", "spp_pose_get_lambda", "spp_pose_chi2", "spp_pose_solve_step", "spp_pose_optimize",
@@ -109,6 +109,7 @@ def load_library() -> C.CDLL:
     lib.spp_schur_marginals.argtypes = [vp, C.c_double, dp, dp]
     lib.spp_schur_get_reduced_system.argtypes = [vp, u64p, dp, dp, u8p]
     lib.spp_dense_posdef_solve.argtypes = [vp, C.c_size_t, dp, dp]
+    lib.spp_dense_panel_factor.argtypes = [vp, C.c_size_t, C.c_size_t, dp]
     lib.spp_nccl_get_unique_id.argtypes = [C.c_void_p]
     lib.spp_set_nccl.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
     lib.spp_schur_set_rcs_solver.argtypes = [vp, C.c_int]
@@ -458,6 +459,12 @@ class Context:
         x = np.array(b, np.float64, copy=True)
         self._check(self.lib.spp_dense_posdef_solve(self.h, A.shape[0], A.ctypes.data_as(C.POINTER(C.c_double)), _dp(x)))
         return x
+
+    def dense_panel_factor(self, panel) -> np.ndarray:
+        """panel: (n_rows, n_cols) array; returns [R11 (upper triangle) | R11^-T A12] of the same shape."""
+        p = np.asfortranarray(panel, np.float64).copy(order="F")
+        self._check(self.lib.spp_dense_panel_factor(self.h, p.shape[0], p.shape[1], p.ctypes.data_as(C.POINTER(C.c_double))))
+        return p
 
     # ---- block-sparse Cholesky (slot: CLinearSolver_UberBlock) -------------------------------------
     def chol_symbolic(self, block_size: int, col_ptr, row_idx, order=None) -> np.ndarray:

@@ -584,7 +584,8 @@ void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_col
 		SPP_CUDA(cudaDeviceGetAttribute(&ch.n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
 		SPP_CUDA(cudaFuncSetAttribute(k_chol_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)df::SMEM_BYTES));
 	}
-	if(ch.df_nb != NB || ch.df_njh != NJH) {
+	DenseChol::DfTaskList &tl = ch.df_tasks[((uint64_t)NB << 32) | NJH];
+	if(!tl.n_tasks) {
 		// Worker tasks sorted by the key  i + (j - i) / beta  (row i, tile column j): row-major order with the tiles far from the
 		// diagonal pushed back behind the near-diagonal tiles of the following rows, which the critical chain needs first. Any
 		// beta > 1 keeps the order topological (a tile's operands (k, i), (k, j), k < i, have smaller keys). The partial sums
@@ -607,25 +608,24 @@ void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_col
 		std::vector<uint32_t> tasks;
 		for(size_t q = 0; q < keyed.size(); ++ q)
 			tasks.push_back(keyed[q].second);
-		ch.df_tasks.upload(tasks, st);
+		tl.codes.upload(tasks, st);
 		SPP_CUDA(cudaStreamSynchronize(st)); // the host vector goes out of scope
-		ch.df_nb = NB; ch.df_njh = NJH; ch.df_n_tasks = tasks.size();
+		tl.n_tasks = tasks.size();
 	}
 	if(ch.df_A != A || ch.df_ld != ld || ch.df_cols != n_cols || ch.df_Rinv != Rinv) {
 		make_tensor_map(&ch.df_maps[0], A, ld, n_cols, ld, 16, 128);
 		make_tensor_map(&ch.df_maps[1], A, ld, n_cols, ld, 16, 64);
 		make_tensor_map(&ch.df_maps[2], A, ld, n_cols, ld, 16, 16);
 		make_tensor_map(&ch.df_maps[3], Rinv, CH_NB, NB * CH_NB, CH_NB, 16, 128);
-		make_tensor_map(&ch.df_maps[4], Rinv, CH_NB, NB * CH_NB, CH_NB, 16, 16);
 		ch.df_A = A; ch.df_ld = ld; ch.df_cols = n_cols; ch.df_Rinv = Rinv;
 	}
 	const size_t n_flags = 4 + 4 * NB + 2 * NB * NJH;
 	ch.df_flags.resize(n_flags);
 	SPP_CUDA(cudaMemsetAsync(ch.df_flags.p(), 0, n_flags * sizeof(int), st));
 	df::Args args;
-	args.A = A; args.Rinv = Rinv; args.info = info; args.flags = ch.df_flags.p(); args.tasks = ch.df_tasks.p();
-	args.ld = ld; args.NB = (int)NB; args.NJH = (int)NJH; args.n_tasks = (int)ch.df_n_tasks;
-	const size_t n_ctas = std::min((size_t)ch.n_sms, 1 + df::G + ch.df_n_tasks);
+	args.A = A; args.Rinv = Rinv; args.info = info; args.flags = ch.df_flags.p(); args.tasks = tl.codes.p();
+	args.ld = ld; args.NB = (int)NB; args.NJH = (int)NJH; args.n_tasks = (int)tl.n_tasks;
+	const size_t n_ctas = std::min((size_t)ch.n_sms, 1 + df::G + tl.n_tasks);
 	static const bool timing = getenv("SPP_CHOL_TIMING") != 0;
 	DBuf<unsigned long long> dbg;
 	args.dbg = 0;
@@ -642,7 +642,7 @@ void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_col
 		}
 		SPP_CUDA(cudaEventRecord(ctx->phase_ev[PH_CHOL_KERNEL][0], st));
 	}
-	k_chol_dataflow<<<(unsigned)n_ctas, df::THREADS, df::SMEM_BYTES, st>>>(ch.df_maps[0], ch.df_maps[1], ch.df_maps[2], ch.df_maps[3], ch.df_maps[4], args);
+	k_chol_dataflow<<<(unsigned)n_ctas, df::THREADS, df::SMEM_BYTES, st>>>(ch.df_maps[0], ch.df_maps[1], ch.df_maps[2], ch.df_maps[3], args);
 	LAUNCH_CHECK(ctx);
 	if(ctx->async_mode) {
 		SPP_CUDA(cudaEventRecord(ctx->phase_ev[PH_CHOL_KERNEL][1], st));

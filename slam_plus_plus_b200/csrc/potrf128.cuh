@@ -2,6 +2,7 @@
 // block in one CTA and invert the triangular factor. Kept in a header so that tools/micro/potrf_bench.cu can
 // time it in isolation. Include inside namespace spp after CH_NB is defined.
 #pragma once
+#include <type_traits>
 #include <cuda_pipeline_primitives.h>
 
 // ---- diagonal block: factor + invert -----------------------------------------------------------------
@@ -420,14 +421,16 @@ __device__ __forceinline__ void potrf128_block(double *__restrict__ Akk, size_t 
 	TR(42);
 	inv_level<8>(sm, warp, g, t);
 	TR(43);
-	// the 16 x 16 diagonal blocks of the inverse (upper parts; the buffer is zero below the diagonal)
-	#pragma unroll 4
-	for(int idx = tid; idx < 8 * 16 * 16; idx += PT) {
-		const int b = idx >> 8, c = (idx >> 4) & 15, r = idx & 15;
-		if(r <= c)
-			Rinv_out[(size_t)(16 * b + c) * CH_NB + 16 * b + r] = TC(16 * b + r, 16 * b + c);
+	if constexpr(!std::is_same<Hook, PotrfNoHook>::value) {
+		// the 16 x 16 diagonal blocks of the inverse (upper parts; the buffer is zero below the diagonal)
+		#pragma unroll 4
+		for(int idx = tid; idx < 8 * 16 * 16; idx += PT) {
+			const int b = idx >> 8, c = (idx >> 4) & 15, r = idx & 15;
+			if(r <= c)
+				Rinv_out[(size_t)(16 * b + c) * CH_NB + 16 * b + r] = TC(16 * b + r, 16 * b + c);
+		}
+		after_x16();
 	}
-	after_x16();
 	inv_level<16>(sm, warp, g, t);
 	TR(44);
 	inv_level<32>(sm, warp, g, t);

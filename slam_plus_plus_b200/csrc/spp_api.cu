@@ -38,6 +38,9 @@ void schur_backsubstitute(spp_ctx *ctx);
 size_t dense_chol_ld(size_t n);
 size_t dense_chol_storage(size_t n);
 int dense_chol_solve_device(spp_ctx *ctx, double *A, size_t n, double *d_rhs_x);
+void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols, double *Rinv, int *info, bool identity_tail);
+void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_cols, double *Rinv, int *info);
+bool dense_chol_dataflow_enabled();
 int schur_marginals_current(spp_ctx *ctx, double alpha, double *d_cam_cov, double *d_pt_cov);
 int pose_marginals(spp_ctx *ctx, double *d_cov);
 void slot_symbolic(spp_ctx *ctx, size_t n, const uint64_t *col_dims, const uint64_t *col_ptr, const uint64_t *row_idx,
@@ -1221,6 +1224,32 @@ int spp_schur_get_rcs_residual(spp_ctx_t ctx, double *p_relative_residual)
 	out.download(h, 2, ctx->stream);
 	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
 	*p_relative_residual = (h[1] > 0)? sqrt(h[0] / h[1]) : sqrt(h[0]);
+	API_END(ctx)
+}
+
+int spp_dense_panel_factor(spp_ctx_t ctx, size_t n_rows, size_t n_cols, double *p_panel)
+{
+	int rc = SPP_OK;
+	API_BEGIN(ctx)
+	if(!n_rows || n_rows % 128 || n_cols % 128 || n_cols < n_rows || !p_panel) throw invalid_error("bad panel shape");
+	DBuf<double> A, Rinv;
+	DBuf<int> info;
+	A.upload(p_panel, n_rows * n_cols, ctx->stream);
+	Rinv.resize((n_rows / 128) * 128 * 128);
+	Rinv.zero(ctx->stream);
+	info.resize(1);
+	info.zero(ctx->stream);
+	if(dense_chol_dataflow_enabled())
+		dense_chol_factor_dataflow(ctx, A.p(), n_rows, n_cols, Rinv.p(), info.p());
+	else
+		dense_chol_factor_panel(ctx, A.p(), n_rows, n_cols, Rinv.p(), info.p(), false);
+	int h_info = 0;
+	SPP_CUDA(cudaMemcpyAsync(&h_info, info.p(), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	A.download(p_panel, n_rows * n_cols, ctx->stream);
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	if(h_info < 0) throw cuda_error("dense panel factorisation: the dataflow kernel's watchdog fired");
+	rc = h_info? SPP_NOT_POSDEF : SPP_OK;
+	if(rc != SPP_OK) return rc;
 	API_END(ctx)
 }
 

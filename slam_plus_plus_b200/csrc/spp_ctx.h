@@ -3,6 +3,7 @@
 
 #include "spp_common.cuh"
 #include "block_ordering.h"
+#include <map>
 #include <cuda.h> // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace spp {
@@ -193,7 +194,8 @@ struct DenseChol {
 	int force_tile;           // SPP_CHOL_TILE: force the bulk tile shape (0: 128x128, 1: 128x64, 2: 64x64)
 	// persistent dataflow factorisation (chol_dataflow.cuh)
 	DBuf<int> df_flags;       // task / role counters, watchdog, tile flags (zeroed before every launch)
-	DBuf<uint32_t> df_tasks;  // worker task list of the (df_nb, df_njh) shape
+	struct DfTaskList { DBuf<uint32_t> codes; size_t n_tasks; DfTaskList() : n_tasks(0) {} };
+	std::map<uint64_t, DfTaskList> df_tasks; // worker task lists by panel shape (panels << 32 | half-tile columns): built once per shape
 	size_t df_nb, df_njh, df_n_tasks;
 	CUtensorMap df_maps[5];   // TMA descriptors of (df_A, df_ld, df_cols) and df_Rinv
 	const void *df_A, *df_Rinv;

@@ -33,6 +33,8 @@ namespace spp {
 
 void dense_chol_factor_panel(spp_ctx *ctx, double *A, size_t ld, size_t n_cols, double *Rinv, int *info, bool identity_tail = false);
 void dense_chol_factor_single_panel(spp_ctx *ctx, cudaStream_t stream, double *A, size_t n_cols, double *Rinv, int *info);
+void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_cols, double *Rinv, int *info);
+bool dense_chol_dataflow_enabled();
 void dense_chol_backsolve_panel(spp_ctx *ctx, cudaStream_t stream, const double *A, size_t ld, const double *Rinv, double *y, int *flags);
 void schur_fetch_host_pattern(spp_ctx *ctx);
 
@@ -485,7 +487,12 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 		} else {
 			if(pending[s]) // every update into this panel went to one side stream, in elimination order
 				SPP_CUDA(cudaStreamWaitEvent(st, sc.ev_target[s], 0));
-			dense_chol_factor_panel(ctx, Ps, ld, cols, sc.d_Rinv.p() + (size_t)sc.rinv_first[s] * SN_NB * SN_NB, sc.d_info.p());
+			// wide supernodes: the persistent dataflow factorisation (one kernel, no read-modify-write passes over the panel)
+			static const size_t df_min = getenv("SPP_SNODE_DATAFLOW_MIN")? (size_t)atol(getenv("SPP_SNODE_DATAFLOW_MIN")) : 1024;
+			if(df_min && ld >= df_min && dense_chol_dataflow_enabled())
+				dense_chol_factor_dataflow(ctx, Ps, ld, cols, sc.d_Rinv.p() + (size_t)sc.rinv_first[s] * SN_NB * SN_NB, sc.d_info.p());
+			else
+				dense_chol_factor_panel(ctx, Ps, ld, cols, sc.d_Rinv.p() + (size_t)sc.rinv_first[s] * SN_NB * SN_NB, sc.d_info.p());
 		}
 		if(profile) lap(&t_factor[s]);
 		if(!single_stream && (sc.upd_ptr[s + 1] > sc.upd_ptr[s] || on_side))
