@@ -8,150 +8,7 @@
 
 namespace spp {
 
-// ---- approximate minimum degree -------------------------------------------------------------------------
-
-namespace {
-
-enum { ST_VAR = 0, ST_ELEM = 1, ST_DEAD = 2, ST_DENSE = 3 };
-
-struct DegreeLists { // doubly linked bucket lists, LIFO within a bucket
-	std::vector<int32_t> head, next, prev;
-	size_t min_deg;
-	DegreeLists(size_t n) : head(n + 1, -1), next(n, -1), prev(n, -1), min_deg(0) {}
-	void insert(uint32_t i, size_t d)
-	{
-		next[i] = head[d];
-		prev[i] = -1;
-		if(head[d] >= 0) prev[head[d]] = (int32_t)i;
-		head[d] = (int32_t)i;
-		if(d < min_deg) min_deg = d;
-	}
-	void remove(uint32_t i, size_t d)
-	{
-		if(prev[i] >= 0) next[prev[i]] = next[i];
-		else head[d] = next[i];
-		if(next[i] >= 0) prev[next[i]] = prev[i];
-	}
-	uint32_t pop_min()
-	{
-		while(head[min_deg] < 0) ++ min_deg;
-		const uint32_t p = (uint32_t)head[min_deg];
-		remove(p, min_deg);
-		return p;
-	}
-};
-
-} // namespace
-
-void amd_block_ordering(size_t n, const uint64_t *col_ptr, const uint64_t *row_idx, std::vector<uint32_t> &order)
-{
-	order.clear();
-	order.reserve(n);
-	if(!n) return;
-	std::vector<std::vector<uint32_t> > adjv(n), adje(n), elem(n);
-	{
-		std::vector<uint32_t> cnt(n, 0);
-		for(size_t c = 0; c < n; ++ c)
-			for(uint64_t k = col_ptr[c]; k < col_ptr[c + 1]; ++ k)
-				if(row_idx[k] != c) { ++ cnt[c]; ++ cnt[row_idx[k]]; }
-		for(size_t i = 0; i < n; ++ i) adjv[i].reserve(cnt[i]);
-		for(size_t c = 0; c < n; ++ c) {
-			for(uint64_t k = col_ptr[c]; k < col_ptr[c + 1]; ++ k) {
-				const size_t r = row_idx[k];
-				if(r >= n) throw std::runtime_error("block ordering: row index out of range");
-				if(r != c) { adjv[r].push_back((uint32_t)c); adjv[c].push_back((uint32_t)r); }
-			}
-		}
-		for(size_t i = 0; i < n; ++ i) {
-			std::sort(adjv[i].begin(), adjv[i].end());
-			adjv[i].erase(std::unique(adjv[i].begin(), adjv[i].end()), adjv[i].end());
-		}
-	}
-	std::vector<uint8_t> state(n, ST_VAR);
-	// rows much denser than the rest are ordered last (they would fill whatever they touch anyway)
-	const size_t dense_thr = std::max<size_t>(16, (size_t)(10.0 * sqrt((double)n)));
-	std::vector<uint32_t> dense;
-	for(size_t i = 0; i < n; ++ i)
-		if(adjv[i].size() > dense_thr) { state[i] = ST_DENSE; dense.push_back((uint32_t)i); }
-	if(!dense.empty()) {
-		for(size_t i = 0; i < n; ++ i) {
-			if(state[i] == ST_DENSE) continue;
-			std::vector<uint32_t> &a = adjv[i];
-			a.erase(std::remove_if(a.begin(), a.end(), [&](uint32_t v) { return state[v] == ST_DENSE; }), a.end());
-		}
-	}
-	const size_t n_live = n - dense.size();
-	std::vector<uint32_t> degree(n, 0), mark(n, 0), wmark(n, 0), Lp;
-	std::vector<int64_t> w(n, 0);
-	DegreeLists lists(n);
-	lists.min_deg = n;
-	for(size_t i = 0; i < n; ++ i) {
-		if(state[i] != ST_VAR) continue;
-		degree[i] = (uint32_t)adjv[i].size();
-		lists.insert((uint32_t)i, degree[i]);
-	}
-	uint32_t stamp = 0;
-	for(size_t k = 0; k < n_live; ++ k) {
-		const uint32_t p = lists.pop_min();
-		++ stamp;
-		mark[p] = stamp;
-		Lp.clear();
-		for(uint32_t v : adjv[p])
-			if(state[v] == ST_VAR && mark[v] != stamp) { mark[v] = stamp; Lp.push_back(v); }
-		for(uint32_t e : adje[p]) {
-			if(state[e] != ST_ELEM) continue;
-			for(uint32_t v : elem[e])
-				if(state[v] == ST_VAR && mark[v] != stamp) { mark[v] = stamp; Lp.push_back(v); }
-			state[e] = ST_DEAD; // absorbed into the new element
-			std::vector<uint32_t>().swap(elem[e]);
-		}
-		state[p] = ST_ELEM;
-		order.push_back(p);
-		std::vector<uint32_t>().swap(adjv[p]);
-		std::vector<uint32_t>().swap(adje[p]);
-		// w[e] = |L_e \ L_p| for every element adjacent to a variable of L_p
-		for(uint32_t i : Lp) {
-			for(uint32_t e : adje[i]) {
-				if(state[e] != ST_ELEM) continue;
-				if(wmark[e] != stamp) { wmark[e] = stamp; w[e] = (int64_t)elem[e].size(); }
-				-- w[e];
-			}
-		}
-		const size_t lp = Lp.size(), remaining = n_live - k - 1;
-		for(uint32_t i : Lp) {
-			lists.remove(i, degree[i]);
-			std::vector<uint32_t> &ei = adje[i];
-			size_t out = 0;
-			uint64_t sum = 0;
-			for(uint32_t e : ei) {
-				if(state[e] != ST_ELEM) continue;
-				if(w[e] == 0) { // L_e is a subset of L_p: aggressive absorption
-					state[e] = ST_DEAD;
-					std::vector<uint32_t>().swap(elem[e]);
-					continue;
-				}
-				ei[out ++] = e;
-				sum += (uint64_t)w[e];
-			}
-			ei.resize(out);
-			ei.push_back(p);
-			std::vector<uint32_t> &vi = adjv[i];
-			out = 0;
-			for(uint32_t v : vi)
-				if(state[v] == ST_VAR && mark[v] != stamp) vi[out ++] = v; // members of L_p are reached through element p now
-			vi.resize(out);
-			uint64_t d = std::min<uint64_t>(remaining, (uint64_t)degree[i] + lp - 1);
-			d = std::min<uint64_t>(d, vi.size() + (lp - 1) + sum);
-			degree[i] = (uint32_t)d;
-			lists.insert(i, d);
-		}
-		elem[p] = Lp;
-	}
-	std::stable_sort(dense.begin(), dense.end(), [&](uint32_t a, uint32_t b) { return adjv[a].size() < adjv[b].size(); });
-	order.insert(order.end(), dense.begin(), dense.end());
-}
-
-// ---- elimination tree ---------------------------------------------------------------------------------------
+// ---- elimination tree, postorder, supernodes ----------------------------------------------------------------
 
 // for every permuted column j, the permuted rows i < j of the symmetric pattern (unsorted)
 static void permuted_upper(size_t n, const uint64_t *col_ptr, const uint64_t *row_idx, const std::vector<uint32_t> &inv,
@@ -196,45 +53,6 @@ static void elimination_tree(size_t n, const std::vector<uint64_t> &ptr, const s
 			}
 		}
 	}
-}
-
-void etree_postorder(size_t n, const uint64_t *col_ptr, const uint64_t *row_idx, std::vector<uint32_t> &order)
-{
-	if(order.size() != n) throw std::runtime_error("etree_postorder: bad ordering");
-	std::vector<uint32_t> inv(n);
-	for(size_t i = 0; i < n; ++ i) inv[order[i]] = (uint32_t)i;
-	std::vector<uint64_t> ptr;
-	std::vector<uint32_t> idx, parent;
-	permuted_upper(n, col_ptr, row_idx, inv, ptr, idx);
-	elimination_tree(n, ptr, idx, parent);
-	const uint32_t none = 0xffffffffu;
-	// children lists in ascending order
-	std::vector<int32_t> head(n, -1), next(n, -1);
-	for(size_t jj = n; jj > 0; -- jj) {
-		const size_t j = jj - 1;
-		if(parent[j] != none) { next[j] = head[parent[j]]; head[parent[j]] = (int32_t)j; }
-	}
-	std::vector<uint32_t> post;
-	post.reserve(n);
-	std::vector<uint32_t> stack;
-	for(size_t r = 0; r < n; ++ r) {
-		if(parent[r] != none) continue;
-		stack.push_back((uint32_t)r);
-		while(!stack.empty()) {
-			const uint32_t v = stack.back();
-			if(head[v] >= 0) { // descend into the next unvisited child
-				const uint32_t c = (uint32_t)head[v];
-				head[v] = next[c];
-				stack.push_back(c);
-			} else {
-				post.push_back(v);
-				stack.pop_back();
-			}
-		}
-	}
-	std::vector<uint32_t> composed(n);
-	for(size_t k = 0; k < n; ++ k) composed[k] = order[post[k]];
-	order.swap(composed);
 }
 
 // ---- symbolic factorisation, supernodes -------------------------------------------------------------------
@@ -384,8 +202,7 @@ extern "C" int spp_block_ordering(size_t n_block_cols, const uint64_t *p_col_ptr
 		return SPP_ERR_INVALID;
 	try {
 		std::vector<uint32_t> order;
-		spp::amd_block_ordering(n_block_cols, p_col_ptr, p_row_idx, order);
-		spp::etree_postorder(n_block_cols, p_col_ptr, p_row_idx, order);
+		spp::amd_exact_ordering(n_block_cols, p_col_ptr, p_row_idx, order);
 		for(size_t i = 0; i < n_block_cols; ++ i) p_order[i] = order[i];
 	} catch(const std::bad_alloc&) {
 		return SPP_ERR_NOMEM;

@@ -5,10 +5,9 @@
 // Reference functions replaced: CMatrixOrdering::p_BlockOrdering (src/slam/OrderingMagic.cpp:
 // 701-1033, which hands the block graph of A + A^T to SuiteSparse's amd_l2), CUberBlockMatrix::Build_EliminationTree
 // (src/slam/BlockMatrix.cpp:9403) and the per-column ereach of CholeskyOf_FBS (include/slam/BlockMatrixFBS.inl:
-// 2341-2513). The ordering here is an approximate-minimum-degree ordering written from the published algorithm
-// (Amestoy, Davis, Duff 1996: quotient graph, element absorption, approximate external degrees, aggressive
-// absorption, dense-row deferral); it is not SuiteSparse's code and its tie-breaking differs, so callers that need the
-// reference's permutation bit for bit pass that permutation in (the reference-side adapter does).
+// 2341-2513). The ordering (amd_exact.cpp) is the approximate-minimum-degree ordering of Amestoy, Davis and Duff with
+// the tie-breaking conventions of the SuiteSparse release the reference vendors, so the standalone paths eliminate in
+// the reference's order, permutation for permutation (tests/test_ordering_cpu.py, against the reference's own output).
 #pragma once
 
 #include <stdint.h>
@@ -17,12 +16,9 @@
 
 namespace spp {
 
-// Upper block structure in CSC (rows ascending, diagonal present). order[new position] = original block column.
-void amd_block_ordering(size_t n, const uint64_t *col_ptr, const uint64_t *row_idx, std::vector<uint32_t> &order);
-
-// Elimination tree of the permuted matrix and a postordering of it (children before parents, subtrees contiguous);
-// composes the postorder into order. Fill is unchanged by this.
-void etree_postorder(size_t n, const uint64_t *col_ptr, const uint64_t *row_idx, std::vector<uint32_t> &order);
+// Upper block structure in CSC (diagonal present or not; a full symmetric pattern is fine too). order[new position] =
+// original block column: the reference's permutation bit for bit (see amd_exact.cpp).
+void amd_exact_ordering(size_t n, const uint64_t *col_ptr, const uint64_t *row_idx, std::vector<uint32_t> &order);
 
 struct Supernodes {
 	size_t n;                          // block columns

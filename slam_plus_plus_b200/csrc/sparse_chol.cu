@@ -61,10 +61,8 @@ void sparse_chol_symbolic(spp_ctx *ctx, size_t n, size_t B, const uint64_t *col_
 			seen[p_order_in[i]] = 1;
 			sc.h_order[i] = (uint32_t)p_order_in[i];
 		}
-	} else { // the library's own approximate minimum degree + elimination-tree postorder (block_ordering.cpp)
-		amd_block_ordering(n, col_ptr, row_idx, sc.h_order);
-		etree_postorder(n, col_ptr, row_idx, sc.h_order);
-	}
+	} else // approximate minimum degree, the reference's permutation (amd_exact.cpp)
+		amd_exact_ordering(n, col_ptr, row_idx, sc.h_order);
 	std::vector<uint32_t> inv(n);
 	for(size_t i = 0; i < n; ++ i)
 		inv[sc.h_order[i]] = (uint32_t)i;

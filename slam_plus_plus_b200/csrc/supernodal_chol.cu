@@ -76,10 +76,8 @@ void snode_symbolic(spp_ctx *ctx, size_t n, const std::vector<uint32_t> &blk_row
 		if(sc.user_order.size() != n)
 			throw invalid_error("supernodal Cholesky: the ordering given by spp_schur_set_rcs_ordering has the wrong size");
 		sc.h_order.assign(sc.user_order.begin(), sc.user_order.end());
-	} else {
-		amd_block_ordering(n, col_ptr.data(), row_idx.data(), sc.h_order);
-		etree_postorder(n, col_ptr.data(), row_idx.data(), sc.h_order);
-	}
+	} else // approximate minimum degree, the reference's permutation (amd_exact.cpp)
+		amd_exact_ordering(n, col_ptr.data(), row_idx.data(), sc.h_order);
 	static const double relax_zeros = getenv("SPP_SNODE_RELAX")? atof(getenv("SPP_SNODE_RELAX")) : 0.05;
 	static const size_t relax_small = getenv("SPP_SNODE_SMALL")? (size_t)atoi(getenv("SPP_SNODE_SMALL")) : 16;
 	supernodal_symbolic(n, col_ptr.data(), row_idx.data(), sc.h_order, relax_zeros, relax_small, (size_t)1 << 30, sc.sn);
