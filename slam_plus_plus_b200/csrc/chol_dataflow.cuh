@@ -15,7 +15,10 @@
 //   chain   (1 CTA)  for every panel i: waits for the final diagonal tile, factors it and inverts the factor
 //                    (potrf128_block), publishes f2[i]
 //   helpers (8 CTAs) the two tiles on the critical chain, each split into eight 16-column slices:
-//                    H1(i): R(i, i+1) = Rinv(i)^T T(i, i+1);   H2(i): D(i+1) = T(i+1, i+1) - R(i, i+1)^T R(i, i+1)
+//                    H1(i): R(i, i+1) = R(i, i)^-T T(i, i+1) by blocked substitution with the inverses of the 16 x 16
+//                    diagonal blocks -- available a quarter into the chain CTA's inversion, whose remaining levels (the
+//                    full inverse the workers multiply with) thus run beside H1 / H2, off the chain;
+//                    H2(i): D(i+1) = T(i+1, i+1) - R(i, i+1)^T R(i, i+1)
 //                    (T = the partial sums the workers prepared in advance)
 //   workers (rest)   take tile tasks (i, 64-column half) from a queue in row-major order: accumulate the whole sum over k
 //                    in registers (128 x 64 accumulator, 8 warps of 32 x 32), waiting for each operand tile's flag,
@@ -44,6 +47,7 @@ constexpr uint32_t STAGING_OFF = STAGES * STAGE_BYTES;           // 147456: the 
 constexpr uint32_t BAR_OFF = STAGING_OFF + 65536;                // 212992
 constexpr uint32_t SMEM_BYTES = BAR_OFF + 256 + 1024;            // + alignment slack
 static_assert(HSTAGES * HSTAGE_BYTES <= BAR_OFF, "helper stages overlap the barriers");
+constexpr uint32_t AS_OFF = STAGING_OFF, YS_OFF = STAGING_OFF + 2048; // helpers (H1): one 16 x 16 block / the solved blocks as B operands
 constexpr unsigned SPIN_LIMIT = 1u << 21;
 #ifndef SPP_DF_FENCE_ALL
 #define SPP_DF_FENCE_ALL 0
@@ -194,7 +198,7 @@ __device__ __forceinline__ void release_stage(uint32_t bar_empty_st, bool odd, i
 
 __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_constant__ CUtensorMap mapA,
 	const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapR,
-	const df::Args p)
+	const __grid_constant__ CUtensorMap mapX, const df::Args p)
 {
 	using namespace df;
 	extern __shared__ __align__(16) unsigned char df_raw[];
@@ -205,10 +209,11 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 	const int NB = p.NB, NJH = p.NJH;
 	const size_t ld = p.ld;
 	// flags: [0] next task, [1] role ticket, [2] abort, f2[NB] (diagonal block i factored and inverted), h1cnt[NB]
-	// (slices of R(i, i+1) done), dcnt[NB] (slices of the final diagonal tile i done), NB spare words, rdy[NB][NJH]
-	// (R(i, half) final), part[NB][NJH] (partial sums of a chain tile stored)
+	// (slices of R(i, i+1) done), dcnt[NB] (slices of the final diagonal tile i done), f1[NB] (diagonal block i factored, the
+	// inverses of its 16 x 16 diagonal blocks stored), rdy[NB][NJH] (R(i, half) final), part[NB][NJH] (partial sums of a
+	// chain tile stored)
 	int *f_next = p.flags, *f_ticket = p.flags + 1, *f_abort = p.flags + 2;
-	int *f2 = p.flags + 4, *h1cnt = f2 + NB, *dcnt = h1cnt + NB, *rdy = dcnt + 2 * NB, *part = rdy + (size_t)NB * NJH;
+	int *f2 = p.flags + 4, *h1cnt = f2 + NB, *dcnt = h1cnt + NB, *f1 = dcnt + NB, *rdy = f1 + NB, *part = rdy + (size_t)NB * NJH;
 
 	if(tid == 0)
 		s_role = atomicAdd(f_ticket, 1);
@@ -228,7 +233,16 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 			if(p.dbg && tid == 0)
 				p.dbg[i] = gtime();
 			potrf128_block(p.A + ((size_t)i * CH_NB) * ld + (size_t)i * CH_NB, ld, p.Rinv + (size_t)i * (CH_NB * CH_NB), p.info,
-				i * CH_NB + 1, 0, PotrfNoHook());
+				i * CH_NB + 1, 0, [&]() { // R(i, i) and the inverses of its 16 x 16 diagonal blocks are stored: the helpers may start
+					if(FENCE_ALL) { __threadfence(); fence_proxy_async(); }
+					POTRF_SYNC();
+					if(tid == 0) {
+						fence_proxy_async();
+						st_release(f1 + i, 1);
+						if(p.dbg)
+							p.dbg[NB + i] = gtime();
+					}
+				});
 			if(FENCE_ALL) { __threadfence(); fence_proxy_async(); }
 			POTRF_SYNC();
 			if(tid == 0) {
@@ -268,10 +282,11 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 				return;
 			for(int i = 0; i + 1 < NB; ++ i) {
 				for(int phase = 0; phase < 2; ++ phase) {
-					if(phase == 0) { // H1: Rinv(i) and the partial sums of tile (i, i+1)
-						wait_ge(f2 + i, 1, f_abort, 2000 + i);
+					if(phase == 0) { // H1: R(i, i), the inverses of its 16 x 16 diagonal blocks and the partial sums of tile (i, i+1)
 						wait_ge(part + (size_t)i * NJH + 2 * (i + 1), 1, f_abort, 3000 + i);
 						wait_ge(part + (size_t)i * NJH + 2 * (i + 1) + 1, 1, f_abort, 3000 + i);
+						mbar_arrive(bar_tfull + 8 * (i & 1)); // the consumers fetch the partial sums while the diagonal block is still being factored
+						wait_ge(f1 + i, 1, f_abort, 2000 + i);
 					} else { // H2: all of R(i, i+1) and the partial sums of the diagonal tile i+1
 						wait_ge(h1cnt + i, G, f_abort, 4000 + i);
 						wait_ge(part + (size_t)(i + 1) * NJH + 2 * (i + 1), 1, f_abort, 5000 + i);
@@ -284,11 +299,13 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 							mbar_wait(bar_empty + 8 * st, (use - 1) & 1, f_abort);
 						const uint32_t dst = base + st * HSTAGE_BYTES;
 						mbar_expect_tx(bar_full + 8 * st, HSTAGE_BYTES);
-						if(phase == 0)
-							tma_load_2d(dst, &mapR, 16 * c, i * CH_NB, bar_full + 8 * st);
-						else
+						if(phase == 0) { // rows 16 c .. of R(i, i) and the inverse of its c-th 16 x 16 diagonal block
+							tma_load_2d(dst, &mapA, i * CH_NB + 16 * c, i * CH_NB, bar_full + 8 * st);
+							tma_load_2d(dst + A_BYTES, &mapX, 16 * c, i * CH_NB + 16 * c, bar_full + 8 * st);
+						} else { // rows 16 c .. of R(i, i+1): all columns / this helper's slice
 							tma_load_2d(dst, &mapA, i * CH_NB + 16 * c, (i + 1) * CH_NB, bar_full + 8 * st);
-						tma_load_2d(dst + A_BYTES, &mapH, i * CH_NB + 16 * c, (i + 1) * CH_NB + 16 * h, bar_full + 8 * st);
+							tma_load_2d(dst + A_BYTES, &mapH, i * CH_NB + 16 * c, (i + 1) * CH_NB + 16 * h, bar_full + 8 * st);
+						}
 					}
 				}
 			}
@@ -299,24 +316,58 @@ __global__ void __launch_bounds__(df::THREADS, 1) k_chol_dataflow(const __grid_c
 			// element (m, n) of the slice: m = 16 warp + 8 a + g, n = 16 h + 8 b + 2 t + e
 			double *out1 = p.A + ((size_t)(i + 1) * CH_NB + 16 * h + 2 * t) * ld + (size_t)i * CH_NB + 16 * warp + g;
 			double *out2 = out1 + CH_NB;
-			{ // H1: R(i, i+1)(:, slice) = Rinv(i)^T T(:, slice); Rinv(k, m) = 0 for k > m: chunks c <= warp
-				double acc[2][2][2] = {};
-				for(int c = 0; c < 8; ++ c, ++ cnt) {
-					const uint32_t st = cnt % HSTAGES, use = cnt / HSTAGES;
-					mbar_wait(bar_full + 8 * st, use & 1, f_abort);
-					bool odd = false;
-					if(c <= warp)
-						odd = mma_chunk<2, 2, false>(acc, base + st * HSTAGE_BYTES + a_off, base + st * HSTAGE_BYTES + b_off, g, t);
-					release_stage(bar_empty + 8 * st, odd, lane);
-				}
+			{ // H1: R(i, i+1)(:, slice) = R(i, i)^-T T(:, slice) by blocked forward substitution, 16 rows (one chunk) at a time:
+			  // warp w owns rows 16 w ..; step c: warp c multiplies its block by the inverse of the c-th diagonal block (the
+			  // solved block goes to shared memory as a B operand and to global memory), the warps below subtract
+			  // R(c, w)^T Y_c from theirs
+				mbar_wait(bar_tfull + 8 * (i & 1), (i >> 1) & 1, f_abort); // the producer has seen the partial sums' flags
+				double acc[2][2][2];
 				#pragma unroll
 				for(int a = 0; a < 2; ++ a)
 					#pragma unroll
 					for(int b = 0; b < 2; ++ b) {
-						out1[(size_t)(8 * b) * ld + 8 * a] = acc[a][b][0];
-						out1[(size_t)(8 * b + 1) * ld + 8 * a] = acc[a][b][1];
+						acc[a][b][0] = __ldcg(out1 + (size_t)(8 * b) * ld + 8 * a);
+						acc[a][b][1] = __ldcg(out1 + (size_t)(8 * b + 1) * ld + 8 * a);
 					}
-				if(FENCE_ALL) { __threadfence(); fence_proxy_async(); }
+				const uint32_t row_off = (uint32_t)(g * 128 + (t & 1) * 8);
+				for(int c = 0; c < 8; ++ c, ++ cnt) {
+					const uint32_t st = cnt % HSTAGES, use = cnt / HSTAGES;
+					mbar_wait(bar_full + 8 * st, use & 1, f_abort);
+					const uint32_t stage = base + st * HSTAGE_BYTES;
+					bool odd = false;
+					if(warp == c) {
+						#pragma unroll
+						for(int a = 0; a < 2; ++ a)
+							#pragma unroll
+							for(int b = 0; b < 2; ++ b)
+								#pragma unroll
+								for(int q = 0; q < 2; ++ q) { // element (k, n) of the block -> row n, swizzled
+									const int k = 8 * a + g, n = 8 * b + 2 * t + q;
+									asm volatile("st.shared.f64 [%0], %1;" :: "r"(base + AS_OFF + (uint32_t)(n * 128 + (((k >> 1) ^ (n & 7)) << 4) + (k & 1) * 8)),
+										"d"(acc[a][b][q]) : "memory");
+								}
+						__syncwarp();
+						double y[2][2][2] = {};
+						odd = mma_chunk<2, 2, false>(y, stage + A_BYTES + row_off, base + AS_OFF + row_off, g, t);
+						#pragma unroll
+						for(int a = 0; a < 2; ++ a)
+							#pragma unroll
+							for(int b = 0; b < 2; ++ b) {
+								#pragma unroll
+								for(int q = 0; q < 2; ++ q) {
+									const int k = 8 * a + g, n = 8 * b + 2 * t + q;
+									asm volatile("st.shared.f64 [%0], %1;" :: "r"(base + YS_OFF + (uint32_t)(c * 2048 + n * 128 + (((k >> 1) ^ (n & 7)) << 4) + (k & 1) * 8)),
+										"d"(y[a][b][q]) : "memory");
+								}
+								out1[(size_t)(8 * b) * ld + 8 * a] = y[a][b][0];
+								out1[(size_t)(8 * b + 1) * ld + 8 * a] = y[a][b][1];
+							}
+					}
+					bar_consumers();
+					if(warp > c)
+						odd = mma_chunk<2, 2, true>(acc, stage + (uint32_t)(16 * warp * 128) + row_off, base + YS_OFF + (uint32_t)(c * 2048) + row_off, g, t);
+					release_stage(bar_empty + 8 * st, odd, lane);
+				}
 				bar_consumers();
 				if(tid == 0) {
 					fence_proxy_async();

@@ -617,6 +617,7 @@ void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_col
 		make_tensor_map(&ch.df_maps[1], A, ld, n_cols, ld, 16, 64);
 		make_tensor_map(&ch.df_maps[2], A, ld, n_cols, ld, 16, 16);
 		make_tensor_map(&ch.df_maps[3], Rinv, CH_NB, NB * CH_NB, CH_NB, 16, 128);
+		make_tensor_map(&ch.df_maps[4], Rinv, CH_NB, NB * CH_NB, CH_NB, 16, 16);
 		ch.df_A = A; ch.df_ld = ld; ch.df_cols = n_cols; ch.df_Rinv = Rinv;
 	}
 	const size_t n_flags = 4 + 4 * NB + 2 * NB * NJH;
@@ -642,7 +643,7 @@ void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_col
 		}
 		SPP_CUDA(cudaEventRecord(ctx->phase_ev[PH_CHOL_KERNEL][0], st));
 	}
-	k_chol_dataflow<<<(unsigned)n_ctas, df::THREADS, df::SMEM_BYTES, st>>>(ch.df_maps[0], ch.df_maps[1], ch.df_maps[2], ch.df_maps[3], args);
+	k_chol_dataflow<<<(unsigned)n_ctas, df::THREADS, df::SMEM_BYTES, st>>>(ch.df_maps[0], ch.df_maps[1], ch.df_maps[2], ch.df_maps[3], ch.df_maps[4], args);
 	LAUNCH_CHECK(ctx);
 	if(ctx->async_mode) {
 		SPP_CUDA(cudaEventRecord(ctx->phase_ev[PH_CHOL_KERNEL][1], st));
