@@ -329,12 +329,16 @@ class Context:
         self._check(self.lib.spp_ba_get_partition(self.h, C.byref(b), C.byref(e)))
         return int(b.value), int(e.value)
 
-    def ba_get_states(self):
+    def ba_get_states(self, out_cams=None, out_pts=None):
         """Camera states and landmark positions; on a partitioned context only this rank's landmark slice
-        (ba_get_partition) is filled, the rest is zero."""
+        (ba_get_partition) is filled, the rest is zero. out_cams (C, 6) / out_pts (P, 3): float64 C-contiguous buffers of the
+        caller (e.g. page-locked ones: the device-to-host copy then runs at the full rate of the link), returned filled."""
         c, p, _, _ = self._ba_dims
-        cs = np.empty((c, 6))
-        ps = np.zeros((p, 3))
+        cs = np.empty((c, 6)) if out_cams is None else out_cams
+        ps = np.zeros((p, 3)) if out_pts is None else out_pts
+        for a, shape in ((cs, (c, 6)), (ps, (p, 3))):
+            if a.shape != shape or a.dtype != np.float64 or not a.flags.c_contiguous or not a.flags.writeable:
+                raise ValueError(f"output buffer must be a writeable C-contiguous float64 array of shape {shape}")
         self._check(self.lib.spp_ba_get_states(self.h, _dp(cs), _dp(ps)))
         return cs, ps
 

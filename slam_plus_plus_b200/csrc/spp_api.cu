@@ -713,17 +713,27 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 	ba.n_vertices = n_vertices;
 	ba.vtype.assign(p_vertex_type, p_vertex_type + n_vertices);
 	ba.vertex_local.resize(n_vertices);
-	ba.cam_vertex.clear();
-	ba.pt_vertex.clear();
-	for(size_t v = 0; v < n_vertices; ++ v) {
-		if(p_vertex_type[v] == 0) {
-			ba.vertex_local[v] = (uint32_t)ba.cam_vertex.size();
-			ba.cam_vertex.push_back((uint32_t)v);
-		} else if(p_vertex_type[v] == 1) {
-			ba.vertex_local[v] = (uint32_t)ba.pt_vertex.size();
-			ba.pt_vertex.push_back((uint32_t)v);
-		} else
-			throw invalid_error("vertex type must be 0 (camera) or 1 (point)");
+	{ // local index of every vertex within its type, and the two inverse lists (half a million vertices: no push_back)
+		size_t n_cam = 0;
+		for(size_t v = 0; v < n_vertices; ++ v) {
+			if(p_vertex_type[v] > 1)
+				throw invalid_error("vertex type must be 0 (camera) or 1 (point)");
+			n_cam += p_vertex_type[v] == 0;
+		}
+		ba.cam_vertex.resize(n_cam);
+		ba.pt_vertex.resize(n_vertices - n_cam);
+		uint32_t ic = 0, ip = 0;
+		uint32_t *p_local = n_vertices? &ba.vertex_local[0] : 0, *p_cv = n_cam? &ba.cam_vertex[0] : 0,
+			*p_pv = (n_vertices - n_cam)? &ba.pt_vertex[0] : 0;
+		for(size_t v = 0; v < n_vertices; ++ v) {
+			if(p_vertex_type[v] == 0) {
+				p_local[v] = ic;
+				p_cv[ic ++] = (uint32_t)v;
+			} else {
+				p_local[v] = ip;
+				p_pv[ip ++] = (uint32_t)v;
+			}
+		}
 	}
 	const size_t C = ba.cam_vertex.size(), P = ba.pt_vertex.size(), O = n_observations;
 	if((C && !p_cam_params) || (P && !p_points))
