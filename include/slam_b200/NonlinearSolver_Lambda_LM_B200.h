@@ -37,9 +37,11 @@
 #include <stdexcept>
 #include <new>
 #include <vector>
+#include <algorithm>
 #include <string>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "slam/FlatSystem.h"         // reference
 #include "slam/BA_Types.h"           // reference: CVertexCam, CVertexXYZ, CEdgeP2C3D
@@ -89,6 +91,8 @@ protected:
 	double m_f_upload_time, m_f_optimize_time, m_f_download_time; /**< @brief wall-clock split of Optimize() */
 	double m_f_marginals_time; /**< @brief wall-clock time of the marginals recovery */
 	size_t m_n_optimize_num; /**< @brief Optimize() calls that ran the solver (incremental drop-in test: same count as the reference) */
+	size_t m_n_append_num; /**< @brief uploads that only sent the new vertices and edges (spp_ba_append_graph) */
+	double m_f_gather_time, m_f_library_upload_time; /**< @brief split of the upload time: reading the system / the library call */
 
 	bool m_b_uploaded; /**< @brief the device holds the system described by the arrays below */
 	std::vector<uint8_t> m_vertex_type, m_prev_vertex_type;
@@ -152,7 +156,7 @@ public:
 		:_TyBase(r_system, t_incremental_config, t_marginals_config, b_verbose, linear_solver, false),
 		m_p_context(0), m_n_iteration_num(0),
 		m_n_gathered_edge_num(0), m_f_device_ms(0), m_f_upload_time(0), m_f_optimize_time(0), m_f_download_time(0),
-		m_f_marginals_time(0), m_n_optimize_num(0), m_b_uploaded(false)
+		m_f_marginals_time(0), m_n_optimize_num(0), m_n_append_num(0), m_f_gather_time(0), m_f_library_upload_time(0), m_b_uploaded(false)
 	{
 		if(t_marginals_config.b_calculate && t_marginals_config.n_relinearize_policy != mpart_Diagonal)
 			throw std::runtime_error("CNonlinearSolver_Lambda_LM_B200: only the block diagonal of the marginal covariances (mpart_Diagonal) is provided");
@@ -172,6 +176,12 @@ public:
 		return m_n_optimize_num;
 	}
 
+	/** number of uploads that only sent what was new (incremental use) */
+	inline size_t n_Append_Num() const
+	{
+		return m_n_append_num;
+	}
+
 	/** the device context, e.g. for spp_schur_set_rcs_solver() */
 	inline spp_ctx_t p_Context()
 	{
@@ -186,8 +196,10 @@ public:
 			printf("solver spent %f seconds in parallelizable section (updating lambda; disparity %g seconds)\n",
 				m_f_device_ms * 1e-3, f_total_time - m_f_device_ms * 1e-3);
 		printf("out of which:\n\tdevice (libspp_b200: lambda, rhs, schur, linsolve, update, chi2): %f\n", m_f_device_ms * 1e-3);
-		printf("host side of Optimize(): flatten + upload + structure %f, spp_ba_optimize %f, download + write-back %f\n",
-			m_f_upload_time, m_f_optimize_time, m_f_download_time);
+		printf("host side of Optimize(): flatten + upload + structure %f (" PRIsize " appends of new vertices / edges only), spp_ba_optimize %f, download + write-back %f\n",
+			m_f_upload_time, m_n_append_num, m_f_optimize_time, m_f_download_time);
+		printf("\tupload: reading the system %f, library (spp_ba_set_graph / spp_ba_append_graph / spp_ba_set_states) %f\n",
+			m_f_gather_time, m_f_library_upload_time);
 		if(m_t_marginals_config.b_calculate)
 			printf("solver spent %f seconds in marginals (spp_ba_marginals + the block matrix)\n", m_f_marginals_time);
 	}
@@ -290,9 +302,20 @@ protected:
 	/** flattens the system and hands it to the library; what is already on the device is not sent again */
 	void Upload() // throw(std::bad_alloc, std::runtime_error)
 	{
+		CTimer upload_timer;
+		struct CSplitTimes { // whichever way Upload() is left: the rest of its time was spent in the library
+			CTimer &m_r_timer; double &m_r_f_gather, &m_r_f_library; double m_f_gathered;
+			CSplitTimes(CTimer &r_timer, double &r_f_gather, double &r_f_library)
+				:m_r_timer(r_timer), m_r_f_gather(r_f_gather), m_r_f_library(r_f_library), m_f_gathered(0) {}
+			~CSplitTimes() { m_r_f_gather += m_f_gathered; m_r_f_library += m_r_timer.f_Time() - m_f_gathered; }
+		} split_times(upload_timer, m_f_gather_time, m_f_library_upload_time);
 		m_prev_vertex_type.swap(m_vertex_type); m_prev_cams.swap(m_cams); m_prev_points.swap(m_points);
 		m_vertex_type.clear(); m_cams.clear(); m_points.clear();
+		m_vertex_type.reserve(m_prev_vertex_type.size() + 1024);
+		m_cams.reserve(m_prev_cams.size() + 1024);
+		m_points.reserve(m_prev_points.size() + 4096);
 		m_r_system.r_Vertex_Pool().For_Each(CGatherVertices(*this)); // the states may have been changed by the caller
+		split_times.m_f_gathered = upload_timer.f_Time();
 		const size_t n_edge_num = m_r_system.r_Edge_Pool().n_Size();
 		const bool b_same_structure = m_b_uploaded && n_edge_num == m_n_gathered_edge_num && m_vertex_type == m_prev_vertex_type;
 		if(b_same_structure) {
@@ -312,10 +335,44 @@ protected:
 		if(n_edge_num < m_n_gathered_edge_num) { // not an append-only change: start over
 			m_obs_point.clear(); m_obs_camera.clear(); m_z.clear(); m_info.clear();
 			m_n_gathered_edge_num = 0;
+			m_b_uploaded = false;
 		}
+		const size_t n_prev_edge_num = m_n_gathered_edge_num;
 		if(n_edge_num > m_n_gathered_edge_num)
 			m_r_system.r_Edge_Pool().For_Each(m_n_gathered_edge_num, n_edge_num, CGatherEdges(*this)); // the new edges only
 		m_n_gathered_edge_num = n_edge_num;
+		split_times.m_f_gathered = upload_timer.f_Time();
+		// the system only grew (incremental BA: vertices and edges are appended between two Optimize() calls): the new
+		// vertices and edges alone go to the device, the structure is rebuilt there (spp_ba_append_graph)
+		const size_t n_prev_vertex_num = m_prev_vertex_type.size(), n_prev_cam_num = m_prev_cams.size() / 11,
+			n_prev_point_num = m_prev_points.size() / 3;
+		bool b_grew = m_b_uploaded && !getenv("SPP_ADAPTER_NO_APPEND") && m_vertex_type.size() >= n_prev_vertex_num &&
+			std::equal(m_prev_vertex_type.begin(), m_prev_vertex_type.end(), m_vertex_type.begin());
+		for(size_t i = 0; i < n_prev_cam_num && b_grew; ++ i) // (the intrinsics of the cameras already there must not have changed)
+			for(int j = 6; j < 11; ++ j) b_grew = b_grew && m_cams[i * 11 + j] == m_prev_cams[i * 11 + j];
+		if(b_grew) {
+			const size_t n_new_vertex_num = m_vertex_type.size() - n_prev_vertex_num, n_new_edge_num = n_edge_num - n_prev_edge_num;
+			int n_result = spp_ba_append_graph(m_p_context, n_new_vertex_num, (n_new_vertex_num)? &m_vertex_type[n_prev_vertex_num] : 0,
+				(m_cams.size() > n_prev_cam_num * 11)? &m_cams[n_prev_cam_num * 11] : 0,
+				(m_points.size() > n_prev_point_num * 3)? &m_points[n_prev_point_num * 3] : 0, n_new_edge_num,
+				(n_new_edge_num)? &m_obs_point[n_prev_edge_num] : 0, (n_new_edge_num)? &m_obs_camera[n_prev_edge_num] : 0,
+				(n_new_edge_num)? &m_z[n_prev_edge_num * 2] : 0, (n_new_edge_num)? &m_info[n_prev_edge_num * 4] : 0);
+			if(n_result == SPP_OK) {
+				++ m_n_append_num;
+				bool b_same_states = std::equal(m_prev_points.begin(), m_prev_points.end(), m_points.begin());
+				for(size_t i = 0; i < n_prev_cam_num && b_same_states; ++ i)
+					for(int j = 0; j < 6; ++ j) b_same_states = b_same_states && m_cams[i * 11 + j] == m_prev_cams[i * 11 + j];
+				if(!b_same_states) { // the caller moved vertices that are on the device already
+					m_cam_states.resize((m_cams.size() / 11) * 6);
+					for(size_t i = 0, n = m_cams.size() / 11; i < n; ++ i)
+						for(int j = 0; j < 6; ++ j) m_cam_states[i * 6 + j] = m_cams[i * 11 + j];
+					Check(spp_ba_set_states(m_p_context, m_cam_states.empty()? 0 : &m_cam_states[0], m_points.empty()? 0 : &m_points[0]));
+				}
+				return;
+			}
+			if(n_result != SPP_ERR_INVALID) // (invalid: this context cannot append -- e.g. several ranks -- the whole graph follows)
+				Check(n_result);
+		}
 		Check(spp_ba_set_graph(m_p_context, m_vertex_type.size(), m_vertex_type.empty()? 0 : &m_vertex_type[0],
 			m_cams.empty()? 0 : &m_cams[0], m_points.empty()? 0 : &m_points[0], m_obs_point.size(),
 			m_obs_point.empty()? 0 : &m_obs_point[0], m_obs_camera.empty()? 0 : &m_obs_camera[0],

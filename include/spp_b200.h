@@ -138,6 +138,21 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 	const double *p_cam_params, const double *p_points, size_t n_observations,
 	const uint64_t *p_obs_point, const uint64_t *p_obs_camera, const double *p_z, const double *p_info);
 
+/* Appends vertices and observations to the graph on the device: incremental bundle adjustment, where cameras and their
+ * landmarks arrive in batches between two Optimize() calls (the reference's system is append-only as
+ * well, CFlatSystem::r_Get_Vertex / r_Add_Edge, FlatSystem.h:578-745, and its solver extends lambda for the new vertices
+ * and edges only, NonlinearSolver_Lambda_Base.h:1665-1684). Arrays as for spp_ba_set_graph, holding the NEW vertices and
+ * observations only; vertex ids continue the numbering (the first new vertex has id = vertices so far), observations may
+ * reference old and new vertices. The states of the vertices already there stay as they are on the device (the result
+ * of the last optimisation, or what spp_ba_set_states put there). The result is the same, bit for bit, as
+ * spp_ba_set_graph of the concatenated arrays followed by spp_ba_set_states of the old vertices' current states -- but
+ * only the new data cross the link; the structure is rebuilt on the device from the staged copies. Single-GPU contexts
+ * whose graph was set by spp_ba_set_graph (device-side analysis); SPP_ERR_INVALID otherwise, the caller then falls
+ * back to spp_ba_set_graph. */
+int spp_ba_append_graph(spp_ctx_t ctx, size_t n_new_vertices, const uint8_t *p_vertex_type,
+	const double *p_cam_params, const double *p_points, size_t n_new_observations,
+	const uint64_t *p_obs_point, const uint64_t *p_obs_camera, const double *p_z, const double *p_info);
+
 /* Overwrite / read the vertex states (CBAOptimizer::r_Vertex_State, BAOptimizer.cpp:196-204).
  * p_cam_states[6 * C] (t, axis-angle), p_points[3 * P]; either pointer may be NULL. */
 int spp_ba_set_states(spp_ctx_t ctx, const double *p_cam_states, const double *p_points);

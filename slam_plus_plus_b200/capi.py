@@ -23,7 +23,7 @@ MAX_TRACE = 64
 # every symbol include/spp_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "spp_create", "spp_destroy", "spp_last_error", "spp_describe", "spp_kernel_launches", "spp_stream",
-    "spp_synchronize", "spp_set_allreduce", "spp_partition_landmarks", "spp_rcs_block_pattern", "spp_ba_get_partition", "spp_ba_set_graph", "spp_ba_set_states", "spp_ba_get_states",
+    "spp_synchronize", "spp_set_allreduce", "spp_partition_landmarks", "spp_rcs_block_pattern", "spp_ba_get_partition", "spp_ba_set_graph", "spp_ba_append_graph", "spp_ba_set_states", "spp_ba_get_states",
     "spp_ba_restore_initial", "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_get_blocks", "spp_ba_chi2", "spp_ba_solve_step",
     "spp_ba_optimize", "spp_ba_marginals", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_marginals",
     "spp_schur_get_reduced_system",
@@ -93,6 +93,7 @@ def load_library() -> C.CDLL:
                                           C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.spp_ba_get_partition.argtypes = [vp, u64p, u64p]
     lib.spp_ba_set_graph.argtypes = [vp, C.c_size_t, u8p, dp, dp, C.c_size_t, u64p, u64p, dp, dp]
+    lib.spp_ba_append_graph.argtypes = [vp, C.c_size_t, u8p, dp, dp, C.c_size_t, u64p, u64p, dp, dp]
     lib.spp_ba_set_states.argtypes = [vp, dp, dp]
     lib.spp_ba_get_states.argtypes = [vp, dp, dp]
     lib.spp_ba_restore_initial.argtypes = [vp]
@@ -318,6 +319,27 @@ class Context:
         self._ba_dims = (int(cams.shape[0]), int(pts.shape[0]), int(op.shape[0]), int(vtype.shape[0]))
         self._check(self.lib.spp_ba_set_graph(self.h, vtype.shape[0], _u8p(vtype), _dp(cams), _dp(pts), op.shape[0],
                                               _u64p(op), _u64p(oc), _dp(z), _dp(info)))
+
+    def ba_append_graph(self, g):
+        """g: the NEW vertices and observations only (same layout as for ba_set_graph; vertex ids continue the numbering)."""
+        vtype = np.ascontiguousarray(g.vtype, np.uint8)
+        cams = np.ascontiguousarray(g.cams, np.float64).reshape(-1, 11)
+        pts = np.ascontiguousarray(g.pts, np.float64).reshape(-1, 3)
+        op = np.ascontiguousarray(g.obs_pt, np.uint64)
+        oc = np.ascontiguousarray(g.obs_cam, np.uint64)
+        z = np.ascontiguousarray(g.z, np.float64).reshape(-1, 2)
+        info = np.ascontiguousarray(g.info, np.float64).reshape(-1, 2, 2)
+        n_c, n_p, n_o = int(np.count_nonzero(vtype == 0)), int(np.count_nonzero(vtype == 1)), int(op.shape[0])
+        if vtype.ndim != 1 or n_c + n_p != vtype.shape[0]:
+            raise ValueError("vtype must be a vector of 0 (camera) / 1 (point)")
+        if cams.shape[0] != n_c or pts.shape[0] != n_p:
+            raise ValueError(f"cams must be ({n_c}, 11) and pts ({n_p}, 3), got {cams.shape} and {pts.shape}")
+        if oc.shape != (n_o,) or z.shape[0] != n_o or info.shape[0] != n_o:
+            raise ValueError("obs_pt, obs_cam, z (O, 2) and info (O, 2, 2) must have the same length")
+        self._check(self.lib.spp_ba_append_graph(self.h, vtype.shape[0], _u8p(vtype), _dp(cams), _dp(pts), n_o,
+                                                 _u64p(op), _u64p(oc), _dp(z), _dp(info)))
+        c0, p0, o0, v0 = self._ba_dims
+        self._ba_dims = (c0 + n_c, p0 + n_p, o0 + n_o, v0 + int(vtype.shape[0]))
 
     def ba_set_states(self, cam_states=None, pts=None):
         cs = None if cam_states is None else np.ascontiguousarray(cam_states, np.float64)

@@ -19,6 +19,8 @@ void build_schur_structure(spp_ctx *ctx, size_t C, size_t P, const std::vector<u
 bool schur_structure_device_supported(size_t C);
 void ba_upload_and_analyse_device(spp_ctx *ctx, size_t C, size_t P, size_t O, const uint64_t *p_obs_point,
 	const uint64_t *p_obs_camera, const double *p_z, const double *p_info);
+void ba_append_and_analyse_device(spp_ctx *ctx, size_t C, size_t P, size_t O_old, size_t O_new, const uint64_t *p_obs_point,
+	const uint64_t *p_obs_camera, const double *p_z, const double *p_info);
 void ba_upload_and_analyse_device_sliced(spp_ctx *ctx, size_t C, size_t P, size_t O, const uint64_t *p_obs_point,
 	const uint64_t *p_obs_camera, const double *p_z, const double *p_info);
 void ba_fetch_host_maps(spp_ctx *ctx);
@@ -550,6 +552,14 @@ int spp_create(int device, spp_ctx_t *p_ctx)
 		return SPP_ERR_CUDA;
 	}
 	char buf[256];
+	if(spp::dbuf_use_pool()) { // freed device buffers stay in the pool (see dbuf_malloc); spp_destroy trims it
+		cudaMemPool_t pool;
+		if(cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+			uint64_t n_threshold = UINT64_MAX;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &n_threshold);
+		}
+		(void)cudaGetLastError();
+	}
 	snprintf(buf, sizeof(buf), "spp_b200 0.1 sm_%d%d %s (%d SMs)", prop.major, prop.minor, prop.name, prop.multiProcessorCount);
 	ctx->description = buf;
 	*p_ctx = ctx;
@@ -563,6 +573,10 @@ void spp_destroy(spp_ctx_t ctx)
 	cudaSetDevice(ctx->device);
 	if(ctx->stream)
 		cudaStreamSynchronize(ctx->stream);
+	if(getenv("SPP_ALLOC_STATS")) {
+		const spp::DBufStats &as = spp::DBufStats::get();
+		fprintf(stderr, "[spp alloc] %zu cudaMalloc (%.1f MB), %zu cudaFree, %.1f ms in both\n", as.n_malloc, as.bytes * 1e-6, as.n_free, as.ms);
+	}
 	if(ctx->nccl_comm) {
 		// the stream is idle: ncclCommAbort frees the communicator without waiting for the other ranks (ncclCommDestroy
 		// finalises collectively and hangs when a peer has already left)
@@ -596,7 +610,15 @@ void spp_destroy(spp_ctx_t ctx)
 	for(size_t i = 0; i < sc.ev_factor.size(); ++ i) {
 		cudaEventDestroy(sc.ev_factor[i]); cudaEventDestroy(sc.ev_target[i]); cudaEventDestroy(sc.ev_x[i]);
 	}
+	const int n_device = ctx->device;
 	delete ctx;
+	if(spp::dbuf_use_pool()) { // what the context's buffers held goes back to the driver
+		cudaMemPool_t pool;
+		cudaDeviceSynchronize();
+		if(cudaDeviceGetDefaultMemPool(&pool, n_device) == cudaSuccess)
+			cudaMemPoolTrimTo(pool, 0);
+		(void)cudaGetLastError();
+	}
 }
 
 const char *spp_last_error(spp_ctx_t ctx)
@@ -704,6 +726,7 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 	} copy_guard = {ctx};
 	BAProblem &ba = ctx->ba;
 	ba.valid = false;
+	ba.raw_on_device = false;
 	ctx->slot.valid = false;
 	ctx->slot.filled = false;
 	ctx->snode.valid = false;
@@ -756,6 +779,8 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 		ba_upload_and_analyse_device(ctx, C, P, O, p_obs_point, p_obs_camera, p_z, p_info);
 		ba.pts.upload(p_points, P * 3, st);
 		ba.pts0.upload(p_points, P * 3, st);
+		ba.raw_on_device = true;
+		ba.n_obs_raw = O;
 	} else if(ctx->world > 1 && schur_structure_device_supported(C) && !getenv("SPP_HOST_SYMBOLIC")) {
 		// several ranks: the same analysis on the device, for the whole graph (global block list, track lengths) and
 		// then for this rank's landmark slice
@@ -845,6 +870,91 @@ int spp_ba_set_graph(spp_ctx_t ctx, size_t n_vertices, const uint8_t *p_vertex_t
 	ba.partial.resize(4 * 1024);
 	ba.maxdiag.resize(1);
 	SPP_CUDA(cudaStreamSynchronize(st));
+	ba.linearised = false;
+	ba.valid = true;
+	API_END(ctx)
+}
+
+int spp_ba_append_graph(spp_ctx_t ctx, size_t n_new_vertices, const uint8_t *p_vertex_type,
+	const double *p_cam_params, const double *p_points, size_t n_new_observations,
+	const uint64_t *p_obs_point, const uint64_t *p_obs_camera, const double *p_z, const double *p_info)
+{
+	API_BEGIN(ctx)
+	struct CopyGuard {
+		spp_ctx *c;
+		~CopyGuard() { if(c->copy_stream) cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); }
+	} copy_guard = {ctx};
+	BAProblem &ba = ctx->ba;
+	if(!ba.valid || !ba.raw_on_device || ctx->world != 1)
+		throw invalid_error("spp_ba_append_graph: needs a graph set by spp_ba_set_graph on a single-GPU context (device-side analysis)");
+	if((n_new_vertices && !p_vertex_type) || (n_new_observations && (!p_obs_point || !p_obs_camera || !p_z || !p_info)))
+		throw invalid_error("null argument");
+	size_t n_new_cams = 0;
+	for(size_t v = 0; v < n_new_vertices; ++ v) {
+		if(p_vertex_type[v] > 1)
+			throw invalid_error("vertex type must be 0 (camera) or 1 (point)");
+		n_new_cams += p_vertex_type[v] == 0;
+	}
+	const size_t n_new_pts = n_new_vertices - n_new_cams;
+	if((n_new_cams && !p_cam_params) || (n_new_pts && !p_points))
+		throw invalid_error("null vertex data");
+	const size_t V0 = ba.n_vertices, C0 = ba.cam_vertex.size(), P0 = ba.pt_vertex.size(), O0 = ba.n_obs_raw;
+	const size_t C = C0 + n_new_cams, P = P0 + n_new_pts;
+	if(!schur_structure_device_supported(C))
+		throw invalid_error("spp_ba_append_graph: too many cameras for the device-side analysis");
+	// from here on the context holds no valid graph until the analysis went through
+	ba.valid = false;
+	ctx->slot.valid = false;
+	ctx->slot.filled = false;
+	ctx->snode.valid = false;
+	ctx->sys.n_blocks_global = 0;
+	ba.raw_on_device = false;
+	ba.vtype.insert(ba.vtype.end(), p_vertex_type, p_vertex_type + n_new_vertices);
+	ba.vertex_local.resize(V0 + n_new_vertices);
+	for(size_t v = 0; v < n_new_vertices; ++ v) {
+		if(p_vertex_type[v] == 0) {
+			ba.vertex_local[V0 + v] = (uint32_t)ba.cam_vertex.size();
+			ba.cam_vertex.push_back(uint32_t(V0 + v));
+		} else {
+			ba.vertex_local[V0 + v] = (uint32_t)ba.pt_vertex.size();
+			ba.pt_vertex.push_back(uint32_t(V0 + v));
+		}
+	}
+	ba.n_vertices = V0 + n_new_vertices;
+	if(!V0 && n_new_vertices) { // (an empty graph was set before: vertex id 0 arrives now)
+		ba.uf_is_cam = p_vertex_type[0] == 0;
+		ba.uf_index = 0;
+	}
+	cudaStream_t st = ctx->stream;
+	// the vertices already there keep their current (and their initial) states; the new ones go behind them
+	std::vector<double> cs(n_new_cams * 6), ci(n_new_cams * 5);
+	for(size_t c = 0; c < n_new_cams; ++ c) {
+		for(int k = 0; k < 6; ++ k) cs[c * 6 + k] = p_cam_params[c * 11 + k];
+		for(int k = 0; k < 5; ++ k) ci[c * 5 + k] = p_cam_params[c * 11 + 6 + k];
+	}
+	ba.cam_state.grow_keep(C * 6, st);
+	ba.cam_state0.grow_keep(C * 6, st);
+	ba.cam_intr.grow_keep(C * 5, st);
+	ba.pts.grow_keep(P * 3, st);
+	ba.pts0.grow_keep(P * 3, st);
+	if(n_new_cams) {
+		SPP_CUDA(cudaMemcpyAsync(ba.cam_state.p() + C0 * 6, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+		SPP_CUDA(cudaMemcpyAsync(ba.cam_state0.p() + C0 * 6, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+		SPP_CUDA(cudaMemcpyAsync(ba.cam_intr.p() + C0 * 5, ci.data(), ci.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+	}
+	if(n_new_pts) {
+		SPP_CUDA(cudaMemcpyAsync(ba.pts.p() + P0 * 3, p_points, n_new_pts * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+		SPP_CUDA(cudaMemcpyAsync(ba.pts0.p() + P0 * 3, p_points, n_new_pts * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+	}
+	ba.P_global = P;
+	ba.pt_begin = 0;
+	ba.pt_end = P;
+	ba_append_and_analyse_device(ctx, C, P, O0, n_new_observations, p_obs_point, p_obs_camera, p_z, p_info);
+	ba.camRt.resize(C * 84);
+	ba.camK.resize(C * 5);
+	SPP_CUDA(cudaStreamSynchronize(st)); // the host vectors go out of scope
+	ba.n_obs_raw = O0 + n_new_observations;
+	ba.raw_on_device = true;
 	ba.linearised = false;
 	ba.valid = true;
 	API_END(ctx)

@@ -61,6 +61,8 @@ struct BAProblem {
 	std::vector<uint32_t> h_obs_cam, h_obs_pt; // host copies (track order, fetched on demand)
 	DBuf<uint32_t> d_obs_orig;           // the same map on the device
 	bool host_maps_valid;
+	bool raw_on_device;                  // the caller's arrays (edge insertion order) are still staged on the device: the graph can be appended to
+	size_t n_obs_raw;                    // observations staged
 	int uf_is_cam; long uf_index;        // vertex id 0 carries the unary factor (-1: added by another rank)
 	size_t P_global, pt_begin, pt_end;   // landmark slice of this rank (multi-GPU)
 	int jac_mode;
@@ -75,7 +77,7 @@ struct BAProblem {
 	DBuf<double> partial;                         // reduction scratch
 	DBuf<unsigned long long> maxdiag;             // [1] bits of the max per-edge Hessian diagonal
 	bool linearised;
-	BAProblem() : valid(false), n_vertices(0), host_maps_valid(false), uf_is_cam(1), uf_index(0), P_global(0), pt_begin(0),
+	BAProblem() : valid(false), n_vertices(0), host_maps_valid(false), raw_on_device(false), n_obs_raw(0), uf_is_cam(1), uf_index(0), P_global(0), pt_begin(0),
 		pt_end(0), jac_mode(0), linearised(false) {}
 };
 

@@ -13,6 +13,8 @@
 // Sorting and scanning use CUB (radix sort is stable, which is what keeps every list in landmark order); the
 // enumeration kernels are below. Integer work only; nothing here runs per LM iteration.
 
+#include <chrono>
+#include <string>
 #include "spp_ctx.h"
 #include <algorithm>
 #include <cub/cub.cuh>
@@ -209,9 +211,30 @@ bool schur_structure_device_supported(size_t C)
 
 // d_ocam / d_opt: local camera / point index per observation in edge insertion order (device).
 // Fills the device structure of ctx->sys and d_obs_orig (track position -> edge index).
+// SPP_SYMBOLIC_TIMING: wall-clock marks of the device-side analysis on stderr (each mark synchronises the stream)
+struct SgMarks {
+	bool on;
+	cudaStream_t st;
+	std::chrono::steady_clock::time_point t0;
+	std::string line;
+	explicit SgMarks(cudaStream_t s) : on(getenv("SPP_SYMBOLIC_TIMING") != 0), st(s), t0(std::chrono::steady_clock::now()) {}
+	void mark(const char *what)
+	{
+		if(!on) return;
+		cudaStreamSynchronize(st);
+		const auto t1 = std::chrono::steady_clock::now();
+		char buf[96];
+		snprintf(buf, sizeof(buf), " %s %.2f", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		line += buf;
+		t0 = t1;
+	}
+	~SgMarks() { if(on && !line.empty()) fprintf(stderr, "[spp symbolic ms]%s\n", line.c_str()); }
+};
+
 void build_schur_structure_device(spp_ctx *ctx, size_t C, size_t P, size_t O, const uint32_t *d_ocam, const uint32_t *d_opt,
 	DBuf<uint32_t> &d_obs_orig)
 {
+	SgMarks marks(ctx->stream);
 	SchurSystem &s = ctx->sys;
 	SymbolicScratch &w = ctx->sym;
 	cudaStream_t st = ctx->stream;
@@ -238,6 +261,7 @@ void build_schur_structure_device(spp_ctx *ctx, size_t C, size_t P, size_t O, co
 		k_sg_track_gather<<<n_blocks(O, T), T, 0, st>>>(O, d_obs_orig.p(), d_ocam, s.obs_cam.p(), w.pos_of_edge.p());
 		LAUNCH_CHECK(ctx);
 	}
+	marks.mark("tracks");
 	// pt_ptr / cam_ptr: histogram + exclusive scan
 	w.cnt.resize(std::max(P, C) + 1);
 	s.pt_ptr.resize(P + 1);
@@ -260,6 +284,7 @@ void build_schur_structure_device(spp_ctx *ctx, size_t C, size_t P, size_t O, co
 	w.keys_out.resize(O);
 	sort_pairs(ctx, tmp, d_ocam, w.keys_out.p(), w.pos_of_edge.p(), s.cam_obs.p(), O, bits_for(C));
 
+	marks.mark("ptr+camlists");
 	// ---- off-diagonal pairs: count per enumeration slot
 	const size_t n_t = (C + SG_TILE - 1) / SG_TILE, L = n_t * n_t * SG_TILE * SG_TILE;
 	w.cnt_lin.resize(L);
@@ -295,6 +320,7 @@ void build_schur_structure_device(spp_ctx *ctx, size_t C, size_t P, size_t O, co
 	if(*h_err == 2)
 		throw invalid_error("a landmark is observed twice by the same camera (duplicate edge)");
 	const size_t n_off_blk = *h_nblk, n_off = *h_noff, n_blk = C + n_off_blk, n_pairs = O + n_off;
+	marks.mark("count");
 
 	// ---- block list
 	s.blk_row.resize(n_blk); s.blk_col.resize(n_blk); s.blk_ptr.resize(n_blk + 1);
@@ -310,6 +336,7 @@ void build_schur_structure_device(spp_ctx *ctx, size_t C, size_t P, size_t O, co
 	k_sg_set_u64<<<1, 1, 0, st>>>(s.blk_ptr.p() + n_blk, n_pairs);
 	LAUNCH_CHECK(ctx);
 
+	marks.mark("blocks");
 	// ---- pair lists: diagonal blocks = the camera's observations in landmark order (ascending track position) ...
 	s.pair_a.resize(n_pairs); s.pair_b.resize(n_pairs);
 	sort_pairs(ctx, tmp, s.obs_cam.p(), w.keys_out.p(), w.iota.p(), s.pair_a.p(), O, bits_for(C));
@@ -332,11 +359,13 @@ void build_schur_structure_device(spp_ctx *ctx, size_t C, size_t P, size_t O, co
 		k_sg_split_pairs<<<n_blocks(n_off, T), T, 0, st>>>(n_off, w.pval_out.p(), s.pair_a.p() + O, s.pair_b.p() + O);
 		LAUNCH_CHECK(ctx);
 	}
+	marks.mark("pairs");
 	s.n_blocks = n_blk;
 	s.n_pairs = n_pairs;
 	s.U.resize(C * 36); s.V.resize(P * 9); s.W.resize(O * 18);
 	s.gc.resize(C * 6); s.gp.resize(P * 3);
 	s.dxc.resize(C * 6); s.dxp.resize(P * 3);
+	marks.mark("lambda buffers");
 }
 
 // copies z / info to the staging buffers on the context's copy stream; records ctx->copy_done
@@ -359,6 +388,8 @@ static void upload_measurements_async(spp_ctx *ctx, const double *p_z, const dou
 	SPP_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
 }
 
+void ba_analyse_device_resident(spp_ctx *ctx, size_t C, size_t P, size_t O);
+
 // uploads the caller's observation arrays, derives the per-edge local indices, builds the structure and gathers the
 // measurements into track order -- the device-side body of spp_ba_set_graph for a single-GPU context
 void ba_upload_and_analyse_device(spp_ctx *ctx, size_t C, size_t P, size_t O, const uint64_t *p_obs_point,
@@ -375,6 +406,17 @@ void ba_upload_and_analyse_device(spp_ctx *ctx, size_t C, size_t P, size_t O, co
 	// the measurements (two thirds of the bytes) are only needed when the structure is known: their copy runs on a
 	// second stream beside the analysis kernels (truly asynchronous when the caller's buffers are pinned)
 	upload_measurements_async(ctx, p_z, p_info, O);
+	ba_analyse_device_resident(ctx, C, P, O);
+}
+
+// the part of the analysis that only needs what is already on the device: per-edge local indices from the staged vertex
+// ids, the structure, the measurements gathered into track order (behind the measurement copy of the side stream)
+void ba_analyse_device_resident(spp_ctx *ctx, size_t C, size_t P, size_t O)
+{
+	BAProblem &ba = ctx->ba;
+	SymbolicScratch &w = ctx->sym;
+	cudaStream_t st = ctx->stream;
+	const unsigned T = 256;
 	w.ocam.resize(O); w.opt.resize(O);
 	w.err.resize(1);
 	SPP_CUDA(cudaMemsetAsync(w.err.p(), 0, sizeof(int), st));
@@ -400,6 +442,35 @@ void ba_upload_and_analyse_device(spp_ctx *ctx, size_t C, size_t P, size_t O, co
 		LAUNCH_CHECK(ctx);
 	}
 	ba.host_maps_valid = false;
+}
+
+// Appends to the staged graph (spp_ba_append_graph): the vertex tables are sent again (a few bytes per vertex), the new
+// observations' ids and measurements go behind the ones already staged in edge insertion order, and the analysis runs
+// on the whole graph from device memory -- nothing that is already there crosses the link again
+void ba_append_and_analyse_device(spp_ctx *ctx, size_t C, size_t P, size_t O_old, size_t O_new, const uint64_t *p_obs_point,
+	const uint64_t *p_obs_camera, const double *p_z, const double *p_info)
+{
+	BAProblem &ba = ctx->ba;
+	SymbolicScratch &w = ctx->sym;
+	cudaStream_t st = ctx->stream;
+	if(w.obs_pt_id.size() != O_old || w.obs_cam_id.size() != O_old || w.z_in.size() != O_old * 2 || w.info_in.size() != O_old * 4)
+		throw invalid_error("spp_ba_append_graph: the staged graph is gone (another graph was analysed in between)");
+	const size_t O = O_old + O_new;
+	w.vtype.upload(ba.vtype.data(), ba.n_vertices, st);
+	w.vlocal.upload(ba.vertex_local.data(), ba.n_vertices, st);
+	SPP_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0)); // nothing of the previous graph's copy is still in flight
+	w.obs_pt_id.grow_keep(O, st);
+	w.obs_cam_id.grow_keep(O, st);
+	w.z_in.grow_keep(O * 2, st);
+	w.info_in.grow_keep(O * 4, st);
+	if(O_new) {
+		SPP_CUDA(cudaMemcpyAsync(w.obs_pt_id.p() + O_old, p_obs_point, O_new * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+		SPP_CUDA(cudaMemcpyAsync(w.obs_cam_id.p() + O_old, p_obs_camera, O_new * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+		SPP_CUDA(cudaMemcpyAsync(w.z_in.p() + O_old * 2, p_z, O_new * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+		SPP_CUDA(cudaMemcpyAsync(w.info_in.p() + O_old * 4, p_info, O_new * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+	}
+	SPP_CUDA(cudaEventRecord(ctx->copy_done, st)); // what ba_analyse_device_resident waits for
+	ba_analyse_device_resident(ctx, C, P, O);
 }
 
 // ---- several ranks: this rank keeps a contiguous slice of the landmarks ---------------------------------------------
