@@ -160,3 +160,36 @@ def test_sparse_path_is_bit_reproducible(sparse_ctx):
     assert info["supernodes"] > 10 and info["updates"] > 20
     assert np.array_equal(a, b)
     assert sparse_ctx.schur_get_rcs_residual() < 1e-13
+
+
+def test_bal_sixteenth_against_the_reference_itself(tmp_path):
+    """The 1/16 sub-sequence of the BAL-13682 shape that bench.py times the reference on (855 cameras; the full shape
+    does not finish on the CPU): the UNMODIFIED reference (oracle/_ref/ref_driver_ba, its dense Schur path) against this
+    library with the block-sparse (supernodal) reduced-camera-system solver forced, and with the dense one -- the final
+    chi2 of Optimize(2, 0) within the north-star 1e-6, the two device paths within 1e-7 of each other (measured 2e-9:
+    their increments differ in the 13th digit, and the second linearisation -- forward differences with delta = 1e-9 --
+    amplifies that by 1e9 eps in the Jacobians)."""
+    import subprocess
+    from slam_plus_plus_b200 import capi, graphs, sppio
+    ref_bin = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "ref_driver_ba")
+    if not os.path.exists(ref_bin):
+        pytest.skip("oracle/_ref/ref_driver_ba not built (needs /root/reference at build time)")
+    g = graphs.make_ba(13682 // 16, 4456117 // 16, 13682, mean_extra_track=4.5, max_track=120, max_stride=12, loops=1)
+    gp, dp = str(tmp_path / "g.bin"), str(tmp_path / "ref.dump")
+    sppio.write_graph(gp, g)
+    subprocess.run([ref_bin, "time", gp, dp, "2", "0"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    chi2_ref = float(sppio.read_dump(dp)["chi2"][0])
+    chi2 = {}
+    for mode in (capi.RCS_SPARSE, capi.RCS_DENSE):
+        ctx = capi.Context(0)
+        ctx.schur_set_rcs_solver(mode)
+        ctx.ba_set_graph(g)
+        rep = ctx.ba_optimize(2, 0.0)
+        chi2[mode] = rep["chi2_final"]
+        if mode == capi.RCS_SPARSE:
+            info = ctx.schur_get_rcs_info()
+            assert info["cameras"] == g.n_cams and info["supernodes"] >= 1
+        ctx.close()
+    assert abs(chi2[capi.RCS_SPARSE] - chi2_ref) <= 1e-6 * chi2_ref, (chi2, chi2_ref)
+    assert abs(chi2[capi.RCS_DENSE] - chi2_ref) <= 1e-6 * chi2_ref, (chi2, chi2_ref)
+    assert abs(chi2[capi.RCS_SPARSE] - chi2[capi.RCS_DENSE]) <= 1e-7 * chi2_ref
