@@ -50,7 +50,11 @@ for f in BlockMatrix Debug LinearSolver_Schur LinearSolver_Schur_GPU LinearSolve
 	echo "$REF/src/slam/$f.cpp $OBJ/slam_$f.o $CXX" >> "$LIST"
 done
 for d in "${DRIVERS[@]}"; do
-	# the drop-in driver also sees the product's public headers (C ABI + reference-side adapter)
+	# the drop-in driver also sees the product's public headers (C ABI + reference-side adapter): a driver object older
+	# than any of them (or than the dump helper) is stale
+	if [ -f "$OBJ/ref_driver_$d.o" ] && [ -n "$(find "$HERE/../include" "$HERE/spp_dump.h" -newer "$OBJ/ref_driver_$d.o" -type f 2>/dev/null | head -1)" ]; then
+		rm -f "$OBJ/ref_driver_$d.o"
+	fi
 	echo "$HERE/ref_driver_$d.cpp $OBJ/ref_driver_$d.o $CXX -I$HERE/../include" >> "$LIST"
 done
 for f in "$REF"/src/csparse/*.c; do
