@@ -32,6 +32,11 @@
 // the barrier, as in a cooperative-groups grid barrier); the reader spins with ld.acquire and issues fence.proxy.async
 // before its TMA loads. A watchdog turns a wait that never ends (a bug, not
 // a data condition) into an error instead of a hung device.
+// Inside a CTA, a consumer warp hands a pipeline stage back to the producer through release_stage(): the mbarrier
+// arrive is made control-dependent on the values of the fragments just loaded, because an arrive issued back to back
+// with the last ld.shared of the stage let the refill overtake that load ("stage release").
+// -DSPP_DF_FENCE_ALL=1 (debugging aid, no effect on results): every writer thread fences before the CTA barrier that
+// precedes a flag publication, instead of relying on the cumulativity of the publishing thread's release.
 #pragma once
 #include <cuda.h>
 
