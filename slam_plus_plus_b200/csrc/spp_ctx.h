@@ -172,13 +172,20 @@ struct SupernodalChol {
 	DBuf<uint64_t> d_asm_dst, d_rhs_dst, d_pad_off;
 	DBuf<double> d_L, d_Rinv, d_x, d_part;
 	DBuf<int> d_info;                      // [0] first non-positive pivot, [1..] backsolve flags
-	double factor_flops;                   // of the numeric phase as executed (amalgamation zeros included)
+	double factor_flops;                   // of the numeric phase as executed by THIS rank (amalgamation zeros included)
+	double factor_flops_total;             // the same for the whole factorisation (equal on one rank)
+	// several ranks: subtrees of the supernodal elimination tree belong to one rank each, the supernodes above them
+	// (owner -1: "shared") are factored by every rank after the contributions to their panels have been summed
+	std::vector<int> owner;                // [ns] rank that factors supernode s, -1: every rank
+	bool distributed;                      // some supernode has an owner
+	DBuf<double> d_flag;                   // [1] "a non-positive pivot somewhere", summed over the ranks
 	// side streams: the updates into one target panel all go to the same stream (fixed order: deterministic), the
 	// updates of one supernode into different targets and the independent subtrees of the backward solve run side by side
 	enum { N_STREAMS = 8 };
 	cudaStream_t side[N_STREAMS];
 	std::vector<cudaEvent_t> ev_factor, ev_target, ev_x;
-	SupernodalChol() : valid(false), mode(0), n(0), n_rinv_blocks(0), n_s_blocks(0), max_part(0), factor_flops(0)
+	SupernodalChol() : valid(false), mode(0), n(0), n_rinv_blocks(0), n_s_blocks(0), max_part(0), factor_flops(0),
+		factor_flops_total(0), distributed(false)
 	{
 		for(int i = 0; i < N_STREAMS; ++ i) side[i] = 0;
 	}

@@ -37,6 +37,7 @@ void dense_chol_factor_dataflow(spp_ctx *ctx, double *A, size_t ld, size_t n_col
 bool dense_chol_dataflow_enabled();
 void dense_chol_backsolve_panel(spp_ctx *ctx, cudaStream_t stream, const double *A, size_t ld, const double *Rinv, double *y, int *flags);
 void schur_fetch_host_pattern(spp_ctx *ctx);
+void allreduce_device(spp_ctx *ctx, double *d_ptr, size_t n);
 
 #define LAUNCH_CHECK(ctx) do { ++ (ctx)->n_launches; SPP_CUDA(cudaGetLastError()); } while(0)
 
@@ -118,6 +119,69 @@ void snode_symbolic(spp_ctx *ctx, size_t n, const std::vector<uint32_t> &blk_row
 			sc.max_part = std::max(sc.max_part, ld * ((h + SN_GEMV_COLS - 1) / SN_GEMV_COLS));
 	}
 	sc.n_rinv_blocks = n_rinv;
+	sc.factor_flops_total = sc.factor_flops;
+
+	// ---- several ranks: who factors what. The work of a supernode (its panel and the updates it sends) is summed over
+	// subtrees; supernodes whose subtree weighs more than a threshold stay with every rank ("shared": the top of the
+	// tree, an upward-closed set), the subtrees hanging below them go to the least loaded rank, heaviest first. The
+	// threshold is the one (of a few multiples of total / world) with the smallest predicted time = shared work + the
+	// heaviest rank. Every rank computes the same plan from the same structure.
+	sc.owner.assign(ns, -1);
+	sc.distributed = false;
+	if(ctx->world > 1 && ns > 1 && !getenv("SPP_SNODE_REPLICATED")) {
+		std::vector<double> work(ns), sub(ns);
+		for(size_t s = 0; s < ns; ++ s) {
+			const double w = 6.0 * (sn.first[s + 1] - sn.first[s]), h = 6.0 * (sn.row_ptr[s + 1] - sn.row_ptr[s]);
+			work[s] = sub[s] = w * w * w / 3 + w * w * h + w * h * h;
+		}
+		for(size_t s = 0; s < ns; ++ s) // a postorder: children precede their parent
+			if(sn.parent[s] != 0xffffffffu) sub[sn.parent[s]] += sub[s];
+		const double f_total = sc.factor_flops_total;
+		double f_best = f_total * 0.97; // a plan must save at least 3 % to be worth the exchange
+		std::vector<int> plan(ns);
+		static const double p_theta[] = {0.125, 0.25, 0.5, 1.0, 2.0};
+		for(size_t k = 0; k < sizeof(p_theta) / sizeof(p_theta[0]); ++ k) {
+			const double f_limit = f_total / ctx->world * p_theta[k];
+			double f_shared = 0;
+			std::vector<size_t> roots;
+			for(size_t s = 0; s < ns; ++ s) {
+				if(sub[s] > f_limit) { plan[s] = -1; f_shared += work[s]; }
+				else {
+					plan[s] = -2;
+					if(sn.parent[s] == 0xffffffffu || sub[sn.parent[s]] > f_limit) roots.push_back(s);
+				}
+			}
+			std::stable_sort(roots.begin(), roots.end(), [&](size_t a, size_t b) { return sub[a] > sub[b]; });
+			std::vector<double> load(ctx->world, 0.0);
+			for(size_t q = 0; q < roots.size(); ++ q) {
+				const int r = int(std::min_element(load.begin(), load.end()) - load.begin());
+				load[r] += sub[roots[q]];
+				plan[roots[q]] = r;
+			}
+			for(size_t ss = ns; ss > 0; -- ss) { // parents before children: a subtree inherits the rank of its root
+				const size_t s = ss - 1;
+				if(plan[s] == -2) plan[s] = plan[sn.parent[s]];
+			}
+			const double f_time = f_shared + *std::max_element(load.begin(), load.end());
+			if(f_time < f_best) {
+				f_best = f_time;
+				sc.owner = plan;
+				sc.distributed = true;
+			}
+		}
+		if(sc.distributed) {
+			sc.factor_flops = 0;
+			for(size_t s = 0; s < ns; ++ s)
+				if(sc.owner[s] < 0 || sc.owner[s] == ctx->rank) sc.factor_flops += work[s];
+		}
+		if(getenv("SPP_SNODE_VERBOSE")) {
+			size_t n_shared = 0;
+			for(size_t s = 0; s < ns; ++ s) n_shared += sc.owner[s] < 0;
+			fprintf(stderr, "[spp snode] rank %d of %d: %s, %zu of %zu supernodes shared, this rank executes %.3e of %.3e flops (predicted time %.1f %% of one rank's)\n",
+				ctx->rank, ctx->world, sc.distributed? "subtrees distributed" : "replicated", n_shared, ns, sc.factor_flops, f_total,
+				100 * f_best / f_total);
+		}
+	}
 
 	// position of a block row inside panel t: own columns first, then the structure
 	auto col_pos = [&](size_t t, uint32_t rb) -> uint32_t {
@@ -191,6 +255,7 @@ void snode_symbolic(spp_ctx *ctx, size_t n, const std::vector<uint32_t> &blk_row
 	sc.d_x.resize(n * 6);
 	sc.d_part.resize(std::max<size_t>(sc.max_part, 1) * SupernodalChol::N_STREAMS);
 	sc.d_info.resize(1 + n_rinv);
+	sc.d_flag.resize(1);
 	SPP_CUDA(cudaStreamSynchronize(st));
 	if(getenv("SPP_SNODE_VERBOSE"))
 		fprintf(stderr, "[spp snode] n %zu, S blocks %zu, supernodes %zu, factor blocks %llu (exact %llu), panels %.2f GB, %.3e flops, %zu updates\n",
@@ -390,15 +455,29 @@ __global__ void k_snode_gemv_reduce(size_t ld, size_t n_chunks, const double *__
 }
 
 // x of the supernode's own columns: into the permuted solution (for the descendants) and, un-permuted, into dx
+// (several ranks: the x of a shared supernode is the same everywhere and the increments are summed over the ranks at the
+// end, so only rank 0 writes it to dx: b_write_dx)
 __global__ void k_snode_store_x(size_t w, size_t first_scalar, const double *__restrict__ y, const uint32_t *__restrict__ order,
-	double *__restrict__ x, double *__restrict__ dx)
+	double *__restrict__ x, double *__restrict__ dx, bool b_write_dx)
 {
 	const size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
 	if(r >= w) return;
 	const double v = y[r];
 	const size_t j = first_scalar + r;
 	x[j] = v;
-	dx[(size_t)order[j / 6] * 6 + j % 6] = v;
+	if(b_write_dx)
+		dx[(size_t)order[j / 6] * 6 + j % 6] = v;
+}
+
+// the status of the factorisation must be the same on every rank (a non-positive pivot in a subtree is seen by its owner
+// only): flag = (info != 0), summed over the ranks, then info = its own value or "somewhere" (1)
+__global__ void k_snode_info_to_flag(const int *__restrict__ info, double *__restrict__ flag)
+{
+	*flag = (*info != 0)? 1.0 : 0.0;
+}
+__global__ void k_snode_flag_to_info(const double *__restrict__ flag, int *__restrict__ info)
+{
+	if(*flag > 0 && *info == 0) *info = 1;
 }
 
 // ---- numeric phase ----------------------------------------------------------------------------------------
@@ -451,6 +530,13 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 	LAUNCH_CHECK(ctx);
 	k_snode_assemble_rhs<<<n_blocks(n * 6, 256), 256, 0, st>>>(n * 6, d_b, sc.d_rhs_dst.p(), L);
 	LAUNCH_CHECK(ctx);
+	const bool dist = sc.distributed && ctx->world > 1;
+	if(dist && ctx->rank != 0) { // the shared panels are summed over the ranks: S, the right-hand side and the identity
+		for(size_t s = 0; s < ns; ++ s) { // padding come from rank 0 alone, the others contribute their subtrees' updates
+			if(sc.owner[s] < 0)
+				SPP_CUDA(cudaMemsetAsync(L + sc.panel_off[s], 0, (size_t)sc.panel_ld[s] * sc.panel_cols[s] * sizeof(double), st));
+		}
+	}
 	// SPP_SNODE_PROFILE: serialised per-supernode timing of the two parts of the numeric phase (diagnostics)
 	std::vector<float> t_factor(profile? ns : 0), t_update(profile? ns : 0);
 	auto lap = [&](float *acc) {
@@ -468,7 +554,7 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 	if(!single_stream)
 		SPP_CUDA(cudaEventRecord(sc.ev_x[0], st)); // "panels assembled" (the backward solve re-records ev_x later)
 	// factorisation, elimination order (a postorder: every descendant of t precedes t)
-	for(size_t s = 0; s < ns; ++ s) {
+	auto factor_and_update = [&](size_t s) {
 		double *Ps = L + sc.panel_off[s];
 		const size_t ld = sc.panel_ld[s], cols = sc.panel_cols[s];
 		// a supernode with a single diagonal block is factored on the side stream that carries the updates into it (no
@@ -527,14 +613,48 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 			}
 		}
 		if(profile) lap(&t_update[s]);
+	};
+	if(!dist) {
+		for(size_t s = 0; s < ns; ++ s)
+			factor_and_update(s);
+	} else {
+		// this rank's subtrees first (their updates reach their own panels and the shared ones) ...
+		for(size_t s = 0; s < ns; ++ s)
+			if(sc.owner[s] == ctx->rank) factor_and_update(s);
+		// ... then the shared panels are summed over the ranks ...
+		for(size_t s = 0; s < ns; ++ s) {
+			if(sc.owner[s] >= 0) continue;
+			if(pending[s]) {
+				SPP_CUDA(cudaStreamWaitEvent(st, sc.ev_target[s], 0));
+				pending[s] = 0;
+			}
+		}
+		for(size_t s = 0; s < ns; ++ s)
+			if(sc.owner[s] < 0) allreduce_device(ctx, L + sc.panel_off[s], (size_t)sc.panel_ld[s] * sc.panel_cols[s]);
+		if(!single_stream) { // side streams that factor narrow shared supernodes wait for the sums, not just for the assembly
+			SPP_CUDA(cudaEventRecord(sc.ev_x[0], st));
+			for(int i = 0; i < SupernodalChol::N_STREAMS; ++ i) assembled_seen[i] = 0;
+		}
+		// ... and every rank factors the top of the tree
+		for(size_t s = 0; s < ns; ++ s)
+			if(sc.owner[s] < 0) factor_and_update(s);
 	}
 	if(!single_stream) {
 		for(int i = 0; i < SupernodalChol::N_STREAMS; ++ i) { // supernodes factored on the side streams (roots among them)
 			if(side_used[i])
 				SPP_CUDA(cudaStreamWaitEvent(st, sc.ev_factor[side_used[i] - 1], 0));
 		}
-		SPP_CUDA(cudaEventRecord(sc.ev_factor[ns - 1], st)); // "factorisation complete"
 	}
+	if(dist) { // one status for all ranks; the increments of the subtrees are summed at the end: start from zero
+		k_snode_info_to_flag<<<1, 1, 0, st>>>(sc.d_info.p(), sc.d_flag.p());
+		LAUNCH_CHECK(ctx);
+		allreduce_device(ctx, sc.d_flag.p(), 1);
+		k_snode_flag_to_info<<<1, 1, 0, st>>>(sc.d_flag.p(), sc.d_info.p());
+		LAUNCH_CHECK(ctx);
+		SPP_CUDA(cudaMemsetAsync(d_dx, 0, n * 6 * sizeof(double), st)); // (d_b, which d_dx may alias, went into the panels)
+	}
+	if(!single_stream)
+		SPP_CUDA(cudaEventRecord(sc.ev_factor[ns - 1], st)); // "factorisation complete"
 	if(profile) {
 		double tf = 0, tu = 0, ff = 0, fu = 0, tf_small = 0, tu_small = 0;
 		size_t n_small = 0;
@@ -563,6 +683,8 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 	// grandparents'), so independent subtrees are solved side by side
 	for(size_t ss = ns; ss > 0; -- ss) {
 		const size_t s = ss - 1;
+		if(dist && sc.owner[s] >= 0 && sc.owner[s] != ctx->rank)
+			continue; // another rank's subtree
 		double *Ps = L + sc.panel_off[s];
 		const size_t ld = sc.panel_ld[s], w = 6 * (size_t)(sn.first[s + 1] - sn.first[s]);
 		const size_t h = 6 * (size_t)(sn.row_ptr[s + 1] - sn.row_ptr[s]);
@@ -586,7 +708,8 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 		}
 		dense_chol_backsolve_panel(ctx, sb, Ps, ld, sc.d_Rinv.p() + (size_t)sc.rinv_first[s] * SN_NB * SN_NB, y,
 			sc.d_info.p() + 1 + sc.rinv_first[s]);
-		k_snode_store_x<<<n_blocks(w, 128), 128, 0, sb>>>(w, 6 * (size_t)sn.first[s], y, sc.d_order.p(), sc.d_x.p(), d_dx);
+		k_snode_store_x<<<n_blocks(w, 128), 128, 0, sb>>>(w, 6 * (size_t)sn.first[s], y, sc.d_order.p(), sc.d_x.p(), d_dx,
+			!dist || sc.owner[s] >= 0 || ctx->rank == 0);
 		LAUNCH_CHECK(ctx);
 		if(!single_stream)
 			SPP_CUDA(cudaEventRecord(sc.ev_x[s], sb));
@@ -597,6 +720,8 @@ int snode_factor_solve(spp_ctx *ctx, const double *d_Sblk, const double *d_b, do
 			SPP_CUDA(cudaStreamWaitEvent(st, sc.ev_target[i % ns], 0));
 		}
 	}
+	if(dist)
+		allreduce_device(ctx, d_dx, n * 6); // every rank needs all the camera increments
 	if(profile) {
 		float t_back = 0;
 		lap(&t_back);
