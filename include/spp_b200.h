@@ -257,6 +257,12 @@ int spp_schur_set_rcs_ordering(spp_ctx_t ctx, size_t n_cameras, const uint64_t *
  * (amalgamation zeros included), flops of one numeric factorisation, bytes of factor storage, supernode updates. */
 int spp_schur_get_rcs_info(spp_ctx_t ctx, uint64_t *p_order, double *p_stats);
 
+/* Several ranks: who factors which supernode of the block-sparse reduced camera system. p_owner[supernodes] (the count
+ * is p_stats[2] of spp_schur_get_rcs_info): the rank that owns the supernode's subtree, or -1 for the supernodes at the
+ * top of the elimination tree that every rank factors after the contributions to their panels have been summed
+ * (all -1 on one rank, or when sharing the work out would not pay). The reference has no counterpart. */
+int spp_schur_get_rcs_owners(spp_ctx_t ctx, int32_t *p_owner);
+
 /* After a successful solve on the block-sparse path: || S dx_cam - b || / || b || of the reduced camera system, evaluated
  * on the device from the block list of S (which survives the factorisation) -- the size-independent check of stage 3
  * at sizes where no dense copy of S can be taken (BAL-13682 shape). The reference has no counterpart. */

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "spp_ba_restore_initial", "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_get_blocks", "spp_ba_chi2", "spp_ba_solve_step",
     "spp_ba_optimize", "spp_ba_marginals", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_marginals",
     "spp_schur_get_reduced_system",
-    "spp_schur_set_rcs_solver", "spp_schur_set_rcs_ordering", "spp_schur_get_rcs_info", "spp_schur_get_rcs_residual", "spp_block_ordering",
+    "spp_schur_set_rcs_solver", "spp_schur_set_rcs_ordering", "spp_schur_get_rcs_info", "spp_schur_get_rcs_owners", "spp_schur_get_rcs_residual", "spp_block_ordering",
     "spp_block_symbolic_stats", "spp_dense_posdef_solve", "spp_dense_panel_factor", "spp_nccl_get_unique_id", "spp_set_nccl",
     "spp_chol_symbolic", "spp_chol_solve", "spp_chol_get_factor",
     "spp_pose_set_graph", "spp_pose_set_ordering", "spp_pose_set_states", "spp_pose_get_states", "spp_pose_restore_initial",
@@ -114,6 +114,7 @@ def load_library() -> C.CDLL:
     lib.spp_nccl_get_unique_id.argtypes = [C.c_void_p]
     lib.spp_set_nccl.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
     lib.spp_schur_set_rcs_solver.argtypes = [vp, C.c_int]
+    lib.spp_schur_get_rcs_owners.argtypes = [vp, C.POINTER(C.c_int32)]
     lib.spp_schur_set_rcs_ordering.argtypes = [vp, C.c_size_t, u64p]
     lib.spp_schur_get_rcs_info.argtypes = [vp, u64p, dp]
     lib.spp_schur_get_rcs_residual.argtypes = [vp, dp]
@@ -466,6 +467,13 @@ class Context:
         else:
             o = np.ascontiguousarray(order, np.uint64)
             self._check(self.lib.spp_schur_set_rcs_ordering(self.h, len(o), _u64p(o)))
+
+    def schur_get_rcs_owners(self) -> np.ndarray:
+        """per supernode of the block-sparse reduced camera system: the rank that factors it, -1 = every rank"""
+        n = int(self.schur_get_rcs_info()["supernodes"])
+        o = np.zeros(n, np.int32)
+        self._check(self.lib.spp_schur_get_rcs_owners(self.h, o.ctypes.data_as(C.POINTER(C.c_int32))))
+        return o
 
     def schur_get_rcs_info(self) -> dict:
         st = np.zeros(8)

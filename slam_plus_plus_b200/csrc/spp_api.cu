@@ -1324,6 +1324,17 @@ int spp_schur_get_rcs_info(spp_ctx_t ctx, uint64_t *p_order, double *p_stats)
 	API_END(ctx)
 }
 
+int spp_schur_get_rcs_owners(spp_ctx_t ctx, int32_t *p_owner)
+{
+	API_BEGIN(ctx)
+	SupernodalChol &sc = ctx->snode;
+	if(!sc.valid) throw invalid_error("no block-sparse factorisation of a reduced camera system yet");
+	if(!p_owner) throw invalid_error("null argument");
+	for(size_t s = 0, ns = sc.sn.n_super(); s < ns; ++ s)
+		p_owner[s] = (s < sc.owner.size())? sc.owner[s] : -1;
+	API_END(ctx)
+}
+
 int spp_schur_get_rcs_residual(spp_ctx_t ctx, double *p_relative_residual)
 {
 	API_BEGIN(ctx)

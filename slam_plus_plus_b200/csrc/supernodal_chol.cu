@@ -137,7 +137,8 @@ void snode_symbolic(spp_ctx *ctx, size_t n, const std::vector<uint32_t> &blk_row
 		for(size_t s = 0; s < ns; ++ s) // a postorder: children precede their parent
 			if(sn.parent[s] != 0xffffffffu) sub[sn.parent[s]] += sub[s];
 		const double f_total = sc.factor_flops_total;
-		double f_best = f_total * 0.97; // a plan must save at least 3 % to be worth the exchange
+		// a plan must save at least 3 % to be worth the exchange (SPP_SNODE_DISTRIBUTE_ALWAYS: any saving, for tests)
+		double f_best = getenv("SPP_SNODE_DISTRIBUTE_ALWAYS")? f_total * (1 - 1e-9) : f_total * 0.97;
 		std::vector<int> plan(ns);
 		static const double p_theta[] = {0.125, 0.25, 0.5, 1.0, 2.0};
 		for(size_t k = 0; k < sizeof(p_theta) / sizeof(p_theta[0]); ++ k) {

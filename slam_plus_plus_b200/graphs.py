@@ -135,6 +135,9 @@ BA_SHAPES = {
     # max_stride 12: the reduced camera system has 2.4 % non-zero blocks ("locality window so that S fill is 1-3 %")
     "bal13682": (13682, 4456117, 13682, dict(mean_extra_track=4.5, max_track=120, max_stride=12, loops=3)),
     "mid": (100, 20000, 100, dict(mean_extra_track=3.0, max_track=30, max_stride=3)),
+    # a long sequence with short tracks: the elimination tree of its reduced camera system branches (multi-GPU tests of
+    # the block-sparse factorisation shared out by subtrees)
+    "seq300": (300, 20000, 7, dict(mean_extra_track=2.0, max_track=8, max_stride=2, loops=1)),
     "small": (24, 1500, 24, dict(mean_extra_track=3.0, max_track=12, max_stride=2)),
     "tiny": (6, 40, 6, dict(mean_extra_track=2.0, max_track=5, max_stride=1)),
 }

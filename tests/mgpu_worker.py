@@ -86,7 +86,8 @@ def run_gpu(rank, world):
     rep = ctx.ba_optimize(5, 0.0)
     cs, ps = ctx.ba_get_states()
     ps = parallel.gather_points(ctx, ps)
-    out = dict(chi2_initial=rep["chi2_initial"], chi2_final=rep["chi2_final"], trace_chi2=rep["trace_chi2"],
+    owners = [int(o) for o in ctx.schur_get_rcs_owners()] if os.environ.get("SPP_TEST_RCS") == "sparse" else []
+    out = dict(owners=owners, chi2_initial=rep["chi2_initial"], chi2_final=rep["chi2_final"], trace_chi2=rep["trace_chi2"],
                accepted=rep["trace_accepted"], alpha_initial=rep["alpha_initial"], part=ctx.ba_get_partition(),
                ms=rep["ms"])
     if rank == 0:

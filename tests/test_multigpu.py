@@ -77,6 +77,24 @@ def test_global_block_pattern_of_the_reduced_camera_system():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("comm", ["nccl", "hook"])
+def test_block_sparse_factorisation_shared_out_by_subtrees_matches_single_gpu(comm):
+    """two ranks, block-sparse reduced camera system of a 300-camera sequence whose elimination tree branches: each rank
+    factors its own subtrees, the shared top after the panels have been summed (supernodal_chol.cu) -- against one GPU"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = _launch("gpu", 2, env=dict(SPP_TEST_RCS="sparse", SPP_TEST_COMM=comm, SPP_TEST_SHAPE="seq300", SPP_SNODE_DISTRIBUTE_ALWAYS="1"))
+    assert {0, 1} <= set(out["owners"]) and -1 in out["owners"], out["owners"]  # both ranks own subtrees, the top is shared
+    one = out["single"]
+    assert out["accepted"] == one["accepted"]
+    for a, b in zip(out["trace_chi2"], one["trace_chi2"]):
+        assert abs(a - b) <= 1e-8 * b
+    assert abs(out["chi2_final"] - one["chi2_final"]) <= 1e-7 * one["chi2_final"]
+    assert out["err_cams"] < 1e-4 and out["err_pts"] < 1e-4, (out["err_cams"], out["err_pts"])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("rcs,comm", [("dense", "nccl"), ("sparse", "nccl"), ("dense", "hook")])
 def test_sharded_lm_on_two_gpus_matches_single_gpu(rcs, comm):
     """comm = nccl: the library's own communicator (spp_set_nccl, ncclAllReduce issued by libspp_b200.so);
