@@ -268,16 +268,24 @@ int spp_schur_get_rcs_owners(spp_ctx_t ctx, int32_t *p_owner);
  * at sizes where no dense copy of S can be taken (BAL-13682 shape). The reference has no counterpart. */
 int spp_schur_get_rcs_residual(spp_ctx_t ctx, double *p_relative_residual);
 
-/* Pure host helpers (no context, no GPU). spp_block_ordering: the library's fill-reducing ordering (approximate
- * minimum degree on the block graph of A + A^T, then a postorder of the elimination tree) of an upper block-triangular
- * structure in block CSC (rows ascending, diagonal present) -- what CMatrixOrdering::p_BlockOrdering / amd_l2 does in
- * the reference; same quality of fill, not the same permutation. spp_block_symbolic_stats: symbolic Cholesky under an
+/* Pure host helpers (no context, no GPU). spp_block_ordering: the fill-reducing ordering (approximate minimum degree on
+ * the block graph of A + A^T) of a block structure in block CSC (upper, lower or both triangles; diagonal present or
+ * not) -- what CMatrixOrdering::p_BlockOrdering / SuiteSparse amd_l2 does in the reference (src/slam/OrderingMagic.cpp:
+ * 701-1033), and the same permutation entry for entry (csrc/amd_exact.cpp). spp_block_symbolic_stats: symbolic Cholesky under an
  * ordering (NULL = natural): p_col_count[n] blocks per column of the factor, p_parent[n] elimination tree
  * (UINT64_MAX = root), p_stats[3] = blocks of the factor, sum of count^2, maximal supernodes. Any output may be NULL.
  * (CUberBlockMatrix::Build_EliminationTree, src/slam/BlockMatrix.cpp:9403.) */
 int spp_block_ordering(size_t n_block_cols, const uint64_t *p_col_ptr, const uint64_t *p_row_idx, uint64_t *p_order);
 int spp_block_symbolic_stats(size_t n_block_cols, const uint64_t *p_col_ptr, const uint64_t *p_row_idx,
 	const uint64_t *p_order, uint64_t *p_col_count, uint64_t *p_parent, double *p_stats);
+/* Several ranks: the plan that shares the block-sparse factorisation of a reduced camera system out over n_world ranks
+ * (pure host helper; the solver computes the same plan internally, spp_schur_get_rcs_owners reports it). Under the
+ * ordering p_order (NULL = natural) and the solver's supernode amalgamation: p_owner[n_block_cols] = for every PERMUTED
+ * block column the rank that factors its supernode, -1 = every rank (the top of the elimination tree); p_stats[3] =
+ * predicted time as a fraction of the replicated factorisation (1 = no plan saves f_min_saving), supernodes, shared
+ * supernodes. The reference has no counterpart (single process). */
+int spp_block_subtree_owners(size_t n_block_cols, const uint64_t *p_col_ptr, const uint64_t *p_row_idx,
+	const uint64_t *p_order, int n_world, double f_min_saving, int32_t *p_owner, double *p_stats);
 
 /* ---- dense FP64 Cholesky (the reduced camera system solver) ----------------------------------------- */
 

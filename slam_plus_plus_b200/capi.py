@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "spp_ba_optimize", "spp_ba_marginals", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_marginals",
     "spp_schur_get_reduced_system",
     "spp_schur_set_rcs_solver", "spp_schur_set_rcs_ordering", "spp_schur_get_rcs_info", "spp_schur_get_rcs_owners", "spp_schur_get_rcs_residual", "spp_block_ordering",
-    "spp_block_symbolic_stats", "spp_dense_posdef_solve", "spp_dense_panel_factor", "spp_nccl_get_unique_id", "spp_set_nccl",
+    "spp_block_symbolic_stats", "spp_block_subtree_owners", "spp_dense_posdef_solve", "spp_dense_panel_factor", "spp_nccl_get_unique_id", "spp_set_nccl",
     "spp_chol_symbolic", "spp_chol_solve", "spp_chol_get_factor",
     "spp_pose_set_graph", "spp_pose_set_ordering", "spp_pose_set_states", "spp_pose_get_states", "spp_pose_restore_initial",
     "spp_pose_linearise", "spp_pose_get_lambda", "spp_pose_chi2", "spp_pose_solve_step", "spp_pose_optimize",
@@ -115,6 +115,7 @@ def load_library() -> C.CDLL:
     lib.spp_set_nccl.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
     lib.spp_schur_set_rcs_solver.argtypes = [vp, C.c_int]
     lib.spp_schur_get_rcs_owners.argtypes = [vp, C.POINTER(C.c_int32)]
+    lib.spp_block_subtree_owners.argtypes = [C.c_size_t, u64p, u64p, u64p, C.c_int, C.c_double, C.POINTER(C.c_int32), dp]
     lib.spp_schur_set_rcs_ordering.argtypes = [vp, C.c_size_t, u64p]
     lib.spp_schur_get_rcs_info.argtypes = [vp, u64p, dp]
     lib.spp_schur_get_rcs_residual.argtypes = [vp, dp]
@@ -203,6 +204,24 @@ def block_symbolic_stats(col_ptr, row_idx, order=None) -> dict:
     if rc != SPP_OK:
         raise RuntimeError(f"spp_block_symbolic_stats failed: {rc}")
     return dict(col_count=cnt, parent=par, nnzb_factor=int(st[0]), sum_count_sq=float(st[1]), supernodes=int(st[2]))
+
+
+def block_subtree_owners(col_ptr, row_idx, order, world: int, min_saving: float = 0.03):
+    """The plan that shares the block-sparse factorisation out over `world` ranks (host helper): owner of every PERMUTED
+    block column (-1: factored by every rank), predicted time as a fraction of the replicated factorisation, supernodes,
+    shared supernodes."""
+    lib = load_library()
+    col_ptr = np.ascontiguousarray(col_ptr, np.uint64)
+    row_idx = np.ascontiguousarray(row_idx, np.uint64)
+    n = len(col_ptr) - 1
+    o = None if order is None else np.ascontiguousarray(order, np.uint64)
+    own = np.zeros(n, np.int32)
+    st = np.zeros(3)
+    rc = lib.spp_block_subtree_owners(n, _u64p(col_ptr), _u64p(row_idx), _u64p(o), int(world), float(min_saving),
+                                      own.ctypes.data_as(C.POINTER(C.c_int32)), _dp(st))
+    if rc != SPP_OK:
+        raise RuntimeError(f"spp_block_subtree_owners failed: {rc}")
+    return dict(owner=own, predicted=float(st[0]), supernodes=int(st[1]), shared=int(st[2]))
 
 
 class SppError(RuntimeError):

@@ -192,6 +192,60 @@ void supernodal_symbolic(size_t n, const uint64_t *col_ptr, const uint64_t *row_
 			out.level[out.parent[s]] = std::max(out.level[out.parent[s]], out.level[s] + 1);
 }
 
+double plan_subtree_owners(const Supernodes &sn, int world, double min_saving, std::vector<int> &owner, std::vector<double> &work)
+{
+	const size_t ns = sn.n_super();
+	owner.assign(ns, -1);
+	work.assign(ns, 0.0);
+	std::vector<double> sub(ns);
+	double f_total = 0;
+	for(size_t s = 0; s < ns; ++ s) {
+		const double w = 6.0 * (sn.first[s + 1] - sn.first[s]), h = 6.0 * (sn.row_ptr[s + 1] - sn.row_ptr[s]);
+		work[s] = sub[s] = w * w * w / 3 + w * w * h + w * h * h;
+		f_total += work[s];
+	}
+	if(world < 2 || ns < 2 || !(f_total > 0))
+		return 1.0;
+	for(size_t s = 0; s < ns; ++ s) // a postorder: children precede their parent
+		if(sn.parent[s] != 0xffffffffu) sub[sn.parent[s]] += sub[s];
+	double f_best = f_total * (1 - min_saving);
+	bool b_found = false;
+	std::vector<int> plan(ns);
+	static const double p_theta[] = {0.125, 0.25, 0.5, 1.0, 2.0};
+	for(size_t k = 0; k < sizeof(p_theta) / sizeof(p_theta[0]); ++ k) {
+		const double f_limit = f_total / world * p_theta[k];
+		double f_shared = 0;
+		std::vector<size_t> roots;
+		for(size_t s = 0; s < ns; ++ s) {
+			if(sub[s] > f_limit) {
+				plan[s] = -1;
+				f_shared += work[s];
+			} else {
+				plan[s] = -2;
+				if(sn.parent[s] == 0xffffffffu || sub[sn.parent[s]] > f_limit) roots.push_back(s);
+			}
+		}
+		std::stable_sort(roots.begin(), roots.end(), [&](size_t a, size_t b) { return sub[a] > sub[b]; });
+		std::vector<double> load(world, 0.0);
+		for(size_t q = 0; q < roots.size(); ++ q) {
+			const int r = int(std::min_element(load.begin(), load.end()) - load.begin());
+			load[r] += sub[roots[q]];
+			plan[roots[q]] = r;
+		}
+		for(size_t ss = ns; ss > 0; -- ss) { // parents before children: a subtree inherits the rank of its root
+			const size_t s = ss - 1;
+			if(plan[s] == -2) plan[s] = plan[sn.parent[s]];
+		}
+		const double f_time = f_shared + *std::max_element(load.begin(), load.end());
+		if(f_time < f_best) {
+			f_best = f_time;
+			owner = plan;
+			b_found = true;
+		}
+	}
+	return b_found? f_best / f_total : 1.0;
+}
+
 } // namespace spp
 
 // ---- C ABI: pure host helpers (no context, no GPU) ------------------------------------------------------------
@@ -233,6 +287,39 @@ extern "C" int spp_block_symbolic_stats(size_t n_block_cols, const uint64_t *p_c
 			p_stats[0] = (double)sn.nnzb_exact;
 			p_stats[1] = sn.flops_blocks;
 			p_stats[2] = (double)sn.n_super();
+		}
+	} catch(const std::bad_alloc&) {
+		return SPP_ERR_NOMEM;
+	} catch(const std::exception&) {
+		return SPP_ERR_INVALID;
+	}
+	return SPP_OK;
+}
+
+extern "C" int spp_block_subtree_owners(size_t n_block_cols, const uint64_t *p_col_ptr, const uint64_t *p_row_idx,
+	const uint64_t *p_order, int n_world, double f_min_saving, int32_t *p_owner, double *p_stats)
+{
+	if(!p_col_ptr || !p_row_idx || n_world < 1)
+		return SPP_ERR_INVALID;
+	try {
+		std::vector<uint32_t> order(n_block_cols);
+		for(size_t i = 0; i < n_block_cols; ++ i) {
+			if(p_order && p_order[i] >= n_block_cols) return SPP_ERR_INVALID;
+			order[i] = p_order? (uint32_t)p_order[i] : (uint32_t)i;
+		}
+		spp::Supernodes sn;
+		spp::supernodal_symbolic(n_block_cols, p_col_ptr, p_row_idx, order, 0.05, 16, (size_t)1 << 30, sn); // the solver's amalgamation defaults
+		std::vector<int> owner;
+		std::vector<double> work;
+		const double f_time = spp::plan_subtree_owners(sn, n_world, f_min_saving, owner, work);
+		size_t n_shared = 0;
+		for(size_t s = 0; s < owner.size(); ++ s) n_shared += owner[s] < 0;
+		if(p_owner)
+			for(size_t j = 0; j < n_block_cols; ++ j) p_owner[j] = owner[sn.col_super[j]];
+		if(p_stats) {
+			p_stats[0] = f_time;
+			p_stats[1] = (double)sn.n_super();
+			p_stats[2] = (double)n_shared;
 		}
 	} catch(const std::bad_alloc&) {
 		return SPP_ERR_NOMEM;

