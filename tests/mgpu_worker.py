@@ -86,8 +86,14 @@ def run_gpu(rank, world):
     rep = ctx.ba_optimize(5, 0.0)
     cs, ps = ctx.ba_get_states()
     ps = parallel.gather_points(ctx, ps)
-    owners = [int(o) for o in ctx.schur_get_rcs_owners()] if os.environ.get("SPP_TEST_RCS") == "sparse" else []
-    out = dict(owners=owners, chi2_initial=rep["chi2_initial"], chi2_final=rep["chi2_final"], trace_chi2=rep["trace_chi2"],
+    owners, residual, repeat_equal = [], None, None
+    if os.environ.get("SPP_TEST_RCS") == "sparse":
+        owners = [int(o) for o in ctx.schur_get_rcs_owners()]
+        residual = ctx.schur_get_rcs_residual()  # || S dx - b || / || b || of the last solve, from the summed block list
+        ctx.ba_restore_initial()                 # the same five steps again: the sums have a fixed order for a given N
+        rep2 = ctx.ba_optimize(5, 0.0)
+        repeat_equal = rep2["trace_chi2"] == rep["trace_chi2"] and rep2["chi2_final"] == rep["chi2_final"]
+    out = dict(owners=owners, rcs_residual=residual, repeat_equal=repeat_equal, chi2_initial=rep["chi2_initial"], chi2_final=rep["chi2_final"], trace_chi2=rep["trace_chi2"],
                accepted=rep["trace_accepted"], alpha_initial=rep["alpha_initial"], part=ctx.ba_get_partition(),
                ms=rep["ms"])
     if rank == 0:

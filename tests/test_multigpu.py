@@ -86,13 +86,16 @@ def test_block_sparse_factorisation_shared_out_by_subtrees_matches_single_gpu(co
         pytest.skip("needs 2 GPUs")
     out = _launch("gpu", 2, env=dict(SPP_TEST_RCS="sparse", SPP_TEST_COMM=comm, SPP_TEST_SHAPE="seq300", SPP_SNODE_DISTRIBUTE_ALWAYS="1"))
     assert {0, 1} <= set(out["owners"]) and -1 in out["owners"], out["owners"]  # both ranks own subtrees, the top is shared
+    assert out["rcs_residual"] < 1e-10, out["rcs_residual"]  # the distributed factorisation solves the summed system
+    assert out["repeat_equal"]                                # and is bit-reproducible for a given number of ranks
     one = out["single"]
     assert out["accepted"] == one["accepted"]
     for a, b in zip(out["trace_chi2"], one["trace_chi2"]):
         # other summation order than one GPU (partial systems, then the contributions to the shared panels), amplified by
-        # every re-linearisation with forward differences: measured 1.4e-8 on this 300-camera sequence; north star 1e-6
-        assert abs(a - b) <= 1e-7 * b
-    assert abs(out["chi2_final"] - one["chi2_final"]) <= 1e-7 * one["chi2_final"]
+        # every re-linearisation with forward differences: measured 1e-8 ... 2e-7 on this 300-camera sequence (it depends
+        # on the all-reduce algorithm NCCL picks for the box's topology); north star 1e-6
+        assert abs(a - b) <= 1e-6 * b
+    assert abs(out["chi2_final"] - one["chi2_final"]) <= 1e-6 * one["chi2_final"]
     assert out["err_cams"] < 1e-4 and out["err_pts"] < 1e-4, (out["err_cams"], out["err_pts"])
 
 
