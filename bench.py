@@ -183,6 +183,8 @@ def check_chi2(args, rep):
     rank count) to ~1e-8 after five iterations; the bound asserted is 1e-6 (north_star)."""
     path = os.path.join(ROOT, "profiles", "chi2_trace.json")
     key = f"{args.shape}/lm{args.lm_iters}"
+    if args.jacobians != "fd":
+        return {"checked": False, "why": "the committed trace is that of the forward-difference (parity) mode"}
     if args.write_chi2_trace:  # a path: gpurun only brings gpurun_out/ back, the file is then committed as profiles/chi2_trace.json
         out = args.write_chi2_trace
         d = json.load(open(out)) if os.path.exists(out) else (json.load(open(path)) if os.path.exists(path) else {})
@@ -248,6 +250,8 @@ def measure_ba(args, torch, dist, dev, rank, world, local):
     if world > 1:
         from slam_plus_plus_b200.parallel import attach_nccl
         attach_nccl(ctx, rank, world)  # ncclAllReduce inside libspp_b200.so; torch.distributed only carries the unique id
+    if args.jacobians == "analytic":  # the production variant; the default (forward differences) is the reference's parity mode
+        ctx.ba_set_jacobian_mode(capi.JAC_ANALYTIC)
     t0 = time.time()
     ctx.ba_set_graph(g)
     setup_s = time.time() - t0
@@ -358,7 +362,8 @@ def measure_ba(args, torch, dist, dev, rank, world, local):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.shape}-shape BA, LM Optimize({args.lm_iters}, 0) per step, Schur + dense FP64 Cholesky",
                    "cameras": Cn, "points": P, "observations": O, "lm_iterations_per_step": n_iters / args.steps,
-                   "jacobians": "forward differences, delta=1e-9 (reference parity mode)",
+                   "jacobians": "forward differences, delta=1e-9 (reference parity mode)" if args.jacobians == "fd" else
+                                "analytic (closed-form derivatives; agrees with the forward differences at their noise floor)",
                    "l2_policy": "inputs larger than L2 (W+Y 817 MB, S 220 MB vs 126 MB L2)",
                    "parallelism": f"landmark-sharded x{world}" if world > 1 else "single GPU",
                    "symbolic_setup_s": setup_s},
@@ -521,6 +526,9 @@ def main():
     ap.add_argument("--shape", default="venice871")
     ap.add_argument("--lm-iters", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--jacobians", choices=["fd", "analytic"], default="fd",
+                    help="fd: forward differences with delta = 1e-9, the reference's own Jacobians (parity mode, the default and "
+                         "the configuration of the headline number); analytic: closed-form derivatives")
     ap.add_argument("--no-bal", action="store_true", help="skip the BAL-13682-shape block of the headline line")
     ap.add_argument("--write-chi2-trace", default="", metavar="PATH", help="single-GPU run: record the final chi2 of each shape in this "
                     "JSON file (committed as profiles/chi2_trace.json, which every later run is checked against)")
