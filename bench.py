@@ -398,7 +398,9 @@ def measure_ba(args, torch, dist, dev, rank, world, local):
         line["config"]["rcs"] = {k: v for k, v in rcs_info.items() if k != "order"}
         line["e2e"] = {"value": 1e3 * e2e_s / max(e2e_iters, 1), "unit": "ms per LM iteration (whole call sequence)", "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                       "note": "spp_ba_set_graph(host, incl. symbolic analysis and ordering) + spp_ba_optimize + spp_ba_get_states"}
+                       "note": "spp_ba_set_graph(host, incl. the device-side structure analysis) + spp_ba_optimize + spp_ba_get_states; the ordering and "
+                               "symbolic analysis of the block-sparse factorisation are reused when the same block pattern is uploaded again "
+                               "(as the reference reuses its symbolic decomposition while the structure is unchanged)"}
     if world == 1 and not args.no_cpu_baseline and sparse_rcs:
         # the reference cannot finish this shape in bounded time (sparse block Cholesky of ~3e12 flop on one thread): bounded sample
         try:

@@ -176,6 +176,13 @@ struct SupernodalChol {
 	double factor_flops_total;             // the same for the whole factorisation (equal on one rank)
 	// several ranks: subtrees of the supernodal elimination tree belong to one rank each, the supernodes above them
 	// (owner -1: "shared") are factored by every rank after the contributions to their panels have been summed
+	// what the symbolic analysis in memory was made for: the same block list under the same ordering request on the same
+	// rank layout needs no new one (the reference, too, orders and analyses only when the structure changed,
+	// LinearSolver_Schur.h:1566-1606)
+	std::vector<uint32_t> sym_row, sym_col;
+	std::vector<uint64_t> sym_user_order;
+	int sym_world, sym_rank;
+	bool sym_kept;
 	std::vector<int> owner;                // [ns] rank that factors supernode s, -1: every rank
 	bool distributed;                      // some supernode has an owner
 	DBuf<double> d_flag;                   // [1] "a non-positive pivot somewhere", summed over the ranks
@@ -185,7 +192,7 @@ struct SupernodalChol {
 	cudaStream_t side[N_STREAMS];
 	std::vector<cudaEvent_t> ev_factor, ev_target, ev_x;
 	SupernodalChol() : valid(false), mode(0), n(0), n_rinv_blocks(0), n_s_blocks(0), max_part(0), factor_flops(0),
-		factor_flops_total(0), distributed(false)
+		factor_flops_total(0), sym_world(0), sym_rank(0), sym_kept(false), distributed(false)
 	{
 		for(int i = 0; i < N_STREAMS; ++ i) side[i] = 0;
 	}

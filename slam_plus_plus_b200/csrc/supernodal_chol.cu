@@ -56,6 +56,12 @@ void snode_symbolic(spp_ctx *ctx, size_t n, const std::vector<uint32_t> &blk_row
 {
 	SupernodalChol &sc = ctx->snode;
 	sc.valid = false;
+	if(sc.sym_kept && sc.n == n && sc.sym_world == ctx->world && sc.sym_rank == ctx->rank && sc.sym_user_order == sc.user_order &&
+	   sc.sym_row == blk_row && sc.sym_col == blk_col && !getenv("SPP_SNODE_NO_REUSE")) {
+		sc.valid = true; // the same structure was uploaded again (new measurements / states): ordering, supernodes, maps and
+		return;          // panel layout on the device are still the right ones
+	}
+	sc.sym_kept = false;
 	sc.n = n;
 	const size_t nb = blk_row.size();
 	sc.n_s_blocks = nb;
@@ -226,6 +232,9 @@ void snode_symbolic(spp_ctx *ctx, size_t n, const std::vector<uint32_t> &blk_row
 		fprintf(stderr, "[spp snode] n %zu, S blocks %zu, supernodes %zu, factor blocks %llu (exact %llu), panels %.2f GB, %.3e flops, %zu updates\n",
 			n, nb, ns, (unsigned long long)sn.nnzb_factor, (unsigned long long)sn.nnzb_exact, total * 8e-9, sc.factor_flops,
 			sc.updates.size());
+	sc.sym_row = blk_row; sc.sym_col = blk_col; sc.sym_user_order = sc.user_order;
+	sc.sym_world = ctx->world; sc.sym_rank = ctx->rank;
+	sc.sym_kept = true;
 	sc.valid = true;
 }
 
