@@ -585,12 +585,22 @@ void ba_upload_and_analyse_device_sliced(spp_ctx *ctx, size_t C, size_t P, size_
 	SPP_CUDA(cudaStreamSynchronize(st));
 	{
 		const size_t ng = s.n_blocks_global;
-		std::vector<std::pair<uint64_t, uint32_t> > keys(ng);
-		for(size_t b = 0; b < ng; ++ b)
+		std::vector<uint32_t> slot(s.n_blocks);
+		// both lists come out of the same enumeration (diagonal blocks, then the off-diagonal ones by tile and position), so
+		// the slice's list is a subsequence of the global one: one merging pass locates every block ...
+		size_t n_located = 0;
+		for(size_t b = 0, gb = 0; b < s.n_blocks && gb < ng; ++ b) {
+			while(gb < ng && (s.h_gblk_row[gb] != s.h_blk_row[b] || s.h_gblk_col[gb] != s.h_blk_col[b])) ++ gb;
+			if(gb == ng) break;
+			slot[b] = (uint32_t)gb ++;
+			++ n_located;
+		}
+		// ... and should the orders ever differ, a sort of the global keys and binary searches do
+		std::vector<std::pair<uint64_t, uint32_t> > keys((n_located == s.n_blocks)? 0 : ng);
+		for(size_t b = 0; b < keys.size(); ++ b)
 			keys[b] = std::make_pair((uint64_t)s.h_gblk_row[b] * C + s.h_gblk_col[b], (uint32_t)b);
 		std::sort(keys.begin(), keys.end());
-		std::vector<uint32_t> slot(s.n_blocks);
-		for(size_t b = 0; b < s.n_blocks; ++ b) {
+		for(size_t b = 0; b < s.n_blocks && n_located != s.n_blocks; ++ b) {
 			const uint64_t k = (uint64_t)s.h_blk_row[b] * C + s.h_blk_col[b];
 			std::vector<std::pair<uint64_t, uint32_t> >::const_iterator it =
 				std::lower_bound(keys.begin(), keys.end(), std::make_pair(k, (uint32_t)0));
