@@ -261,7 +261,9 @@ public:
 		if(t_report.status == SPP_NOT_POSDEF)
 			fprintf(stderr, "warning: Cholesky failed\n"); // as the reference (the loop stops)
 		m_cam_states.resize((m_cams.size() / 11) * 6);
-		Check(spp_ba_get_states(m_p_context, m_cam_states.empty()? 0 : &m_cam_states[0], m_points.empty()? 0 : &m_points[0]));
+		// (all vertices: on a context that was given a communicator -- spp_set_nccl(p_Context(), ...) on every rank, each
+		// with the whole system -- the landmark slices of the ranks are summed into one array on the device)
+		Check(spp_ba_gather_states(m_p_context, m_cam_states.empty()? 0 : &m_cam_states[0], m_points.empty()? 0 : &m_points[0]));
 		m_r_system.r_Vertex_Pool().For_Each(CScatterVertices(m_cam_states.empty()? 0 : &m_cam_states[0],
 			m_points.empty()? 0 : &m_points[0]));
 		for(size_t i = 0, n = m_cams.size() / 11; i < n; ++ i) // the cached copy follows: the device and the system agree

@@ -158,6 +158,14 @@ int spp_ba_append_graph(spp_ctx_t ctx, size_t n_new_vertices, const uint8_t *p_v
 int spp_ba_set_states(spp_ctx_t ctx, const double *p_cam_states, const double *p_points);
 int spp_ba_get_states(spp_ctx_t ctx, double *p_cam_states, double *p_points);
 
+/* Several ranks: the states of ALL vertices on every rank -- the cameras are replicated, the landmark slices are summed
+ * into one array with one all-reduce on the device (a collective: every rank calls it). On one rank the same as
+ * spp_ba_get_states. p_cam_states[6 * C], p_points[3 * P] of the whole graph; either may be NULL (on several ranks all
+ * of them must then pass NULL for the points, or none). The reference has no counterpart (single process); the slot-3
+ * adapter writes these states back into the caller's system, so that an application whose ranks all hold the whole
+ * CFlatSystem sees the same optimised system everywhere. */
+int spp_ba_gather_states(spp_ctx_t ctx, double *p_cam_states, double *p_points);
+
 /* Restores the vertex states uploaded by the last spp_ba_set_graph() from a device-side snapshot (no host
  * traffic); lets a benchmark repeat Optimize() on the same resident problem. No reference counterpart. */
 int spp_ba_restore_initial(spp_ctx_t ctx);

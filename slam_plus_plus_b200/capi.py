@@ -23,7 +23,7 @@ MAX_TRACE = 64
 # every symbol include/spp_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "spp_create", "spp_destroy", "spp_last_error", "spp_describe", "spp_kernel_launches", "spp_stream",
-    "spp_synchronize", "spp_set_allreduce", "spp_partition_landmarks", "spp_rcs_block_pattern", "spp_ba_get_partition", "spp_ba_set_graph", "spp_ba_append_graph", "spp_ba_set_states", "spp_ba_get_states",
+    "spp_synchronize", "spp_set_allreduce", "spp_partition_landmarks", "spp_rcs_block_pattern", "spp_ba_get_partition", "spp_ba_set_graph", "spp_ba_append_graph", "spp_ba_set_states", "spp_ba_get_states", "spp_ba_gather_states",
     "spp_ba_restore_initial", "spp_ba_set_jacobian_mode", "spp_ba_linearise", "spp_ba_get_lambda", "spp_ba_get_blocks", "spp_ba_chi2", "spp_ba_solve_step",
     "spp_ba_optimize", "spp_ba_marginals", "spp_schur_symbolic", "spp_schur_solve", "spp_schur_marginals",
     "spp_schur_get_reduced_system",
@@ -93,6 +93,7 @@ def load_library() -> C.CDLL:
                                           C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.spp_ba_get_partition.argtypes = [vp, u64p, u64p]
     lib.spp_ba_set_graph.argtypes = [vp, C.c_size_t, u8p, dp, dp, C.c_size_t, u64p, u64p, dp, dp]
+    lib.spp_ba_gather_states.argtypes = [vp, dp, dp]
     lib.spp_ba_append_graph.argtypes = [vp, C.c_size_t, u8p, dp, dp, C.c_size_t, u64p, u64p, dp, dp]
     lib.spp_ba_set_states.argtypes = [vp, dp, dp]
     lib.spp_ba_get_states.argtypes = [vp, dp, dp]
@@ -382,6 +383,13 @@ class Context:
             if a.shape != shape or a.dtype != np.float64 or not a.flags.c_contiguous or not a.flags.writeable:
                 raise ValueError(f"output buffer must be a writeable C-contiguous float64 array of shape {shape}")
         self._check(self.lib.spp_ba_get_states(self.h, _dp(cs), _dp(ps)))
+        return cs, ps
+
+    def ba_gather_states(self):
+        """All camera states and all landmark positions on every rank (a collective on a partitioned context)."""
+        c, p, _, _ = self._ba_dims
+        cs, ps = np.empty((c, 6)), np.zeros((p, 3))
+        self._check(self.lib.spp_ba_gather_states(self.h, _dp(cs), _dp(ps)))
         return cs, ps
 
     def ba_restore_initial(self):

@@ -994,6 +994,29 @@ int spp_ba_get_states(spp_ctx_t ctx, double *p_cam_states, double *p_points)
 	API_END(ctx)
 }
 
+int spp_ba_gather_states(spp_ctx_t ctx, double *p_cam_states, double *p_points)
+{
+	API_BEGIN(ctx)
+	BAProblem &ba = ctx->ba;
+	if(!ba.valid) throw invalid_error("no BA graph");
+	if(p_cam_states) // the cameras are replicated: every rank holds the same states
+		ba.cam_state.download(p_cam_states, ctx->sys.C * 6, ctx->stream);
+	if(p_points) {
+		if(ctx->world > 1) { // every rank contributes its landmark slice to a zeroed array of all landmarks; one sum
+			DBuf<double> &all = ctx->sys.cov_pt; // (scratch of the marginals, which a partitioned context does not provide)
+			all.resize(ba.P_global * 3);
+			all.zero(ctx->stream);
+			SPP_CUDA(cudaMemcpyAsync(all.p() + ba.pt_begin * 3, ba.pts.p(), ctx->sys.P * 3 * sizeof(double), cudaMemcpyDeviceToDevice,
+				ctx->stream));
+			allreduce_device(ctx, all.p(), ba.P_global * 3);
+			all.download(p_points, ba.P_global * 3, ctx->stream);
+		} else
+			ba.pts.download(p_points, ctx->sys.P * 3, ctx->stream);
+	}
+	SPP_CUDA(cudaStreamSynchronize(ctx->stream));
+	API_END(ctx)
+}
+
 int spp_ba_restore_initial(spp_ctx_t ctx)
 {
 	API_BEGIN(ctx)

@@ -86,6 +86,8 @@ def run_gpu(rank, world):
     rep = ctx.ba_optimize(5, 0.0)
     cs, ps = ctx.ba_get_states()
     ps = parallel.gather_points(ctx, ps)
+    cs_all, ps_all = ctx.ba_gather_states()  # the same through the library's own collective
+    gathered_equal = bool(np.array_equal(cs_all, cs) and np.array_equal(ps_all, ps))
     owners, residual, repeat_equal = [], None, None
     if os.environ.get("SPP_TEST_RCS") == "sparse":
         owners = [int(o) for o in ctx.schur_get_rcs_owners()]
@@ -93,7 +95,7 @@ def run_gpu(rank, world):
         ctx.ba_restore_initial()                 # the same five steps again: the sums have a fixed order for a given N
         rep2 = ctx.ba_optimize(5, 0.0)
         repeat_equal = rep2["trace_chi2"] == rep["trace_chi2"] and rep2["chi2_final"] == rep["chi2_final"]
-    out = dict(owners=owners, rcs_residual=residual, repeat_equal=repeat_equal, chi2_initial=rep["chi2_initial"], chi2_final=rep["chi2_final"], trace_chi2=rep["trace_chi2"],
+    out = dict(gathered_equal=gathered_equal, owners=owners, rcs_residual=residual, repeat_equal=repeat_equal, chi2_initial=rep["chi2_initial"], chi2_final=rep["chi2_final"], trace_chi2=rep["trace_chi2"],
                accepted=rep["trace_accepted"], alpha_initial=rep["alpha_initial"], part=ctx.ba_get_partition(),
                ms=rep["ms"])
     if rank == 0:

@@ -109,6 +109,7 @@ def test_sharded_lm_on_two_gpus_matches_single_gpu(rcs, comm):
         pytest.skip("needs 2 GPUs")
     out = _launch("gpu", 2, env=dict(SPP_TEST_RCS=rcs, SPP_TEST_COMM=comm))
     one = out["single"]
+    assert out["gathered_equal"]  # spp_ba_gather_states = the landmark slices put together by torch.distributed
     assert out["accepted"] == one["accepted"]
     assert abs(out["alpha_initial"] - one["alpha_initial"]) <= 1e-12 * one["alpha_initial"]
     for a, b in zip(out["trace_chi2"], one["trace_chi2"]):
