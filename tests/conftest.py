@@ -30,6 +30,14 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(scope="session")
+def bal_rcs_pattern():
+    """block pattern of the reduced camera system of the BAL-13682 shape (13 682 block columns, 2.27 M upper blocks):
+    half a minute of numpy, shared by the CPU tests that need it"""
+    from slam_plus_plus_b200 import graphs
+    return graphs.rcs_block_pattern(graphs.ba_shape("bal13682"))
+
+
 def lambda_to_dense(col_dims, col_ptr, row_idx, vals, symmetric=True):
     """Block structure (reference layout: upper block-triangular, column-major blocks) -> dense matrix."""
     col_dims = np.asarray(col_dims, np.int64)

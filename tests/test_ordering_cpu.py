@@ -72,11 +72,10 @@ def test_ordering_is_the_reference_permutation(name):
     assert np.array_equal(own, ref), "first difference at position %d" % np.flatnonzero(own != ref)[0]
 
 
-def test_ordering_is_the_reference_permutation_bal13682():
+def test_ordering_is_the_reference_permutation_bal13682(bal_rcs_pattern):
     """the block-sparse reduced camera system of BASELINE's configs[1]: 13682 block columns, 2.27 M upper blocks"""
-    from slam_plus_plus_b200 import graphs
     d = np.load(os.path.join(GOLDEN, "order_ref.npz"))
-    col_ptr, row_idx = graphs.rcs_block_pattern(graphs.ba_shape("bal13682"))
+    col_ptr, row_idx = bal_rcs_pattern
     own = capi.block_ordering(col_ptr, row_idx)
     assert np.array_equal(own, d["rcs_bal13682.order"].astype(np.uint64))
 
@@ -175,12 +174,11 @@ def test_subtree_plan_properties(name, world):
     assert strict["predicted"] == 1.0 and (strict["owner"] == -1).all()
 
 
-def test_subtree_plan_bal13682():
+def test_subtree_plan_bal13682(bal_rcs_pattern):
     """the BAL-13682 reduced camera system: the plan the solver uses on 2 / 4 / 8 ranks (measured factor times on 2 and 4
     GPUs follow the prediction to a few per cent)"""
-    from slam_plus_plus_b200 import graphs
     d = np.load(os.path.join(GOLDEN, "order_ref.npz"))
-    col_ptr, row_idx = graphs.rcs_block_pattern(graphs.ba_shape("bal13682"))
+    col_ptr, row_idx = bal_rcs_pattern
     order = d["rcs_bal13682.order"].astype(np.uint64)
     pred = {}
     for world in (2, 4, 8):
